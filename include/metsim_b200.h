@@ -1,0 +1,178 @@
+/* metsim_b200 -- C ABI of the B200-native MTCLIM hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces a piece of the reference's
+ * per-cell Python path (citations are path:line in the UW-Hydro/MetSim checkout).  Signatures are
+ * plain C: pointers, sizes, POD structs.  No torch / pandas / xarray types cross this line.
+ *
+ * Conventions
+ *   - every array is cell-fastest: daily [D][ld], sub-daily [D*tpd][ld], state [90][ld],
+ *     monthly [12][ld]; "ld" (leading dimension, in elements) >= n_cells.
+ *   - `msb_dev_*` arguments are DEVICE pointers owned by the caller; `stream` is a cudaStream_t
+ *     passed as void* (0 = default stream).  Nothing is allocated behind the caller's back except
+ *     inside msb_run_host(), which owns its device buffers for the duration of the call.
+ *   - every function returns 0 on success, <0 on error (MSB_E_*); msb_last_error() gives the text.
+ *     Errors mirror the reference's exceptions (e.g. t_max < t_min -> MSB_E_DTR_NEGATIVE,
+ *     metsim/metsim.py:612-614).  There is no CPU fallback anywhere in this library.
+ */
+#ifndef METSIM_B200_H
+#define METSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_VERSION 100
+
+enum {
+  MSB_OK = 0,
+  MSB_E_ARG = -1,          /* bad argument / unsupported option */
+  MSB_E_CUDA = -2,         /* CUDA runtime error */
+  MSB_E_DTR_NEGATIVE = -3, /* t_max < t_min somewhere (ValueError, metsim.py:612-614) */
+  MSB_E_NOT_CONVERGED = -4,/* tdew fixed point exceeded max_iter (the reference would spin) */
+  MSB_E_KNOTS = -5,        /* PCHIP knots not strictly increasing (scipy raises ValueError) */
+  MSB_E_NOMEM = -6
+};
+
+enum { MSB_PREC_UNIFORM = 0, MSB_PREC_TRIANGLE = 1, MSB_PREC_MIX = 2 };
+enum { MSB_LW_DEFAULT = 0, MSB_LW_TVA = 1, MSB_LW_ANDERSON = 2, MSB_LW_BRUTSAERT = 3,
+       MSB_LW_SATTERLUND = 4, MSB_LW_IDSO = 5, MSB_LW_PRATA = 6 };
+enum { MSB_CLOUD_DEFAULT = 0, MSB_CLOUD_DEARDORFF = 1 };
+
+/* sub-daily output variables, metsim/metsim.py:660-666 (out_var_check) */
+enum {
+  MSB_V_TEMP = 0, MSB_V_PREC, MSB_V_SHORTWAVE, MSB_V_LONGWAVE, MSB_V_VAPOR_PRESSURE,
+  MSB_V_REL_HUMID, MSB_V_AIR_PRESSURE, MSB_V_SPEC_HUMID, MSB_V_TSKC, MSB_V_WIND,
+  MSB_N_SUBVARS
+};
+/* daily variables produced by the MTCLIM pass, metsim/methods/mtclim.py:50-79 (+ driver columns) */
+enum {
+  MSB_D_T_DAY = 0, MSB_D_TFMAX, MSB_D_TSKC, MSB_D_TDEW, MSB_D_VAPOR_PRESSURE, MSB_D_SHORTWAVE,
+  MSB_D_PET, MSB_D_DAYLENGTH, MSB_D_POTRAD, MSB_D_TT_MAX, MSB_D_SEASONAL_PREC,
+  MSB_D_SMOOTHED_DTR, MSB_N_DAILYVARS
+};
+
+/* the keys of MetSim.params that the hot path reads (metsim/metsim.py:140-171) */
+typedef struct msb_params {
+  int32_t time_step;   /* minutes; divides 1440; 1440 = daily mode */
+  int32_t prec_type;   /* MSB_PREC_* */
+  int32_t utc_offset;  /* bool */
+  int32_t lw_type;     /* MSB_LW_* */
+  int32_t lw_cloud;    /* MSB_CLOUD_* */
+  int32_t max_iter;    /* cap on tdew evaluations (<= 64 supported per call chain) */
+  double sw_prec_thresh, rain_scalar, tdew_tol, tmax_daylength_fraction, tday_coef, lapse_rate;
+} msb_params;
+
+/* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of
+ * physics.py:177-285: only tt_max0 depends on elevation, everything else on latitude alone). */
+#define MSB_TINY_PER_DAY 2880
+#define MSB_Q_LD 2888        /* row pitch of the signed prefix table: entries 0..2880, [2881]=row total */
+#define MSB_TT_TERMS 28      /* Taylor terms of tt_max0 in the pressure ratio */
+#define MSB_TT_P0 0.68       /* expansion point of the pressure ratio p = t1**t2 */
+#define MSB_STATE_DAYS 90
+
+typedef struct msb_solar_tables {
+  int32_t n_lat;        /* number of unique latitude rows */
+  double *daylength;    /* [n_lat][366]  s            physics.py:236 */
+  double *potrad;       /* [n_lat][366]  W m-2        physics.py:276 */
+  double *rise_min;     /* [n_lat][366]  minutes, 240 default applied  disaggregate.py:163-182 */
+  double *set_min;      /* [n_lat][366]  minutes, 960 default applied */
+  double *q;            /* [n_lat][365][MSB_Q_LD] signed prefix sums of the normalised row */
+  double *tt_coef;      /* [n_lat][365][MSB_TT_TERMS] Taylor coefficients of tt_max0(p) */
+} msb_solar_tables;
+
+/* inputs of one shard (contiguous chunk of active cells), all device pointers */
+typedef struct msb_forcing {
+  int32_t n_cells, n_days;
+  int64_t ld;              /* leading dimension of every [*][ld] array */
+  const double *lon, *elev;          /* [n_cells]; lon in degrees, any range */
+  const int32_t *lat_row;            /* [n_cells] index into the solar tables */
+  const int32_t *doy, *month;        /* [n_days] 1-based day of year / month */
+  const double *t_min, *t_max, *prec;/* [n_days][ld] */
+  const double *wind;                /* [n_days][ld] or NULL */
+  const double *st_t_min, *st_t_max, *st_prec; /* [90][ld] state, metsim.py:589-618 */
+  const double *t_pk12, *dur12;      /* [12][ld] or NULL (needed for triangle / mix) */
+  const double *t_end;               /* [2][ld] or NULL  (disaggregate.py:250-253) */
+  /* Optional columns the reference driver hands to method.run(df, params) ready-made
+   * (metsim.py:736-739, :601-616).  When non-NULL the daily pass uses them instead of deriving
+   * them from the state / solar tables -- this is the exact contract of the per-cell callable. */
+  const double *given_seasonal_prec, *given_smoothed_dtr;   /* [n_days][ld] or NULL (both) */
+  const double *given_daylength, *given_potrad, *given_tt_max; /* [n_days][ld] or NULL (all three) */
+} msb_forcing;
+
+typedef struct msb_daily {
+  double *var[MSB_N_DAILYVARS];      /* [n_days][ld] each; TSKC, VAPOR_PRESSURE, SHORTWAVE are
+                                        required by the disaggregation, the rest may be NULL */
+  int32_t *n_iter;                   /* [n_cells] tdew evaluations used (0 = not converged) */
+  double *partial;                   /* scratch, msb_daily_scratch_bytes() */
+  int32_t *status;                   /* [4] device error flags (dtr<0, knots, ...) */
+} msb_daily;
+
+typedef struct msb_subdaily {
+  void *var[MSB_N_SUBVARS];          /* [n_steps][ld] each, NULL = not requested */
+  double scale[MSB_N_SUBVARS];       /* out = value*scale + offset  (metsim/units.py:3-59) */
+  double offset[MSB_N_SUBVARS];
+  int32_t dtype;                     /* 4 = float32 (reference default out_precision), 8 = float64 */
+  int64_t ld;
+  int32_t day0, day1;                /* produce days [day0, day1); var[] points at step day0*tpd */
+} msb_subdaily;
+
+int msb_version(void);
+const char *msb_last_error(void);
+void msb_default_params(msb_params *p);                          /* metsim.py:140-171 */
+
+/* ---- solar geometry: physics.py:177-285 + disaggregate.py:133-201 (rise/set) ---------------
+ * Host prelude (glibc libm, decides the sunrise sign bit-for-bit like the reference) + table
+ * kernel.  lat_deg is a HOST array of the unique latitudes; tables are DEVICE buffers sized by
+ * msb_solar_table_bytes().  host_ws must hold msb_solar_prelude_bytes(n_lat) bytes (pinned
+ * memory makes the upload asynchronous), dev_ws the same number of bytes on the device. */
+size_t msb_solar_prelude_bytes(int n_lat);
+int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_elems, size_t *tt_elems);
+int msb_solar_tables_build(int n_lat, const double *lat_deg_host, void *host_ws, void *dev_ws,
+                           const msb_solar_tables *tables, int n_host_threads, void *stream);
+
+/* ---- daily MTCLIM: mtclim.py:28-80 (run), metsim.py:589-618 (rolling means) ---------------- */
+size_t msb_daily_scratch_bytes(int n_cells, int n_days);
+int msb_mtclim_daily(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
+                     const msb_daily *out, void *stream);
+/* reads back status/n_iter flags (synchronises the stream); returns MSB_OK or the first error */
+int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
+
+/* ---- sub-daily disaggregation: disaggregate.py:34-680, units.py:3-59 ----------------------- */
+int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
+                     const msb_daily *daily, const msb_subdaily *out, void *stream);
+
+/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [5][n]
+ * (1/x, exp(x), sqrt(x), 1.2345678901234567/x, svp(x) in kPa).  Used by the parity tests. */
+int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream);
+
+/* ---- whole path with HOST buffers (what a reference-side binding calls) ---------------------
+ * Replaces the cell loop of MetSim.run_slice (metsim.py:477-493): unique-latitude tables,
+ * H2D of the forcings, daily pass, time-tiled disaggregation with double-buffered D2H into
+ * the caller's host arrays.  lat is per cell (degrees).  out_host[v] is [n_days*tpd][n_cells]
+ * (dtype per out_dtype) or NULL.  daily_host[v] is [n_days][n_cells] float64 or NULL. */
+typedef struct msb_host_run {
+  int32_t n_cells, n_days, device;
+  const double *lat, *lon, *elev;
+  const int32_t *doy, *month;
+  const double *t_min, *t_max, *prec, *wind;
+  const double *st_t_min, *st_t_max, *st_prec;
+  const double *t_pk12, *dur12, *t_end;
+  void *out_host[MSB_N_SUBVARS];
+  double scale[MSB_N_SUBVARS], offset[MSB_N_SUBVARS];
+  int32_t out_dtype;                 /* 4 or 8 */
+  double *daily_host[MSB_N_DAILYVARS];
+  int32_t *n_iter_host;              /* [n_cells] or NULL */
+  int32_t tile_days;                 /* 0 = choose */
+  int32_t out_is_ring;               /* !=0: out_host[v] holds only 2*tile_days*tpd steps and is
+                                        reused as a ring (a streaming writer drains it) */
+  double ms_solar, ms_h2d, ms_daily, ms_disagg_total; /* filled on return (CUDA events) */
+} msb_host_run;
+int msb_run_host(const msb_params *p, msb_host_run *run);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,318 @@
+// Daily MTCLIM pass: rolling means, cloud transmittance, the dew-point fixed point and PET.
+//
+// Reference: metsim/methods/mtclim.py:28-80 (run) with its helpers :83-256,
+// metsim/physics.py:28-152 (calc_pet, atm_pres, svp) and the driver's rolling means
+// metsim/metsim.py:589-618.
+//
+// The reference iterates vapor_pressure -> shortwave -> pet -> tdew on a cell's whole record
+// until the RMS change over ALL days drops below tdew_tol.  Per day the map is independent; days
+// couple only through the number of evaluations.  B200 design: one thread per (cell, day chunk),
+// cells on the lanes so every [D][N] access is coalesced;
+//   pass 1  runs 8 evaluations per day in registers and accumulates sum_d (tdew_k - tdew_{k-1})^2
+//           per k into a [chunk][k][cell] scratch array (deterministic, no atomics);
+//   reduce  adds the chunks in fixed order and picks the evaluation count n* exactly as the
+//           reference's while-loop would;
+//   pass 2  replays n* evaluations and writes the daily outputs.
+// No per-iteration state ever touches HBM.
+#include <cstring>
+
+#include "msb_common.cuh"
+
+namespace msb {
+
+constexpr int kEvalsPerRound = 8;
+constexpr int kDailyThreads = 128;
+
+struct DailyLaunch {
+  int chunk_len, n_chunks;
+};
+
+static DailyLaunch daily_launch(int n_cells, int n_days) {
+  // aim for >= ~2M threads, chunks of at least 8 days
+  long want = (2L << 20) / (n_cells > 0 ? n_cells : 1) + 1;
+  long max_chunks = (n_days + 7) / 8;
+  long nc = want < 1 ? 1 : want;
+  if (nc > max_chunks) nc = max_chunks;
+  if (nc > 64) nc = 64;
+  if (nc < 1) nc = 1;
+  DailyLaunch l;
+  l.chunk_len = (int)((n_days + nc - 1) / nc);
+  l.n_chunks = (n_days + l.chunk_len - 1) / l.chunk_len;
+  return l;
+}
+
+struct DayInv {
+  double t_min, dtr, sp80, tfmax, tt_max, potrad, daylength, t_day, c1, lhvap;
+};
+
+// one evaluation of the reference's loop body for one day (mtclim.py:65-71)
+__device__ __forceinline__ double tdew_step(const DayInv &v, double tdew_old) {
+  double vp = svp_ref(tdew_old);                                   // mtclim.py:197-214
+  double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);         // mtclim.py:233
+  double sw = v.potrad * t_tmax * v.tfmax;                         // mtclim.py:234
+  double rnet = sw * 0.72;                                         // physics.py:62
+  double pet = ((v.c1 * rnet * v.daylength) / v.lhvap) / 10. * 10.0;  // physics.py:92-96, mtclim.py:161
+  double ratio = pet / v.sp80;                                     // mtclim.py:189
+  double r2 = ratio * ratio;
+  return (v.t_min + kKelvin) *
+             (-0.127 + 1.121 * (1.003 - 1.444 * ratio + 12.312 * r2 - 32.766 * (r2 * ratio)) +
+              0.0006 * v.dtr) - kKelvin;                           // mtclim.py:190-194
+}
+
+struct CellConst {
+  double pa, px;       // air pressure (Pa), p - p0 for the tt_max0 series
+  const double *tt, *dayl, *potrad;  // per-latitude-row table bases
+};
+
+__device__ __forceinline__ CellConst cell_const(const msb_params &p, const msb_forcing &f,
+                                                const msb_solar_tables &t, int cell) {
+  CellConst c;
+  double elev = f.elev[cell];
+  double t1 = 1.0 - (p.lapse_rate * elev) / kTStd;        // physics.py:118-121, :206-208
+  double t2 = kGStd / (p.lapse_rate * (kR / kMA));
+  double pr = pow(t1, t2);
+  c.pa = kPStd * pr;
+  c.px = pr - MSB_TT_P0;
+  if (f.given_daylength == nullptr) {
+    int row = f.lat_row[cell];
+    c.tt = t.tt_coef + (size_t)row * 365 * kTT;
+    c.dayl = t.daylength + (size_t)row * kRows;
+    c.potrad = t.potrad + (size_t)row * kRows;
+  } else {
+    c.tt = c.dayl = c.potrad = nullptr;
+  }
+  return c;
+}
+
+// window sums for day d (inclusive), reading the 90-day state for negative indices
+__device__ __forceinline__ double hist(const double *cur, const double *st, long ld, int cell,
+                                       int k) {
+  return (k < 0) ? st[(size_t)(kState + k) * ld + cell] : cur[(size_t)k * ld + cell];
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kDailyThreads)
+daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int chunk_len,
+             int k_off, int max_evals) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= f.n_cells) return;
+  const int chunk = blockIdx.y;
+  const int D = f.n_days;
+  const long ld = f.ld;
+  const int d_lo = chunk * chunk_len;
+  const int d_hi = min(D, d_lo + chunk_len);
+  int n_evals = 0;
+  if (PASS == 1) {
+    if (k_off > 0 && out.n_iter[cell] != 0) return;  // converged in an earlier round
+  } else {
+    n_evals = out.n_iter[cell];
+    if (n_evals == 0) {                               // never converged: flag, use the cap
+      n_evals = max_evals;
+      out.status[1] = 1;
+    }
+  }
+  const CellConst cc = cell_const(p, f, t, cell);
+
+  // rolling windows (metsim.py:601-616): 90-day precipitation, 30-day temperature range
+  const bool roll = f.given_seasonal_prec == nullptr;
+  const bool solar = f.given_daylength == nullptr;
+  double s_prec = 0.0, s_dtr = 0.0;
+  if (roll) {
+    for (int k = d_lo - 89; k < d_lo; ++k) s_prec += hist(f.prec, f.st_prec, ld, cell, k);
+    for (int k = d_lo - 29; k < d_lo; ++k)
+      s_dtr += hist(f.t_max, f.st_t_max, ld, cell, k) - hist(f.t_min, f.st_t_min, ld, cell, k);
+  }
+
+  double acc[kEvalsPerRound];
+#pragma unroll
+  for (int k = 0; k < kEvalsPerRound; ++k) acc[k] = 0.0;
+
+  for (int d = d_lo; d < d_hi; ++d) {
+    const size_t o = (size_t)d * ld + cell;
+    DayInv v;
+    const double t_min = f.t_min[o], t_max = f.t_max[o], prec = f.prec[o];
+    v.t_min = t_min;
+    v.dtr = t_max - t_min;
+    if (v.dtr < 0.0) out.status[0] = 1;                 // ValueError, metsim.py:612-614
+    double seasonal, sm_dtr;
+    if (roll) {
+      s_prec += prec;
+      s_dtr += v.dtr;
+      seasonal = kDaysPerYear * (s_prec / 90.0);
+      sm_dtr = s_dtr / 30.0;
+      // slide the windows for the next day
+      s_prec -= hist(f.prec, f.st_prec, ld, cell, d - 89);
+      s_dtr -= hist(f.t_max, f.st_t_max, ld, cell, d - 29) - hist(f.t_min, f.st_t_min, ld, cell, d - 29);
+    } else {
+      seasonal = f.given_seasonal_prec[o];
+      sm_dtr = f.given_smoothed_dtr[o];
+    }
+    v.sp80 = seasonal < 80.0 ? 80.0 : seasonal;        // mtclim.py:187-188
+
+    if (solar) {
+      const int y = f.doy[d] - 1;
+      v.daylength = cc.dayl[y];
+      v.potrad = cc.potrad[y];
+      // tt_max0(p): Horner in (p - p0), coefficients per (latitude, yday)
+      const double *c = cc.tt + (size_t)min(y, 364) * kTT;
+      double s = c[kTT - 1];
+#pragma unroll
+      for (int m = kTT - 2; m >= 0; --m) s = fma(s, cc.px, c[m]);
+      v.tt_max = s;
+    } else {
+      v.daylength = f.given_daylength[o];
+      v.potrad = f.given_potrad[o];
+      v.tt_max = f.given_tt_max[o];
+    }
+    const double t_mean = (t_min + t_max) / 2;                          // mtclim.py:103-104
+    v.t_day = ((t_max - t_mean) * p.tday_coef) + t_mean;
+    const double b = kB0 + kB1 * exp(-kB2 * sm_dtr);                   // mtclim.py:129-133
+    double tf = 1.0 - 0.9 * exp(-b * (v.dtr * sqrt(v.dtr)));            // dtr**1.5
+    if (prec > p.sw_prec_thresh) tf *= p.rain_scalar;
+    v.tfmax = tf;
+    {  // day-invariant part of calc_pet (physics.py:62-92)
+      v.lhvap = 2.5023e6 - 2430.54 * v.t_day;
+      const double gamma = kCp * cc.pa / (v.lhvap * kEps);
+      const double t1 = v.t_day + 0.2, t2 = v.t_day - 0.2;
+      const double s = (svp_ref(t1) - svp_ref(t2)) / (t1 - t2);
+      v.c1 = 1.26 * (s / (s + gamma));
+    }
+
+    double tdew = t_min;                                                // mtclim.py:54
+    if (PASS == 1) {
+      for (int k = 0; k < k_off; ++k) tdew = tdew_step(v, tdew);
+#pragma unroll
+      for (int k = 0; k < kEvalsPerRound; ++k) {
+        const double nxt = tdew_step(v, tdew);
+        const double df = nxt - tdew;
+        acc[k] = fma(df, df, acc[k]);
+        tdew = nxt;
+      }
+    } else {
+      for (int k = 0; k < n_evals; ++k) tdew = tdew_step(v, tdew);
+      const double vp = svp_ref(tdew);                                  // mtclim.py:73-79
+      const double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);
+      const double sw = v.potrad * t_tmax * v.tfmax;
+      const double pet = ((v.c1 * (sw * 0.72) * v.daylength) / v.lhvap) / 10. * 10.0;
+      const double tskc = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
+      double *const *o_ = out.var;
+      if (o_[MSB_D_T_DAY]) o_[MSB_D_T_DAY][o] = v.t_day;
+      if (o_[MSB_D_TFMAX]) o_[MSB_D_TFMAX][o] = tf;
+      if (o_[MSB_D_TSKC]) o_[MSB_D_TSKC][o] = tskc;
+      if (o_[MSB_D_TDEW]) o_[MSB_D_TDEW][o] = tdew;
+      if (o_[MSB_D_VAPOR_PRESSURE]) o_[MSB_D_VAPOR_PRESSURE][o] = vp;
+      if (o_[MSB_D_SHORTWAVE]) o_[MSB_D_SHORTWAVE][o] = sw;
+      if (o_[MSB_D_PET]) o_[MSB_D_PET][o] = pet;
+      if (o_[MSB_D_DAYLENGTH]) o_[MSB_D_DAYLENGTH][o] = v.daylength;
+      if (o_[MSB_D_POTRAD]) o_[MSB_D_POTRAD][o] = v.potrad;
+      if (o_[MSB_D_TT_MAX]) o_[MSB_D_TT_MAX][o] = v.tt_max;
+      if (o_[MSB_D_SEASONAL_PREC]) o_[MSB_D_SEASONAL_PREC][o] = seasonal;
+      if (o_[MSB_D_SMOOTHED_DTR]) o_[MSB_D_SMOOTHED_DTR][o] = sm_dtr;
+    }
+  }
+  if (PASS == 1) {
+#pragma unroll
+    for (int k = 0; k < kEvalsPerRound; ++k)
+      out.partial[((size_t)chunk * kEvalsPerRound + k) * f.n_cells + cell] = acc[k];
+  }
+}
+
+// while np.sqrt(np.mean((tdew_temp - tdew_old)**2)) > tdew_tol  (mtclim.py:63)
+__global__ void daily_reduce_kernel(msb_params p, int n_cells, int n_days, int n_chunks, int k_off,
+                                    const double *__restrict__ partial, int32_t *n_iter) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  if (k_off == 0) n_iter[cell] = 0;
+  else if (n_iter[cell] != 0) return;
+  for (int k = 0; k < kEvalsPerRound; ++k) {
+    double s = 0.0;
+    for (int c = 0; c < n_chunks; ++c) s += partial[((size_t)c * kEvalsPerRound + k) * n_cells + cell];
+    const double rms = sqrt(s / (double)n_days);
+    if (!(rms > p.tdew_tol)) { n_iter[cell] = k_off + k + 1; return; }
+  }
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" size_t msb_daily_scratch_bytes(int n_cells, int n_days) {
+  if (n_cells <= 0 || n_days <= 0) return 0;
+  DailyLaunch l = daily_launch(n_cells, n_days);
+  return (size_t)l.n_chunks * kEvalsPerRound * (size_t)n_cells * sizeof(double);
+}
+
+static int check_forcing(const msb_forcing *f, const char *who) {
+  if (!f || f->n_cells <= 0 || f->n_days < 2 || f->ld < f->n_cells) {
+    set_error("%s: bad forcing shape (n_cells=%d n_days=%d ld=%lld)", who, f ? f->n_cells : 0,
+              f ? f->n_days : 0, f ? (long long)f->ld : 0LL);
+    return MSB_E_ARG;
+  }
+  const bool roll = f->given_seasonal_prec == nullptr, solar = f->given_daylength == nullptr;
+  if (!roll && !f->given_smoothed_dtr) { set_error("%s: given_smoothed_dtr missing", who); return MSB_E_ARG; }
+  if (!solar && (!f->given_potrad || !f->given_tt_max)) { set_error("%s: given_potrad/given_tt_max missing", who); return MSB_E_ARG; }
+  if (!f->elev || !f->t_min || !f->t_max || !f->prec ||
+      (roll && (!f->st_t_min || !f->st_t_max || !f->st_prec)) ||
+      (solar && (!f->lat_row || !f->doy))) {
+    set_error("%s: a required forcing pointer is NULL", who);
+    return MSB_E_ARG;
+  }
+  return MSB_OK;
+}
+
+extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
+                                const msb_solar_tables *t, const msb_daily *out, void *stream) {
+  if (!p || !out) { set_error("msb_mtclim_daily: NULL argument"); return MSB_E_ARG; }
+  int rc = check_forcing(f, "msb_mtclim_daily");
+  if (rc) return rc;
+  msb_solar_tables no_tables;
+  memset(&no_tables, 0, sizeof(no_tables));
+  if (!t) {
+    if (!f->given_daylength) { set_error("msb_mtclim_daily: solar tables required"); return MSB_E_ARG; }
+    t = &no_tables;
+  }
+  if (!out->n_iter || !out->partial || !out->status) {
+    set_error("msb_mtclim_daily: n_iter / partial / status buffers are required");
+    return MSB_E_ARG;
+  }
+  if (!(p->lapse_rate != 0.0)) { set_error("msb_mtclim_daily: lapse_rate must be non-zero"); return MSB_E_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DailyLaunch l = daily_launch(f->n_cells, f->n_days);
+  dim3 grid((f->n_cells + kDailyThreads - 1) / kDailyThreads, l.n_chunks);
+  int max_iter = p->max_iter > 0 ? p->max_iter : 24;
+  int rounds = (max_iter + kEvalsPerRound - 1) / kEvalsPerRound;
+  if (rounds > 8) rounds = 8;
+  MSB_CUDA(cudaMemsetAsync(out->status, 0, 4 * sizeof(int32_t), st));
+  for (int r = 0; r < rounds; ++r) {
+    int k_off = r * kEvalsPerRound;
+    daily_kernel<1><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, k_off, 0);
+    daily_reduce_kernel<<<(f->n_cells + 255) / 256, 256, 0, st>>>(*p, f->n_cells, f->n_days,
+                                                                  l.n_chunks, k_off, out->partial,
+                                                                  out->n_iter);
+  }
+  daily_kernel<2><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0,
+                                                  rounds * kEvalsPerRound);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}
+
+extern "C" int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream) {
+  if (!f || !out || !out->status) { set_error("msb_daily_check: NULL argument"); return MSB_E_ARG; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int32_t h[4] = {0, 0, 0, 0};
+  MSB_CUDA(cudaMemcpyAsync(h, out->status, sizeof(h), cudaMemcpyDeviceToHost, st));
+  MSB_CUDA(cudaStreamSynchronize(st));
+  if (h[0]) {
+    set_error("Daily maximum temperature lower than daily minimum temperature!");
+    return MSB_E_DTR_NEGATIVE;
+  }
+  if (h[1]) {
+    set_error("tdew fixed point did not reach tdew_tol within max_iter evaluations");
+    return MSB_E_NOT_CONVERGED;
+  }
+  if (h[2]) {
+    set_error("`x` must be strictly increasing sequence. (temperature knots)");
+    return MSB_E_KNOTS;
+  }
+  return MSB_OK;
+}

@@ -1,0 +1,308 @@
+// Solar geometry for the unique latitudes of a shard.
+//
+// Reference: metsim/physics.py:177-285 (solar_geom) builds, PER CELL, a 366x2880 table of
+// 30-second radiation fractions plus daylength / flat_potrad / tt_max0, and
+// metsim/disaggregate.py:133-201 (set_min_max_hour) re-derives sunrise/sunset from that table.
+// Only tt_max0 depends on the cell's elevation; everything else depends on latitude alone.
+//
+// B200 design (not a port):
+//  * K0, host, glibc libm: per (latitude, yday) the five scalars that decide index placement --
+//    cosegeom, sinegeom, hss, the step count of numba's arange and the zenith cosine of the first
+//    step.  That first value is mathematically 0 and numerically +-1e-17; its SIGN moves the
+//    sunrise index by one step, so it must come from the same libm the reference runs on.
+//  * K1, device, one CTA per (yday, latitude): the normalised row is built in shared memory and
+//    reduced to what the other kernels need -- daylength, potrad, rise/set minutes, a SIGNED
+//    PREFIX TABLE q[] from which any window sum of the row is two loads, and Taylor
+//    coefficients of tt_max0 in the pressure ratio p (so the per-cell part is a Horner chain).
+#include <algorithm>
+#include <cmath>
+#include <thread>
+#include <vector>
+
+#include "msb_common.cuh"
+
+namespace msb {
+
+struct PreludeView {
+  double *cosegeom, *sinegeom, *hss, *cza0;  // [n_lat][365]
+  int32_t *nstep;                            // [n_lat][365]
+};
+
+static PreludeView prelude_view(void *base, int n_lat) {
+  PreludeView v;
+  size_t n = (size_t)n_lat * 365;
+  double *d = reinterpret_cast<double *>(base);
+  v.cosegeom = d;
+  v.sinegeom = d + n;
+  v.hss = d + 2 * n;
+  v.cza0 = d + 3 * n;
+  v.nstep = reinterpret_cast<int32_t *>(d + 4 * n);
+  return v;
+}
+
+// K0 -- physics.py:212-236, :243 (first iteration of the hour-angle loop).  Compiled by the host
+// compiler with -ffp-contract=off: numba/LLVM does not fuse multiply-add.
+static void prelude_rows(const double *lat_deg, int r0, int r1, PreludeView v) {
+  const double dh = kSwRadDt / kSecPerRad;
+  for (int r = r0; r < r1; ++r) {
+    double lat = std::fmin(std::fmax(lat_deg[r] * kRadPerDeg, -M_PI / 2.), M_PI / 2.0);
+    double coslat = std::cos(lat), sinlat = std::sin(lat);
+    for (int i = 0; i < 365; ++i) {
+      double decl = kMinDecl * std::cos((i + kDaysOff) * kRadPerDay);
+      double cosdecl = std::cos(decl), sindecl = std::sin(decl);
+      double cosegeom = coslat * cosdecl;
+      double sinegeom = sinlat * sindecl;
+      double coshss = std::fmin(std::fmax(-sinegeom / cosegeom, -1.0), 1.0);
+      double hss = std::acos(coshss);
+      double start = -hss;
+      long n = (long)std::ceil((hss - start) / dh);  // numba arange length
+      if (n < 0) n = 0;
+      double cosh0 = std::cos(start);
+      volatile double prod = cosegeom * cosh0;        // keep the product rounded on its own
+      double cza0 = prod + sinegeom;
+      size_t o = (size_t)r * 365 + i;
+      v.cosegeom[o] = cosegeom;
+      v.sinegeom[o] = sinegeom;
+      v.hss[o] = hss;
+      v.cza0[o] = cza0;
+      v.nstep[o] = (int32_t)n;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kK1Threads = 256;
+constexpr int kChunk = 12;                       // 240 active scan threads x 12 = 2880
+constexpr int kScanThreads = kTiny / kChunk;     // 240
+
+__constant__ double c_optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.37, 4.72, 5.12, 5.60,
+                                   6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
+
+__device__ __forceinline__ int tiny_index(double h) {
+  // physics.py:264-266, evaluated without contraction
+  double v = __ddiv_rn(__dadd_rn(43200.0, __dmul_rn(h, kSecPerRad)), kSwRadDt);
+  v = fmin(fmax(v, 0.0), (double)(kTiny - 1));
+  return (int)v;
+}
+
+// deterministic block sum (fixed tree): warp shuffles then warp 0
+__device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (l < (blockDim.x >> 5)) ? red[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (l == 0) red[0] = v;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(kK1Threads)
+solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
+                  const double *__restrict__ g_sinegeom, const double *__restrict__ g_hss,
+                  const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
+                  msb_solar_tables tb) {
+  __shared__ double row[kTiny];
+  __shared__ double red[32];
+  __shared__ double mom[kTT];
+  __shared__ double chunk_tot[kScanThreads];
+  __shared__ int s_rise, s_set;
+
+  const int i = blockIdx.x % 365;   // yday row 0..364
+  const int r = blockIdx.x / 365;   // latitude row
+  const size_t o = (size_t)r * 365 + i;
+  const double cosegeom = g_cosegeom[o], sinegeom = g_sinegeom[o], hss = g_hss[o];
+  const double cza_first = g_cza0[o];
+  const int n = g_nstep[o];
+  const double dh = kSwRadDt / kSecPerRad;
+  const double kLnTBase = -0.13926206733350766;  // ln(0.87)
+
+  for (int j = threadIdx.x; j < kTiny; j += blockDim.x) row[j] = 0.0;
+  if (threadIdx.x < kTT) mom[threadIdx.x] = 0.0;
+  if (threadIdx.x == 0) { s_rise = -1; s_set = -1; }
+  __syncthreads();
+
+  // physics.py:238-239
+  const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
+  const double start = -hss;
+
+  double sum_dfa = 0.0;
+  double m_loc[kTT];
+#pragma unroll
+  for (int m = 0; m < kTT; ++m) m_loc[m] = 0.0;
+
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double h = __dadd_rn(start, __dmul_rn((double)k, dh));
+    double cza = (k == 0) ? cza_first : __dadd_rn(__dmul_rn(cosegeom, cos(h)), sinegeom);
+    double dfa = 0.0;
+    if (cza > 0.0) {
+      dfa = beam * cza;                                  // physics.py:252
+      double am = 1.0 / (cza + 0.0000001);
+      if (am > 2.9) {
+        int ami = (int)(acos(cza) / kRadPerDeg) - 69;
+        ami = min(max(ami, 0), 20);
+        am = c_optam[ami];
+      }
+      sum_dfa += dfa;
+      // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
+      double a = am * kLnTBase;
+      double term = exp(a * MSB_TT_P0) * dfa;
+      m_loc[0] += term;
+#pragma unroll
+      for (int m = 1; m < kTT; ++m) {
+        term *= a * (1.0 / (double)m);
+        m_loc[m] += term;
+      }
+    }
+    // "assignment, not accumulation" (physics.py:267): the last k mapping to an index wins
+    int ts = tiny_index(h);
+    bool last = (k == n - 1);
+    if (!last) {
+      double hn = __dadd_rn(start, __dmul_rn((double)(k + 1), dh));
+      last = tiny_index(hn) != ts;
+    }
+    if (last) row[ts] = dfa;
+  }
+
+  const double total = block_sum(sum_dfa, red);
+#pragma unroll
+  for (int m = 0; m < kTT; ++m) {
+    double s = block_sum(m_loc[m], red);
+    if (threadIdx.x == 0) mom[m] = s;
+  }
+  __syncthreads();
+
+  const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
+  const bool has_day = daylength != 0.0;
+  if (has_day && total > 0.0)
+    for (int j = threadIdx.x; j < kTiny; j += blockDim.x) row[j] = row[j] / total;  // :270-271
+  __syncthreads();
+
+  // sunrise / sunset: last j with row[j] <= 0 < row[j+1] / row[j] > 0 >= row[j+1]
+  int rise = -1, set = -1;
+  for (int j = threadIdx.x; j < kTiny - 1; j += blockDim.x) {
+    int a = row[j] > 0.0, b = row[j + 1] > 0.0;
+    if (b - a > 0) rise = max(rise, j);
+    if (b - a < 0) set = max(set, j);
+  }
+  if (rise >= 0) atomicMax(&s_rise, rise);
+  if (set >= 0) atomicMax(&s_set, set);
+
+  // signed prefix table: q[j] = sum_{i<j} row[i] for j <= 1440, -sum_{i>=j} row[i] for j > 1440
+  double *q = tb.q + ((size_t)r * 365 + i) * kQLd;
+  double loc[kChunk];
+  double csum = 0.0;
+  const int t = threadIdx.x;
+  const bool fwd = t < kScanThreads / 2;
+  if (t < kScanThreads) {
+    if (fwd) {
+      for (int e = 0; e < kChunk; ++e) { loc[e] = csum; csum += row[t * kChunk + e]; }
+    } else {
+      for (int e = kChunk - 1; e >= 0; --e) { csum += row[t * kChunk + e]; loc[e] = csum; }
+    }
+    chunk_tot[t] = csum;
+  }
+  __syncthreads();
+  if (t < kScanThreads) {
+    double base = 0.0;
+    if (fwd) { for (int c = 0; c < t; ++c) base += chunk_tot[c]; }
+    else { for (int c = kScanThreads - 1; c > t; --c) base += chunk_tot[c]; }
+    if (fwd) { for (int e = 0; e < kChunk; ++e) q[t * kChunk + e] = base + loc[e]; }
+    else { for (int e = 0; e < kChunk; ++e) if (t * kChunk + e > kNoon) q[t * kChunk + e] = -(base + loc[e]); }
+  }
+  if (t == 0) {
+    double first_half = 0.0, second_half = 0.0;
+    for (int c = 0; c < kScanThreads / 2; ++c) first_half += chunk_tot[c];
+    for (int c = kScanThreads - 1; c >= kScanThreads / 2; --c) second_half += chunk_tot[c];
+    q[kNoon] = first_half;           // prefix up to (not including) tiny step 1440
+    q[kTiny] = -0.0;                 // empty suffix
+    q[kTiny + 1] = first_half + second_half;  // row total (1 up to rounding, 0 for polar night)
+    for (int e = kTiny + 2; e < kQLd; ++e) q[e] = 0.0;
+  }
+  __syncthreads();
+
+  if (t == 0) {
+    const double step_min = kSwRadDt / 60.0;
+    double rise_m = (s_rise >= 0) ? s_rise * step_min : 0.0;
+    double set_m = (s_set >= 0) ? s_set * step_min : 0.0;
+    const double day_tot = (kSecPerDay / kSwRadDt) * (kSwRadDt / 60.0);
+    if (rise_m == 0.0) rise_m = day_tot / 6;       // disaggregate.py:179-182
+    if (set_m == 0.0) set_m = 4 * day_tot / 6;
+    double potrad = has_day ? total / daylength : 0.0;                      // physics.py:276-280
+    size_t s = (size_t)r * kRows + i;
+    tb.daylength[s] = daylength;
+    tb.potrad[s] = potrad;
+    tb.rise_min[s] = rise_m;
+    tb.set_min[s] = set_m;
+    if (i == 364) {  // row 365 copies row 364, physics.py:281-284
+      tb.daylength[s + 1] = daylength;
+      tb.potrad[s + 1] = potrad;
+      tb.rise_min[s + 1] = rise_m;
+      tb.set_min[s + 1] = set_m;
+    }
+  }
+  if (t < kTT) {
+    // tt_max0(p) = sum_trans/sum_flat_potrad (physics.py:275); 0 when there is no daylight
+    double c = (has_day && total > 0.0) ? mom[t] / total : 0.0;
+    tb.tt_coef[((size_t)r * 365 + i) * kTT + t] = c;
+  }
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" size_t msb_solar_prelude_bytes(int n_lat) {
+  size_t n = (size_t)(n_lat > 0 ? n_lat : 0) * 365;
+  return n * (4 * sizeof(double) + sizeof(int32_t)) + 64;
+}
+
+extern "C" int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_elems,
+                                     size_t *tt_elems) {
+  if (n_lat <= 0) { set_error("msb_solar_table_sizes: n_lat must be > 0"); return MSB_E_ARG; }
+  if (small_elems) *small_elems = (size_t)n_lat * kRows;
+  if (q_elems) *q_elems = (size_t)n_lat * 365 * kQLd;
+  if (tt_elems) *tt_elems = (size_t)n_lat * 365 * kTT;
+  return MSB_OK;
+}
+
+extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, void *host_ws,
+                                      void *dev_ws, const msb_solar_tables *tb,
+                                      int n_host_threads, void *stream) {
+  if (n_lat <= 0 || !lat_deg_host || !host_ws || !dev_ws || !tb) {
+    set_error("msb_solar_tables_build: null/empty argument");
+    return MSB_E_ARG;
+  }
+  if (!tb->daylength || !tb->potrad || !tb->rise_min || !tb->set_min || !tb->q || !tb->tt_coef ||
+      tb->n_lat != n_lat) {
+    set_error("msb_solar_tables_build: table buffers missing or n_lat mismatch");
+    return MSB_E_ARG;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PreludeView hv = prelude_view(host_ws, n_lat);
+  int nt = std::max(1, std::min(n_host_threads, n_lat));
+  if (nt == 1) {
+    prelude_rows(lat_deg_host, 0, n_lat, hv);
+  } else {
+    std::vector<std::thread> pool;
+    int per = (n_lat + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+      int r0 = t * per, r1 = std::min(n_lat, r0 + per);
+      if (r0 >= r1) break;
+      pool.emplace_back(prelude_rows, lat_deg_host, r0, r1, hv);
+    }
+    for (auto &th : pool) th.join();
+  }
+  size_t bytes = msb_solar_prelude_bytes(n_lat) - 64;
+  MSB_CUDA(cudaMemcpyAsync(dev_ws, host_ws, bytes, cudaMemcpyHostToDevice, st));
+  PreludeView dv = prelude_view(dev_ws, n_lat);
+  unsigned grid = 365u * (unsigned)n_lat;
+  solar_rows_kernel<<<grid, kK1Threads, 0, st>>>(n_lat, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0,
+                                                 dv.nstep, *tb);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}

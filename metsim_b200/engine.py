@@ -1,0 +1,313 @@
+"""Batched, device-resident driver of the CUDA path: the B200 form of ``MetSim.run_slice``.
+
+Reference call chain replaced here (metsim/metsim.py):
+``run_slice`` :456-493 -> per-cell ``wrap_run_cell`` :693-796 -> ``solar_geom`` ->
+``method.run`` -> ``disaggregate``.  One :class:`Engine` holds one shard (a contiguous chunk of
+active cells) on one GPU; PyTorch supplies device memory and the stream, every kernel is in
+``csrc/libmetsim_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DAILY_VARS, SUB_VARS
+
+KELVIN = 273.15
+DEFAULT_OUT_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_humid")
+
+
+def unit_scale_offset(var: str, units: str | None, ts: int):
+    """(scale, offset) equivalent of metsim/units.py:3-59 for one variable."""
+    if units is None:
+        return 1.0, 0.0
+    table = {
+        "prec": {"mm timestep-1": (1.0, 0.0), "mm h-1": (1.0 / (ts / 60.0), 0.0),
+                 "mm s-1": (1.0 / (ts * 60.0), 0.0)},
+        "pet": {"mm timestep-1": (1.0, 0.0), "mm h-1": (1.0 / (ts / 60.0), 0.0),
+                "mm s-1": (1.0 / (ts * 60.0), 0.0)},
+        "shortwave": {"W m-2": (1.0, 0.0)},
+        "longwave": {"W m-2": (1.0, 0.0)},
+        "temp": {"C": (1.0, 0.0), "K": (1.0, KELVIN)},
+        "t_min": {"C": (1.0, 0.0), "K": (1.0, KELVIN)},
+        "t_max": {"C": (1.0, 0.0), "K": (1.0, KELVIN)},
+        "vapor_pressure": {"Pa": (1.0, 0.0), "hPa": (1.0 / 100.0, 0.0), "kPa": (1.0 / 1000.0, 0.0)},
+        "air_pressure": {"kPa": (1.0, 0.0), "hPa": (100.0, 0.0), "Pa": (1000.0, 0.0)},
+        "tskc": {"fraction": (1.0, 0.0), "%": (100.0, 0.0)},
+        "rel_humid": {"%": (1.0, 0.0), "fraction": (1.0 / 100.0, 0.0)},
+        "spec_humid": {"g g-1": (1.0, 0.0)},
+        "wind": {"m s-1": (1.0, 0.0)},
+        "daylength": {"s": (1.0, 0.0)},
+    }
+    try:
+        return table[var][units]
+    except KeyError:
+        raise ValueError(f"Could not find unit conversion for {var} to {units}!")
+
+
+def calendar_vectors(start, n_days: int):
+    """1-based day-of-year and month per day (standard calendar), as int32 numpy arrays."""
+    d0 = np.datetime64(start, "D")
+    days = d0 + np.arange(n_days)
+    years = days.astype("datetime64[Y]")
+    doy = (days - years.astype("datetime64[D]")).astype(np.int64) + 1
+    month = days.astype("datetime64[M]").astype(np.int64) % 12 + 1
+    return doy.astype(np.int32), month.astype(np.int32)
+
+
+class Engine:
+    """One shard of cells on one B200.
+
+    Arrays are cell-fastest: daily ``[D][N]``, state ``[90][N]``, monthly ``[12][N]``.  Inputs may
+    be numpy arrays (copied through pinned memory) or CUDA tensors (used in place).
+    """
+
+    def __init__(self, params: dict | None = None, device: str | int | torch.device = "cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("metsim_b200 needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.user_params = dict(params or {})
+        self.params = _lib.make_params(self.user_params)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._t = {}
+        self._tables = None
+        self._daily = None
+        self.n_cells = self.n_days = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, a, dtype, shape=None):
+        if a is None:
+            return None
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=dtype).contiguous()
+        else:
+            h = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+            t = h.pin_memory().to(self.device, non_blocking=True)
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {shape}, got {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    @property
+    def tpd(self) -> int:
+        ts = self.params.time_step
+        return 1440 // ts if ts < 1440 else 1
+
+    # ------------------------------------------------------------------ inputs
+    def load(self, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
+             state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None):
+        f64, i32 = torch.float64, torch.int32
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            t = self._t
+            t["t_min"] = self._dev(t_min, f64)
+            d, n = t["t_min"].shape
+            self.n_days, self.n_cells = int(d), int(n)
+            t["t_max"] = self._dev(t_max, f64, (d, n))
+            t["prec"] = self._dev(prec, f64, (d, n))
+            t["wind"] = self._dev(wind, f64, (d, n))
+            for k, v in (("st_t_min", state_t_min), ("st_t_max", state_t_max), ("st_prec", state_prec)):
+                t[k] = self._dev(v, f64, (90, n))
+            t["t_pk12"] = self._dev(t_pk12, f64, (12, n))
+            t["dur12"] = self._dev(dur12, f64, (12, n))
+            t["t_end"] = self._dev(t_end, f64, (2, n))
+            t["lon"] = self._dev(lon, f64, (n,))
+            t["elev"] = self._dev(elev, f64, (n,))
+            t["doy"] = self._dev(doy, i32, (d,))
+            t["month"] = self._dev(month, i32, (d,))
+            # unique latitudes -> rows of the solar tables
+            if isinstance(lat, torch.Tensor):
+                u, inv = torch.unique(lat.to(self.device, f64), return_inverse=True)
+                self._ulat = u.cpu().numpy().astype(np.float64)
+                t["lat_row"] = inv.to(i32).contiguous()
+            else:
+                u, inv = np.unique(np.asarray(lat, dtype=np.float64), return_inverse=True)
+                self._ulat = np.ascontiguousarray(u)
+                t["lat_row"] = self._dev(inv.astype(np.int32), i32, (n,))
+        self._tables = None
+        self._daily = None
+        return self
+
+    def _forcing(self) -> _lib.Forcing:
+        t = self._t
+        f = _lib.Forcing()
+        f.n_cells, f.n_days, f.ld = self.n_cells, self.n_days, self.n_cells
+        for name in ("lon", "elev", "lat_row", "doy", "month", "t_min", "t_max", "prec", "wind",
+                     "st_t_min", "st_t_max", "st_prec", "t_pk12", "dur12", "t_end"):
+            setattr(f, name, self._ptr(t.get(name)))
+        return f
+
+    # ------------------------------------------------------------------ solar tables
+    def build_solar(self, n_host_threads: int | None = None):
+        n_lat = len(self._ulat)
+        small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(self.lib.msb_solar_table_sizes(n_lat, C.byref(small), C.byref(q), C.byref(tt)))
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            opts = dict(dtype=torch.float64, device=self.device)
+            tb = {k: torch.empty(small.value, **opts) for k in ("daylength", "potrad", "rise_min", "set_min")}
+            tb["q"] = torch.empty(q.value, **opts)
+            tb["tt_coef"] = torch.empty(tt.value, **opts)
+            nbytes = self.lib.msb_solar_prelude_bytes(n_lat)
+            host_ws = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            dev_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            st = _lib.SolarTables()
+            st.n_lat = n_lat
+            for k, v in tb.items():
+                setattr(st, k, self._ptr(v))
+            nthr = n_host_threads or min(os.cpu_count() or 1, 32)
+            _lib.check(self.lib.msb_solar_tables_build(
+                n_lat, self._ulat.ctypes.data_as(C.c_void_p), C.c_void_p(host_ws.data_ptr()),
+                C.c_void_p(dev_ws.data_ptr()), C.byref(st), nthr,
+                C.c_void_p(self.stream.cuda_stream)))
+        self._tables = (st, tb, host_ws, dev_ws)
+        return tb
+
+    # ------------------------------------------------------------------ daily MTCLIM
+    def daily(self, want=DAILY_VARS):
+        if self._tables is None:
+            self.build_solar()
+        st = self._tables[0]
+        n, d = self.n_cells, self.n_days
+        need = {"tskc", "vapor_pressure", "shortwave"} | set(want)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            out = {k: torch.empty((d, n), dtype=torch.float64, device=self.device)
+                   for k in DAILY_VARS if k in need}
+            n_iter = torch.zeros(n, dtype=torch.int32, device=self.device)
+            scratch = torch.empty(self.lib.msb_daily_scratch_bytes(n, d) // 8 + 1,
+                                  dtype=torch.float64, device=self.device)
+            status = torch.zeros(4, dtype=torch.int32, device=self.device)
+            dl = _lib.Daily()
+            for i, k in enumerate(DAILY_VARS):
+                dl.var[i] = out[k].data_ptr() if k in out else None
+            dl.n_iter, dl.partial, dl.status = (self._ptr(n_iter), self._ptr(scratch), self._ptr(status))
+            f = self._forcing()
+            _lib.check(self.lib.msb_mtclim_daily(C.byref(self.params), C.byref(f), C.byref(st),
+                                                 C.byref(dl), C.c_void_p(self.stream.cuda_stream)))
+        out["n_iter"] = n_iter
+        self._daily = (dl, out, scratch, status)
+        return out
+
+    def check(self):
+        """Synchronise and raise what the reference would have raised (ValueError for t_max<t_min)."""
+        if self._daily is None:
+            return
+        f = self._forcing()
+        _lib.check(self.lib.msb_daily_check(C.byref(f), C.byref(self._daily[0]),
+                                            C.c_void_p(self.stream.cuda_stream)))
+
+    # ------------------------------------------------------------------ sub-daily
+    def disaggregate(self, out_vars=DEFAULT_OUT_VARS, day0: int = 0, day1: int | None = None,
+                     out_dtype=torch.float32, units: dict | None = None, out: dict | None = None):
+        """Disaggregate days [day0, day1) into ``{var: tensor[(day1-day0)*tpd][N]}``.
+
+        ``out`` may hold preallocated tensors (a ring buffer); ``units`` maps var -> unit string as
+        in the reference's ``out_vars[...]['units']``."""
+        if self._daily is None:
+            self.daily(want=())
+        day1 = self.n_days if day1 is None else day1
+        ts = self.params.time_step
+        if ts >= 1440:
+            raise ValueError("time_step 1440 is daily mode: use daily()")
+        steps = (day1 - day0) * self.tpd
+        n = self.n_cells
+        res = {}
+        sd = _lib.SubDaily()
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            for i, v in enumerate(SUB_VARS):
+                sd.scale[i], sd.offset[i] = 1.0, 0.0
+                if v not in out_vars or (v == "wind" and self._t.get("wind") is None):
+                    sd.var[i] = None
+                    continue
+                if out is not None and v in out:
+                    tns = out[v]
+                    assert tns.dtype == out_dtype and tns.shape[0] >= steps and tns.shape[1] == n
+                else:
+                    tns = torch.empty((steps, n), dtype=out_dtype, device=self.device)
+                res[v] = tns
+                sd.var[i] = tns.data_ptr()
+                sd.scale[i], sd.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
+            sd.dtype = 4 if out_dtype == torch.float32 else 8
+            sd.ld, sd.day0, sd.day1 = n, day0, day1
+            f = self._forcing()
+            _lib.check(self.lib.msb_disaggregate(C.byref(self.params), C.byref(f),
+                                                 C.byref(self._tables[0]), C.byref(self._daily[0]),
+                                                 C.byref(sd), C.c_void_p(self.stream.cuda_stream)))
+        return res
+
+    def run(self, out_vars=DEFAULT_OUT_VARS, out_dtype=torch.float32, units=None, daily_vars=()):
+        """solar tables -> daily -> disaggregate for the whole record; returns tensors."""
+        self.build_solar()
+        daily = self.daily(want=daily_vars)
+        res = {}
+        if self.params.time_step < 1440:
+            res = self.disaggregate(out_vars, 0, self.n_days, out_dtype, units)
+        self.check()
+        self.stream.synchronize()
+        res["daily"] = daily
+        return res
+
+
+def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
+             state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
+             out_vars=DEFAULT_OUT_VARS, out_dtype=np.float32, units: dict | None = None,
+             daily_vars=(), device: int = 0, tile_days: int = 0, out: dict | None = None,
+             ring: bool = False, timings: dict | None = None) -> dict:
+    """Whole path with HOST (numpy) buffers through ``msb_run_host``: the call a reference-side
+    binding makes in place of the cell loop of ``MetSim.run_slice`` (metsim/metsim.py:477-493).
+    Host-to-device and device-to-host copies happen inside."""
+    lib = _lib.lib()
+    p = _lib.make_params(params)
+    ts = p.time_step
+    f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    t_min = f64(t_min)
+    d, n = t_min.shape
+    tpd = 1440 // ts if ts < 1440 else 1
+    arrs = dict(lat=f64(lat), lon=f64(lon), elev=f64(elev), t_min=t_min, t_max=f64(t_max),
+                prec=f64(prec), wind=f64(wind), st_t_min=f64(state_t_min),
+                st_t_max=f64(state_t_max), st_prec=f64(state_prec), t_pk12=f64(t_pk12),
+                dur12=f64(dur12), t_end=f64(t_end))
+    arrs["doy"] = np.ascontiguousarray(doy, dtype=np.int32)
+    arrs["month"] = np.ascontiguousarray(month, dtype=np.int32)
+    run = _lib.HostRun()
+    run.n_cells, run.n_days, run.device = n, d, device
+    for k, a in arrs.items():
+        setattr(run, k, None if a is None else a.ctypes.data_as(C.c_void_p))
+    res = {}
+    odt = np.dtype(out_dtype)
+    run.out_dtype = odt.itemsize
+    run.tile_days = int(tile_days)
+    run.out_is_ring = int(bool(ring))
+    for i, v in enumerate(SUB_VARS):
+        run.scale[i], run.offset[i] = 1.0, 0.0
+        if ts >= 1440 or v not in out_vars or (v == "wind" and wind is None):
+            run.out_host[i] = None
+            continue
+        if out is not None and v in out:
+            res[v] = out[v]
+        else:
+            res[v] = np.empty((d * tpd, n), dtype=odt)
+        run.out_host[i] = res[v].ctypes.data_as(C.c_void_p)
+        run.scale[i], run.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
+    daily = {}
+    for i, v in enumerate(DAILY_VARS):
+        if v in daily_vars:
+            daily[v] = np.empty((d, n), dtype=np.float64)
+            run.daily_host[i] = daily[v].ctypes.data_as(C.c_void_p)
+        else:
+            run.daily_host[i] = None
+    n_iter = np.zeros(n, dtype=np.int32)
+    run.n_iter_host = n_iter.ctypes.data_as(C.c_void_p)
+    _lib.check(lib.msb_run_host(C.byref(p), C.byref(run)))
+    daily["n_iter"] = n_iter
+    res["daily"] = daily
+    if timings is not None:
+        timings.update(ms_h2d=run.ms_h2d, ms_solar=run.ms_solar, ms_daily=run.ms_daily,
+                       ms_disagg_total=run.ms_disagg_total)
+    return res

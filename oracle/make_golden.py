@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the REAL reference.
+
+Needs the reference checkout (default /root/reference); run in the build container:
+
+    python -m oracle.make_golden
+
+Every fixture holds the inputs (float64) and the outputs of the unmodified reference functions
+(through oracle/reference_harness.py).  The fixtures travel to the GPU box, the reference does
+not.  Fixture families:
+
+* ``stehekin_*``   the reference's only known-answer test (metsim/tests/test_metsim.py:397-464):
+                   VIC binary forcings of cell 48.3125/-120.5625 for 1949, domain stehekin.nc,
+                   plus the reference repo's own golden tables (validated_48.3125_-120.5625 and
+                   three_hourly_48.3125_-120.5625, stored as float32).  state_vic.nc is HDF5 and
+                   not readable in this image, so the 90-day state is DECLARED SYNTHETIC: the last
+                   90 days of the 1949 record.
+* ``testdomain``   BASELINE config #1: metsim/data/test.nc + domain.nc (81 cells, 31 days, 30 min,
+                   triangle, utc_offset), float32 inputs upcast exactly to float64; state_nc.nc is
+                   HDF5 too, so the state is a declared synthetic one (seeded).  Reference outputs
+                   are kept for 9 of the 81 cells.
+* ``synth_*``      seeded synthetic cells sweeping time step, precipitation type, utc offset,
+                   long-wave options, hemispheres, a polar cell and a supplied ``t_end``.
+"""
+from __future__ import annotations
+
+import os
+import struct
+import sys
+
+import numpy as np
+import pandas as pd
+from scipy.io import netcdf_file
+
+from oracle import reference_harness as rh
+from oracle.validate_oracle import synth_cell
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+SUB = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_humid", "air_pressure",
+       "spec_humid", "tskc", "wind")
+DAILY = ("t_day", "tfmax", "tskc", "tdew", "vapor_pressure", "shortwave", "pet", "daylength",
+         "potrad", "tt_max", "seasonal_prec", "smoothed_dtr")
+
+
+def pack(cells, params, outs):
+    """cells: list of cell dicts (same length records) -> dict of stacked arrays [D][N]."""
+    st = lambda k: np.stack([np.asarray(c[k], dtype=np.float64) for c in cells], axis=1)
+    d = len(cells[0]["t_min"])
+    dates = pd.date_range(cells[0]["start"], periods=d, freq="D")
+    z = dict(lat=np.array([c["lat"] for c in cells]), lon=np.array([c["lon"] for c in cells]),
+             elev=np.array([c["elev"] for c in cells]), start=np.array(cells[0]["start"]),
+             doy=dates.dayofyear.values.astype(np.int32), month=dates.month.values.astype(np.int32),
+             t_min=st("t_min"), t_max=st("t_max"), prec=st("prec"), wind=st("wind"),
+             state_t_min=st("state_t_min"), state_t_max=st("state_t_max"),
+             state_prec=st("state_prec"), t_pk12=st("t_pk12"), dur12=st("dur12"))
+    if cells[0].get("t_end") is not None:
+        z["t_end"] = st("t_end")
+    for k, v in params.items():
+        z["param_" + k] = np.array(v)
+    for k in DAILY:
+        z["ref_daily_" + k] = np.stack([o["daily"][k] for o in outs], axis=1)
+    if "sub" in outs[0]:
+        for k in SUB:
+            z["ref_sub_" + k] = np.stack([o["sub"][k] for o in outs], axis=1)
+    return z
+
+
+def read_vic_binary(path, n_days):
+    """VIC4 binary: u16/40, i16/100 x3 interleaved (metsim/io.py:324-352)."""
+    raw = open(path, "rb").read(8 * n_days)
+    vals = struct.iter_unpack("<Hhhh", raw)
+    a = np.array(list(vals), dtype=np.float64)
+    return a[:, 0] / 40.0, a[:, 1] / 100.0, a[:, 2] / 100.0, a[:, 3] / 100.0
+
+
+def stehekin(root):
+    data = os.path.join(root, "metsim", "data")
+    dom = netcdf_file(os.path.join(data, "stehekin.nc"), "r", mmap=False)
+    la, lo = 1, 4
+    lat, lon = float(dom.variables["lat"].data[la]), float(dom.variables["lon"].data[lo])
+    elev = float(dom.variables["elev"].data[la, lo])
+    assert abs(lat - 48.3125) < 1e-9 and abs(lon + 120.5625) < 1e-9
+    prec, tmax, tmin, wind = read_vic_binary(os.path.join(data, "binary", "data_48.3125_-120.5625"), 365)
+    cell = dict(lat=lat, lon=lon, elev=elev, start="1949-01-01", t_min=tmin, t_max=tmax, prec=prec,
+                wind=wind, state_t_min=tmin[-90:], state_t_max=tmax[-90:], state_prec=prec[-90:],
+                t_pk12=dom.variables["t_pk"].data[:, la, lo].astype(np.float64),
+                dur12=dom.variables["dur"].data[:, la, lo].astype(np.float64))
+    for ts, fname, tag in ((60, "validated_48.3125_-120.5625", "hourly"),
+                           (180, "three_hourly_48.3125_-120.5625", "3hourly")):
+        params = dict(time_step=ts)  # reference defaults otherwise: uniform prec, no utc offset
+        out = rh.run_cell(cell, params)
+        z = pack([cell], params, [out])
+        good = pd.read_table(os.path.join(data, fname), header=None).values.astype(np.float32)
+        z["repo_golden"] = good
+        z["repo_golden_columns"] = np.array(["prec", "temp", "shortwave", "longwave", "vapor_pressure",
+                                             "wind", "rel_humid", "spec_humid", "air_pressure"])
+        np.savez_compressed(os.path.join(GOLDEN, f"stehekin_{tag}.npz"), **z)
+        print("stehekin", tag, good.shape)
+
+
+def testdomain(root):
+    data = os.path.join(root, "metsim", "data")
+    frc = netcdf_file(os.path.join(data, "test.nc"), "r", mmap=False)
+    dom = netcdf_file(os.path.join(data, "domain.nc"), "r", mmap=False)
+    lat, lon = dom.variables["lat"].data.astype(float), dom.variables["lon"].data.astype(float)
+    rng = np.random.default_rng(19500101)
+    cells = []
+    for i in range(9):
+        for j in range(9):
+            g = lambda n: frc.variables[n].data[:, i, j].astype(np.float64)
+            st_tmin = g("Tmin")[:1] + rng.normal(0, 2.5, 90)
+            cells.append(dict(lat=lat[i], lon=lon[j], elev=float(dom.variables["elev"].data[i, j]),
+                              start="1950-01-01", t_min=g("Tmin"), t_max=g("Tmax"), prec=g("Prec"),
+                              wind=g("wind"), state_t_min=st_tmin,
+                              state_t_max=st_tmin + rng.uniform(3, 15, 90),
+                              state_prec=(rng.random(90) < 0.3) * rng.gamma(0.8, 6, 90),
+                              t_pk12=dom.variables["t_pk"].data[:, i, j].astype(np.float64),
+                              dur12=dom.variables["dur"].data[:, i, j].astype(np.float64)))
+    params = dict(time_step=30, prec_type="triangle", utc_offset=True)  # examples/example_nc.conf
+    keep = [0, 10, 20, 30, 40, 50, 60, 70, 80]
+    outs = [rh.run_cell(cells[k], params) for k in keep]
+    z = pack(cells, params, outs)
+    z["ref_cells"] = np.array(keep, dtype=np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "testdomain.npz"), **z)
+    print("testdomain", len(cells), "cells, reference outputs for", len(keep))
+
+
+def synth():
+    rng = np.random.default_rng(20261019)
+    groups = {
+        "synth_hourly_triangle_utc": (dict(time_step=60, prec_type="triangle", utc_offset=True), "2001-11-15", 75),
+        "synth_3hourly_mix_utc": (dict(time_step=180, prec_type="mix", utc_offset=True), "2003-12-20", 80),
+        "synth_30min_uniform_local": (dict(time_step=30, prec_type="uniform", utc_offset=False), "2000-02-10", 40),
+        "synth_15min_triangle_utc": (dict(time_step=15, prec_type="triangle", utc_offset=True), "1999-12-01", 35),
+        "synth_6hourly_mix_tend": (dict(time_step=360, prec_type="mix", utc_offset=True), "2004-02-20", 45),
+        "synth_2hourly_anderson_tva": (dict(time_step=120, prec_type="triangle", utc_offset=True,
+                                            lw_type="anderson", lw_cloud="default", sw_prec_thresh=0.5,
+                                            rain_scalar=0.7, tday_coef=0.5, tmax_daylength_fraction=0.6,
+                                            tdew_tol=1e-8), "2004-06-01", 40),
+        "synth_daily": (dict(time_step=1440), "2001-01-01", 120),
+    }
+    sites = [(48.3125, -120.5625, 1668.15), (30.03125, -100.03125, 519.0), (-33.9, 151.2, 30.0),
+             (0.25, 0.0, 2200.0), (64.9, 179.9, 410.0), (70.3, -179.75, 5.0), (-54.75, 25.5, 0.0),
+             (83.75, -45.25, 800.0), (25.03125, -67.03125, 3900.0), (41.2, -105.1, 1900.0)]
+    for name, (params, start, d) in groups.items():
+        cells = [synth_cell(rng, la, lo, el, start, d) for la, lo, el in sites]
+        if name.endswith("tend"):
+            for c in cells:
+                c["t_end"] = [c["t_min"][-1] - 1.5, c["t_max"][-1] + 2.0]
+        outs = [rh.run_cell(c, params) for c in cells]
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **pack(cells, params, outs))
+        print(name, len(cells), "cells x", d, "days")
+
+
+def main():
+    root = rh.find_reference_root()
+    if root is None:
+        sys.exit("reference checkout not found")
+    os.makedirs(GOLDEN, exist_ok=True)
+    import warnings
+    warnings.filterwarnings("ignore")
+    stehekin(root)
+    testdomain(root)
+    synth()
+
+
+if __name__ == "__main__":
+    main()

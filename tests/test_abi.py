@@ -1,0 +1,63 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol that
+include/metsim_b200.h declares.  No compute calls here (no GPU)."""
+import ctypes as C
+import os
+import re
+
+from metsim_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "metsim_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(msb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_defaults_and_error_text():
+    lib = _lib.lib()
+    assert lib.msb_version() == 100
+    p = _lib.make_params({})
+    # metsim/metsim.py:140-171
+    assert (p.time_step, p.prec_type, p.utc_offset) == (60, 0, 0)
+    assert (p.lw_type, p.lw_cloud) == (_lib.LW_TYPES["prata"], _lib.LW_CLOUD["cloud_deardorff"])
+    assert (p.tdew_tol, p.rain_scalar, p.tday_coef, p.lapse_rate) == (1e-6, 0.75, 0.45, 0.0065)
+    assert p.tmax_daylength_fraction == 0.67 and p.sw_prec_thresh == 0.0
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    rc = lib.msb_solar_table_sizes(0, None, None, None)
+    assert rc == _lib.E_ARG and b"n_lat" in lib.msb_last_error()
+    small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert lib.msb_solar_table_sizes(3, C.byref(small), C.byref(q), C.byref(tt)) == 0
+    assert (small.value, q.value, tt.value) == (3 * 366, 3 * 365 * _lib.Q_LD, 3 * 365 * _lib.TT_TERMS)
+    assert lib.msb_daily_scratch_bytes(1000, 365) % 8 == 0 and lib.msb_daily_scratch_bytes(1000, 365) > 0
+    assert lib.msb_mtclim_daily(None, None, None, None, None) == _lib.E_ARG
+    assert lib.msb_disaggregate(None, None, None, None, None, None) == _lib.E_ARG
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by the header on LP64 (natural alignment)
+    assert C.sizeof(_lib.Params) == 6 * 4 + 6 * 8
+    assert C.sizeof(_lib.SolarTables) == 8 + 6 * 8
+    assert C.sizeof(_lib.Forcing) == 16 + 20 * 8
+    assert C.sizeof(_lib.Daily) == (12 + 3) * 8
+    assert C.sizeof(_lib.SubDaily) == 10 * 8 * 3 + 8 + 8 + 8
+
+
+def test_param_translation_errors_match_reference():
+    import pytest
+    with pytest.raises(ValueError):
+        _lib.make_params({"lw_type": "bogus"})      # metsim.py:673-680
+    with pytest.raises(ValueError):
+        _lib.make_params({"lw_cloud": "bogus"})
+    p = _lib.make_params({"prec_type": "MIX", "lw_type": "TVA", "time_step": "180", "utc_offset": True})
+    assert (p.prec_type, p.lw_type, p.time_step, p.utc_offset) == (2, 1, 180, 1)

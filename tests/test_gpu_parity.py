@@ -1,0 +1,322 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated
+golden vectors.  Needs a B200; every test is marked gpu.
+
+Bar (BASELINE.json north_star): bit-exact for integer / indexing work, max relative error <= 1e-9
+on every fp64 output variable (relative error with the per-variable floor of msb_testutil.FLOORS).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import msb_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_run(inputs, params, out_dtype=None, units=None):
+    import torch
+    from metsim_b200.engine import Engine
+    from metsim_b200._lib import DAILY_VARS, SUB_VARS
+    eng = Engine(params)
+    eng.load(**{k: inputs.get(k) for k in util.INPUT_KEYS})
+    res = eng.run(out_vars=SUB_VARS, out_dtype=out_dtype or torch.float64, units=units,
+                  daily_vars=DAILY_VARS)
+    out = {k: v.cpu().numpy() for k, v in res.items() if k != "daily"}
+    out["daily"] = {k: v.cpu().numpy() for k, v in res["daily"].items()}
+    return out
+
+
+def compare_to_oracle(got, want, ctx, tol=util.TOL):
+    worst = {}
+    for oname, ename in util.DAILY.items():
+        worst[oname] = util.assert_close(got["daily"][ename], want[oname], oname, context=ctx, tol=tol)
+    for v in util.SUB:
+        if v in want and v in got:
+            worst[v] = util.assert_close(got[v], want[v], v, context=ctx, tol=tol)
+    np.testing.assert_array_equal(got["daily"]["n_iter"], want["n_iter"], err_msg=ctx + ": tdew evaluations")
+    return worst
+
+
+def test_fp64_building_blocks_accuracy():
+    """rcp / exp / sqrt / div sequences of msb_common.cuh: <= 4 ulp-ish against numpy."""
+    import torch
+    from metsim_b200 import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(1e-3, 5e3, 200000), rng.uniform(150.0, 400.0, 100000),
+                        10.0 ** rng.uniform(-6, 6, 50000)])
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty((5, x.size), dtype=torch.float64, device="cuda")
+    _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.max(np.abs(o[0] * x - 1.0)) < 1e-15
+    assert np.max(np.abs(o[2] / np.sqrt(x) - 1.0)) < 1e-15
+    assert np.max(np.abs(o[3] * x / 1.2345678901234567 - 1.0)) < 1e-15
+    # exp over the argument range the kernels use
+    xe = rng.uniform(-40.0, 40.0, x.size)
+    xd.copy_(torch.from_numpy(xe))
+    _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.max(np.abs(o[1] / np.exp(xe) - 1.0)) < 2e-15
+    # svp in kPa over meteorological temperatures (physics.py:124-152)
+    t = rng.uniform(-80.0, 60.0, x.size)
+    xd.copy_(torch.from_numpy(t))
+    _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    svp = 0.61078 * np.exp(17.269 * t / (237.3 + t))
+    svp[t < 0] *= 1.0 + .00972 * t[t < 0] + .000042 * t[t < 0] ** 2
+    assert np.max(np.abs(out.cpu().numpy()[4] / svp - 1.0)) < 1e-13
+
+
+def test_solar_tables_against_oracle_table():
+    """Per-latitude tables vs the oracle's per-cell 366x2880 table: rise/set indices bit-exact
+    (this is the sunrise-sign hazard), window sums of the prefix table <= 1e-12 absolute."""
+    import torch
+    from metsim_b200.engine import Engine
+    from oracle import oracle_lib
+    lats = np.array([48.3125, 30.03125, -33.9, 0.25, 64.9, 70.3, -54.75, 83.75, 25.03125, 57.46875])
+    n = lats.size
+    eng = Engine({})
+    dummy = np.zeros((2, n))
+    eng.load(lat=lats, lon=np.zeros(n), elev=np.zeros(n), doy=[1, 2], month=[1, 1], t_min=dummy,
+             t_max=dummy + 1, prec=dummy, state_t_min=np.zeros((90, n)),
+             state_t_max=np.ones((90, n)), state_prec=np.zeros((90, n)))
+    tb = {k: v.cpu().numpy() for k, v in eng.build_solar().items()}
+    torch.cuda.synchronize()
+    ulat = eng._ulat
+    q = tb["q"].reshape(n, 365, -1)
+    rng = np.random.default_rng(3)
+    for r, lat in enumerate(ulat):
+        trf, dayl, potrad, _ = oracle_lib.solar_geom(0.0, float(lat))
+        np.testing.assert_allclose(tb["daylength"].reshape(n, 366)[r], dayl, rtol=1e-15)
+        np.testing.assert_allclose(tb["potrad"].reshape(n, 366)[r], potrad, rtol=1e-13)
+        # rise / set (disaggregate.py:163-182), bit-exact
+        mask = np.diff((trf > 0).astype(int), axis=1)
+        rise, sett = np.zeros(366), np.zeros(366)
+        for i, j in zip(*np.where(mask > 0)):
+            rise[i] = j * 0.5
+        for i, j in zip(*np.where(mask < 0)):
+            sett[i] = j * 0.5
+        rise[rise == 0] = 240.0
+        sett[sett == 0] = 960.0
+        np.testing.assert_array_equal(tb["rise_min"].reshape(n, 366)[r], rise)
+        np.testing.assert_array_equal(tb["set_min"].reshape(n, 366)[r], sett)
+        # window sums
+        for y in rng.integers(0, 365, 12):
+            c = np.concatenate([[0.0], np.cumsum(trf[y])])
+            a = rng.integers(0, 2880, 64)
+            b = np.minimum(a + rng.integers(1, 721, 64), 2880)
+            w = q[r, y, b] - q[r, y, a] + np.where((a <= 1440) & (b > 1440), q[r, y, 2881], 0.0)
+            np.testing.assert_allclose(w, c[b] - c[a], atol=2e-13, rtol=0)
+
+
+@pytest.mark.parametrize("path", util.golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_matches_reference_golden(path):
+    inputs, params, ref_daily, ref_sub, extra = util.load_golden(path)
+    got = engine_run(inputs, params)
+    cells = extra.get("ref_cells")
+    pick = (lambda a: a[:, cells]) if cells is not None else (lambda a: a)
+    ctx = os.path.basename(path)
+    for oname, ename in util.DAILY.items():
+        util.assert_close(pick(got["daily"][ename]), ref_daily[ename], oname, context=ctx)
+    for v, want in ref_sub.items():
+        util.assert_close(pick(got[v]), want, v, context=ctx)
+
+
+CASES = [
+    ("conus_16th_hourly", 640, 120, {}),
+    ("global_half_deg", 700, 90, {}),
+    ("conus_16th_10yr_3h_mix", 300, 400, {}),
+    ("global_8th_30yr_15min", 256, 45, {}),
+    ("test_domain", None, None, {}),
+    ("conus_16th_hourly", 200, 60, {"utc_offset": False, "prec_type": "uniform", "time_step": 30}),
+    ("global_half_deg", 333, 70, {"lw_type": "satterlund", "lw_cloud": "default", "time_step": 120}),
+    ("global_half_deg", 200, 50, {"lw_type": "idso", "time_step": 360, "prec_type": "mix"}),
+    ("global_half_deg", 200, 50, {"lw_type": "brutsaert", "time_step": 20}),
+]
+
+
+@pytest.mark.parametrize("name,cells,days,over", CASES,
+                         ids=[f"{c[0]}-{c[1]}x{c[2]}-{i}" for i, c in enumerate(CASES)])
+def test_cuda_matches_oracle_on_seeded_configs(name, cells, days, over):
+    from metsim_b200 import synth
+    from oracle import oracle_lib
+    f, params = synth.make_config(name, max_cells=cells, n_days=days)
+    params.update(over)
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    got = engine_run(f, params)
+    compare_to_oracle(got, want, f"{name} {over}")
+
+
+def test_edge_longitudes_polar_and_wraparound():
+    """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
+    from metsim_b200 import synth
+    from oracle import oracle_lib
+    rng = np.random.default_rng(11)
+    lat = np.array([89.5, -89.5, 66.6, 0.0, 45.0, 45.0, 45.0, 45.0, 78.2, -71.0])
+    lon = np.array([10.0, -10.0, 180.0, -180.0, 359.9, 540.0, -359.75, 0.125, -179.99, 179.99])
+    for d, start in ((2, "2001-06-20"), (20, "2000-12-20"), (20, "2001-06-10")):
+        f = synth.make_forcing(lat, lon, d, start, rng)
+        for ts, pt in ((60, "triangle"), (180, "mix"), (360, "uniform")):
+            params = dict(time_step=ts, prec_type=pt, utc_offset=True)
+            want = oracle_lib.run(params, **util.oracle_kwargs(f))
+            got = engine_run(f, params)
+            compare_to_oracle(got, want, f"edge d={d} ts={ts} {pt}")
+
+
+def test_precipitation_nan_days_and_fill():
+    """Degenerate triangle days (0/0 -> NaN day, disaggregate.py:327) in runs, at the start and at
+    the end of the record, with the ffill/bfill of disaggregate.py:130."""
+    from metsim_b200 import synth
+    from oracle import oracle_lib
+    rng = np.random.default_rng(5)
+    n, d = 64, 40
+    lat = rng.uniform(25, 50, n)
+    lon = rng.uniform(-125, -67, n)
+    f = synth.make_forcing(lat, lon, d, "2001-12-01", rng)   # December: t_pk = dur = prec
+    f["prec"] = np.where(rng.random((d, n)) < 0.5, rng.uniform(0.01, 0.6, (d, n)), f["prec"])
+    f["prec"][:3, ::2] = 0.3      # leading NaN days -> bfill
+    f["prec"][-4:, 1::2] = 0.2    # trailing NaN days -> ffill
+    f["prec"][:, 7] = 0.25        # an all-NaN column stays NaN
+    for ts in (60, 180, 15):
+        params = dict(time_step=ts, prec_type="triangle", utc_offset=True)
+        want = oracle_lib.run(params, **util.oracle_kwargs(f))
+        assert np.isnan(want["prec"][:, 7]).all()
+        got = engine_run(f, params)
+        compare_to_oracle(got, want, f"nan-days ts={ts}")
+        # placement is integer work: zero / non-zero pattern must be identical
+        np.testing.assert_array_equal(got["prec"] == 0, want["prec"] == 0)
+
+
+def test_run_host_equals_device_path_and_tiling():
+    """msb_run_host (host buffers, tiles, double-buffered D2H) is bit-identical to the
+    device-resident path, for several tile sizes and the ring-buffer mode."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import run_host
+    from metsim_b200._lib import DAILY_VARS, SUB_VARS
+    f, params = synth.make_config("conus_16th_hourly", max_cells=500, n_days=37)
+    ref = engine_run(f, params, out_dtype=torch.float32)
+    kw = {k: f.get(k) for k in util.INPUT_KEYS}
+    for tile in (0, 1, 5, 16, 37):
+        got = run_host(params, out_vars=SUB_VARS, daily_vars=DAILY_VARS, tile_days=tile, **kw)
+        for v in SUB_VARS:
+            np.testing.assert_array_equal(got[v], ref[v], err_msg=f"{v} tile={tile}")
+        for v in DAILY_VARS:
+            np.testing.assert_array_equal(got["daily"][v], ref["daily"][v], err_msg=v)
+    # ring: only the last two tiles survive, at slot (tile index & 1)
+    tile, tpd = 5, 24
+    ring = {v: np.empty((2 * tile * tpd, 500), dtype=np.float32) for v in ("temp", "prec")}
+    run_host(params, out_vars=("temp", "prec"), tile_days=tile, out=ring, ring=True, **kw)
+    n_tiles = -(-37 // tile)
+    for k in (n_tiles - 2, n_tiles - 1):
+        d0, d1 = k * tile, min(37, (k + 1) * tile)
+        slot = (k & 1) * tile * tpd
+        np.testing.assert_array_equal(ring["temp"][slot:slot + (d1 - d0) * tpd], ref["temp"][d0 * tpd:d1 * tpd])
+
+
+def test_float32_outputs_and_unit_conversion():
+    """out_precision f4 (reference default, metsim.py:154) and the converters of units.py."""
+    import torch
+    from metsim_b200 import synth
+    f, params = synth.make_config("global_half_deg", max_cells=128, n_days=20)
+    base = engine_run(f, params)
+    f32 = engine_run(f, params, out_dtype=torch.float32)
+    for v in util.SUB:
+        np.testing.assert_array_equal(f32[v], base[v].astype(np.float32), err_msg=v)
+    units = {"temp": "K", "prec": "mm s-1", "vapor_pressure": "hPa", "air_pressure": "Pa",
+             "tskc": "%", "rel_humid": "fraction"}
+    conv = engine_run(f, params, units=units)
+    ts = params["time_step"]
+    np.testing.assert_allclose(conv["temp"], base["temp"] + 273.15, rtol=1e-15)
+    np.testing.assert_allclose(conv["prec"], base["prec"] / (ts * 60.0), rtol=1e-15)
+    np.testing.assert_allclose(conv["vapor_pressure"], base["vapor_pressure"] / 100.0, rtol=1e-15)
+    np.testing.assert_allclose(conv["air_pressure"], base["air_pressure"] * 1000.0, rtol=1e-15)
+    np.testing.assert_allclose(conv["tskc"], base["tskc"] * 100.0, rtol=1e-15)
+    np.testing.assert_allclose(conv["rel_humid"], base["rel_humid"] / 100.0, rtol=1e-15)
+
+
+def test_errors_mirror_the_reference():
+    from metsim_b200 import synth
+    from metsim_b200._lib import MetsimB200Error
+    f, params = synth.make_config("global_half_deg", max_cells=64, n_days=12)
+    bad = dict(f)
+    bad["t_max"] = f["t_max"].copy()
+    bad["t_max"][3, 5] = bad["t_min"][3, 5] - 0.5
+    with pytest.raises(ValueError, match="lower than daily minimum"):   # metsim.py:612-614
+        engine_run(bad, params)
+    with pytest.raises(MetsimB200Error, match="Time step"):            # metsim.py:641-646
+        engine_run(f, dict(params, time_step=7))
+    with pytest.raises(MetsimB200Error, match="t_pk12"):
+        engine_run({k: v for k, v in f.items() if k not in ("t_pk12", "dur12")},
+                   dict(params, prec_type="triangle"))
+
+
+def test_registry_method_module_run_df():
+    """metsim_b200.methods.mtclim_b200.run(df, params): the per-cell callable of the reference
+    registry (metsim.py:139, :744) on golden inputs; adds the 7 columns in place, returns df."""
+    import pandas as pd
+    from metsim_b200 import registry
+    from metsim_b200.methods import mtclim_b200
+    methods = {}
+    registry.register(methods)
+    assert methods["mtclim_b200"] is mtclim_b200 and callable(methods["mtclim_b200"].run)
+    inputs, params, ref_daily, _, _ = util.load_golden(os.path.join(util.GOLDEN, "synth_hourly_triangle_utc.npz"))
+    for c in (0, 3, 5):
+        df = pd.DataFrame({k: inputs[k][:, c] for k in ("t_min", "t_max", "prec")})
+        for k in ("seasonal_prec", "smoothed_dtr", "daylength", "potrad", "tt_max"):
+            df[k] = ref_daily[k][:, c]
+        df["dtr"] = df["t_max"] - df["t_min"]
+        p = dict(params, elev=float(inputs["elev"][c]), lapse_rate=0.0065, tday_coef=0.45,
+                 sw_prec_thresh=0.0, rain_scalar=0.75, lw_cloud="cloud_deardorff", tdew_tol=1e-6)
+        out = mtclim_b200.run(df, p)
+        assert out is df
+        for oname, ename in util.DAILY.items():
+            if ename in mtclim_b200.ADDED_COLUMNS:
+                util.assert_close(df[ename].values, ref_daily[ename][:, c], oname, context=f"run(df) cell {c}")
+
+
+def test_full_size_properties_conus_hourly_slice():
+    """Size-independent properties at the BASELINE grid width (482,560 cells), a few days:
+    precipitation mass is conserved per record (roll only moves it), shortwave energy equals the
+    daily totals, rel_humid <= 100, vapour pressure <= saturation, results independent of the
+    day-tile decomposition."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    rng = np.random.default_rng(synth.SEED)
+    lat, lon = synth.grid_cells("conus1/16", rng)
+    d = 6
+    f = synth.make_forcing_torch(lat, lon, d, "2001-01-01", "cuda")
+    eng = Engine(dict(time_step=60, prec_type="triangle", utc_offset=True))
+    eng.load(**f)
+    eng.build_solar()
+    daily = eng.daily(want=("shortwave", "daylength"))
+    full = eng.disaggregate(("temp", "prec", "shortwave", "vapor_pressure", "rel_humid"), 0, d, torch.float64)
+    eng.check()
+    torch.cuda.synchronize()
+    tot = full["prec"].sum(0)
+    ref = f["prec"].sum(0)
+    assert torch.allclose(tot, ref, rtol=1e-11, atol=1e-11)
+    # without the utc roll every day is self-contained: hourly energy == daily sw * daylength
+    loc = Engine(dict(time_step=60, prec_type="triangle", utc_offset=False))
+    loc.load(**f)
+    loc.build_solar()
+    dl = loc.daily(want=("shortwave", "daylength"))
+    sub = loc.disaggregate(("shortwave", "prec"), 0, d, torch.float64)
+    loc.check()
+    torch.cuda.synchronize()
+    e_sub = sub["shortwave"].reshape(d, 24, -1).sum(1) * 3600.0
+    assert torch.allclose(e_sub, dl["shortwave"] * dl["daylength"], rtol=1e-11, atol=1e-9)
+    p_sub = sub["prec"].reshape(d, 24, -1).sum(1)
+    assert torch.allclose(p_sub, f["prec"], rtol=1e-11, atol=1e-11)
+    assert float(full["rel_humid"].max()) <= 100.0
+    assert bool((full["vapor_pressure"] >= 0).all())
+    part = eng.disaggregate(("temp", "prec"), 2, 5, torch.float64)
+    torch.cuda.synchronize()
+    assert torch.equal(part["temp"], full["temp"][2 * 24:5 * 24])
+    assert torch.equal(part["prec"], full["prec"][2 * 24:5 * 24])

@@ -1,0 +1,59 @@
+"""The oracle (oracle/metsim_oracle.c) against reference-generated golden vectors and against the
+reference repository's own known-answer tables.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_lib
+import msb_testutil as util
+
+
+@pytest.mark.parametrize("path", util.golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_matches_reference_outputs(path):
+    inputs, params, ref_daily, ref_sub, extra = util.load_golden(path)
+    got = oracle_lib.run(params, **util.oracle_kwargs(inputs))
+    cells = extra.get("ref_cells")
+    pick = (lambda a: a[:, cells]) if cells is not None else (lambda a: a)
+    for oname, gname in util.DAILY.items():
+        util.assert_close(pick(got[oname]), ref_daily[gname], oname, context=os.path.basename(path))
+    for v, want in ref_sub.items():
+        util.assert_close(pick(got[v]), want, v, context=os.path.basename(path))
+
+
+@pytest.mark.parametrize("tag,tol", [("hourly", 0.03), ("3hourly", 0.2)])
+def test_oracle_vs_reference_repo_known_answer(tag, tol):
+    """metsim/tests/test_metsim.py:397-464 (test_disaggregation_values): NRMSE against the repo's
+    validated tables, with the reference's own thresholds (0.03 hourly, 0.2 three-hourly).  The
+    90-day state is a declared synthetic one (state_vic.nc is HDF5, unreadable here)."""
+    inputs, params, _, _, extra = util.load_golden(os.path.join(util.GOLDEN, f"stehekin_{tag}.npz"))
+    got = oracle_lib.run(params, **util.oracle_kwargs(inputs))
+    good = extra["repo_golden"].astype(np.float64)
+    for j, var in enumerate(extra["repo_golden_columns"]):
+        out = got[str(var)][:, 0]
+        h = max(good[:, j].max(), out.max())
+        l = min(good[:, j].min(), out.min())
+        nrmse = np.sqrt(np.mean((good[:, j] - out) ** 2)) / (h - l)
+        assert nrmse < tol, (var, nrmse)
+
+
+def test_oracle_solar_geom_table_properties():
+    trf, dayl, potrad, ttmax = oracle_lib.solar_geom(500.0, 45.0)
+    assert trf.shape == (366, 2880)
+    np.testing.assert_array_equal(trf[365], trf[364])          # physics.py:281-284
+    sums = trf[:365].sum(axis=1)
+    np.testing.assert_allclose(sums[dayl[:365] > 0], 1.0, rtol=1e-12)
+    assert (dayl > 0).all() and (dayl <= 86400).all()
+    assert (ttmax > 0.3).all() and (ttmax < 0.9).all()
+    # polar night: no daylight rows are all zero, daylength 0
+    trf, dayl, potrad, ttmax = oracle_lib.solar_geom(0.0, 85.0)
+    assert (dayl == 0).any() and (trf[dayl == 0] == 0).all()
+
+
+def test_oracle_rejects_negative_dtr():
+    inputs, params, *_ = util.load_golden(os.path.join(util.GOLDEN, "synth_daily.npz"))
+    bad = dict(inputs)
+    bad["t_max"] = inputs["t_max"].copy()
+    bad["t_max"][5, 2] = bad["t_min"][5, 2] - 1.0
+    with pytest.raises(ValueError):
+        oracle_lib.run(params, **util.oracle_kwargs(bad))
