@@ -164,12 +164,29 @@ __device__ __forceinline__ double svp_kpa(double t, const double *etab) {
 }
 
 // ---- precipitation: one day's per-minute shape in closed form (disaggregate.py:294-329) ------
+// np.linspace(0, 1, n) is i*step with the LAST element forced to exactly 1 (rising) / 0 (falling);
+// both end points are reproduced exactly so that zero / non-zero placement is bit-exact.
 struct PrecDay {
-  int p0, np, q0, nq;      // rising minutes [p0, p0+np), falling minutes [q0, q0+nq)
-  double stepp, stepq, f;  // linspace steps and P / sum(prec_day)
-  double u;                // uniform per-minute amount, used when np < 0
+  int p0, np, npf, q0, nq; // rising minutes [p0, p0+np) (np <= npf after the peak overwrite),
+                           // falling minutes [q0, q0+nq);  np < 0: uniform day
+  double stepp, stepq, f;  // linspace steps and P / sum(prec_day); uniform: f = P/1440
   bool nan;
 };
+
+__device__ __forceinline__ double tri_rise(const PrecDay &pd, int ia, int ib) {
+  // sum_{i=ia}^{ib-1} v_i, v_i = i*stepp for i < npf-1, v_{npf-1} = 1 (npf > 1), v_0 = 0 (npf == 1)
+  if (ib <= ia) return 0.0;
+  double s = 0.0;
+  if (ib == pd.npf && pd.npf > 1) { s = 1.0; --ib; }
+  if (ib > ia) s += pd.stepp * (0.5 * (double)((ia + ib - 1) * (ib - ia)));
+  return s;
+}
+__device__ __forceinline__ double tri_fall(const PrecDay &pd, int ja, int jb) {
+  // v_j = 1 + j*stepq for j < nq-1, v_{nq-1} = 0 (nq > 1), v_0 = 1 (nq == 1)
+  if (jb == pd.nq && pd.nq > 1) --jb;
+  if (jb <= ja) return 0.0;
+  return (double)(jb - ja) + pd.stepq * (0.5 * (double)((ja + jb - 1) * (jb - ja)));
+}
 
 __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_forcing &f,
                                                int cell, int d, PrecDay &pd) {
@@ -180,7 +197,7 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
                        (p.prec_type == MSB_PREC_MIX && f.t_min[o] < 0.0);
   if (uniform) {
     pd.np = -1;
-    pd.u = P / (double)kMinPerDay;
+    pd.f = P / (double)kMinPerDay;
     return;
   }
   // metsim.py:278-284: month m (1..12) takes domain entry m (0..11); December keeps prec
@@ -195,28 +212,24 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
   int nq = (hi_q >= lo_q) ? (int)(hi_q - lo_q) + 1 : 0;
   pd.p0 = (np > 0) ? (int)lo_p : 0;
   pd.q0 = (nq > 0) ? (int)lo_q : 0;
+  pd.npf = np;
   pd.stepp = (np > 1) ? 1.0 / (double)(np - 1) : 0.0;      // np.linspace(0, 1, np)
   pd.stepq = (nq > 1) ? -1.0 / (double)(nq - 1) : 0.0;     // np.linspace(1, 0, nq)
   // the falling assignment comes second and overwrites the shared peak minute (:322-323)
   if (nq > 0 && np > 0 && pd.p0 + np - 1 >= pd.q0) np = max(pd.q0 - pd.p0, 0);
   pd.np = np;
   pd.nq = nq;
-  const double sr = pd.stepp * (0.5 * (double)((np - 1) * np));
-  const double sf = (double)nq + pd.stepq * (0.5 * (double)((nq - 1) * nq));
-  const double S = (np > 0 ? sr : 0.0) + (nq > 0 ? sf : 0.0);
+  const double S = tri_rise(pd, 0, np) + tri_fall(pd, 0, nq);
   pd.nan = !(S != 0.0) || !(P == P);   // 0/0 or x/0 * 0 -> NaN day (:327)
   pd.f = P / S;
 }
 
 // sum of the day's per-minute values over minutes [a, b), 0 <= a < b <= 1440
 __device__ __forceinline__ double prec_day_sum(const PrecDay &pd, int a, int b) {
-  if (pd.np < 0) return (double)(b - a) * pd.u;
-  double s = 0.0;
-  int ia = max(a, pd.p0) - pd.p0, ib = min(b, pd.p0 + pd.np) - pd.p0;
-  if (ib > ia) s = pd.stepp * (0.5 * (double)((ia + ib - 1) * (ib - ia)));
-  int ja = max(a, pd.q0) - pd.q0, jb = min(b, pd.q0 + pd.nq) - pd.q0;
-  if (jb > ja) s += (double)(jb - ja) + pd.stepq * (0.5 * (double)((ja + jb - 1) * (jb - ja)));
-  return pd.f * s;
+  if (pd.np < 0) return (double)(b - a) * pd.f;
+  const int ia = max(a - pd.p0, 0), ib = min(b - pd.p0, pd.np);
+  const int ja = max(a - pd.q0, 0), jb = min(b - pd.q0, pd.nq);
+  return pd.f * (tri_rise(pd, ia, ib) + tri_fall(pd, ja, jb));
 }
 
 // value of output step i for the rolled per-minute record (disaggregate.py:347-351); NaN when the
@@ -296,15 +309,19 @@ __device__ __forceinline__ double longwave(const msb_params &p, double temp_c, d
   return emis * kStefanB * (t2 * t2);
 }
 
-template <typename OutT>
+template <typename OutT, bool UNITS>
 __device__ __forceinline__ void put(const msb_subdaily &o, int v, size_t idx, double val) {
   OutT *ptr = reinterpret_cast<OutT *>(o.var[v]);
-  if (ptr) ptr[idx] = (OutT)fma(val, o.scale[v], o.offset[v]);
+  if (UNITS) val = fma(val, o.scale[v], o.offset[v]);
+  __stcs(ptr + idx, (OutT)val);   // streaming store: outputs are never re-read by this kernel
 }
 
-template <typename OutT, bool FAST_LW>
-__global__ void __launch_bounds__(kDisaggThreads)
-disagg_kernel(const DisaggArgs a) {
+// One thread = one cell x one tile of days.  Per output day the rolled series (np.roll by a
+// whole number of minutes / 30 s steps) touch exactly two source days, "lo" and "hi", split at a
+// fixed boundary; lo/hi values are carried across days in registers (hi becomes lo).
+template <typename OutT, bool FAST_LW, bool UNITS>
+__global__ void __launch_bounds__(kDisaggThreads, 4)
+disagg_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[64];
   exp_table_init(etab);
   __syncthreads();
@@ -321,8 +338,9 @@ disagg_kernel(const DisaggArgs a) {
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
-  c.off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0; // :349,:376,:611
-  c.off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;     // :655
+  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376,:611
+  const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
+  c.off_min = off_min; c.off_tiny = off_tiny;
   c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
   c.frac = p.tmax_daylength_fraction;
   const int row = f.lat_row[cell];
@@ -335,20 +353,19 @@ disagg_kernel(const DisaggArgs a) {
   c.t_end = f.t_end;
 
   const double elev = f.elev[cell];
-  const double pr_num = -(elev * kGStd);                   // pressure :401-402
-  const double pr_corr = 0.5 * elev * -p.lapse_rate;
+  const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
+  const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
   const long ld = f.ld;
   const long T = (long)D * tpd;
   const int C = 2 * ts;                                     // tiny steps per output step (:660)
   const double sw_den = 3600.0 * ((double)ts / 60.0);       // :645
+  const double inv_ts = 1.0 / (double)ts;
 
   // ---- vapour pressure interpolant: knots (t_t_min[d], vp_daily[d]/1000), NaN outside --------
   const double xv_first = vp_knot_x(c, 0), xv_last = vp_knot_x(c, D - 1);
-  // first / last output step inside [xv_first, xv_last]
-  const long i_head = (xv_first > 0.0) ? (long)ceil(xv_first / ts) : 0;
-  const long i_tail = (long)floor(xv_last / ts);
+  const long i_head = (xv_first > 0.0) ? (long)ceil(xv_first / ts) : 0;   // first step >= x_v[0]
+  const long i_tail = (long)floor(xv_last / ts);                          // last step <= x_v[D-1]
   int vd = min(max(d_lo, 1), D - 1);                         // upper knot index, clip [1, D-1]
-  // (walk left/right so that x_v[vd-1] < x <= x_v[vd] for the first step of the tile)
   {
     const double x0 = (double)ts * (double)((long)d_lo * tpd);
     while (vd > 1 && !(vp_knot_x(c, vd - 1) < x0)) --vd;
@@ -386,44 +403,59 @@ disagg_kernel(const DisaggArgs a) {
     vp_tail = fmin(v, svp_kpa(tt, etab));
   }
   const bool vp_all_nan = (i_head > i_tail) || i_head >= T || i_tail < 0;
+  // steps of this tile with a special vapour pressure: [i_lo, i_sp0) head, (i_sp1, i_hi) tail
+  const long i_sp0 = vp_all_nan ? i_hi : i_head;
+  const long i_sp1 = vp_all_nan ? i_lo - 1 : i_tail;
 
-  // ---- rolled daily values: previous / current / next day with wrap-around (np.roll) ---------
+  // ---- rolled daily series: each output day reads source days d+qm ("lo") and d+qm+1 ("hi") ---
   const bool want_prec = a.out.var[MSB_V_PREC] != nullptr;
   const bool want_wind = a.out.var[MSB_V_WIND] != nullptr && f.wind != nullptr;
   const bool want_sw = a.out.var[MSB_V_SHORTWAVE] != nullptr;
+  const bool want_lw = a.out.var[MSB_V_LONGWAVE] != nullptr;
+  const bool want_sh = a.out.var[MSB_V_SPEC_HUMID] != nullptr;
+  const bool want_tk = a.out.var[MSB_V_TSKC] != nullptr;
   auto wrap = [D](int d) { return d < 0 ? d + D : (d >= D ? d - D : d); };
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     return (a.sw_d[(size_t)d * ld + cell] * c.dayl[f.doy[d] - 1]) / sw_den;
   };
-  PrecDay pdm, pdc, pdn;
-  double tk_m, tk_c, tk_n, wd_m = 0, wd_c = 0, wd_n = 0, rd_m = 0, rd_c = 0, rd_n = 0;
+  const int qm = off_min < 0 ? -1 : 0;          // floor(off_min / 1440), |off_min| <= 720
+  const int bm = (qm + 1) * kMinPerDay - off_min;  // minute-of-output-day where "hi" starts
+  const int qs = off_tiny < 0 ? -1 : 0;
+  const int bs = (qs + 1) * kTiny - off_tiny;      // tiny-step-of-output-day where "hi" starts
+  const int cs = -qs * kTiny + off_tiny;           // column of tiny step 0 of the day in the lo row
+
+  PrecDay pd_lo, pd_hi;
+  double tk_lo, tk_hi, wd_lo = 0, wd_hi = 0, rd_lo = 0, rd_hi = 0;
   {
-    const int dm = wrap(d_lo - 1), dn = wrap(d_lo + 1);
-    tk_m = a.tskc_d[(size_t)dm * ld + cell];
-    tk_c = a.tskc_d[(size_t)d_lo * ld + cell];
-    tk_n = a.tskc_d[(size_t)dn * ld + cell];
-    if (want_wind) {
-      wd_m = f.wind[(size_t)dm * ld + cell];
-      wd_c = f.wind[(size_t)d_lo * ld + cell];
-      wd_n = f.wind[(size_t)dn * ld + cell];
-    }
-    if (want_sw) { rd_m = rad_of(dm); rd_c = rad_of(d_lo); rd_n = rad_of(dn); }
-    if (want_prec) {
-      prec_day_setup(p, f, cell, dm, pdm);
-      prec_day_setup(p, f, cell, d_lo, pdc);
-      prec_day_setup(p, f, cell, dn, pdn);
-    }
+    const int dl = wrap(d_lo + qm), dh = wrap(d_lo + qm + 1);
+    tk_lo = a.tskc_d[(size_t)dl * ld + cell];
+    tk_hi = a.tskc_d[(size_t)dh * ld + cell];
+    if (want_wind) { wd_lo = f.wind[(size_t)dl * ld + cell]; wd_hi = f.wind[(size_t)dh * ld + cell]; }
+    if (want_prec) { prec_day_setup(p, f, cell, dl, pd_lo); prec_day_setup(p, f, cell, dh, pd_hi); }
+    if (want_sw) { rd_lo = rad_of(wrap(d_lo + qs)); rd_hi = rad_of(wrap(d_lo + qs + 1)); }
   }
   double prec_last = nan("");   // last valid precipitation step (ffill carry)
   bool prec_last_known = false;
 
-  for (int d = d_lo; d < d_hi; ++d) {
-    const int y = f.doy[d] - 1;
-    for (int t = 0; t < tpd; ++t) {
-      const long i = (long)d * tpd + t;
-      const double x = (double)ts * (double)i;
-      const size_t oidx = (size_t)(i - (long)a.out.day0 * tpd) * (size_t)a.out.ld + cell;
+  long i = i_lo;
+  size_t oidx = (size_t)(i_lo - (long)a.out.day0 * tpd) * (size_t)a.out.ld + cell;
+  double x = (double)ts * (double)i_lo;
+  const double dx = (double)ts;
+  const size_t ostride = (size_t)a.out.ld;
 
+  for (int d = d_lo; d < d_hi; ++d) {
+    const double *q_lo = nullptr, *q_hi = nullptr;
+    if (want_sw) {
+      const int y = f.doy[d] - 1;
+      int yl = y + qs, yh = y + qs + 1;
+      yl = yl < 0 ? yl + kRows : yl;                 // table rolls over its own 366 rows (:656)
+      yh = yh >= kRows ? yh - kRows : yh;
+      q_lo = c.qrow + (size_t)min(yl, 364) * kQLd;   // row 365 is a copy of row 364
+      q_hi = c.qrow + (size_t)min(yh, 364) * kQLd;
+    }
+    int mt = 0;   // minute of the output day at the start of the step
+    int st = 0;   // tiny step of the output day at the start of the step
+    for (int t = 0; t < tpd; ++t, ++i, x += dx, oidx += ostride, mt += ts, st += C) {
       // -- temperature (PCHIP) --
       if (cub.k < c.nk - 2 && x >= cub.x1) {
         int k = cub.k + 1;
@@ -436,10 +468,7 @@ disagg_kernel(const DisaggArgs a) {
 
       // -- vapour pressure (linear, clamped to saturation, NaN ends filled) --
       double vp;
-      if (vp_all_nan) vp = nan("");
-      else if (i < i_head) vp = vp_head;
-      else if (i > i_tail) vp = vp_tail;
-      else {
+      if (i >= i_sp0 && i <= i_sp1) {
         while (vd < D - 1 && xvh < x) {     // searchsorted(side='left')
           ++vd;
           xvl = xvh; yvl = yvh;
@@ -449,53 +478,55 @@ disagg_kernel(const DisaggArgs a) {
         }
         vp = ((x - xvl) * vinv) * yvh + ((xvh - x) * vinv) * yvl;   // scipy _interpolate.py:513-516
         vp = fmin(vp, es);                                         // disaggregate.py:486-487
+      } else {
+        vp = vp_all_nan ? nan("") : (i < i_sp0 ? vp_head : vp_tail);
       }
 
-      // -- relative humidity :444-446, air pressure :401-403, specific humidity :423-424 --
+      // -- relative humidity :444-446, air pressure :401-403 --
       const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);   // 100*1000*vp/(svp in Pa)
-      const double ap = kPStd * exp_tab(pr_num * rcp_nr(kRDry * (kKelvin + temp + pr_corr)), etab) / 1000.0;
+      const double ap = (kPStd / 1000.0) * exp_tab(pr_num * rcp_nr(pr_corr + temp), etab);
 
       // -- rolled block means of tskc / wind :355-380, :593-615 --
-      const int m0 = ts * t + c.off_min;              // first original minute, relative to day d
-      const int dq = floordiv(m0, kMinPerDay);        // -1, 0, +1
-      const int rem = m0 - dq * kMinPerDay;
-      const int n1 = min(ts, kMinPerDay - rem);
-      const double w1 = (double)n1, w2 = (double)(ts - n1);
-      double tskc, wind = 0.0;
-      {
-        const double va = dq < 0 ? tk_m : (dq == 0 ? tk_c : tk_n);
-        const double vb = dq < 0 ? tk_c : tk_n;       // dq == +1 never straddles further
-        tskc = (n1 == ts) ? va : (w1 * va + w2 * vb) / (double)ts;
-      }
-      if (want_wind) {
-        const double va = dq < 0 ? wd_m : (dq == 0 ? wd_c : wd_n);
-        const double vb = dq < 0 ? wd_c : wd_n;
-        wind = (n1 == ts) ? va : (w1 * va + w2 * vb) / (double)ts;
-      }
+      // minutes [mt, mt+ts) of the output day: before bm they come from "lo", from bm on from "hi"
+      const int n1 = min(max(bm - mt, 0), ts);      // minutes taken from lo
+      const bool all_lo = n1 == ts, all_hi = n1 == 0;
+      double tskc;
+      if (all_lo) tskc = tk_lo;
+      else if (all_hi) tskc = tk_hi;
+      else tskc = ((double)n1 * tk_lo + (double)(ts - n1) * tk_hi) * inv_ts;
 
-      put<OutT>(a.out, MSB_V_TEMP, oidx, temp);
-      put<OutT>(a.out, MSB_V_VAPOR_PRESSURE, oidx, vp);
-      put<OutT>(a.out, MSB_V_REL_HUMID, oidx, rh);
-      put<OutT>(a.out, MSB_V_AIR_PRESSURE, oidx, ap);
-      put<OutT>(a.out, MSB_V_TSKC, oidx, tskc);
-      if (want_wind) put<OutT>(a.out, MSB_V_WIND, oidx, wind);
-      if (a.out.var[MSB_V_SPEC_HUMID]) {
-        const double mix = (kEps * vp) * rcp_nr(ap - vp);
-        put<OutT>(a.out, MSB_V_SPEC_HUMID, oidx, mix * rcp_nr(1 + mix));
+      if (a.out.var[MSB_V_TEMP]) put<OutT, UNITS>(a.out, MSB_V_TEMP, oidx, temp);
+      if (a.out.var[MSB_V_VAPOR_PRESSURE]) put<OutT, UNITS>(a.out, MSB_V_VAPOR_PRESSURE, oidx, vp);
+      if (a.out.var[MSB_V_REL_HUMID]) put<OutT, UNITS>(a.out, MSB_V_REL_HUMID, oidx, rh);
+      if (a.out.var[MSB_V_AIR_PRESSURE]) put<OutT, UNITS>(a.out, MSB_V_AIR_PRESSURE, oidx, ap);
+      if (want_tk) put<OutT, UNITS>(a.out, MSB_V_TSKC, oidx, tskc);
+      if (want_wind) {
+        double wind;
+        if (all_lo) wind = wd_lo;
+        else if (all_hi) wind = wd_hi;
+        else wind = ((double)n1 * wd_lo + (double)(ts - n1) * wd_hi) * inv_ts;
+        put<OutT, UNITS>(a.out, MSB_V_WIND, oidx, wind);
       }
-      if (a.out.var[MSB_V_LONGWAVE])
-        put<OutT>(a.out, MSB_V_LONGWAVE, oidx, longwave<FAST_LW>(p, temp, vp, tskc, etab));
+      if (want_sh) {   // specific humidity :423-424
+        const double mix = (kEps * vp) * rcp_nr(ap - vp);
+        put<OutT, UNITS>(a.out, MSB_V_SPEC_HUMID, oidx, mix * rcp_nr(1 + mix));
+      }
+      if (want_lw) put<OutT, UNITS>(a.out, MSB_V_LONGWAVE, oidx, longwave<FAST_LW>(p, temp, vp, tskc, etab));
 
       // -- precipitation :265-352 --
       if (want_prec) {
-        const PrecDay &pa = dq < 0 ? pdm : (dq == 0 ? pdc : pdn);
-        double v;
-        bool isnan_ = pa.nan;
-        v = prec_day_sum(pa, rem, rem + n1);
+        // source minutes: lo day [mt - bm + 1440, ...) for the first n1, hi day [max(mt-bm,0), ...)
+        double v = 0.0;
+        bool isnan_ = false;
+        if (n1 > 0) {
+          const int ra = mt - bm + kMinPerDay;
+          isnan_ = pd_lo.nan;
+          v = prec_day_sum(pd_lo, ra, ra + n1);
+        }
         if (n1 < ts) {
-          const PrecDay &pb = dq < 0 ? pdc : pdn;
-          isnan_ |= pb.nan;
-          v += prec_day_sum(pb, 0, ts - n1);
+          const int ra = max(mt - bm, 0);
+          isnan_ |= pd_hi.nan;
+          v += prec_day_sum(pd_hi, ra, ra + (ts - n1));
         }
         if (isnan_) {
           if (!prec_last_known) { prec_last = prec_fill(p, f, c, i); prec_last_known = true; }
@@ -504,37 +535,35 @@ disagg_kernel(const DisaggArgs a) {
           prec_last = v;
           prec_last_known = true;
         }
-        put<OutT>(a.out, MSB_V_PREC, oidx, v);
+        put<OutT, UNITS>(a.out, MSB_V_PREC, oidx, v);
       }
 
-      // -- shortwave :618-680 --
+      // -- shortwave :618-680: tiny steps [st, st+C) of the output day, lo row before bs --
       if (want_sw) {
-        const int sa = t * C + c.off_tiny, sb = sa + C;   // tiny steps relative to day start
-        const int qa = floordiv(sa, kTiny);
-        const int split = (qa + 1) * kTiny;               // next (shifted) day boundary
+        const int k1 = min(max(bs - st, 0), C);     // tiny steps taken from the lo row
         double sw = 0.0;
-        {
-          const int e = min(sb, split);
-          int yr = y + qa; yr = yr < 0 ? yr + kRows : (yr >= kRows ? yr - kRows : yr);
-          const double r = qa < 0 ? rd_m : (qa == 0 ? rd_c : rd_n);
-          sw = r * row_window(c, yr, sa - qa * kTiny, e - qa * kTiny);
+        if (k1 > 0) {
+          const int ca = st + cs, cb = ca + k1;
+          double w = q_lo[cb] - q_lo[ca];
+          if (ca <= kNoon && cb > kNoon) w += q_lo[kTiny + 1];
+          sw = rd_lo * w;
         }
-        if (sb > split) {
-          const int qb = qa + 1;
-          int yr = y + qb; yr = yr < 0 ? yr + kRows : (yr >= kRows ? yr - kRows : yr);
-          const double r = qb < 0 ? rd_m : (qb == 0 ? rd_c : rd_n);
-          sw += r * row_window(c, yr, 0, sb - split);
+        if (k1 < C) {
+          const int ca = max(st - bs, 0), cb = ca + (C - k1);
+          double w = q_hi[cb] - q_hi[ca];
+          if (ca <= kNoon && cb > kNoon) w += q_hi[kTiny + 1];
+          sw = fma(rd_hi, w, sw);
         }
-        put<OutT>(a.out, MSB_V_SHORTWAVE, oidx, sw);
+        put<OutT, UNITS>(a.out, MSB_V_SHORTWAVE, oidx, sw);
       }
     }
-    // ---- advance the rolled neighbours to the next day ----
+    // ---- the next output day: hi becomes lo ----
     if (d + 1 < d_hi) {
-      const int dn = wrap(d + 2);
-      tk_m = tk_c; tk_c = tk_n; tk_n = a.tskc_d[(size_t)dn * ld + cell];
-      if (want_wind) { wd_m = wd_c; wd_c = wd_n; wd_n = f.wind[(size_t)dn * ld + cell]; }
-      if (want_sw) { rd_m = rd_c; rd_c = rd_n; rd_n = rad_of(dn); }
-      if (want_prec) { pdm = pdc; pdc = pdn; prec_day_setup(p, f, cell, dn, pdn); }
+      const int dh = wrap(d + 1 + qm + 1);
+      tk_lo = tk_hi; tk_hi = a.tskc_d[(size_t)dh * ld + cell];
+      if (want_wind) { wd_lo = wd_hi; wd_hi = f.wind[(size_t)dh * ld + cell]; }
+      if (want_prec) { pd_lo = pd_hi; prec_day_setup(p, f, cell, dh, pd_hi); }
+      if (want_sw) { rd_lo = rd_hi; rd_hi = rad_of(wrap(d + 1 + qs + 1)); }
     }
   }
 }
@@ -607,13 +636,18 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   dim3 grid(cell_blocks, (n_days + tile - 1) / tile);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool fast_lw = p->lw_type == MSB_LW_PRATA && p->lw_cloud == MSB_CLOUD_DEARDORFF;
+  bool units = false;
+  for (int v = 0; v < MSB_N_SUBVARS; ++v)
+    if (out->var[v] && (out->scale[v] != 1.0 || out->offset[v] != 0.0)) units = true;
+#define MSB_LAUNCH(T, F, U) disagg_kernel<T, F, U><<<grid, kDisaggThreads, 0, st>>>(a)
   if (out->dtype == 4) {
-    if (fast_lw) disagg_kernel<float, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else disagg_kernel<float, false><<<grid, kDisaggThreads, 0, st>>>(a);
+    if (units) { if (fast_lw) MSB_LAUNCH(float, true, true); else MSB_LAUNCH(float, false, true); }
+    else { if (fast_lw) MSB_LAUNCH(float, true, false); else MSB_LAUNCH(float, false, false); }
   } else {
-    if (fast_lw) disagg_kernel<double, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else disagg_kernel<double, false><<<grid, kDisaggThreads, 0, st>>>(a);
+    if (units) { if (fast_lw) MSB_LAUNCH(double, true, true); else MSB_LAUNCH(double, false, true); }
+    else { if (fast_lw) MSB_LAUNCH(double, true, false); else MSB_LAUNCH(double, false, false); }
   }
+#undef MSB_LAUNCH
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }

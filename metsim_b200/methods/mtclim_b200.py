@@ -32,7 +32,7 @@ def run(df, params: dict):
     p = _lib.make_params({k: params[k] for k in _READ_PARAMS if k in params})
     n_days = len(df)
     col = lambda name: torch.from_numpy(
-        np.ascontiguousarray(df[name].values, dtype=np.float64).reshape(n_days, 1)).to(dev)
+        np.array(df[name].values, dtype=np.float64, copy=True).reshape(n_days, 1)).to(dev)
     cols = {k: col(k) for k in ("t_min", "t_max", "prec", "seasonal_prec", "smoothed_dtr",
                                 "daylength", "potrad", "tt_max")}
     if "dtr" in df and (np.asarray(df["dtr"].values) < 0).any():

@@ -85,8 +85,9 @@ def test_solar_tables_against_oracle_table():
     eng.load(lat=lats, lon=np.zeros(n), elev=np.zeros(n), doy=[1, 2], month=[1, 1], t_min=dummy,
              t_max=dummy + 1, prec=dummy, state_t_min=np.zeros((90, n)),
              state_t_max=np.ones((90, n)), state_prec=np.zeros((90, n)))
-    tb = {k: v.cpu().numpy() for k, v in eng.build_solar().items()}
-    torch.cuda.synchronize()
+    tbd = eng.build_solar()
+    eng.stream.synchronize()
+    tb = {k: v.cpu().numpy() for k, v in tbd.items()}
     ulat = eng._ulat
     q = tb["q"].reshape(n, 365, -1)
     rng = np.random.default_rng(3)
@@ -174,7 +175,7 @@ def test_precipitation_nan_days_and_fill():
     from metsim_b200 import synth
     from oracle import oracle_lib
     rng = np.random.default_rng(5)
-    n, d = 64, 40
+    n, d = 64, 31
     lat = rng.uniform(25, 50, n)
     lon = rng.uniform(-125, -67, n)
     f = synth.make_forcing(lat, lon, d, "2001-12-01", rng)   # December: t_pk = dur = prec
