@@ -41,22 +41,34 @@ static DailyLaunch daily_launch(int n_cells, int n_days) {
   return l;
 }
 
+// Day-invariant factors of one evaluation of the reference's loop body (mtclim.py:65-71):
+//   vp = svp(tdew); t_tmax = max(tt_max + ABASE*vp, 1e-4); sw = potrad*t_tmax*tfmax
+//   pet = 1.26*s/(s+gamma)*(0.72*sw)*daylength/lhvap        (physics.py:62-96, x/10*10)
+//   ratio = pet/max(seasonal_prec, 80)
+//   tdew' = (t_min+K)*(-0.127 + 1.121*(1.003 - 1.444r + 12.312r^2 - 32.766r^3) + 0.0006*dtr) - K
 struct DayInv {
-  double t_min, dtr, sp80, tfmax, tt_max, potrad, daylength, t_day, c1, lhvap;
+  double tk;      // t_min + KELVIN
+  double base;    // -0.127 + 1.121*1.003 + 0.0006*dtr
+  double g;       // potrad * tfmax
+  double tt_max;
+  double b;       // ratio per unit shortwave: 1.26*s/(s+gamma)*0.72*daylength/lhvap/sp80
 };
 
-// one evaluation of the reference's loop body for one day (mtclim.py:65-71)
-__device__ __forceinline__ double tdew_step(const DayInv &v, double tdew_old) {
-  double vp = svp_ref(tdew_old);                                   // mtclim.py:197-214
-  double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);         // mtclim.py:233
-  double sw = v.potrad * t_tmax * v.tfmax;                         // mtclim.py:234
-  double rnet = sw * 0.72;                                         // physics.py:62
-  double pet = ((v.c1 * rnet * v.daylength) / v.lhvap) / 10. * 10.0;  // physics.py:92-96, mtclim.py:161
-  double ratio = pet / v.sp80;                                     // mtclim.py:189
-  double r2 = ratio * ratio;
-  return (v.t_min + kKelvin) *
-             (-0.127 + 1.121 * (1.003 - 1.444 * ratio + 12.312 * r2 - 32.766 * (r2 * ratio)) +
-              0.0006 * v.dtr) - kKelvin;                           // mtclim.py:190-194
+// svp in Pa (physics.py:124-152) on the fast fp64 path of msb_common.cuh
+__device__ __forceinline__ double svp_pa(double t, const double *etab) {
+  const double r = rcp_nr(237.3 + t);
+  const double arg = fma(-17.269 * 237.3, r, 17.269);   // 17.269*t/(237.3+t)
+  double s = 610.78 * exp_tab(arg, etab);
+  if (t < 0.0) s *= fma(fma(.000042, t, .00972), t, 1.0);
+  return s;
+}
+
+__device__ __forceinline__ double tdew_step(const DayInv &v, double tdew_old, const double *etab) {
+  const double vp = svp_pa(tdew_old, etab);
+  const double t_tmax = fmax(fma(kABase, vp, v.tt_max), 0.0001);
+  const double r = (v.g * t_tmax) * v.b;
+  const double poly = r * fma(r, fma(r, -32.766, 12.312), -1.444);
+  return fma(v.tk, fma(1.121, poly, v.base), -kKelvin);
 }
 
 struct CellConst {
@@ -94,6 +106,9 @@ template <int PASS>
 __global__ void __launch_bounds__(kDailyThreads)
 daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int chunk_len,
              int k_off, int max_evals) {
+  __shared__ double etab[64];
+  exp_table_init(etab);
+  __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= f.n_cells) return;
   const int chunk = blockIdx.y;
@@ -131,13 +146,12 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
     const size_t o = (size_t)d * ld + cell;
     DayInv v;
     const double t_min = f.t_min[o], t_max = f.t_max[o], prec = f.prec[o];
-    v.t_min = t_min;
-    v.dtr = t_max - t_min;
-    if (v.dtr < 0.0) out.status[0] = 1;                 // ValueError, metsim.py:612-614
+    const double dtr = t_max - t_min;
+    if (dtr < 0.0) out.status[0] = 1;                   // ValueError, metsim.py:612-614
     double seasonal, sm_dtr;
     if (roll) {
       s_prec += prec;
-      s_dtr += v.dtr;
+      s_dtr += dtr;
       seasonal = kDaysPerYear * (s_prec / 90.0);
       sm_dtr = s_dtr / 30.0;
       // slide the windows for the next day
@@ -147,12 +161,13 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
       seasonal = f.given_seasonal_prec[o];
       sm_dtr = f.given_smoothed_dtr[o];
     }
-    v.sp80 = seasonal < 80.0 ? 80.0 : seasonal;        // mtclim.py:187-188
+    const double sp80 = seasonal < 80.0 ? 80.0 : seasonal;   // mtclim.py:187-188
+    double daylength, potrad;
 
     if (solar) {
       const int y = f.doy[d] - 1;
-      v.daylength = cc.dayl[y];
-      v.potrad = cc.potrad[y];
+      daylength = cc.dayl[y];
+      potrad = cc.potrad[y];
       // tt_max0(p): Horner in (p - p0), coefficients per (latitude, yday)
       const double *c = cc.tt + (size_t)min(y, 364) * kTT;
       double s = c[kTT - 1];
@@ -160,51 +175,53 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
       for (int m = kTT - 2; m >= 0; --m) s = fma(s, cc.px, c[m]);
       v.tt_max = s;
     } else {
-      v.daylength = f.given_daylength[o];
-      v.potrad = f.given_potrad[o];
+      daylength = f.given_daylength[o];
+      potrad = f.given_potrad[o];
       v.tt_max = f.given_tt_max[o];
     }
     const double t_mean = (t_min + t_max) / 2;                          // mtclim.py:103-104
-    v.t_day = ((t_max - t_mean) * p.tday_coef) + t_mean;
-    const double b = kB0 + kB1 * exp(-kB2 * sm_dtr);                   // mtclim.py:129-133
-    double tf = 1.0 - 0.9 * exp(-b * (v.dtr * sqrt(v.dtr)));            // dtr**1.5
+    const double t_day = ((t_max - t_mean) * p.tday_coef) + t_mean;
+    const double bb = kB0 + kB1 * exp_tab(-kB2 * sm_dtr, etab);        // mtclim.py:129-133
+    double tf = 1.0 - 0.9 * exp_tab(-bb * (dtr * sqrt_nr(fmax(dtr, 1e-300))), etab);  // dtr**1.5
     if (prec > p.sw_prec_thresh) tf *= p.rain_scalar;
-    v.tfmax = tf;
-    {  // day-invariant part of calc_pet (physics.py:62-92)
-      v.lhvap = 2.5023e6 - 2430.54 * v.t_day;
-      const double gamma = kCp * cc.pa / (v.lhvap * kEps);
-      const double t1 = v.t_day + 0.2, t2 = v.t_day - 0.2;
-      const double s = (svp_ref(t1) - svp_ref(t2)) / (t1 - t2);
-      v.c1 = 1.26 * (s / (s + gamma));
-    }
+    // day-invariant part of calc_pet (physics.py:62-92)
+    const double lhvap = 2.5023e6 - 2430.54 * t_day;
+    const double gamma = kCp * cc.pa / (lhvap * kEps);
+    const double t1 = t_day + 0.2, t2 = t_day - 0.2;
+    const double sl = (svp_pa(t1, etab) - svp_pa(t2, etab)) / (t1 - t2);
+    const double c1 = 1.26 * (sl / (sl + gamma));
+    v.tk = t_min + kKelvin;
+    v.base = -0.127 + 1.121 * 1.003 + 0.0006 * dtr;
+    v.g = potrad * tf;
+    v.b = ((c1 * 0.72) * daylength / lhvap) / sp80;
 
     double tdew = t_min;                                                // mtclim.py:54
     if (PASS == 1) {
-      for (int k = 0; k < k_off; ++k) tdew = tdew_step(v, tdew);
+      for (int k = 0; k < k_off; ++k) tdew = tdew_step(v, tdew, etab);
 #pragma unroll
       for (int k = 0; k < kEvalsPerRound; ++k) {
-        const double nxt = tdew_step(v, tdew);
+        const double nxt = tdew_step(v, tdew, etab);
         const double df = nxt - tdew;
         acc[k] = fma(df, df, acc[k]);
         tdew = nxt;
       }
     } else {
-      for (int k = 0; k < n_evals; ++k) tdew = tdew_step(v, tdew);
-      const double vp = svp_ref(tdew);                                  // mtclim.py:73-79
+      for (int k = 0; k < n_evals; ++k) tdew = tdew_step(v, tdew, etab);
+      const double vp = svp_pa(tdew, etab);                             // mtclim.py:73-79
       const double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);
-      const double sw = v.potrad * t_tmax * v.tfmax;
-      const double pet = ((v.c1 * (sw * 0.72) * v.daylength) / v.lhvap) / 10. * 10.0;
+      const double sw = potrad * t_tmax * tf;
+      const double pet = ((c1 * (sw * 0.72) * daylength) / lhvap) / 10. * 10.0;
       const double tskc = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
       double *const *o_ = out.var;
-      if (o_[MSB_D_T_DAY]) o_[MSB_D_T_DAY][o] = v.t_day;
+      if (o_[MSB_D_T_DAY]) o_[MSB_D_T_DAY][o] = t_day;
       if (o_[MSB_D_TFMAX]) o_[MSB_D_TFMAX][o] = tf;
       if (o_[MSB_D_TSKC]) o_[MSB_D_TSKC][o] = tskc;
       if (o_[MSB_D_TDEW]) o_[MSB_D_TDEW][o] = tdew;
       if (o_[MSB_D_VAPOR_PRESSURE]) o_[MSB_D_VAPOR_PRESSURE][o] = vp;
       if (o_[MSB_D_SHORTWAVE]) o_[MSB_D_SHORTWAVE][o] = sw;
       if (o_[MSB_D_PET]) o_[MSB_D_PET][o] = pet;
-      if (o_[MSB_D_DAYLENGTH]) o_[MSB_D_DAYLENGTH][o] = v.daylength;
-      if (o_[MSB_D_POTRAD]) o_[MSB_D_POTRAD][o] = v.potrad;
+      if (o_[MSB_D_DAYLENGTH]) o_[MSB_D_DAYLENGTH][o] = daylength;
+      if (o_[MSB_D_POTRAD]) o_[MSB_D_POTRAD][o] = potrad;
       if (o_[MSB_D_TT_MAX]) o_[MSB_D_TT_MAX][o] = v.tt_max;
       if (o_[MSB_D_SEASONAL_PREC]) o_[MSB_D_SEASONAL_PREC][o] = seasonal;
       if (o_[MSB_D_SMOOTHED_DTR]) o_[MSB_D_SMOOTHED_DTR][o] = sm_dtr;

@@ -31,6 +31,7 @@ struct DisaggArgs {
   int32_t *status;
   msb_subdaily out;
   int tpd, tile_days;
+  unsigned var_mask;   // bit v set = out.var[v] requested
 };
 
 // ---- per-thread view of one cell -------------------------------------------------------------
@@ -158,34 +159,43 @@ __device__ __forceinline__ double svp_kpa(double t, const double *etab) {
   const double r = rcp_nr(237.3 + t);
   // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
   const double arg = fma(-17.269 * 237.3, r, 17.269);
-  double s = 0.61078 * exp_tab(arg, etab);
-  if (t < 0.0) s *= fma(fma(.000042, t, .00972), t, 1.0);
-  return s;
+  const double s = 0.61078 * exp_tab(arg, etab);
+  const double corr = fma(fma(.000042, t, .00972), t, 1.0);
+  return s * (t < 0.0 ? corr : 1.0);
 }
 
 // ---- precipitation: one day's per-minute shape in closed form (disaggregate.py:294-329) ------
-// np.linspace(0, 1, n) is i*step with the LAST element forced to exactly 1 (rising) / 0 (falling);
-// both end points are reproduced exactly so that zero / non-zero placement is bit-exact.
+// The day vector is: rising limb np.linspace(0, 1, n+) on minutes [p0, p0+n+), falling limb
+// np.linspace(1, 0, n-) on [q0, q0+n-), the falling assignment second (it overwrites a shared
+// peak minute), everything scaled by P / sum.  linspace is i*step with the LAST element forced to
+// exactly 1 (rising) or 0 (falling).  Any window sum is then
+//     f * ( units + stepp * tri(ia..ib) + count(ja..jb) + stepq * tri(ja..jb) )
+// with every count / triangular number formed in INTEGER arithmetic, so a window that misses the
+// limbs is an exact 0 and zero / non-zero placement is bit-exact.
 struct PrecDay {
-  int p0, np, npf, q0, nq; // rising minutes [p0, p0+np) (np <= npf after the peak overwrite),
-                           // falling minutes [q0, q0+nq);  np < 0: uniform day
-  double stepp, stepq, f;  // linspace steps and P / sum(prec_day); uniform: f = P/1440
+  int p0, nps;   // rising series minutes [p0, p0+nps): value i*stepp
+  int pu;        // minute index (relative to p0) after the forced-1.0 element, INT_MAX if none
+  int q0, nqs;   // falling series minutes [q0, q0+nqs): value 1 + j*stepq (forced 0.0 end excluded)
+  double stepp, stepq, f;   // uniform day: nps < 0 and f = P/1440
   bool nan;
 };
+struct PrecPos { int i, j, u; };   // clamped positions of a minute inside the two limbs
 
-__device__ __forceinline__ double tri_rise(const PrecDay &pd, int ia, int ib) {
-  // sum_{i=ia}^{ib-1} v_i, v_i = i*stepp for i < npf-1, v_{npf-1} = 1 (npf > 1), v_0 = 0 (npf == 1)
-  if (ib <= ia) return 0.0;
-  double s = 0.0;
-  if (ib == pd.npf && pd.npf > 1) { s = 1.0; --ib; }
-  if (ib > ia) s += pd.stepp * (0.5 * (double)((ia + ib - 1) * (ib - ia)));
-  return s;
+__device__ __forceinline__ PrecPos prec_pos(const PrecDay &pd, int m) {
+  PrecPos q;
+  q.i = min(max(m - pd.p0, 0), pd.nps);
+  q.j = min(max(m - pd.q0, 0), pd.nqs);
+  q.u = (m - pd.p0 >= pd.pu) ? 1 : 0;
+  return q;
 }
-__device__ __forceinline__ double tri_fall(const PrecDay &pd, int ja, int jb) {
-  // v_j = 1 + j*stepq for j < nq-1, v_{nq-1} = 0 (nq > 1), v_0 = 1 (nq == 1)
-  if (jb == pd.nq && pd.nq > 1) --jb;
-  if (jb <= ja) return 0.0;
-  return (double)(jb - ja) + pd.stepq * (0.5 * (double)((ja + jb - 1) * (jb - ja)));
+// sum over minutes [a, b) given the positions of a and b (a <= b)
+__device__ __forceinline__ double prec_window(const PrecDay &pd, const PrecPos &a, const PrecPos &b,
+                                              int n_minutes) {
+  if (pd.nps < 0) return (double)n_minutes * pd.f;
+  const int tr = (b.i - 1) * b.i - (a.i - 1) * a.i;   // 2 * sum_{i=a.i}^{b.i-1} i
+  const int tf = (b.j - 1) * b.j - (a.j - 1) * a.j;
+  const double s = (double)(b.u - a.u + b.j - a.j) + 0.5 * (pd.stepp * (double)tr + pd.stepq * (double)tf);
+  return pd.f * s;
 }
 
 __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_forcing &f,
@@ -196,7 +206,7 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
   const bool uniform = p.prec_type == MSB_PREC_UNIFORM ||
                        (p.prec_type == MSB_PREC_MIX && f.t_min[o] < 0.0);
   if (uniform) {
-    pd.np = -1;
+    pd.nps = -1;
     pd.f = P / (double)kMinPerDay;
     return;
   }
@@ -208,28 +218,24 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
   // integer minutes m with t_start <= m <= t_pk, and t_pk <= m <= t_stop, clipped to the day
   const double lo_p = fmax(ceil(t_start), 0.0), hi_p = fmin(floor(t_pk), 1439.0);
   const double lo_q = fmax(ceil(t_pk), 0.0), hi_q = fmin(floor(t_stop), 1439.0);
-  int np = (hi_p >= lo_p) ? (int)(hi_p - lo_p) + 1 : 0;
-  int nq = (hi_q >= lo_q) ? (int)(hi_q - lo_q) + 1 : 0;
-  pd.p0 = (np > 0) ? (int)lo_p : 0;
+  const int npf = (hi_p >= lo_p) ? (int)(hi_p - lo_p) + 1 : 0;
+  const int nq = (hi_q >= lo_q) ? (int)(hi_q - lo_q) + 1 : 0;
+  pd.p0 = (npf > 0) ? (int)lo_p : 0;
   pd.q0 = (nq > 0) ? (int)lo_q : 0;
-  pd.npf = np;
-  pd.stepp = (np > 1) ? 1.0 / (double)(np - 1) : 0.0;      // np.linspace(0, 1, np)
+  pd.stepp = (npf > 1) ? 1.0 / (double)(npf - 1) : 0.0;    // np.linspace(0, 1, npf)
   pd.stepq = (nq > 1) ? -1.0 / (double)(nq - 1) : 0.0;     // np.linspace(1, 0, nq)
   // the falling assignment comes second and overwrites the shared peak minute (:322-323)
-  if (nq > 0 && np > 0 && pd.p0 + np - 1 >= pd.q0) np = max(pd.q0 - pd.p0, 0);
-  pd.np = np;
-  pd.nq = nq;
-  const double S = tri_rise(pd, 0, np) + tri_fall(pd, 0, nq);
+  int np = npf;
+  if (nq > 0 && npf > 0 && pd.p0 + npf - 1 >= pd.q0) np = max(pd.q0 - pd.p0, 0);
+  const bool unit = np == npf && npf > 1;                  // forced 1.0 survives the overwrite
+  pd.nps = unit ? npf - 1 : np;
+  pd.pu = unit ? npf : 0x7fffffff;
+  pd.nqs = nq > 1 ? nq - 1 : nq;                           // forced 0.0 end contributes nothing
+  pd.f = 1.0;
+  const PrecPos z = {0, 0, 0}, e = prec_pos(pd, kMinPerDay);
+  const double S = prec_window(pd, z, e, kMinPerDay);      // np.sum(prec_day), :327
   pd.nan = !(S != 0.0) || !(P == P);   // 0/0 or x/0 * 0 -> NaN day (:327)
   pd.f = P / S;
-}
-
-// sum of the day's per-minute values over minutes [a, b), 0 <= a < b <= 1440
-__device__ __forceinline__ double prec_day_sum(const PrecDay &pd, int a, int b) {
-  if (pd.np < 0) return (double)(b - a) * pd.f;
-  const int ia = max(a - pd.p0, 0), ib = min(b - pd.p0, pd.np);
-  const int ja = max(a - pd.q0, 0), jb = min(b - pd.q0, pd.nq);
-  return pd.f * (tri_rise(pd, ia, ib) + tri_fall(pd, ja, jb));
 }
 
 // value of output step i for the rolled per-minute record (disaggregate.py:347-351); NaN when the
@@ -244,12 +250,12 @@ __device__ __noinline__ double prec_step_generic(const msb_params &p, const msb_
   PrecDay pd;
   prec_day_setup(p, f, c.cell, dA, pd);
   if (pd.nan) return nan("");
-  double v = prec_day_sum(pd, rem, rem + n1);
+  double v = prec_window(pd, prec_pos(pd, rem), prec_pos(pd, rem + n1), n1);
   if (n1 < c.ts) {
     const int dB = (dA + 1 == c.D) ? 0 : dA + 1;
     prec_day_setup(p, f, c.cell, dB, pd);
     if (pd.nan) return nan("");
-    v += prec_day_sum(pd, 0, c.ts - n1);
+    v += prec_window(pd, prec_pos(pd, 0), prec_pos(pd, c.ts - n1), c.ts - n1);
   }
   return v;
 }
@@ -316,10 +322,19 @@ __device__ __forceinline__ void put(const msb_subdaily &o, int v, size_t idx, do
   __stcs(ptr + idx, (OutT)val);   // streaming store: outputs are never re-read by this kernel
 }
 
-// One thread = one cell x one tile of days.  Per output day the rolled series (np.roll by a
-// whole number of minutes / 30 s steps) touch exactly two source days, "lo" and "hi", split at a
-// fixed boundary; lo/hi values are carried across days in registers (hi becomes lo).
-template <typename OutT, bool FAST_LW, bool UNITS>
+// variable sets compiled into the kernel: kVarsExample = the 8 variables of
+// examples/example_nc.conf (every pointer known non-NULL, no per-step tests), kVarsAny = runtime
+constexpr int kVarsAny = 0, kVarsExample = 1;
+constexpr unsigned kExampleMask = (1u << MSB_V_TEMP) | (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE) |
+                                  (1u << MSB_V_LONGWAVE) | (1u << MSB_V_VAPOR_PRESSURE) |
+                                  (1u << MSB_V_REL_HUMID) | (1u << MSB_V_AIR_PRESSURE) |
+                                  (1u << MSB_V_WIND);
+
+// One thread = one cell x one tile of days.  np.roll by a whole number of minutes (tskc, wind,
+// prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
+// is read ts minutes per output step; the stream position and the current source day live in
+// registers and "roll" to the next source day once per day.
+template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
 __global__ void __launch_bounds__(kDisaggThreads, 4)
 disagg_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[64];
@@ -334,9 +349,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const int d_lo = a.out.day0 + blockIdx.y * a.tile_days;
   const int d_hi = min(a.out.day1, d_lo + a.tile_days);
   if (d_lo >= d_hi) return;
+  const unsigned mask = VARS == kVarsExample ? kExampleMask : a.var_mask;
+  auto want = [mask](int v) { return (mask >> v) & 1u; };
 
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = f.ld;
+  const int nk = 2 * D + 4;
   const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376,:611
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
@@ -356,18 +374,20 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
   const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
   const long ld = f.ld;
-  const long T = (long)D * tpd;
+  const int T = D * tpd;
   const int C = 2 * ts;                                     // tiny steps per output step (:660)
   const double sw_den = 3600.0 * ((double)ts / 60.0);       // :645
   const double inv_ts = 1.0 / (double)ts;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 
   // ---- vapour pressure interpolant: knots (t_t_min[d], vp_daily[d]/1000), NaN outside --------
   const double xv_first = vp_knot_x(c, 0), xv_last = vp_knot_x(c, D - 1);
-  const long i_head = (xv_first > 0.0) ? (long)ceil(xv_first / ts) : 0;   // first step >= x_v[0]
-  const long i_tail = (long)floor(xv_last / ts);                          // last step <= x_v[D-1]
+  const int i_head = (xv_first > 0.0) ? (int)ceil(xv_first / ts) : 0;   // first step >= x_v[0]
+  const int i_tail = (int)floor(xv_last / ts);                          // last step <= x_v[D-1]
+  const int i_lo = d_lo * tpd, i_hi = d_hi * tpd;
   int vd = min(max(d_lo, 1), D - 1);                         // upper knot index, clip [1, D-1]
   {
-    const double x0 = (double)ts * (double)((long)d_lo * tpd);
+    const double x0 = (double)ts * (double)i_lo;
     while (vd > 1 && !(vp_knot_x(c, vd - 1) < x0)) --vd;
     while (vd < D - 1 && vp_knot_x(c, vd) < x0) ++vd;
   }
@@ -376,15 +396,15 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   double vinv = 1.0 / (xvh - xvl);
 
   Cubic cub;
-  cubic_locate(c, d_lo, (double)ts * (double)((long)d_lo * tpd), cub, a.status);
+  cubic_locate(c, d_lo, (double)ts * (double)i_lo, cub, a.status);
+  if (cub.k >= nk - 2) cub.x1 = kInf;   // last interval: extrapolate, never advance
 
   // head / tail fill values (pandas bfill / ffill of the NaN ends, disaggregate.py:99-101)
   double vp_head = 0.0, vp_tail = 0.0;
-  const long i_lo = (long)d_lo * tpd, i_hi = (long)d_hi * tpd;
   if (i_lo < i_head && i_head < T) {
     const double x = (double)ts * (double)i_head;
     Cubic q2;
-    cubic_locate(c, (int)(i_head / tpd), x, q2, a.status);
+    cubic_locate(c, i_head / tpd, x, q2, a.status);
     const double tt = cubic_eval(q2, x);
     const double x0 = vp_knot_x(c, 0), x1 = vp_knot_x(c, 1);
     const double y0 = a.vp_d[cell] / 1000.0, y1 = a.vp_d[(size_t)ld + cell] / 1000.0;
@@ -394,7 +414,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   if (i_hi - 1 > i_tail && i_tail >= 0) {
     const double x = (double)ts * (double)i_tail;
     Cubic q2;
-    cubic_locate(c, (int)(i_tail / tpd), x, q2, a.status);
+    cubic_locate(c, i_tail / tpd, x, q2, a.status);
     const double tt = cubic_eval(q2, x);
     const double x0 = vp_knot_x(c, D - 2), x1 = vp_knot_x(c, D - 1);
     const double y0 = a.vp_d[(size_t)(D - 2) * ld + cell] / 1000.0;
@@ -403,65 +423,62 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     vp_tail = fmin(v, svp_kpa(tt, etab));
   }
   const bool vp_all_nan = (i_head > i_tail) || i_head >= T || i_tail < 0;
-  // steps of this tile with a special vapour pressure: [i_lo, i_sp0) head, (i_sp1, i_hi) tail
-  const long i_sp0 = vp_all_nan ? i_hi : i_head;
-  const long i_sp1 = vp_all_nan ? i_lo - 1 : i_tail;
+  // steps with an interpolated vapour pressure: [i_sp0, i_sp1]; before: head fill, after: tail
+  const int i_sp0 = vp_all_nan ? i_hi : i_head;
+  const int i_sp1 = vp_all_nan ? i_lo - 1 : i_tail;
+  if (vp_all_nan) vp_head = vp_tail = nan("");
 
-  // ---- rolled daily series: each output day reads source days d+qm ("lo") and d+qm+1 ("hi") ---
-  const bool want_prec = a.out.var[MSB_V_PREC] != nullptr;
-  const bool want_wind = a.out.var[MSB_V_WIND] != nullptr && f.wind != nullptr;
-  const bool want_sw = a.out.var[MSB_V_SHORTWAVE] != nullptr;
-  const bool want_lw = a.out.var[MSB_V_LONGWAVE] != nullptr;
-  const bool want_sh = a.out.var[MSB_V_SPEC_HUMID] != nullptr;
-  const bool want_tk = a.out.var[MSB_V_TSKC] != nullptr;
+  // ---- source streams ------------------------------------------------------------------------
+  const bool want_prec = want(MSB_V_PREC);
+  const bool want_wind = want(MSB_V_WIND) && f.wind != nullptr;
+  const bool want_sw = want(MSB_V_SHORTWAVE);
   auto wrap = [D](int d) { return d < 0 ? d + D : (d >= D ? d - D : d); };
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     return (a.sw_d[(size_t)d * ld + cell] * c.dayl[f.doy[d] - 1]) / sw_den;
   };
+  // minute stream (tskc, wind, prec): source day md, minute sm of that day
   const int qm = off_min < 0 ? -1 : 0;          // floor(off_min / 1440), |off_min| <= 720
-  const int bm = (qm + 1) * kMinPerDay - off_min;  // minute-of-output-day where "hi" starts
-  const int qs = off_tiny < 0 ? -1 : 0;
-  const int bs = (qs + 1) * kTiny - off_tiny;      // tiny-step-of-output-day where "hi" starts
-  const int cs = -qs * kTiny + off_tiny;           // column of tiny step 0 of the day in the lo row
-
-  PrecDay pd_lo, pd_hi;
-  double tk_lo, tk_hi, wd_lo = 0, wd_hi = 0, rd_lo = 0, rd_hi = 0;
-  {
-    const int dl = wrap(d_lo + qm), dh = wrap(d_lo + qm + 1);
-    tk_lo = a.tskc_d[(size_t)dl * ld + cell];
-    tk_hi = a.tskc_d[(size_t)dh * ld + cell];
-    if (want_wind) { wd_lo = f.wind[(size_t)dl * ld + cell]; wd_hi = f.wind[(size_t)dh * ld + cell]; }
-    if (want_prec) { prec_day_setup(p, f, cell, dl, pd_lo); prec_day_setup(p, f, cell, dh, pd_hi); }
-    if (want_sw) { rd_lo = rad_of(wrap(d_lo + qs)); rd_hi = rad_of(wrap(d_lo + qs + 1)); }
-  }
+  int md = wrap(d_lo + qm);
+  int sm = off_min - qm * kMinPerDay;
+  PrecDay pd;
+  double tk_cur = a.tskc_d[(size_t)md * ld + cell];
+  double wd_cur = want_wind ? f.wind[(size_t)md * ld + cell] : 0.0;
+  PrecPos ppos = {0, 0, 0};
+  if (want_prec) { prec_day_setup(p, f, cell, md, pd); ppos = prec_pos(pd, sm); }
   double prec_last = nan("");   // last valid precipitation step (ffill carry)
   bool prec_last_known = false;
+  // tiny-step stream (shortwave): source day sd, tiny step ss of that day, table row per output day
+  const int qs = off_tiny < 0 ? -1 : 0;
+  int sd = wrap(d_lo + qs);
+  int ss = off_tiny - qs * kTiny;
+  double rd_cur = want_sw ? rad_of(sd) : 0.0;
+  const double *q_cur = c.qrow;
+  double qprev = 0.0;
 
-  long i = i_lo;
-  size_t oidx = (size_t)(i_lo - (long)a.out.day0 * tpd) * (size_t)a.out.ld + cell;
+  int i = i_lo;
+  size_t oidx = (size_t)(i_lo - a.out.day0 * tpd) * (size_t)a.out.ld + cell;
   double x = (double)ts * (double)i_lo;
   const double dx = (double)ts;
   const size_t ostride = (size_t)a.out.ld;
 
   for (int d = d_lo; d < d_hi; ++d) {
-    const double *q_lo = nullptr, *q_hi = nullptr;
+    const int y = f.doy[d] - 1;
     if (want_sw) {
-      const int y = f.doy[d] - 1;
-      int yl = y + qs, yh = y + qs + 1;
-      yl = yl < 0 ? yl + kRows : yl;                 // table rolls over its own 366 rows (:656)
-      yh = yh >= kRows ? yh - kRows : yh;
-      q_lo = c.qrow + (size_t)min(yl, 364) * kQLd;   // row 365 is a copy of row 364
-      q_hi = c.qrow + (size_t)min(yh, 364) * kQLd;
+      // every output day starts in the "lo" part of its window: table row y + qs, rolled over the
+      // table's own 366 rows (:656); row 365 is a copy of row 364
+      int yl = y + qs;
+      yl = yl < 0 ? yl + kRows : yl;
+      q_cur = c.qrow + (size_t)min(yl, 364) * kQLd;
+      qprev = q_cur[ss];
     }
-    int mt = 0;   // minute of the output day at the start of the step
-    int st = 0;   // tiny step of the output day at the start of the step
-    for (int t = 0; t < tpd; ++t, ++i, x += dx, oidx += ostride, mt += ts, st += C) {
+    for (int t = 0; t < tpd; ++t, ++i, x += dx, oidx += ostride) {
       // -- temperature (PCHIP) --
-      if (cub.k < c.nk - 2 && x >= cub.x1) {
+      if (x >= cub.x1) {
         int k = cub.k + 1;
         double xn, yn;
-        while (k < c.nk - 2) { knot(c, k + 1, xn, yn); if (x >= xn) ++k; else break; }
+        while (k < nk - 2) { knot(c, k + 1, xn, yn); if (x >= xn) ++k; else break; }
         cubic_setup(c, k, cub, a.status);
+        if (k >= nk - 2) cub.x1 = kInf;
       }
       const double temp = cubic_eval(cub, x);
       const double es = svp_kpa(temp, etab);       // saturation vapour pressure, kPa
@@ -479,91 +496,95 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         vp = ((x - xvl) * vinv) * yvh + ((xvh - x) * vinv) * yvl;   // scipy _interpolate.py:513-516
         vp = fmin(vp, es);                                         // disaggregate.py:486-487
       } else {
-        vp = vp_all_nan ? nan("") : (i < i_sp0 ? vp_head : vp_tail);
+        vp = i < i_sp0 ? vp_head : vp_tail;
       }
 
       // -- relative humidity :444-446, air pressure :401-403 --
       const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);   // 100*1000*vp/(svp in Pa)
       const double ap = (kPStd / 1000.0) * exp_tab(pr_num * rcp_nr(pr_corr + temp), etab);
 
-      // -- rolled block means of tskc / wind :355-380, :593-615 --
-      // minutes [mt, mt+ts) of the output day: before bm they come from "lo", from bm on from "hi"
-      const int n1 = min(max(bm - mt, 0), ts);      // minutes taken from lo
-      const bool all_lo = n1 == ts, all_hi = n1 == 0;
-      double tskc;
-      if (all_lo) tskc = tk_lo;
-      else if (all_hi) tskc = tk_hi;
-      else tskc = ((double)n1 * tk_lo + (double)(ts - n1) * tk_hi) * inv_ts;
-
-      if (a.out.var[MSB_V_TEMP]) put<OutT, UNITS>(a.out, MSB_V_TEMP, oidx, temp);
-      if (a.out.var[MSB_V_VAPOR_PRESSURE]) put<OutT, UNITS>(a.out, MSB_V_VAPOR_PRESSURE, oidx, vp);
-      if (a.out.var[MSB_V_REL_HUMID]) put<OutT, UNITS>(a.out, MSB_V_REL_HUMID, oidx, rh);
-      if (a.out.var[MSB_V_AIR_PRESSURE]) put<OutT, UNITS>(a.out, MSB_V_AIR_PRESSURE, oidx, ap);
-      if (want_tk) put<OutT, UNITS>(a.out, MSB_V_TSKC, oidx, tskc);
-      if (want_wind) {
-        double wind;
-        if (all_lo) wind = wd_lo;
-        else if (all_hi) wind = wd_hi;
-        else wind = ((double)n1 * wd_lo + (double)(ts - n1) * wd_hi) * inv_ts;
-        put<OutT, UNITS>(a.out, MSB_V_WIND, oidx, wind);
+      // -- minute stream: tskc / wind block means :355-380, :593-615; precipitation :265-352 --
+      double tskc, wind, pr = 0.0;
+      sm += ts;
+      if (sm < kMinPerDay) {                      // whole window inside the current source day
+        tskc = tk_cur;
+        wind = wd_cur;
+        if (want_prec) {
+          const PrecPos e = prec_pos(pd, sm);
+          pr = pd.nan ? nan("") : prec_window(pd, ppos, e, ts);
+          ppos = e;
+        }
+      } else {                                    // window reaches the end of the source day: roll
+        const int n2 = sm - kMinPerDay, n1 = ts - n2;   // minutes from the current / next day
+        md = (md + 1 == D) ? 0 : md + 1;
+        const double tk_n = a.tskc_d[(size_t)md * ld + cell];
+        tskc = n2 == 0 ? tk_cur : ((double)n1 * tk_cur + (double)n2 * tk_n) * inv_ts;
+        tk_cur = tk_n;
+        if (want_wind) {
+          const double wd_n = f.wind[(size_t)md * ld + cell];
+          wind = n2 == 0 ? wd_cur : ((double)n1 * wd_cur + (double)n2 * wd_n) * inv_ts;
+          wd_cur = wd_n;
+        } else wind = 0.0;
+        if (want_prec) {
+          pr = pd.nan ? nan("") : prec_window(pd, ppos, prec_pos(pd, kMinPerDay), n1);
+          prec_day_setup(p, f, cell, md, pd);
+          const PrecPos z = {0, 0, 0};
+          ppos = prec_pos(pd, n2);
+          if (n2 > 0) pr = pd.nan ? nan("") : pr + prec_window(pd, z, ppos, n2);
+        }
+        sm = n2;
       }
-      if (want_sh) {   // specific humidity :423-424
+      if (want_prec) {
+        if (pr != pr) {    // NaN day: pandas ffill, then bfill for a leading run (:130)
+          if (!prec_last_known) { prec_last = prec_fill(p, f, c, i); prec_last_known = true; }
+          pr = prec_last;
+        } else {
+          prec_last = pr;
+          prec_last_known = true;
+        }
+      }
+
+      // -- tiny-step stream: shortwave :618-680 --
+      double sw = 0.0;
+      if (want_sw) {
+        const int ca = ss;
+        ss += C;
+        if (ss < kTiny) {
+          const double qn = q_cur[ss];
+          double w = qn - qprev;
+          if (ca <= kNoon && ss > kNoon) w += q_cur[kTiny + 1];
+          qprev = qn;
+          sw = rd_cur * w;
+        } else {                                  // roll to the next source day / table row
+          const int k2 = ss - kTiny;
+          double w = q_cur[kTiny] - qprev;        // [ca, 2880)
+          if (ca <= kNoon) w += q_cur[kTiny + 1];
+          sw = rd_cur * w;
+          sd = (sd + 1 == D) ? 0 : sd + 1;
+          rd_cur = rad_of(sd);
+          int yh = y + qs + 1;
+          yh = yh >= kRows ? yh - kRows : yh;
+          q_cur = c.qrow + (size_t)min(yh, 364) * kQLd;
+          qprev = q_cur[k2];
+          if (k2 > 0) sw = fma(rd_cur, qprev - q_cur[0], sw);   // k2 <= 720 < noon: plain prefix
+          ss = k2;
+        }
+      }
+
+      if (want(MSB_V_TEMP)) put<OutT, UNITS>(a.out, MSB_V_TEMP, oidx, temp);
+      if (want(MSB_V_VAPOR_PRESSURE)) put<OutT, UNITS>(a.out, MSB_V_VAPOR_PRESSURE, oidx, vp);
+      if (want(MSB_V_REL_HUMID)) put<OutT, UNITS>(a.out, MSB_V_REL_HUMID, oidx, rh);
+      if (want(MSB_V_AIR_PRESSURE)) put<OutT, UNITS>(a.out, MSB_V_AIR_PRESSURE, oidx, ap);
+      if (want(MSB_V_TSKC)) put<OutT, UNITS>(a.out, MSB_V_TSKC, oidx, tskc);
+      if (want_wind) put<OutT, UNITS>(a.out, MSB_V_WIND, oidx, wind);
+      if (want(MSB_V_SPEC_HUMID)) {   // specific humidity :423-424
         const double mix = (kEps * vp) * rcp_nr(ap - vp);
         put<OutT, UNITS>(a.out, MSB_V_SPEC_HUMID, oidx, mix * rcp_nr(1 + mix));
       }
-      if (want_lw) put<OutT, UNITS>(a.out, MSB_V_LONGWAVE, oidx, longwave<FAST_LW>(p, temp, vp, tskc, etab));
-
-      // -- precipitation :265-352 --
-      if (want_prec) {
-        // source minutes: lo day [mt - bm + 1440, ...) for the first n1, hi day [max(mt-bm,0), ...)
-        double v = 0.0;
-        bool isnan_ = false;
-        if (n1 > 0) {
-          const int ra = mt - bm + kMinPerDay;
-          isnan_ = pd_lo.nan;
-          v = prec_day_sum(pd_lo, ra, ra + n1);
-        }
-        if (n1 < ts) {
-          const int ra = max(mt - bm, 0);
-          isnan_ |= pd_hi.nan;
-          v += prec_day_sum(pd_hi, ra, ra + (ts - n1));
-        }
-        if (isnan_) {
-          if (!prec_last_known) { prec_last = prec_fill(p, f, c, i); prec_last_known = true; }
-          v = prec_last;
-        } else {
-          prec_last = v;
-          prec_last_known = true;
-        }
-        put<OutT, UNITS>(a.out, MSB_V_PREC, oidx, v);
-      }
-
-      // -- shortwave :618-680: tiny steps [st, st+C) of the output day, lo row before bs --
-      if (want_sw) {
-        const int k1 = min(max(bs - st, 0), C);     // tiny steps taken from the lo row
-        double sw = 0.0;
-        if (k1 > 0) {
-          const int ca = st + cs, cb = ca + k1;
-          double w = q_lo[cb] - q_lo[ca];
-          if (ca <= kNoon && cb > kNoon) w += q_lo[kTiny + 1];
-          sw = rd_lo * w;
-        }
-        if (k1 < C) {
-          const int ca = max(st - bs, 0), cb = ca + (C - k1);
-          double w = q_hi[cb] - q_hi[ca];
-          if (ca <= kNoon && cb > kNoon) w += q_hi[kTiny + 1];
-          sw = fma(rd_hi, w, sw);
-        }
-        put<OutT, UNITS>(a.out, MSB_V_SHORTWAVE, oidx, sw);
-      }
-    }
-    // ---- the next output day: hi becomes lo ----
-    if (d + 1 < d_hi) {
-      const int dh = wrap(d + 1 + qm + 1);
-      tk_lo = tk_hi; tk_hi = a.tskc_d[(size_t)dh * ld + cell];
-      if (want_wind) { wd_lo = wd_hi; wd_hi = f.wind[(size_t)dh * ld + cell]; }
-      if (want_prec) { pd_lo = pd_hi; prec_day_setup(p, f, cell, dh, pd_hi); }
-      if (want_sw) { rd_lo = rd_hi; rd_hi = rad_of(wrap(d + 1 + qs + 1)); }
+      if (want(MSB_V_LONGWAVE))
+        put<OutT, UNITS>(a.out, MSB_V_LONGWAVE, oidx, longwave<FAST_LW>(p, temp, vp, tskc, etab));
+      if (want_prec) put<OutT, UNITS>(a.out, MSB_V_PREC, oidx, pr);
+      if (want_sw) put<OutT, UNITS>(a.out, MSB_V_SHORTWAVE, oidx, sw);
     }
   }
 }
@@ -637,15 +658,20 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool fast_lw = p->lw_type == MSB_LW_PRATA && p->lw_cloud == MSB_CLOUD_DEARDORFF;
   bool units = false;
-  for (int v = 0; v < MSB_N_SUBVARS; ++v)
-    if (out->var[v] && (out->scale[v] != 1.0 || out->offset[v] != 0.0)) units = true;
-#define MSB_LAUNCH(T, F, U) disagg_kernel<T, F, U><<<grid, kDisaggThreads, 0, st>>>(a)
-  if (out->dtype == 4) {
-    if (units) { if (fast_lw) MSB_LAUNCH(float, true, true); else MSB_LAUNCH(float, false, true); }
-    else { if (fast_lw) MSB_LAUNCH(float, true, false); else MSB_LAUNCH(float, false, false); }
+  a.var_mask = 0;
+  for (int v = 0; v < MSB_N_SUBVARS; ++v) {
+    if (!out->var[v] || (v == MSB_V_WIND && !f->wind)) continue;
+    a.var_mask |= 1u << v;
+    if (out->scale[v] != 1.0 || out->offset[v] != 0.0) units = true;
+  }
+  if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
+  const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4;
+#define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
+  if (example) MSB_LAUNCH(float, true, false, kVarsExample);   // reference defaults, 8 variables
+  else if (out->dtype == 4) {
+    if (fast_lw) MSB_LAUNCH(float, true, true, kVarsAny); else MSB_LAUNCH(float, false, true, kVarsAny);
   } else {
-    if (units) { if (fast_lw) MSB_LAUNCH(double, true, true); else MSB_LAUNCH(double, false, true); }
-    else { if (fast_lw) MSB_LAUNCH(double, true, false); else MSB_LAUNCH(double, false, false); }
+    if (fast_lw) MSB_LAUNCH(double, true, true, kVarsAny); else MSB_LAUNCH(double, false, true, kVarsAny);
   }
 #undef MSB_LAUNCH
   MSB_CUDA(cudaGetLastError());

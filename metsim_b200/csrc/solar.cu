@@ -73,7 +73,6 @@ static void prelude_rows(const double *lat_deg, int r0, int r1, PreludeView v) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
 constexpr int kChunk = 12;                       // 240 active scan threads x 12 = 2880
-constexpr int kScanThreads = kTiny / kChunk;     // 240
 
 __constant__ double c_optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.37, 4.72, 5.12, 5.60,
                                    6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
@@ -85,21 +84,14 @@ __device__ __forceinline__ int tiny_index(double h) {
   return (int)v;
 }
 
-// deterministic block sum (fixed tree): warp shuffles then warp 0
-__device__ __forceinline__ double block_sum(double v, double *red /*[32]*/) {
+__device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) red[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = (l < (blockDim.x >> 5)) ? red[l] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (l == 0) red[0] = v;
-  }
-  __syncthreads();
-  return red[0];
+  return v;
 }
+
+constexpr int kWarps = kK1Threads / 32;          // 8
+constexpr int kHalfSlots = kK1Threads / 2;       // 128 scan slots per half, 120 of them used
+constexpr int kHalfChunks = kTiny / 2 / kChunk;  // 120
 
 __global__ void __launch_bounds__(kK1Threads)
 solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
@@ -107,13 +99,14 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
                   const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
                   msb_solar_tables tb) {
   __shared__ double row[kTiny];
-  __shared__ double red[32];
-  __shared__ double mom[kTT];
-  __shared__ double chunk_tot[kScanThreads];
+  __shared__ double qs[kQLd];
+  __shared__ double part[kWarps][kTT + 1];
+  __shared__ double warp_tot[kWarps];
   __shared__ int s_rise, s_set;
 
   const int i = blockIdx.x % 365;   // yday row 0..364
   const int r = blockIdx.x / 365;   // latitude row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t o = (size_t)r * 365 + i;
   const double cosegeom = g_cosegeom[o], sinegeom = g_sinegeom[o], hss = g_hss[o];
   const double cza_first = g_cza0[o];
@@ -121,21 +114,19 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const double dh = kSwRadDt / kSecPerRad;
   const double kLnTBase = -0.13926206733350766;  // ln(0.87)
 
-  for (int j = threadIdx.x; j < kTiny; j += blockDim.x) row[j] = 0.0;
-  if (threadIdx.x < kTT) mom[threadIdx.x] = 0.0;
-  if (threadIdx.x == 0) { s_rise = -1; s_set = -1; }
+  for (int j = tid; j < kTiny; j += kK1Threads) row[j] = 0.0;
+  if (tid == 0) { s_rise = -1; s_set = -1; }
   __syncthreads();
 
   // physics.py:238-239
   const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
   const double start = -hss;
 
-  double sum_dfa = 0.0;
-  double m_loc[kTT];
+  double m_loc[kTT + 1];   // Taylor moments of trans**am, [kTT] = sum of dir_flat_topa
 #pragma unroll
-  for (int m = 0; m < kTT; ++m) m_loc[m] = 0.0;
+  for (int m = 0; m <= kTT; ++m) m_loc[m] = 0.0;
 
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  for (int k = tid; k < n; k += kK1Threads) {
     double h = __dadd_rn(start, __dmul_rn((double)k, dh));
     double cza = (k == 0) ? cza_first : __dadd_rn(__dmul_rn(cosegeom, cos(h)), sinegeom);
     double dfa = 0.0;
@@ -147,7 +138,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
         ami = min(max(ami, 0), 20);
         am = c_optam[ami];
       }
-      sum_dfa += dfa;
+      m_loc[kTT] += dfa;
       // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
       double a = am * kLnTBase;
       double term = exp(a * MSB_TT_P0) * dfa;
@@ -168,23 +159,30 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
     if (last) row[ts] = dfa;
   }
 
-  const double total = block_sum(sum_dfa, red);
+  // deterministic two-level reduction of the kTT+1 accumulators (fixed shuffle tree, fixed order)
 #pragma unroll
-  for (int m = 0; m < kTT; ++m) {
-    double s = block_sum(m_loc[m], red);
-    if (threadIdx.x == 0) mom[m] = s;
+  for (int m = 0; m <= kTT; ++m) {
+    double v = warp_sum(m_loc[m]);
+    if (lane == 0) part[warp][m] = v;
   }
   __syncthreads();
+  if (tid <= kTT) {
+    double v = 0.0;
+    for (int w = 0; w < kWarps; ++w) v += part[w][tid];
+    part[0][tid] = v;
+  }
+  __syncthreads();
+  const double total = part[0][kTT];
 
   const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
   const bool has_day = daylength != 0.0;
   if (has_day && total > 0.0)
-    for (int j = threadIdx.x; j < kTiny; j += blockDim.x) row[j] = row[j] / total;  // :270-271
+    for (int j = tid; j < kTiny; j += kK1Threads) row[j] = row[j] / total;  // :270-271
   __syncthreads();
 
   // sunrise / sunset: last j with row[j] <= 0 < row[j+1] / row[j] > 0 >= row[j+1]
   int rise = -1, set = -1;
-  for (int j = threadIdx.x; j < kTiny - 1; j += blockDim.x) {
+  for (int j = tid; j < kTiny - 1; j += kK1Threads) {
     int a = row[j] > 0.0, b = row[j + 1] > 0.0;
     if (b - a > 0) rise = max(rise, j);
     if (b - a < 0) set = max(set, j);
@@ -192,40 +190,62 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   if (rise >= 0) atomicMax(&s_rise, rise);
   if (set >= 0) atomicMax(&s_set, set);
 
-  // signed prefix table: q[j] = sum_{i<j} row[i] for j <= 1440, -sum_{i>=j} row[i] for j > 1440
-  double *q = tb.q + ((size_t)r * 365 + i) * kQLd;
+  // signed prefix table: q[j] = sum_{i<j} row[i] for j <= 1440, -sum_{i>=j} row[i] for j > 1440.
+  // Threads 0..127 scan the morning half forwards, threads 128..255 the afternoon half backwards,
+  // so small sums near sunrise AND sunset are accumulated from the dark side (no cancellation).
+  const int half = tid / kHalfSlots, slot = tid % kHalfSlots;
+  const bool valid = slot < kHalfChunks;
   double loc[kChunk];
   double csum = 0.0;
-  const int t = threadIdx.x;
-  const bool fwd = t < kScanThreads / 2;
-  if (t < kScanThreads) {
-    if (fwd) {
-      for (int e = 0; e < kChunk; ++e) { loc[e] = csum; csum += row[t * kChunk + e]; }
-    } else {
-      for (int e = kChunk - 1; e >= 0; --e) { csum += row[t * kChunk + e]; loc[e] = csum; }
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < kChunk; ++e) {
+      const int rr = slot * kChunk + e;
+      const int j = half == 0 ? rr : kTiny - 1 - rr;
+      loc[e] = csum;              // exclusive
+      csum += row[j];
     }
-    chunk_tot[t] = csum;
+  }
+  double incl = csum;             // inclusive scan of chunk totals inside the warp
+  for (int o2 = 1; o2 < 32; o2 <<= 1) {
+    double up = __shfl_up_sync(0xffffffffu, incl, o2);
+    if (lane >= o2) incl += up;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  double base = incl - csum;
+  const int w0 = half * (kWarps / 2);
+  for (int w = w0; w < warp; ++w) base += warp_tot[w];
+  double half_tot[2];
+  for (int hh = 0; hh < 2; ++hh) {
+    double v = 0.0;
+    for (int w = hh * (kWarps / 2); w < (hh + 1) * (kWarps / 2); ++w) v += warp_tot[w];
+    half_tot[hh] = v;
+  }
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < kChunk; ++e) {
+      const int rr = slot * kChunk + e;
+      if (half == 0) {
+        qs[rr] = base + loc[e];                                 // prefix, j = rr < 1440
+      } else {
+        const int j = kTiny - 1 - rr;                           // j in [1440, 2879]
+        const double incl_e = base + loc[e] + row[j];           // sum_{i >= j}
+        if (j > kNoon) qs[j] = -incl_e;
+      }
+    }
+  }
+  if (tid == 0) {
+    qs[kNoon] = half_tot[0];                   // prefix up to (not including) tiny step 1440
+    qs[kTiny] = 0.0;                           // empty suffix
+    qs[kTiny + 1] = half_tot[0] + half_tot[1]; // row total (1 up to rounding, 0 for polar night)
+    for (int e = kTiny + 2; e < kQLd; ++e) qs[e] = 0.0;
   }
   __syncthreads();
-  if (t < kScanThreads) {
-    double base = 0.0;
-    if (fwd) { for (int c = 0; c < t; ++c) base += chunk_tot[c]; }
-    else { for (int c = kScanThreads - 1; c > t; --c) base += chunk_tot[c]; }
-    if (fwd) { for (int e = 0; e < kChunk; ++e) q[t * kChunk + e] = base + loc[e]; }
-    else { for (int e = 0; e < kChunk; ++e) if (t * kChunk + e > kNoon) q[t * kChunk + e] = -(base + loc[e]); }
-  }
-  if (t == 0) {
-    double first_half = 0.0, second_half = 0.0;
-    for (int c = 0; c < kScanThreads / 2; ++c) first_half += chunk_tot[c];
-    for (int c = kScanThreads - 1; c >= kScanThreads / 2; --c) second_half += chunk_tot[c];
-    q[kNoon] = first_half;           // prefix up to (not including) tiny step 1440
-    q[kTiny] = -0.0;                 // empty suffix
-    q[kTiny + 1] = first_half + second_half;  // row total (1 up to rounding, 0 for polar night)
-    for (int e = kTiny + 2; e < kQLd; ++e) q[e] = 0.0;
-  }
-  __syncthreads();
+  double *q = tb.q + ((size_t)r * 365 + i) * kQLd;
+  for (int j = tid; j < kQLd; j += kK1Threads) q[j] = qs[j];
 
-  if (t == 0) {
+  if (tid == 0) {
     const double step_min = kSwRadDt / 60.0;
     double rise_m = (s_rise >= 0) ? s_rise * step_min : 0.0;
     double set_m = (s_set >= 0) ? s_set * step_min : 0.0;
@@ -245,10 +265,10 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
       tb.set_min[s + 1] = set_m;
     }
   }
-  if (t < kTT) {
+  if (tid < kTT) {
     // tt_max0(p) = sum_trans/sum_flat_potrad (physics.py:275); 0 when there is no daylight
-    double c = (has_day && total > 0.0) ? mom[t] / total : 0.0;
-    tb.tt_coef[((size_t)r * 365 + i) * kTT + t] = c;
+    double c = (has_day && total > 0.0) ? part[0][tid] / total : 0.0;
+    tb.tt_coef[((size_t)r * 365 + i) * kTT + tid] = c;
   }
 }
 
