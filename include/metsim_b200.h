@@ -144,8 +144,8 @@ int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *daily, const msb_subdaily *out, void *stream);
 
-/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [5][n]
- * (1/x, exp(x), sqrt(x), 1.2345678901234567/x, svp(x) in kPa).  Used by the parity tests. */
+/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [6][n]
+ * (1/x, exp(x), sqrt(x), 1.2345678901234567/x, svp(x) in kPa, raw reciprocal seed).  Used by the parity tests. */
 int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream);
 
 /* ---- whole path with HOST buffers (what a reference-side binding calls) ---------------------

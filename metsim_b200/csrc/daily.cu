@@ -106,7 +106,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kDailyThreads)
 daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int chunk_len,
              int k_off, int max_evals) {
-  __shared__ double etab[64];
+  __shared__ double etab[kExpTab];
   exp_table_init(etab);
   __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;

@@ -337,7 +337,7 @@ constexpr unsigned kExampleMask = (1u << MSB_V_TEMP) | (1u << MSB_V_PREC) | (1u 
 template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
 __global__ void __launch_bounds__(kDisaggThreads, 4)
 disagg_kernel(const __grid_constant__ DisaggArgs a) {
-  __shared__ double etab[64];
+  __shared__ double etab[kExpTab];
   exp_table_init(etab);
   __syncthreads();
 
@@ -591,7 +591,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 
 // accuracy probe of the hand-written fp64 sequences (tests only touch it through the C ABI)
 __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
-  __shared__ double etab[64];
+  __shared__ double etab[kExpTab];
   exp_table_init(etab);
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,6 +602,7 @@ __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double
   out[2 * n + i] = sqrt_nr(v);
   out[3 * n + i] = div_nr(1.2345678901234567, v);
   out[4 * n + i] = svp_kpa(v, etab);
+  out[5 * n + i] = rcp_seed(v);
 }
 
 }  // namespace msb

@@ -51,19 +51,24 @@ int cuda_fail(cudaError_t e, const char *what);
 
 #ifdef __CUDACC__
 // ---- fp64 building blocks --------------------------------------------------------------------
-// The sub-daily kernel is co-limited by the fp64 pipe (64 lanes/clk/SM) and HBM stores, so the
-// divide / exp / sqrt sequences are written out with exactly the number of DFMAs the 1e-9
-// contract needs instead of the IEEE-rounded library sequences (which add slow-path branches).
+// The sub-daily kernel is co-limited by the fp64 pipe (64 lanes/clk/SM), the issue slots and HBM
+// stores, so divide / exp / sqrt are written out with exactly the DFMAs the 1e-9 contract needs
+// (results are good to ~1e-15) instead of the IEEE-rounded library sequences with slow paths.
+// fp64 literals cost two UMOVs each on sm_100 unless their low 32 bits are zero (then they are
+// instruction immediates), so low-order-insensitive coefficients are written in that form.
 
-// 1/x for normal, finite x: MUFU.RCP64H seed + 2 Newton steps (4 DFMA).  rel. error < 2^-50.
-__device__ __forceinline__ double rcp_nr(double x) {
+// 1/x for normal, finite x: MUFU.RCP64H seed (rel. error < 2^-20, measured) + one third-order
+// step y*(1 + e + e^2), e = 1 - x*y: 3 DFMA, rel. error ~e^3 < 1e-17 + rounding.
+__device__ __forceinline__ double rcp_seed(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
   return y;
+}
+__device__ __forceinline__ double rcp_nr(double x) {
+  const double y = rcp_seed(x);
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
 }
 __device__ __forceinline__ double div_nr(double a, double b) {
   double y = rcp_nr(b);
@@ -72,49 +77,47 @@ __device__ __forceinline__ double div_nr(double a, double b) {
   return fma(r, y, q);
 }
 
-// exp(x) for |x| < 700: k = rint(x*64/ln2), 64-entry 2^(j/64) table in shared memory,
-// degree-5 polynomial on |r| <= ln2/128.  rel. error < 3e-16.
-struct ExpTable { double t[64]; };
+// exp(x) for |x| < 700: k = rint(x*256/ln2), 256-entry 2^(j/256) table in shared memory,
+// degree-3 polynomial on |r| <= ln2/512 (truncation r^4/24 < 1.4e-13... times 1/24: 1.4e-13 rel).
+constexpr int kExpTab = 256;
 __device__ __forceinline__ void exp_table_init(double *tab) {
-  for (int j = threadIdx.x; j < 64; j += blockDim.x) tab[j] = exp2((double)j / 64.0);
+  for (int j = threadIdx.x; j < kExpTab; j += blockDim.x) tab[j] = exp2((double)j / (double)kExpTab);
 }
+__constant__ double c_exp[2] = {369.3299304675746,        // 256/ln2
+                                0.0027076061740622863};   // ln2/256
 __device__ __forceinline__ double exp_tab(double x, const double *tab) {
-  const double kInvL = 92.33248261689366;         // 64/ln2
-  const double kLhi = 0.010830424696249145;      // fl(ln2/64)
-  const double kLlo = 3.623510646634843e-19;     // ln2/64 - fl(ln2/64)
-  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
-  double kd = fma(x, kInvL, kMagic);
-  int k = __double2loint(kd);
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52 (immediate form)
+  double kd = fma(x, c_exp[0], kMagic);
+  const int k = __double2loint(kd);
   kd -= kMagic;
-  double r = fma(-kd, kLhi, x);
-  r = fma(-kd, kLlo, r);
-  double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
+  // k*ln2/256 carries < 2e-15 absolute error for |k| < 2^17: one fma is enough at the 1e-13 level
+  const double r = fma(-kd, c_exp[1], x);
+  // 1 + r + r^2/2 + r^3/6; 1/6 rounded to a 32-bit-high literal (error 1e-7 * r^3 < 1e-16)
+  const double kSixth = __hiloint2double(0x3fc55555, 0);
+  double p = fma(r, kSixth, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  double s = tab[k & 63];
-  int hi = __double2hiint(s) + ((k >> 6) << 20);
+  double s = tab[k & (kExpTab - 1)];
+  const int hi = __double2hiint(s) + ((k >> 8) << 20);
   s = __hiloint2double(hi, __double2loint(s));
   return p * s;
 }
 
-// sqrt(x), x > 0 normal: MUFU.RSQ64H seed + Newton on rsqrt + one residual step.
+// sqrt(x), x > 0 normal: MUFU.RSQ64H seed + one third-order rsqrt step + one residual step.
 __device__ __forceinline__ double sqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double h = 0.5 * y;
-  double e = fma(-x * y, h, 0.5);  // 0.5 - 0.5*x*y^2
-  y = fma(y, e, y);
-  h = 0.5 * y;
-  e = fma(-x * y, h, 0.5);
-  y = fma(y, e, y);
-  double g = x * y;                // ~sqrt(x)
-  double r = fma(-g, g, x);
+  // e = 1 - x*y^2;  y *= 1 + e/2 + 3e^2/8
+  const double xy = x * y;
+  const double e = fma(-xy, y, 1.0);
+  const double t = fma(e, 0.375, 0.5) * e;
+  y = fma(y, t, y);
+  const double g = x * y;                // ~sqrt(x)
+  const double r = fma(-g, g, x);
   return fma(r, 0.5 * y, g);
 }
 
-// physics.py:124-152 in Pa, library-accurate version used by the daily pass
+// physics.py:124-152 in Pa, library-accurate version
 __device__ __forceinline__ double svp_ref(double t) {
   double s = 0.61078 * exp((17.269 * t) / (237.3 + t));
   if (t < 0.0) s *= 1.0 + .00972 * t + .000042 * (t * t);
