@@ -141,19 +141,93 @@ def cpu_baseline_run(workload: str, n_days: int | None, cores: int, sample_cells
                                    prec_type=params["prec_type"])
 
 
+_REF_JOB = {}
+
+
+def _ref_worker_init(root, params, start):
+    """Pool initialiser: load the UNMODIFIED reference hot-path modules (baseline/_ref) and pay
+    numba's JIT of solar_geom once per process, outside the timed region."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")      # README.md:119-124 of the reference
+    os.environ.setdefault("NUMBA_NUM_THREADS", "1")
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import reference_harness as rh
+    rh.load_reference(root)
+    rh.load_reference().physics.solar_geom(100.0, 40.0, 0.0065)
+    _REF_JOB.update(rh=rh, params=params, start=start)
+
+
+def _ref_worker_cell(cell):
+    out = _REF_JOB["rh"].run_cell(dict(cell, start=_REF_JOB["start"]), _REF_JOB["params"])
+    return float(np.nansum(out["sub"]["temp"]))        # keep the result alive, return a scalar
+
+
+def reference_python_run(workload, n_days, cores, sample_cells, steps=1, warmup=0):
+    """The reference's OWN functions (physics.solar_geom -> mtclim.run -> disaggregate kernels,
+    loaded unmodified from baseline/_ref through oracle/reference_harness.py) per cell in a
+    multiprocessing pool over all host cores -- BASELINE.md plan B.  Returns None when the
+    reference install is not present."""
+    import multiprocessing as mp
+    from metsim_b200 import synth
+    from oracle import reference_harness as rh
+    root = rh.find_reference_root()
+    if root is None:
+        return None
+    if sample_cells is None:
+        sample_cells = 8 * cores                      # ~0.14 s per cell-year hourly per core
+    f, params = synth.make_config(workload, max_cells=sample_cells, n_days=n_days)
+    start = synth.CONFIGS[workload][2]
+    d, n = f["t_min"].shape
+    tpd = 1440 // params["time_step"]
+    cells = []
+    for c in range(n):
+        cell = {k: float(f[k][c]) for k in ("lat", "lon", "elev")}
+        for k in ("t_min", "t_max", "prec", "wind", "state_t_min", "state_t_max", "state_prec",
+                  "t_pk12", "dur12"):
+            cell[k] = np.ascontiguousarray(f[k][:, c])
+        cells.append(cell)
+    with mp.get_context("spawn").Pool(cores, initializer=_ref_worker_init,
+                                      initargs=(root, dict(params), start)) as pool:
+        chunk = max(1, n // (4 * cores))
+        for _ in range(warmup):
+            pool.map(_ref_worker_cell, cells[:cores], chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_ref_worker_cell, cells, chunksize=chunk)
+        dt = (time.perf_counter() - t0) / steps
+    value = n * d * tpd / dt
+    sample = (f"{n} evenly spaced cells of {workload} x {d} d x {tpd}/d through the reference's own "
+              f"physics.solar_geom + mtclim.run + disaggregate kernels (unmodified modules from "
+              f"baseline/_ref, numba JIT warmed), multiprocessing pool of {cores}; xarray/dask/netCDF "
+              f"driver overhead of the real `ms` excluded (not installable offline)")
+    return value, dt, sample, dict(workload=workload, cells=n, n_days=d, time_step=params["time_step"],
+                                   prec_type=params["prec_type"])
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    value, dt, sample, cfg = cpu_baseline_run(args.workload, args.days, cores, args.sample_cells,
-                                              steps=max(1, args.steps), warmup=max(0, min(args.warmup, 1)))
+    steps, warm = max(1, args.steps), max(0, min(args.warmup, 1))
+    kind = "reference"
+    res = None
+    try:
+        res = reference_python_run(args.workload, args.days, cores, args.sample_cells, steps, warm)
+    except Exception as exc:                           # fall back to the C port, say why
+        sys.stderr.write(f"reference (python) arm failed: {exc!r}; using the C port\n")
+    port = cpu_baseline_run(args.workload, args.days, cores, None, steps=1, warmup=0)
+    if res is None:
+        kind = "port"
+        res = cpu_baseline_run(args.workload, args.days, cores, args.sample_cells, steps=steps, warmup=warm)
+    value, dt, sample, cfg = res
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": sample},
+            "c_port": {"value": port[0], "unit": UNIT, "cores": cores, "sample": port[2]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -314,8 +388,16 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, dt_cpu, sample, _ = cpu_baseline_run(args.workload, args.days, cores, args.sample_cells)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        res, kind = None, "reference"
+        try:
+            res = reference_python_run(args.workload, args.days, cores, args.sample_cells, 1, 1)
+        except Exception as exc:
+            sys.stderr.write(f"reference (python) baseline failed: {exc!r}; using the C port\n")
+        pv, _, psample, _ = cpu_baseline_run(args.workload, args.days, cores, None)
+        if res is None:
+            kind, res = "port", (pv, 0.0, psample, None)
+        cpu = {"value": res[0], "unit": UNIT, "cores": cores, "kind": kind, "sample": res[2],
+               "c_port_value": pv, "c_port_sample": psample}
 
     if rank == 0:
         line = {

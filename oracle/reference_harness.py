@@ -38,7 +38,10 @@ _REF = None
 
 
 def find_reference_root():
-    for cand in (os.environ.get("METSIM_REF"), "/root/reference"):
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # baseline/_ref = offline `pip install --target` of the unmodified reference (git-ignored; it
+    # travels to the GPU box, /root/reference does not)
+    for cand in (os.environ.get("METSIM_REF"), "/root/reference", os.path.join(here, "baseline", "_ref")):
         if cand and os.path.isdir(os.path.join(cand, "metsim", "methods")):
             return cand
     return None
