@@ -69,6 +69,7 @@ typedef struct msb_params {
  * physics.py:177-285: only tt_max0 depends on elevation, everything else on latitude alone). */
 #define MSB_TINY_PER_DAY 2880
 #define MSB_Q_LD 2888        /* row pitch of the signed prefix table: entries 0..2880, [2881]=row total */
+#define MSB_Q_PAD 1024       /* zeroed elements after the last row (the kernel may read one step past a row) */
 #define MSB_TT_TERMS 28      /* Taylor terms of tt_max0 in the pressure ratio */
 #define MSB_TT_P0 0.68       /* expansion point of the pressure ratio p = t1**t2 */
 #define MSB_STATE_DAYS 90
@@ -79,7 +80,7 @@ typedef struct msb_solar_tables {
   double *potrad;       /* [n_lat][366]  W m-2        physics.py:276 */
   double *rise_min;     /* [n_lat][366]  minutes, 240 default applied  disaggregate.py:163-182 */
   double *set_min;      /* [n_lat][366]  minutes, 960 default applied */
-  double *q;            /* [n_lat][365][MSB_Q_LD] signed prefix sums of the normalised row */
+  double *q;            /* [n_lat][365][MSB_Q_LD] (+ MSB_Q_PAD) signed prefix sums of the normalised row */
   double *tt_coef;      /* [n_lat][365][MSB_TT_TERMS] Taylor coefficients of tt_max0(p) */
 } msb_solar_tables;
 
@@ -144,8 +145,9 @@ int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *daily, const msb_subdaily *out, void *stream);
 
-/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [6][n]
- * (1/x, exp(x), sqrt(x), 1.2345678901234567/x, svp(x) in kPa, raw reciprocal seed).  Used by the parity tests. */
+/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [8][n]
+ * (1/x, fast exp(x), fast sqrt(x), 1.2345678901234567/x, svp(x) in kPa, raw reciprocal seed,
+ * accurate exp(x), accurate sqrt(x)).  Used by the parity tests. */
 int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream);
 
 /* ---- whole path with HOST buffers (what a reference-side binding calls) ---------------------

@@ -54,11 +54,12 @@ struct DayInv {
   double b;       // ratio per unit shortwave: 1.26*s/(s+gamma)*0.72*daylength/lhvap/sp80
 };
 
-// svp in Pa (physics.py:124-152) on the fast fp64 path of msb_common.cuh
+// svp in Pa (physics.py:124-152) with the accurate exp of msb_common.cuh (the evaluation count of
+// the fixed point must match the reference exactly)
 __device__ __forceinline__ double svp_pa(double t, const double *etab) {
   const double r = rcp_nr(237.3 + t);
   const double arg = fma(-17.269 * 237.3, r, 17.269);   // 17.269*t/(237.3+t)
-  double s = 610.78 * exp_tab(arg, etab);
+  double s = 610.78 * exp_acc(arg, etab);
   if (t < 0.0) s *= fma(fma(.000042, t, .00972), t, 1.0);
   return s;
 }
@@ -181,8 +182,8 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
     }
     const double t_mean = (t_min + t_max) / 2;                          // mtclim.py:103-104
     const double t_day = ((t_max - t_mean) * p.tday_coef) + t_mean;
-    const double bb = kB0 + kB1 * exp_tab(-kB2 * sm_dtr, etab);        // mtclim.py:129-133
-    double tf = 1.0 - 0.9 * exp_tab(-bb * (dtr * sqrt_nr(fmax(dtr, 1e-300))), etab);  // dtr**1.5
+    const double bb = kB0 + kB1 * exp_acc(-kB2 * sm_dtr, etab);        // mtclim.py:129-133
+    double tf = 1.0 - 0.9 * exp_acc(-bb * (dtr * sqrt_nr(fmax(dtr, 1e-300))), etab);  // dtr**1.5
     if (prec > p.sw_prec_thresh) tf *= p.rain_scalar;
     // day-invariant part of calc_pet (physics.py:62-92)
     const double lhvap = 2.5023e6 - 2430.54 * t_day;

@@ -12,16 +12,27 @@
 // as full 128-byte lines.  What the reference gets from vectors is obtained in closed form:
 //   * np.roll + reshape(-1, ts).sum/mean  -> split of each output window at the (shifted) day
 //     boundary (tskc, wind, prec) -- integer arithmetic, bit-exact placement;
-//   * the per-minute triangle             -> arithmetic series over the clipped limb ranges;
-//   * bincount over 2*ts table entries    -> two loads from the signed prefix table of the
-//     latitude row (solar.cu), one per window edge;
-//   * PchipInterpolator / interp1d        -> a sliding 4-knot window, coefficients rebuilt only
-//     when the output time crosses a knot.
+//   * the per-minute triangle             -> differences of a cumulative arithmetic series whose
+//     positions are clamped in INTEGER arithmetic (exact zeros outside the limbs);
+//   * bincount over 2*ts table entries    -> difference of two entries of the signed prefix table
+//     of the latitude row (solar.cu);
+//   * PchipInterpolator / interp1d        -> the current cubic / linear segment in registers.
+//
+// Loop structure: the kernel is EVENT DRIVEN.  Everything that happens less than once per step --
+// a PCHIP or vapour-pressure knot is crossed, a source day or table row rolls over, the radiation
+// window crosses solar noon -- is a state update done by a cold handler when the step counter
+// reaches the next scheduled event.  Between events the warp runs a tight, call-free, branch-free
+// inner loop of straight-line fp64 arithmetic; the run length is the warp-wide minimum of the
+// lanes' next events (one REDUX per run), so lanes never lose lockstep on the step index.
+// Values that only the handler needs between events live in per-thread shared-memory slots, and
+// the one table load of the hot path is software-pipelined one step ahead.
 #include "msb_common.cuh"
 
 namespace msb {
 
 constexpr int kDisaggThreads = 128;
+constexpr int kNever = 0x7fffffff;
+constexpr int kDayWin = 40;    // staged day-of-year / month window (tile + margins)
 
 struct DisaggArgs {
   msb_params p;
@@ -34,50 +45,59 @@ struct DisaggArgs {
   unsigned var_mask;   // bit v set = out.var[v] requested
 };
 
-// ---- per-thread view of one cell -------------------------------------------------------------
+// ---- per-thread view of one cell (cold: only the event handler and the set-up read it) --------
 struct Cell {
   int cell, D, ts, tpd, nk;
   long ld;
-  int off_min, off_tiny;     // np.roll offsets (minutes / 30 s steps), trunc toward zero
+  int off_min;               // np.roll offset in minutes, trunc toward zero
   double utc_min;            // sunrise/sunset shift, disaggregate.py:184-189
   double frac;
-  const double *rise, *set, *dayl;  // latitude-row tables [366]
-  const double *qrow;               // latitude-row base of the signed prefix table
-  const int32_t *doy, *month;
+  const double *rise, *set;  // latitude-row tables [366]
+  const int32_t *doy;        // global [D]
+  const int *sdoy;           // shared copy of doy[win0 .. win0+nwin)
+  int win0, nwin;
   const double *t_min, *t_max, *st_t_min, *st_t_max, *t_end;
 };
-
-__device__ __forceinline__ int floordiv(int a, int b) {
-  int q = a / b;
-  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+__device__ __forceinline__ int doy_at(const Cell &c, int d) {
+  const unsigned r = (unsigned)(d - c.win0);
+  return r < (unsigned)c.nwin ? c.sdoy[r] : c.doy[d];
 }
 
+// Knot times are built with explicitly rounded operations (numpy never contracts a*b+c, and the
+// same knot must come out bit-identical from every place that evaluates it).
 // knot j of the padded PCHIP sequence (disaggregate.py:236-257); j in [0, 2D+4)
-__device__ __forceinline__ void knot(const Cell &c, int j, double &x, double &y) {
+__device__ __forceinline__ double knot_x(const Cell &c, int j) {
   const int e = (j >> 1) - 1;
   const int de = min(max(e, 0), c.D - 1);
-  const int yd = c.doy[de] - 1;
+  const int yd = doy_at(c, de) - 1;
   const double off = (double)de * 1440.0;
-  const double rt = (c.rise[yd] - c.utc_min) + off;   // :188-195
-  const double st = (c.set[yd] - c.utc_min) + off;
-  if (j & 1) x = (c.frac * (st - rt) + rt) - c.ts;    // t_t_max :198-199
-  else x = rt - c.ts;                                  // t_t_min :200
-  x += 1440.0 * (double)(e - de);                      // padded ends :242-243
-  if (e < 0) {
-    y = (j & 1) ? c.st_t_max[(size_t)(kState - 1) * c.ld + c.cell]
-                : c.st_t_min[(size_t)(kState - 1) * c.ld + c.cell];  // t_begin, metsim.py:753
-  } else if (e >= c.D) {
-    if (c.t_end) y = c.t_end[(size_t)(j & 1) * c.ld + c.cell];
-    else y = (j & 1) ? c.t_max[(size_t)(c.D - 1) * c.ld + c.cell]
-                     : c.t_min[(size_t)(c.D - 1) * c.ld + c.cell];
+  const double rt = __dadd_rn(__dadd_rn(c.rise[yd], -c.utc_min), off);   // :188-195
+  double x;
+  if (j & 1) {
+    const double st = __dadd_rn(__dadd_rn(c.set[yd], -c.utc_min), off);
+    x = __dadd_rn(__dadd_rn(__dmul_rn(c.frac, __dadd_rn(st, -rt)), rt), -(double)c.ts);  // t_t_max :198-199
   } else {
-    y = (j & 1) ? c.t_max[(size_t)e * c.ld + c.cell] : c.t_min[(size_t)e * c.ld + c.cell];
+    x = __dadd_rn(rt, -(double)c.ts);                                    // t_t_min :200
   }
+  return __dadd_rn(x, 1440.0 * (double)(e - de));                        // padded ends :242-243
+}
+__device__ __forceinline__ double knot_y(const Cell &c, int j) {
+  const int e = (j >> 1) - 1;
+  if (e < 0)
+    return (j & 1) ? c.st_t_max[(size_t)(kState - 1) * c.ld + c.cell]
+                   : c.st_t_min[(size_t)(kState - 1) * c.ld + c.cell];  // t_begin, metsim.py:753
+  if (e >= c.D) {
+    if (c.t_end) return c.t_end[(size_t)(j & 1) * c.ld + c.cell];
+    return (j & 1) ? c.t_max[(size_t)(c.D - 1) * c.ld + c.cell]
+                   : c.t_min[(size_t)(c.D - 1) * c.ld + c.cell];
+  }
+  return (j & 1) ? c.t_max[(size_t)e * c.ld + c.cell] : c.t_min[(size_t)e * c.ld + c.cell];
 }
 
 // scipy _cubic.py:279-291
 __device__ __forceinline__ double pchip_edge(double h0, double h1, double m0, double m1) {
-  double d = ((2 * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+  const double num = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(2.0, h0), h1), m0), -__dmul_rn(h0, m1));
+  const double d = div_nr(num, __dadd_rn(h0, h1));
   if (sgn(d) != sgn(m0)) return 0.0;
   if (sgn(m0) != sgn(m1) && fabs(d) > 3.0 * fabs(m0)) return 3.0 * m0;
   return d;
@@ -85,49 +105,74 @@ __device__ __forceinline__ double pchip_edge(double h0, double h1, double m0, do
 // scipy _cubic.py:320-333 (weighted harmonic mean, one division)
 __device__ __forceinline__ double pchip_mid(double h0, double h1, double m0, double m1) {
   if (sgn(m1) != sgn(m0) || m1 == 0.0 || m0 == 0.0) return 0.0;
-  double w1 = 2 * h1 + h0, w2 = h1 + 2 * h0;
-  return ((w1 + w2) * (m0 * m1)) / (w1 * m1 + w2 * m0);
+  const double w1 = __dadd_rn(__dmul_rn(2.0, h1), h0), w2 = __dadd_rn(h1, __dmul_rn(2.0, h0));
+  const double num = __dmul_rn(__dadd_rn(w1, w2), __dmul_rn(m0, m1));
+  const double den = __dadd_rn(__dmul_rn(w1, m1), __dmul_rn(w2, m0));
+  return div_nr(num, den);
 }
 
 struct Cubic {
-  int k;                 // interval index: knots k, k+1
-  double x0, x1;         // knot times
+  double x0, x1;         // knot times of the interval
   double c0, c1, c2, c3; // scipy power basis (CubicHermiteSpline, _cubic.py:158-165)
 };
+// what the next interval can reuse: knot k+1's value, knot k+2, the slope k+1 -> k+2 and the
+// derivative at knot k+1
+struct CubicNext { double y1, x2, y2, m2, d1; };
 
-__device__ __noinline__ void cubic_setup(const Cell &c, int k, Cubic &q, int32_t *status) {
-  double xa, ya, xb, yb, xc, yc, xd, yd;
-  knot(c, k, xb, yb);
-  knot(c, k + 1, xc, yc);
-  const double h1 = xc - xb;
-  const double m1 = (yc - yb) / h1;
-  bool bad = !(h1 > 0.0);
-  double d0, d1;
-  double h0 = 0, m0 = 0, h2 = 0, m2 = 0;
-  if (k > 0) {
-    knot(c, k - 1, xa, ya);
-    h0 = xb - xa;
-    m0 = (yb - ya) / h0;
-    bad |= !(h0 > 0.0);
-  }
-  if (k + 2 < c.nk) {
-    knot(c, k + 2, xd, yd);
-    h2 = xd - xc;
-    m2 = (yd - yc) / h2;
-    bad |= !(h2 > 0.0);
-  }
-  d0 = (k > 0) ? pchip_mid(h0, h1, m0, m1) : pchip_edge(h1, h2, m1, m2);
-  d1 = (k + 2 < c.nk) ? pchip_mid(h1, h2, m1, m2) : pchip_edge(h1, h0, m1, m0);
-  if (bad) status[2] = 1;
-  const double inv = 1.0 / h1;
-  const double tt = (d0 + d1 - 2 * m1) * inv;
-  q.k = k;
+__device__ __forceinline__ void cubic_coeffs(Cubic &q, double xb, double xc, double yb, double h1,
+                                             double m1, double d0, double d1) {
+  const double inv = rcp_nr(h1);
+  const double tt = __dmul_rn(__dadd_rn(__dadd_rn(d0, d1), -__dmul_rn(2.0, m1)), inv);
   q.x0 = xb;
   q.x1 = xc;
-  q.c0 = tt * inv;
-  q.c1 = (m1 - d0) * inv - tt;
+  q.c0 = __dmul_rn(tt, inv);
+  q.c1 = __dadd_rn(__dmul_rn(__dadd_rn(m1, -d0), inv), -tt);
   q.c2 = d0;
   q.c3 = yb;
+}
+
+// coefficients of interval k (knots k, k+1) from the four knots k-1 .. k+2; returns whether `nx`
+// was filled (k+2 exists)
+__device__ __forceinline__ bool cubic_setup(const Cell &c, int k, Cubic &q, CubicNext &nx,
+                                            int32_t *status) {
+  const bool has_a = k > 0, has_d = k + 2 < c.nk;
+  const double xb = knot_x(c, k), xc = knot_x(c, k + 1);
+  const double xa = has_a ? knot_x(c, k - 1) : 0.0, xd = has_d ? knot_x(c, k + 2) : 0.0;
+  const double yb = knot_y(c, k), yc = knot_y(c, k + 1);
+  const double ya = has_a ? knot_y(c, k - 1) : 0.0, yd = has_d ? knot_y(c, k + 2) : 0.0;
+  const double h1 = __dadd_rn(xc, -xb);
+  const double m1 = div_nr(__dadd_rn(yc, -yb), h1);
+  bool bad = !(h1 > 0.0);
+  double h0 = 0, m0 = 0, h2 = 0, m2 = 0;
+  if (has_a) {
+    h0 = __dadd_rn(xb, -xa);
+    m0 = div_nr(__dadd_rn(yb, -ya), h0);
+    bad |= !(h0 > 0.0);
+  }
+  if (has_d) {
+    h2 = __dadd_rn(xd, -xc);
+    m2 = div_nr(__dadd_rn(yd, -yc), h2);
+    bad |= !(h2 > 0.0);
+  }
+  const double d0 = has_a ? pchip_mid(h0, h1, m0, m1) : pchip_edge(h1, h2, m1, m2);
+  const double d1 = has_d ? pchip_mid(h1, h2, m1, m2) : pchip_edge(h1, h0, m1, m0);
+  if (bad) status[2] = 1;
+  cubic_coeffs(q, xb, xc, yb, h1, m1, d0, d1);
+  nx.y1 = yc; nx.x2 = xd; nx.y2 = yd; nx.m2 = m2; nx.d1 = d1;
+  return has_d;
+}
+// interval k+1 from interval k: one new knot (k+3, which must exist and k >= 0)
+__device__ __forceinline__ void cubic_slide(const Cell &c, int k_new, Cubic &q, CubicNext &nx,
+                                            int32_t *status) {
+  const double xb = q.x1, xc = nx.x2, yb = nx.y1, yc = nx.y2;
+  const double h1 = __dadd_rn(xc, -xb), m1 = nx.m2, d0 = nx.d1;
+  const double xd = knot_x(c, k_new + 2), yd = knot_y(c, k_new + 2);
+  const double h2 = __dadd_rn(xd, -xc);
+  const double m2 = div_nr(__dadd_rn(yd, -yc), h2);
+  if (!(h2 > 0.0)) status[2] = 1;
+  const double d1 = pchip_mid(h1, h2, m1, m2);
+  cubic_coeffs(q, xb, xc, yb, h1, m1, d0, d1);
+  nx.y1 = yc; nx.x2 = xd; nx.y2 = yd; nx.m2 = m2; nx.d1 = d1;
 }
 
 __device__ __forceinline__ double cubic_eval(const Cubic &q, double x) {
@@ -135,24 +180,37 @@ __device__ __forceinline__ double cubic_eval(const Cubic &q, double x) {
   return fma(fma(fma(q.c0, s, q.c1), s, q.c2), s, q.c3);
 }
 
-// PPoly interval search: clip(searchsorted_right(x_knots, x) - 1, 0, nk-2), starting two days
-// before `day` (always at or left of the answer) and walking right.
-__device__ __noinline__ void cubic_locate(const Cell &c, int day, double x, Cubic &q,
-                                          int32_t *status) {
-  int k = max(0, 2 * (day + 1) - 4);
-  double xn, yn;
+// PPoly interval search: clip(searchsorted_right(x_knots, x) - 1, 0, nk-2), starting from a guess
+// at or left of the answer and walking right.
+__device__ __forceinline__ int cubic_walk(const Cell &c, int k, double x) {
   while (k < c.nk - 2) {
-    knot(c, k + 1, xn, yn);
-    if (x >= xn) ++k; else break;
+    if (x >= knot_x(c, k + 1)) ++k; else break;
   }
-  cubic_setup(c, k, q, status);
+  return k;
 }
 
-// t_t_min of day d: knot of the vapour-pressure interpolant (disaggregate.py:480)
-__device__ __forceinline__ double vp_knot_x(const Cell &c, int d) {
-  const int yd = c.doy[d] - 1;
-  return ((c.rise[yd] - c.utc_min) + (double)d * 1440.0) - c.ts;
+// smallest step index i with ts*i >= xk  /  ts*i > xk (kNever beyond the int range)
+__device__ __forceinline__ int first_step_ge(double xk, int ts, double inv_ts) {
+  const double q = ceil(xk * inv_ts);
+  if (!(q < 2.0e9)) return kNever;
+  if (q < -2.0e9) return -kNever;
+  int i = (int)q;
+  while ((double)ts * (double)i < xk) ++i;
+  while ((double)ts * (double)(i - 1) >= xk) --i;
+  return i;
 }
+__device__ __forceinline__ int first_step_gt(double xk, int ts, double inv_ts) {
+  const double q = floor(xk * inv_ts) + 1.0;
+  if (!(q < 2.0e9)) return kNever;
+  if (q < -2.0e9) return -kNever;
+  int i = (int)q;
+  while (!((double)ts * (double)i > xk)) ++i;
+  while ((double)ts * (double)(i - 1) > xk) --i;
+  return i;
+}
+
+// t_t_min of day d: knot of the vapour-pressure interpolant (disaggregate.py:480) = PCHIP knot 2d+2
+__device__ __forceinline__ double vp_knot_x(const Cell &c, int d) { return knot_x(c, 2 * d + 2); }
 
 // physics.py:124-152 on the fast fp64 path; returns svp in kPa (svp/MBAR_PER_BAR)
 __device__ __forceinline__ double svp_kpa(double t, const double *etab) {
@@ -164,54 +222,82 @@ __device__ __forceinline__ double svp_kpa(double t, const double *etab) {
   return s * (t < 0.0 ? corr : 1.0);
 }
 
+// ---- hot-loop constants ----------------------------------------------------------------------
+// ptxas re-materialises an fp64 literal as two 32-bit moves at EVERY use (it never keeps an
+// immediate in a register across a loop), which cost ~45 instructions per step.  Values loaded
+// from constant memory are opaque to it, so they are loaded once and stay in (uniform) registers.
+__constant__ double c_hot[10] = {
+    237.3,                          // svp denominator offset, physics.py:149
+    -17.269 * 237.3,                // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
+    17.269 - 0.49301845011612494,   // + ln(0.61078): the factor folded into the exponent
+    .000042, .00972,                // ice correction, physics.py:150-151
+    369.3299304675746,              // 256/ln2
+    0.0027076061740622863,          // ln2/256
+    4.618333172514372,              // ln(P_STD/1000): air pressure in kPa, disaggregate.py:401-403
+    273.15,                         // KELVIN
+    1.2                             // PRATA, disaggregate.py:557-559
+};
+struct HotK { double k237, ka, kb, kc2, kc1, inv_l, l, ln_p, kelvin, k12; };
+__device__ __forceinline__ HotK load_hot() {
+  HotK k;
+  k.k237 = c_hot[0]; k.ka = c_hot[1]; k.kb = c_hot[2]; k.kc2 = c_hot[3]; k.kc1 = c_hot[4];
+  k.inv_l = c_hot[5]; k.l = c_hot[6]; k.ln_p = c_hot[7]; k.kelvin = c_hot[8]; k.k12 = c_hot[9];
+  return k;
+}
+// exp_tab with its two non-immediate constants taken from HotK
+__device__ __forceinline__ double exp_hot(double x, const double *tab, const HotK &K) {
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
+  double kd = fma(x, K.inv_l, kMagic);
+  const int k = __double2loint(kd);
+  kd -= kMagic;
+  const double r = fma(-kd, K.l, x);
+  const double kSixth = __hiloint2double(0x3fc55555, 0);
+  double p = fma(r, kSixth, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return exp_scale(p, k, tab);
+}
+
 // ---- precipitation: one day's per-minute shape in closed form (disaggregate.py:294-329) ------
 // The day vector is: rising limb np.linspace(0, 1, n+) on minutes [p0, p0+n+), falling limb
 // np.linspace(1, 0, n-) on [q0, q0+n-), the falling assignment second (it overwrites a shared
 // peak minute), everything scaled by P / sum.  linspace is i*step with the LAST element forced to
-// exactly 1 (rising) or 0 (falling).  Any window sum is then
-//     f * ( units + stepp * tri(ia..ib) + count(ja..jb) + stepq * tri(ja..jb) )
-// with every count / triangular number formed in INTEGER arithmetic, so a window that misses the
-// limbs is an exact 0 and zero / non-zero placement is bit-exact.
+// exactly 1 (rising) or 0 (falling).  The cumulative sum of the unscaled shape up to minute m is
+//     S(m) = [m >= pth] + j + hsp * (i-1) i + hsq * (j-1) j,
+//     i = clamp(m - p0, 0, nps),  j = clamp(m - q0, 0, nqs)       (integers)
+// and a window is f * (S(end) - S(start)).  Both ends of a window that misses the limbs clamp to
+// the same integers, so its value is an exact 0: zero / non-zero placement is bit-exact.  A
+// uniform day (prec_UNIFORM, :332-343) is the same form with q0 = 0, nqs = 1440, hsq = 0.
 struct PrecDay {
   int p0, nps;   // rising series minutes [p0, p0+nps): value i*stepp
-  int pu;        // minute index (relative to p0) after the forced-1.0 element, INT_MAX if none
+  int pth;       // first minute after the forced-1.0 element, kNever if none
   int q0, nqs;   // falling series minutes [q0, q0+nqs): value 1 + j*stepq (forced 0.0 end excluded)
-  double stepp, stepq, f;   // uniform day: nps < 0 and f = P/1440
-  bool nan;
+  double hsp, hsq, f;   // stepp/2, stepq/2, P/sum (NaN for a 0/0 day, :327)
 };
-struct PrecPos { int i, j, u; };   // clamped positions of a minute inside the two limbs
 
-__device__ __forceinline__ PrecPos prec_pos(const PrecDay &pd, int m) {
-  PrecPos q;
-  q.i = min(max(m - pd.p0, 0), pd.nps);
-  q.j = min(max(m - pd.q0, 0), pd.nqs);
-  q.u = (m - pd.p0 >= pd.pu) ? 1 : 0;
-  return q;
-}
-// sum over minutes [a, b) given the positions of a and b (a <= b)
-__device__ __forceinline__ double prec_window(const PrecDay &pd, const PrecPos &a, const PrecPos &b,
-                                              int n_minutes) {
-  if (pd.nps < 0) return (double)n_minutes * pd.f;
-  const int tr = (b.i - 1) * b.i - (a.i - 1) * a.i;   // 2 * sum_{i=a.i}^{b.i-1} i
-  const int tf = (b.j - 1) * b.j - (a.j - 1) * a.j;
-  const double s = (double)(b.u - a.u + b.j - a.j) + 0.5 * (pd.stepp * (double)tr + pd.stepq * (double)tf);
-  return pd.f * s;
+__device__ __forceinline__ double prec_cum(const PrecDay &pd, int m) {
+  const int i = min(max(m - pd.p0, 0), pd.nps);
+  const int j = min(max(m - pd.q0, 0), pd.nqs);
+  const int u = (m >= pd.pth) ? 1 : 0;
+  const int tr = i * i - i;   // 2 * sum_{k<i} k
+  const int tf = j * j - j;
+  return fma(pd.hsq, (double)tf, fma(pd.hsp, (double)tr, (double)(u + j)));
 }
 
+// m = calendar month of day d (1..12)
 __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_forcing &f,
-                                               int cell, int d, PrecDay &pd) {
+                                               int cell, int d, int m, PrecDay &pd) {
   const size_t o = (size_t)d * f.ld + cell;
   const double P = f.prec[o];
-  pd.nan = false;
   const bool uniform = p.prec_type == MSB_PREC_UNIFORM ||
                        (p.prec_type == MSB_PREC_MIX && f.t_min[o] < 0.0);
   if (uniform) {
-    pd.nps = -1;
-    pd.f = P / (double)kMinPerDay;
+    pd.p0 = 0; pd.nps = 0; pd.pth = kNever; pd.q0 = 0; pd.nqs = kMinPerDay;
+    pd.hsp = 0.0; pd.hsq = 0.0;
+    pd.f = P * (1.0 / (double)kMinPerDay);
     return;
   }
   // metsim.py:278-284: month m (1..12) takes domain entry m (0..11); December keeps prec
-  const int m = f.month[d];
   const double t_pk = (m <= 11) ? f.t_pk12[(size_t)m * f.ld + cell] : P;
   const double t_dur = (m <= 11) ? f.dur12[(size_t)m * f.ld + cell] : P;
   const double t_start = t_pk - 0.5 * t_dur, t_stop = t_pk + 0.5 * t_dur;
@@ -222,24 +308,23 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
   const int nq = (hi_q >= lo_q) ? (int)(hi_q - lo_q) + 1 : 0;
   pd.p0 = (npf > 0) ? (int)lo_p : 0;
   pd.q0 = (nq > 0) ? (int)lo_q : 0;
-  pd.stepp = (npf > 1) ? 1.0 / (double)(npf - 1) : 0.0;    // np.linspace(0, 1, npf)
-  pd.stepq = (nq > 1) ? -1.0 / (double)(nq - 1) : 0.0;     // np.linspace(1, 0, nq)
+  const double stepp = (npf > 1) ? rcp_nr((double)(npf - 1)) : 0.0;   // np.linspace(0, 1, npf)
+  const double stepq = (nq > 1) ? -rcp_nr((double)(nq - 1)) : 0.0;    // np.linspace(1, 0, nq)
   // the falling assignment comes second and overwrites the shared peak minute (:322-323)
   int np = npf;
   if (nq > 0 && npf > 0 && pd.p0 + npf - 1 >= pd.q0) np = max(pd.q0 - pd.p0, 0);
   const bool unit = np == npf && npf > 1;                  // forced 1.0 survives the overwrite
   pd.nps = unit ? npf - 1 : np;
-  pd.pu = unit ? npf : 0x7fffffff;
+  pd.pth = unit ? pd.p0 + npf : kNever;
   pd.nqs = nq > 1 ? nq - 1 : nq;                           // forced 0.0 end contributes nothing
-  pd.f = 1.0;
-  const PrecPos z = {0, 0, 0}, e = prec_pos(pd, kMinPerDay);
-  const double S = prec_window(pd, z, e, kMinPerDay);      // np.sum(prec_day), :327
-  pd.nan = !(S != 0.0) || !(P == P);   // 0/0 or x/0 * 0 -> NaN day (:327)
-  pd.f = P / S;
+  pd.hsp = 0.5 * stepp;
+  pd.hsq = 0.5 * stepq;
+  const double S = prec_cum(pd, kMinPerDay);               // np.sum(prec_day), :327
+  pd.f = (S > 0.0 && P == P) ? div_nr(P, S) : nan("");     // 0/0 or x/0 * 0 -> NaN day (:327)
 }
 
 // value of output step i for the rolled per-minute record (disaggregate.py:347-351); NaN when the
-// window touches a NaN day.  Generic (slow) form used for the fill look-back only.
+// window touches a NaN day.  Generic form used by the NaN-day fix-up pass only.
 __device__ __noinline__ double prec_step_generic(const msb_params &p, const msb_forcing &f,
                                                  const Cell &c, long i) {
   const long M = (long)c.D * kMinPerDay;
@@ -248,14 +333,12 @@ __device__ __noinline__ double prec_step_generic(const msb_params &p, const msb_
   const int dA = (int)(m0 / kMinPerDay), rem = (int)(m0 - (long)dA * kMinPerDay);
   const int n1 = min(c.ts, kMinPerDay - rem);
   PrecDay pd;
-  prec_day_setup(p, f, c.cell, dA, pd);
-  if (pd.nan) return nan("");
-  double v = prec_window(pd, prec_pos(pd, rem), prec_pos(pd, rem + n1), n1);
+  prec_day_setup(p, f, c.cell, dA, f.month[dA], pd);
+  double v = pd.f * (prec_cum(pd, rem + n1) - prec_cum(pd, rem));
   if (n1 < c.ts) {
     const int dB = (dA + 1 == c.D) ? 0 : dA + 1;
-    prec_day_setup(p, f, c.cell, dB, pd);
-    if (pd.nan) return nan("");
-    v += prec_window(pd, prec_pos(pd, 0), prec_pos(pd, c.ts - n1), c.ts - n1);
+    prec_day_setup(p, f, c.cell, dB, f.month[dB], pd);
+    v += pd.f * prec_cum(pd, c.ts - n1);
   }
   return v;
 }
@@ -275,28 +358,32 @@ __device__ __noinline__ double prec_fill(const msb_params &p, const msb_forcing 
   return nan("");
 }
 
-// window sum of the normalised radiation row over tiny steps [ca, cb) of table row `yr`
-__device__ __forceinline__ double row_window(const Cell &c, int yr, int ca, int cb) {
-  const double *q = c.qrow + (size_t)min(yr, 364) * kQLd;
-  double w = q[cb] - q[ca];
-  if (ca <= kNoon && cb > kNoon) w += q[kTiny + 1];
-  return w;
+// vapour pressure of ONE step at an end of the interpolant's support: the value pandas
+// back-fills into the leading NaNs (lo = true: knots 0, 1) or forward-fills into the trailing
+// ones (knots D-2, D-1) -- disaggregate.py:480-487, :99-101.
+__device__ __noinline__ double vp_endpoint(const Cell &c, const double *vp_d, int i, bool lo,
+                                           const double *etab, int32_t *status) {
+  const double x = (double)c.ts * (double)i;
+  Cubic q;
+  CubicNext nx;
+  const int k = cubic_walk(c, max(0, 2 * (i / c.tpd + 1) - 4), x);
+  cubic_setup(c, k, q, nx, status);
+  const double tt = cubic_eval(q, x);
+  const int d0 = lo ? 0 : c.D - 2;
+  const double x0 = vp_knot_x(c, d0), x1 = vp_knot_x(c, d0 + 1);
+  const double y0 = vp_d[(size_t)d0 * c.ld + c.cell] / 1000.0;
+  const double y1 = vp_d[(size_t)(d0 + 1) * c.ld + c.cell] / 1000.0;
+  const double v = ((x - x0) / (x1 - x0)) * y1 + ((x1 - x) / (x1 - x0)) * y0;
+  return fmin(v, svp_kpa(tt, etab));
 }
 
-// disaggregate.py:491-590 without the daily_lw rescale (mtclim method)
-template <bool FAST>
+// disaggregate.py:491-590 without the daily_lw rescale (mtclim method): every lw_type / lw_cloud
+// option with library math (the default PRATA + CLOUD_DEARDORFF pair is inlined in the hot loop)
 __device__ __forceinline__ double longwave(const msb_params &p, double temp_c, double vp_kpa,
-                                           double tskc, const double *etab) {
+                                           double tskc) {
   const double air_temp = temp_c + kKelvin;
   const double vp = vp_kpa * 10;
   double e;
-  if (FAST) {  // PRATA + CLOUD_DEARDORFF, the reference defaults (metsim.py:158-159)
-    const double x = 46.5 * vp * rcp_nr(air_temp);
-    e = 1 - (1 + x) * exp_tab(-sqrt_nr(fma(3., x, 1.2)), etab);
-    const double emis = tskc + (1 - tskc) * e;
-    const double t2 = air_temp * air_temp;
-    return emis * kStefanB * (t2 * t2);
-  }
   switch (p.lw_type) {
     case MSB_LW_ANDERSON: e = 0.68 + 0.036 * sqrt(vp); break;
     case MSB_LW_BRUTSAERT: e = 1.24 * pow(vp / air_temp, 0.14285714); break;
@@ -315,13 +402,6 @@ __device__ __forceinline__ double longwave(const msb_params &p, double temp_c, d
   return emis * kStefanB * (t2 * t2);
 }
 
-template <typename OutT, bool UNITS>
-__device__ __forceinline__ void put(const msb_subdaily &o, int v, size_t idx, double val) {
-  OutT *ptr = reinterpret_cast<OutT *>(o.var[v]);
-  if (UNITS) val = fma(val, o.scale[v], o.offset[v]);
-  __stcs(ptr + idx, (OutT)val);   // streaming store: outputs are never re-read by this kernel
-}
-
 // variable sets compiled into the kernel: kVarsExample = the 8 variables of
 // examples/example_nc.conf (every pointer known non-NULL, no per-step tests), kVarsAny = runtime
 constexpr int kVarsAny = 0, kVarsExample = 1;
@@ -330,261 +410,393 @@ constexpr unsigned kExampleMask = (1u << MSB_V_TEMP) | (1u << MSB_V_PREC) | (1u 
                                   (1u << MSB_V_REL_HUMID) | (1u << MSB_V_AIR_PRESSURE) |
                                   (1u << MSB_V_WIND);
 
+// per-thread shared-memory slots for values that only the event handler touches between events
+enum { kS_Y1 = 0, kS_X2, kS_Y2, kS_M2, kS_D1,   // CubicNext
+       kS_TKN, kS_WDN,                           // tskc / wind of the source day just rolled in
+       kS_ROWTOT,                                // total of the current radiation row (noon event)
+       kS_VPTAIL,                                // forward-fill value of the vapour pressure
+       kS_COUNT };
+
 // One thread = one cell x one tile of days.  np.roll by a whole number of minutes (tskc, wind,
 // prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
-// is read ts minutes per output step; the stream position and the current source day live in
-// registers and "roll" to the next source day once per day.
+// is read ts minutes per output step; the stream positions and the current source day live in
+// registers and roll to the next source day once per day (an event).
 template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
 __global__ void __launch_bounds__(kDisaggThreads, 4)
 disagg_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[kExpTab];
-  exp_table_init(etab);
-  __syncthreads();
-
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= a.f.n_cells) return;
+  __shared__ double slot[kS_COUNT][kDisaggThreads];
+  __shared__ int s_doy[kDayWin], s_month[kDayWin];
   const msb_params &p = a.p;
   const msb_forcing &f = a.f;
   const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
   const int d_lo = a.out.day0 + blockIdx.y * a.tile_days;
   const int d_hi = min(a.out.day1, d_lo + a.tile_days);
-  if (d_lo >= d_hi) return;
+  // day-of-year / month of the days the handler can touch, staged once per CTA
+  const int win0 = max(d_lo - 4, 0), nwin = min(min(d_hi + 4, D) - win0, kDayWin);
+  exp_table_init(etab);
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+    s_doy[j] = f.doy[win0 + j];
+    s_month[j] = f.month[win0 + j];
+  }
+  __syncthreads();
+
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  if (cell >= f.n_cells || d_lo >= d_hi) return;
   const unsigned mask = VARS == kVarsExample ? kExampleMask : a.var_mask;
   auto want = [mask](int v) { return (mask >> v) & 1u; };
+  const bool want_prec = want(MSB_V_PREC);
+  const bool want_wind = want(MSB_V_WIND) && f.wind != nullptr;
+  const bool want_sw = want(MSB_V_SHORTWAVE);
 
+  // ---- cold per-cell constants ----------------------------------------------------------------
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const int nk = 2 * D + 4;
   const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376,:611
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
-  c.off_min = off_min; c.off_tiny = off_tiny;
+  c.off_min = off_min;
   c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
   c.frac = p.tmax_daylength_fraction;
   const int row = f.lat_row[cell];
   c.rise = a.t.rise_min + (size_t)row * kRows;
   c.set = a.t.set_min + (size_t)row * kRows;
-  c.dayl = a.t.daylength + (size_t)row * kRows;
-  c.qrow = a.t.q + (size_t)row * 365 * kQLd;
-  c.doy = f.doy; c.month = f.month;
+  c.doy = f.doy; c.sdoy = s_doy; c.win0 = win0; c.nwin = nwin;
   c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
   c.t_end = f.t_end;
-
-  const double elev = f.elev[cell];
-  const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
-  const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
+  const double *const dayl = a.t.daylength + (size_t)row * kRows;
+  const double *const qrow = a.t.q + (size_t)row * 365 * kQLd;
   const long ld = f.ld;
   const int T = D * tpd;
   const int C = 2 * ts;                                     // tiny steps per output step (:660)
-  const double sw_den = 3600.0 * ((double)ts / 60.0);       // :645
+  const double inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));   // :645
   const double inv_ts = 1.0 / (double)ts;
-  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-
-  // ---- vapour pressure interpolant: knots (t_t_min[d], vp_daily[d]/1000), NaN outside --------
-  const double xv_first = vp_knot_x(c, 0), xv_last = vp_knot_x(c, D - 1);
-  const int i_head = (xv_first > 0.0) ? (int)ceil(xv_first / ts) : 0;   // first step >= x_v[0]
-  const int i_tail = (int)floor(xv_last / ts);                          // last step <= x_v[D-1]
   const int i_lo = d_lo * tpd, i_hi = d_hi * tpd;
-  int vd = min(max(d_lo, 1), D - 1);                         // upper knot index, clip [1, D-1]
-  {
-    const double x0 = (double)ts * (double)i_lo;
-    while (vd > 1 && !(vp_knot_x(c, vd - 1) < x0)) --vd;
-    while (vd < D - 1 && vp_knot_x(c, vd) < x0) ++vd;
-  }
-  double xvl = vp_knot_x(c, vd - 1), xvh = vp_knot_x(c, vd);
-  double yvl = a.vp_d[(size_t)(vd - 1) * ld + cell] / 1000.0, yvh = a.vp_d[(size_t)vd * ld + cell] / 1000.0;
-  double vinv = 1.0 / (xvh - xvl);
-
-  Cubic cub;
-  cubic_locate(c, d_lo, (double)ts * (double)i_lo, cub, a.status);
-  if (cub.k >= nk - 2) cub.x1 = kInf;   // last interval: extrapolate, never advance
-
-  // head / tail fill values (pandas bfill / ffill of the NaN ends, disaggregate.py:99-101)
-  double vp_head = 0.0, vp_tail = 0.0;
-  if (i_lo < i_head && i_head < T) {
-    const double x = (double)ts * (double)i_head;
-    Cubic q2;
-    cubic_locate(c, i_head / tpd, x, q2, a.status);
-    const double tt = cubic_eval(q2, x);
-    const double x0 = vp_knot_x(c, 0), x1 = vp_knot_x(c, 1);
-    const double y0 = a.vp_d[cell] / 1000.0, y1 = a.vp_d[(size_t)ld + cell] / 1000.0;
-    double v = ((x - x0) / (x1 - x0)) * y1 + ((x1 - x) / (x1 - x0)) * y0;
-    vp_head = fmin(v, svp_kpa(tt, etab));
-  }
-  if (i_hi - 1 > i_tail && i_tail >= 0) {
-    const double x = (double)ts * (double)i_tail;
-    Cubic q2;
-    cubic_locate(c, i_tail / tpd, x, q2, a.status);
-    const double tt = cubic_eval(q2, x);
-    const double x0 = vp_knot_x(c, D - 2), x1 = vp_knot_x(c, D - 1);
-    const double y0 = a.vp_d[(size_t)(D - 2) * ld + cell] / 1000.0;
-    const double y1 = a.vp_d[(size_t)(D - 1) * ld + cell] / 1000.0;
-    double v = ((x - x0) / (x1 - x0)) * y1 + ((x1 - x) / (x1 - x0)) * y0;
-    vp_tail = fmin(v, svp_kpa(tt, etab));
-  }
-  const bool vp_all_nan = (i_head > i_tail) || i_head >= T || i_tail < 0;
-  // steps with an interpolated vapour pressure: [i_sp0, i_sp1]; before: head fill, after: tail
-  const int i_sp0 = vp_all_nan ? i_hi : i_head;
-  const int i_sp1 = vp_all_nan ? i_lo - 1 : i_tail;
-  if (vp_all_nan) vp_head = vp_tail = nan("");
-
-  // ---- source streams ------------------------------------------------------------------------
-  const bool want_prec = want(MSB_V_PREC);
-  const bool want_wind = want(MSB_V_WIND) && f.wind != nullptr;
-  const bool want_sw = want(MSB_V_SHORTWAVE);
-  auto wrap = [D](int d) { return d < 0 ? d + D : (d >= D ? d - D : d); };
-  auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
-    return (a.sw_d[(size_t)d * ld + cell] * c.dayl[f.doy[d] - 1]) / sw_den;
+  auto month_at = [&](int d) {
+    const unsigned r = (unsigned)(d - win0);
+    return r < (unsigned)nwin ? s_month[r] : f.month[d];
   };
-  // minute stream (tskc, wind, prec): source day md, minute sm of that day
-  const int qm = off_min < 0 ? -1 : 0;          // floor(off_min / 1440), |off_min| <= 720
-  int md = wrap(d_lo + qm);
-  int sm = off_min - qm * kMinPerDay;
-  PrecDay pd;
-  double tk_cur = a.tskc_d[(size_t)md * ld + cell];
-  double wd_cur = want_wind ? f.wind[(size_t)md * ld + cell] : 0.0;
-  PrecPos ppos = {0, 0, 0};
-  if (want_prec) { prec_day_setup(p, f, cell, md, pd); ppos = prec_pos(pd, sm); }
-  double prec_last = nan("");   // last valid precipitation step (ffill carry)
-  bool prec_last_known = false;
-  // tiny-step stream (shortwave): source day sd, tiny step ss of that day, table row per output day
-  const int qs = off_tiny < 0 ? -1 : 0;
-  int sd = wrap(d_lo + qs);
-  int ss = off_tiny - qs * kTiny;
-  double rd_cur = want_sw ? rad_of(sd) : 0.0;
-  const double *q_cur = c.qrow;
-  double qprev = 0.0;
+  auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
+    return (a.sw_d[(size_t)d * ld + cell] * dayl[doy_at(c, d) - 1]) * inv_sw_den;
+  };
+  auto q_of = [&](int y) {     // table row y rolled over the table's own 366 rows (:656)
+    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
+    return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
+  };
 
-  int i = i_lo;
-  size_t oidx = (size_t)(i_lo - a.out.day0 * tpd) * (size_t)a.out.ld + cell;
+  // ---- hot state ------------------------------------------------------------------------------
+  const double elev = f.elev[cell];
+  const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
+  const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
+  Cubic cub;                                                 // temperature segment
+  cub.x0 = cub.x1 = cub.c0 = cub.c1 = cub.c2 = cub.c3 = 0.0;
+  double xvl = 0.0, yvl = 0.0, vslope = 0.0;                 // vapour-pressure segment
+  bool v_interior = false;                                   // clamp to saturation inside the knots
+  double tk_cur = 0.0, wd_cur = 0.0;                         // minute stream: tskc, wind
+  double tk_a = 0.0, tk_b = 0.0;                             // STEFAN_B * tskc, STEFAN_B * (1 - tskc)
+  const HotK K = load_hot();
+  PrecDay pd;                                                // minute stream: precipitation
+  pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
+  double s_prev = 0.0, p_carry = 0.0;
+  double rd_cur = 0.0, q_prev = 0.0, q_pref = 0.0, sw_carry = 0.0;   // tiny-step stream: shortwave
+  const double *q_cur = qrow;
+
+  // ---- cold state: stream positions and the event schedule ------------------------------------
+  // Both streams start "one day early, one day too far": the roll event of the first step then
+  // installs the true first source day through the same code as every later roll.
+  auto wrap = [D](int d) { return d < 0 ? d + D : (d >= D ? d - D : d); };
+  const int qm = off_min < 0 ? -1 : 0;          // floor(off_min / 1440), |off_min| <= 720
+  int md = wrap(wrap(d_lo + qm) - 1);
+  int sm = off_min - qm * kMinPerDay + kMinPerDay;
+  const int qs = off_tiny < 0 ? -1 : 0;
+  int sd = wrap(wrap(d_lo + qs) - 1);
+  int ss = off_tiny - qs * kTiny + kTiny;
+  int kc = max(0, 2 * (d_lo + 1) - 4);          // PCHIP interval guess (at or left of the answer)
+  bool slide_ok = false;                        // CubicNext slots describe interval kc + 1
+  int vd = 1;                                   // upper knot of the vapour-pressure segment
+  bool had_nan = false;
+  int e_cub = i_lo, e_day = want_sw ? i_lo : kNever;
+  int e_mroll = i_lo, e_mfol = kNever;
+  int e_troll = want_sw ? i_lo : kNever;
+  int e_noon = kNever;
+  if (want_sw) {
+    const int s0 = ss - kTiny;                  // first window [s0, s0 + C)
+    e_noon = i_lo + (s0 <= kNoon ? (kNoon - s0) / C : (kNoon + kTiny - s0) / C);
+  }
+
+  // vapour pressure interpolant: knots (t_t_min[d], vp_daily[d]/1000), NaN outside, the NaN ends
+  // filled by pandas bfill / ffill (disaggregate.py:99-101)
+  int e_vp;
+  {
+    const double xv_first = vp_knot_x(c, 0), xv_last = vp_knot_x(c, D - 1);
+    const int i_head = max(first_step_ge(xv_first, ts, inv_ts), 0);   // first step >= x_v[0]
+    const int i_tail = first_step_gt(xv_last, ts, inv_ts) - 1;        // last step <= x_v[D-1]
+    const bool all_nan = (i_head > i_tail) || i_head >= T || i_tail < 0;
+    double vp_tail = 0.0;
+    if (all_nan) {
+      yvl = nan(""); e_vp = kNever;
+    } else {
+      if (i_hi - 1 > i_tail) vp_tail = vp_endpoint(c, a.vp_d, i_tail, false, etab, a.status);
+      if (i_lo < i_head) {             // head: constant until the first in-range step
+        yvl = vp_endpoint(c, a.vp_d, i_head, true, etab, a.status);
+        e_vp = i_head;
+      } else if (i_lo > i_tail) {      // tail
+        yvl = vp_tail; e_vp = kNever;
+      } else {                         // interior: the handler installs the segment at i_lo
+        const double x0 = (double)ts * (double)i_lo;
+        vd = min(max(d_lo, 1), D - 1);
+        while (vd > 1 && !(vp_knot_x(c, vd - 1) < x0)) --vd;
+        e_vp = i_lo;
+      }
+    }
+    slot[kS_VPTAIL][tid] = vp_tail;
+  }
+
+  int i_event = i_lo;
   double x = (double)ts * (double)i_lo;
   const double dx = (double)ts;
-  const size_t ostride = (size_t)a.out.ld;
+  unsigned ooff = (unsigned)cell;                           // element offset inside the tile
+  const unsigned ostride = (unsigned)a.out.ld;
+  const size_t obase = (size_t)(i_lo - a.out.day0 * tpd) * (size_t)a.out.ld;
+  OutT *const o_temp = reinterpret_cast<OutT *>(a.out.var[MSB_V_TEMP]) + obase;
+  OutT *const o_prec = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + obase;
+  OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + obase;
+  OutT *const o_lw = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]) + obase;
+  OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]) + obase;
+  OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + obase;
+  OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + obase;
+  OutT *const o_sh = reinterpret_cast<OutT *>(a.out.var[MSB_V_SPEC_HUMID]) + obase;
+  OutT *const o_tk = reinterpret_cast<OutT *>(a.out.var[MSB_V_TSKC]) + obase;
+  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + obase;
+  auto put = [&](OutT *ptr, int v, double val) {
+    if (UNITS) val = fma(val, a.out.scale[v], a.out.offset[v]);
+    __stcs(ptr + ooff, (OutT)val);   // streaming store: outputs are never re-read by this kernel
+  };
 
-  for (int d = d_lo; d < d_hi; ++d) {
-    const int y = f.doy[d] - 1;
-    if (want_sw) {
-      // every output day starts in the "lo" part of its window: table row y + qs, rolled over the
-      // table's own 366 rows (:656); row 365 is a copy of row 364
-      int yl = y + qs;
-      yl = yl < 0 ? yl + kRows : yl;
-      q_cur = c.qrow + (size_t)min(yl, 364) * kQLd;
-      qprev = q_cur[ss];
-    }
-    for (int t = 0; t < tpd; ++t, ++i, x += dx, oidx += ostride) {
-      // -- temperature (PCHIP) --
-      if (x >= cub.x1) {
-        int k = cub.k + 1;
-        double xn, yn;
-        while (k < nk - 2) { knot(c, k + 1, xn, yn); if (x >= xn) ++k; else break; }
-        cubic_setup(c, k, cub, a.status);
-        if (k >= nk - 2) cub.x1 = kInf;
+  // Lanes of a warp stay in lockstep on the step index (coalesced stores), so the event-free run
+  // that follows the handler ends at the earliest event of ANY lane of the warp.
+  const unsigned lanes = __activemask();
+  int i = i_lo;
+  while (i < i_hi) {
+    if (i == i_event) {
+      // ================= event handler (cold): pure state updates =============================
+      if (i == e_mfol) {   // step after a straddling roll: tskc / wind settle on the new day
+        tk_cur = slot[kS_TKN][tid];
+        wd_cur = slot[kS_WDN][tid];
+        tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
+        e_mfol = kNever;
       }
-      const double temp = cubic_eval(cub, x);
-      const double es = svp_kpa(temp, etab);       // saturation vapour pressure, kPa
-
-      // -- vapour pressure (linear, clamped to saturation, NaN ends filled) --
-      double vp;
-      if (i >= i_sp0 && i <= i_sp1) {
-        while (vd < D - 1 && xvh < x) {     // searchsorted(side='left')
-          ++vd;
-          xvl = xvh; yvl = yvh;
-          xvh = vp_knot_x(c, vd);
-          yvh = a.vp_d[(size_t)vd * ld + cell] / 1000.0;
-          vinv = 1.0 / (xvh - xvl);
+      if (i == e_mroll) {  // minute stream reaches the end of its source day (:347-351, :376, :611)
+        // at most two passes: a window that STARTS in the next day (clean switch; also how the
+        // first source day of a tile is installed) and / or one that straddles the boundary
+        while (sm + ts > kMinPerDay) {
+          const int mdn = (md + 1 == D) ? 0 : md + 1;
+          const size_t on = (size_t)mdn * ld + cell;
+          const double tk_n = a.tskc_d[on];
+          const double wd_n = want_wind ? f.wind[on] : 0.0;
+          PrecDay pn = pd;
+          if (want_prec) prec_day_setup(p, f, cell, mdn, month_at(mdn), pn);
+          int pos;                         // minute of the new day where the cumulative sum restarts
+          if (sm >= kMinPerDay) {          // clean switch
+            sm -= kMinPerDay;
+            pos = sm;
+            tk_cur = tk_n; wd_cur = wd_n;
+            p_carry = 0.0;
+          } else {                         // straddle: n1 minutes of the old day, n2 of the new one
+            const int n2 = sm + ts - kMinPerDay, n1 = ts - n2;
+            tk_cur = ((double)n1 * tk_cur + (double)n2 * tk_n) * inv_ts;
+            wd_cur = ((double)n1 * wd_cur + (double)n2 * wd_n) * inv_ts;
+            slot[kS_TKN][tid] = tk_n;
+            slot[kS_WDN][tid] = wd_n;
+            e_mfol = i + 1;
+            if (want_prec)   // old-day part + new-day part; the hot path adds f_new * 0 to it
+              p_carry = pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2);
+            pos = n2;
+            sm = n2 - ts;                  // the hot path advances it to n2
+          }
+          md = mdn;
+          if (want_prec) {
+            pd = pn;
+            s_prev = prec_cum(pd, pos);
+            had_nan |= !(pd.f == pd.f) || !(p_carry == p_carry);
+          }
         }
-        vp = ((x - xvl) * vinv) * yvh + ((xvh - x) * vinv) * yvl;   // scipy _interpolate.py:513-516
-        vp = fmin(vp, es);                                         // disaggregate.py:486-487
-      } else {
-        vp = i < i_sp0 ? vp_head : vp_tail;
+        tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
+        e_mroll = i + 1 + (kMinPerDay - (sm + ts)) / ts;
       }
+      // tiny-step stream reaches the end of its source day / table row (:656-678); the clean
+      // switch comes before, the straddle after the day-start row selection (reference order)
+      if (i == e_troll && ss >= kTiny) {
+        sd = (sd + 1 == D) ? 0 : sd + 1;
+        rd_cur = rad_of(sd);
+        // row of the "hi" part of the windows of the output day that holds the previous step
+        q_cur = q_of(doy_at(c, max(i - 1, 0) / tpd) - 1 + qs + 1);
+        ss -= kTiny;
+        q_prev = q_cur[ss];
+        sw_carry = 0.0;
+        slot[kS_ROWTOT][tid] = q_cur[kTiny + 1];
+      }
+      if (i == e_day) {    // output day starts: table row of the "lo" part of its windows (:656)
+        const int d = i / tpd;
+        const double *qn = q_of(doy_at(c, d) - 1 + qs);
+        if (qn != q_cur) {               // only across a year boundary (or at the tile start)
+          q_cur = qn;
+          q_prev = q_cur[ss];
+          slot[kS_ROWTOT][tid] = q_cur[kTiny + 1];
+        }
+        // the roll inside a day installs the row of the next day's "lo" part unless the day of
+        // year jumps: only those day starts need an event
+        e_day = kNever;
+        for (int dd = d; dd + 1 < d_hi; ++dd)
+          if (doy_at(c, dd + 1) != doy_at(c, dd) + 1) { e_day = (dd + 1) * tpd; break; }
+      }
+      if (i == e_troll) {
+        if (ss + C > kTiny) {            // straddle: [ss, 2880) of the old row + [0, k2) of the new
+          const int k2 = ss + C - kTiny;
+          sd = (sd + 1 == D) ? 0 : sd + 1;
+          const double rd_n = rad_of(sd);
+          const double *qn = q_of(doy_at(c, i / tpd) - 1 + qs + 1);
+          const double qk = qn[k2];
+          sw_carry = fma(rd_n, qk - qn[0], rd_cur * (q_cur[kTiny] - q_prev));  // ss > noon as C <= 720
+          q_prev = qk;                   // the hot path then adds rd_new * (q[k2] - q[k2]) = 0
+          ss = k2 - C;                   // the hot path advances it to k2
+          rd_cur = rd_n;
+          q_cur = qn;
+          slot[kS_ROWTOT][tid] = qn[kTiny + 1];
+        }
+        e_troll = i + 1 + (kTiny - (ss + C)) / C;
+      }
+      if (i >= e_vp) {     // vapour-pressure knot crossed (searchsorted side='left')
+        while (vd < D - 1 && vp_knot_x(c, vd) < x) ++vd;
+        const double xh = vp_knot_x(c, vd);
+        if (xh < x) {      // beyond the last knot: forward fill
+          yvl = slot[kS_VPTAIL][tid]; vslope = 0.0; v_interior = false; e_vp = kNever;
+        } else {
+          xvl = vp_knot_x(c, vd - 1);
+          yvl = a.vp_d[(size_t)(vd - 1) * ld + cell] / 1000.0;
+          const double yh = a.vp_d[(size_t)vd * ld + cell] / 1000.0;
+          vslope = div_nr(yh - yvl, xh - xvl);              // scipy _interpolate.py:513-516
+          v_interior = true;
+          e_vp = first_step_gt(xh, ts, inv_ts);
+        }
+      }
+      if (i >= e_cub) {    // PCHIP knot crossed (searchsorted side='right')
+        CubicNext nx;
+        const int kn = cubic_walk(c, kc, x);
+        if (slide_ok && kn == kc + 1 && kn + 2 < nk) {
+          nx.y1 = slot[kS_Y1][tid]; nx.x2 = slot[kS_X2][tid]; nx.y2 = slot[kS_Y2][tid];
+          nx.m2 = slot[kS_M2][tid]; nx.d1 = slot[kS_D1][tid];
+          cubic_slide(c, kn, cub, nx, a.status);
+        } else {
+          slide_ok = cubic_setup(c, kn, cub, nx, a.status);
+        }
+        kc = kn;
+        slot[kS_Y1][tid] = nx.y1; slot[kS_X2][tid] = nx.x2; slot[kS_Y2][tid] = nx.y2;
+        slot[kS_M2][tid] = nx.m2; slot[kS_D1][tid] = nx.d1;
+        e_cub = (kc >= nk - 2) ? kNever : first_step_ge(cub.x1, ts, inv_ts);   // last interval extrapolates
+      }
+      if (i == e_noon) {   // this step's window [ss, ss+C) contains tiny step 1440: add the row total
+        q_prev -= slot[kS_ROWTOT][tid];
+        e_noon += tpd;
+      }
+      if (want_sw) q_pref = q_cur[ss + C];                  // re-prime the pipelined table load
+      i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), e_mroll));
+      i_event = max(i_event, i + 1);
+    }
+    const int i_stop = min(__reduce_min_sync(lanes, i_event), i_hi);
+
+    // ================= hot path: event-free run [i, i_stop) ===================================
+#pragma unroll 1
+    for (; i < i_stop; ++i, x += dx, ooff += ostride) {
+      // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
+      const double temp = cubic_eval(cub, x);
+      const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
+      const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
+      const double es = es0 * (temp < 0.0 ? corr : 1.0);
+
+      // -- vapour pressure (linear, clamped to saturation inside the knots) :480-487 --
+      double vp = fma(x - xvl, vslope, yvl);
+      vp = (v_interior && es < vp) ? es : vp;
 
       // -- relative humidity :444-446, air pressure :401-403 --
       const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);   // 100*1000*vp/(svp in Pa)
-      const double ap = (kPStd / 1000.0) * exp_tab(pr_num * rcp_nr(pr_corr + temp), etab);
+      const double ap = exp_hot(fma(pr_num, rcp_nr(pr_corr + temp), K.ln_p), etab, K);
 
-      // -- minute stream: tskc / wind block means :355-380, :593-615; precipitation :265-352 --
-      double tskc, wind, pr = 0.0;
+      // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF inline; tk_a / tk_b carry STEFAN_B) --
+      double lw = 0.0;
+      if (FAST_LW) {
+        if (VARS == kVarsExample || want(MSB_V_LONGWAVE)) {
+          const double at = temp + K.kelvin;
+          const double xx = (465.0 * vp) * rcp_nr(at);             // 46.5 * (10 vp) / T
+          const double ee = exp_hot(-sqrt_fast(fma(3., xx, K.k12)), etab, K);
+          const double e1 = fma(-(1.0 + xx), ee, 1.0);
+          const double t2 = at * at;
+          lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+        }
+      } else if (want(MSB_V_LONGWAVE)) {
+        lw = longwave(p, temp, vp, tk_cur);
+      }
+
+      // -- minute stream: precipitation :265-352 (tskc / wind are constant between events) --
+      double pr = 0.0;
       sm += ts;
-      if (sm < kMinPerDay) {                      // whole window inside the current source day
-        tskc = tk_cur;
-        wind = wd_cur;
-        if (want_prec) {
-          const PrecPos e = prec_pos(pd, sm);
-          pr = pd.nan ? nan("") : prec_window(pd, ppos, e, ts);
-          ppos = e;
-        }
-      } else {                                    // window reaches the end of the source day: roll
-        const int n2 = sm - kMinPerDay, n1 = ts - n2;   // minutes from the current / next day
-        md = (md + 1 == D) ? 0 : md + 1;
-        const double tk_n = a.tskc_d[(size_t)md * ld + cell];
-        tskc = n2 == 0 ? tk_cur : ((double)n1 * tk_cur + (double)n2 * tk_n) * inv_ts;
-        tk_cur = tk_n;
-        if (want_wind) {
-          const double wd_n = f.wind[(size_t)md * ld + cell];
-          wind = n2 == 0 ? wd_cur : ((double)n1 * wd_cur + (double)n2 * wd_n) * inv_ts;
-          wd_cur = wd_n;
-        } else wind = 0.0;
-        if (want_prec) {
-          pr = pd.nan ? nan("") : prec_window(pd, ppos, prec_pos(pd, kMinPerDay), n1);
-          prec_day_setup(p, f, cell, md, pd);
-          const PrecPos z = {0, 0, 0};
-          ppos = prec_pos(pd, n2);
-          if (n2 > 0) pr = pd.nan ? nan("") : pr + prec_window(pd, z, ppos, n2);
-        }
-        sm = n2;
-      }
       if (want_prec) {
-        if (pr != pr) {    // NaN day: pandas ffill, then bfill for a leading run (:130)
-          if (!prec_last_known) { prec_last = prec_fill(p, f, c, i); prec_last_known = true; }
-          pr = prec_last;
-        } else {
-          prec_last = pr;
-          prec_last_known = true;
-        }
+        const double s1 = prec_cum(pd, sm);
+        pr = fma(pd.f, s1 - s_prev, p_carry);
+        s_prev = s1;
+        p_carry = 0.0;
       }
 
-      // -- tiny-step stream: shortwave :618-680 --
+      // -- tiny-step stream: shortwave :618-680; the table entry was requested one step ago --
       double sw = 0.0;
+      ss += C;
       if (want_sw) {
-        const int ca = ss;
-        ss += C;
-        if (ss < kTiny) {
-          const double qn = q_cur[ss];
-          double w = qn - qprev;
-          if (ca <= kNoon && ss > kNoon) w += q_cur[kTiny + 1];
-          qprev = qn;
-          sw = rd_cur * w;
-        } else {                                  // roll to the next source day / table row
-          const int k2 = ss - kTiny;
-          double w = q_cur[kTiny] - qprev;        // [ca, 2880)
-          if (ca <= kNoon) w += q_cur[kTiny + 1];
-          sw = rd_cur * w;
-          sd = (sd + 1 == D) ? 0 : sd + 1;
-          rd_cur = rad_of(sd);
-          int yh = y + qs + 1;
-          yh = yh >= kRows ? yh - kRows : yh;
-          q_cur = c.qrow + (size_t)min(yh, 364) * kQLd;
-          qprev = q_cur[k2];
-          if (k2 > 0) sw = fma(rd_cur, qprev - q_cur[0], sw);   // k2 <= 720 < noon: plain prefix
-          ss = k2;
-        }
+        const double qn = q_pref;
+        q_pref = q_cur[ss + C];
+        sw = fma(rd_cur, qn - q_prev, sw_carry);
+        q_prev = qn;
+        sw_carry = 0.0;
       }
 
-      if (want(MSB_V_TEMP)) put<OutT, UNITS>(a.out, MSB_V_TEMP, oidx, temp);
-      if (want(MSB_V_VAPOR_PRESSURE)) put<OutT, UNITS>(a.out, MSB_V_VAPOR_PRESSURE, oidx, vp);
-      if (want(MSB_V_REL_HUMID)) put<OutT, UNITS>(a.out, MSB_V_REL_HUMID, oidx, rh);
-      if (want(MSB_V_AIR_PRESSURE)) put<OutT, UNITS>(a.out, MSB_V_AIR_PRESSURE, oidx, ap);
-      if (want(MSB_V_TSKC)) put<OutT, UNITS>(a.out, MSB_V_TSKC, oidx, tskc);
-      if (want_wind) put<OutT, UNITS>(a.out, MSB_V_WIND, oidx, wind);
-      if (want(MSB_V_SPEC_HUMID)) {   // specific humidity :423-424
-        const double mix = (kEps * vp) * rcp_nr(ap - vp);
-        put<OutT, UNITS>(a.out, MSB_V_SPEC_HUMID, oidx, mix * rcp_nr(1 + mix));
+      if (VARS == kVarsExample) {
+        put(o_temp, MSB_V_TEMP, temp);
+        put(o_vp, MSB_V_VAPOR_PRESSURE, vp);
+        put(o_rh, MSB_V_REL_HUMID, rh);
+        put(o_ap, MSB_V_AIR_PRESSURE, ap);
+        put(o_wd, MSB_V_WIND, wd_cur);
+        put(o_lw, MSB_V_LONGWAVE, lw);
+        put(o_prec, MSB_V_PREC, pr);
+        put(o_sw, MSB_V_SHORTWAVE, sw);
+      } else {
+        if (want(MSB_V_TEMP)) put(o_temp, MSB_V_TEMP, temp);
+        if (want(MSB_V_VAPOR_PRESSURE)) put(o_vp, MSB_V_VAPOR_PRESSURE, vp);
+        if (want(MSB_V_REL_HUMID)) put(o_rh, MSB_V_REL_HUMID, rh);
+        if (want(MSB_V_AIR_PRESSURE)) put(o_ap, MSB_V_AIR_PRESSURE, ap);
+        if (want(MSB_V_TSKC)) put(o_tk, MSB_V_TSKC, tk_cur);
+        if (want_wind) put(o_wd, MSB_V_WIND, wd_cur);
+        if (want(MSB_V_SPEC_HUMID)) {   // specific humidity :423-424
+          const double mix = (kEps * vp) * rcp_nr(ap - vp);
+          put(o_sh, MSB_V_SPEC_HUMID, mix * rcp_nr(1 + mix));
+        }
+        if (want(MSB_V_LONGWAVE)) put(o_lw, MSB_V_LONGWAVE, lw);
+        if (want_prec) put(o_prec, MSB_V_PREC, pr);
+        if (want_sw) put(o_sw, MSB_V_SHORTWAVE, sw);
       }
-      if (want(MSB_V_LONGWAVE))
-        put<OutT, UNITS>(a.out, MSB_V_LONGWAVE, oidx, longwave<FAST_LW>(p, temp, vp, tskc, etab));
-      if (want_prec) put<OutT, UNITS>(a.out, MSB_V_PREC, oidx, pr);
-      if (want_sw) put<OutT, UNITS>(a.out, MSB_V_SHORTWAVE, oidx, sw);
+    }
+  }
+
+  // ---- NaN precipitation days (0/0 triangles): pandas ffill, then bfill (disaggregate.py:130) --
+  if (want_prec && had_nan) {
+    double last = 0.0;
+    bool last_known = false;
+    ooff = (unsigned)cell;
+    for (int j = i_lo; j < i_hi; ++j, ooff += ostride) {
+      const double v = prec_step_generic(p, f, c, j);
+      if (v == v) { last = v; last_known = true; continue; }
+      if (!last_known) { last = prec_fill(p, f, c, j); last_known = true; }
+      put(o_prec, MSB_V_PREC, last);
     }
   }
 }
@@ -599,10 +811,12 @@ __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double
   const double v = x[i];
   out[i] = rcp_nr(v);
   out[n + i] = exp_tab(v, etab);
-  out[2 * n + i] = sqrt_nr(v);
+  out[2 * n + i] = sqrt_fast(v);
   out[3 * n + i] = div_nr(1.2345678901234567, v);
   out[4 * n + i] = svp_kpa(v, etab);
   out[5 * n + i] = rcp_seed(v);
+  out[6 * n + i] = exp_acc(v, etab);
+  out[7 * n + i] = sqrt_nr(v);
 }
 
 }  // namespace msb
@@ -650,10 +864,18 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   a.out = *out;
   a.tpd = kMinPerDay / ts;
   const int n_days = out->day1 - out->day0;
-  // enough (cell block) x (day tile) CTAs to cover 148 SMs several waves deep
-  int cell_blocks = (f->n_cells + kDisaggThreads - 1) / kDisaggThreads;
+  // Day tiles: long enough to amortise the per-tile set-up, short enough that (cell blocks x
+  // tiles) fills the 148 SMs x 4 resident CTAs several waves deep, and small enough that the
+  // element offset inside a tile fits the 32-bit store index.
+  const int cell_blocks = (f->n_cells + kDisaggThreads - 1) / kDisaggThreads;
   int tile = 8;
-  while (tile > 1 && (long)cell_blocks * ((n_days + tile - 1) / tile) < 148L * 16) tile >>= 1;
+  while (tile > 1 && (long)cell_blocks * ((n_days + tile - 1) / tile) < 148L * 4 * 4) tile >>= 1;
+  while (tile > 1 && (double)tile * a.tpd * (double)out->ld >= 4.0e9) tile >>= 1;
+  if ((double)tile * a.tpd * (double)out->ld >= 4.0e9) {
+    set_error("msb_disaggregate: one day of output (%d steps x ld %lld) exceeds the 32-bit tile index",
+              a.tpd, (long long)out->ld);
+    return MSB_E_ARG;
+  }
   a.tile_days = tile;
   dim3 grid(cell_blocks, (n_days + tile - 1) / tile);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

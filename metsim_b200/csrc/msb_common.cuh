@@ -78,40 +78,64 @@ __device__ __forceinline__ double div_nr(double a, double b) {
 }
 
 // exp(x) for |x| < 700: k = rint(x*256/ln2), 256-entry 2^(j/256) table in shared memory,
-// degree-3 polynomial on |r| <= ln2/512 (truncation r^4/24 < 1.4e-13... times 1/24: 1.4e-13 rel).
+// polynomial on |r| <= ln2/512.
+//   exp_tab: one-term reduction + cubic, rel. error < 2e-13 -- for values that are only OUTPUT
+//            (the 1e-9 contract leaves three orders of margin);
+//   exp_acc: two-term reduction + quartic, rel. error < 4e-16 -- for the dew-point fixed point,
+//            whose evaluation COUNT must match the reference (an error of 1e-13 flips the stop
+//            test of mtclim.py:63 on roughly one cell in 1e5).
 constexpr int kExpTab = 256;
 __device__ __forceinline__ void exp_table_init(double *tab) {
   for (int j = threadIdx.x; j < kExpTab; j += blockDim.x) tab[j] = exp2((double)j / (double)kExpTab);
 }
-__constant__ double c_exp[2] = {369.3299304675746,        // 256/ln2
-                                0.0027076061740622863};   // ln2/256
-__device__ __forceinline__ double exp_tab(double x, const double *tab) {
-  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52 (immediate form)
-  double kd = fma(x, c_exp[0], kMagic);
-  const int k = __double2loint(kd);
-  kd -= kMagic;
-  // k*ln2/256 carries < 2e-15 absolute error for |k| < 2^17: one fma is enough at the 1e-13 level
-  const double r = fma(-kd, c_exp[1], x);
-  // 1 + r + r^2/2 + r^3/6; 1/6 rounded to a 32-bit-high literal (error 1e-7 * r^3 < 1e-16)
-  const double kSixth = __hiloint2double(0x3fc55555, 0);
-  double p = fma(r, kSixth, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
+__device__ __forceinline__ double exp_scale(double p, int k, const double *tab) {
   double s = tab[k & (kExpTab - 1)];
   const int hi = __double2hiint(s) + ((k >> 8) << 20);
   s = __hiloint2double(hi, __double2loint(s));
   return p * s;
 }
+__device__ __forceinline__ double exp_tab(double x, const double *tab) {
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
+  double kd = fma(x, 369.3299304675746, kMagic);  // 256/ln2
+  const int k = __double2loint(kd);
+  kd -= kMagic;
+  // k*ln2/256 carries < 2e-15 absolute error for |k| < 2^17: one fma is enough at the 1e-13 level
+  const double r = fma(-kd, 0.0027076061740622863, x);
+  // 1 + r + r^2/2 + r^3/6; 1/6 rounded to a 32-bit-high literal (error 1e-7 * r^3 < 1e-16)
+  const double kSixth = __hiloint2double(0x3fc55555, 0);
+  double p = fma(r, kSixth, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return exp_scale(p, k, tab);
+}
+__device__ __forceinline__ double exp_acc(double x, const double *tab) {
+  const double kMagic = 6755399441055744.0;
+  double kd = fma(x, 369.3299304675746, kMagic);
+  const int k = __double2loint(kd);
+  kd -= kMagic;
+  double r = fma(-kd, 0.0027076061740622863, x);     // fl(ln2/256)
+  r = fma(-kd, 9.058776616587108e-20, r);            // ln2/256 - fl(ln2/256)
+  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);           // r^5/120 < 4e-17
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  return exp_scale(p, k, tab);
+}
 
-// sqrt(x), x > 0 normal: MUFU.RSQ64H seed + one third-order rsqrt step + one residual step.
-__device__ __forceinline__ double sqrt_nr(double x) {
+// sqrt(x), x > 0 normal: MUFU.RSQ64H seed + one third-order rsqrt step (e = 1 - x*y^2;
+// y *= 1 + e/2 + 3e^2/8).  sqrt_fast stops there (rel. error ~ e^3 < 1e-17 + 3 roundings),
+// sqrt_nr adds one residual step (< 1 ulp).
+__device__ __forceinline__ double rsqrt_step(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  // e = 1 - x*y^2;  y *= 1 + e/2 + 3e^2/8
   const double xy = x * y;
   const double e = fma(-xy, y, 1.0);
   const double t = fma(e, 0.375, 0.5) * e;
-  y = fma(y, t, y);
+  return fma(y, t, y);
+}
+__device__ __forceinline__ double sqrt_fast(double x) { return x * rsqrt_step(x); }
+__device__ __forceinline__ double sqrt_nr(double x) {
+  const double y = rsqrt_step(x);
   const double g = x * y;                // ~sqrt(x)
   const double r = fma(-g, g, x);
   return fma(r, 0.5 * y, g);

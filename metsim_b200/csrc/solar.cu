@@ -285,7 +285,7 @@ extern "C" int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_e
                                      size_t *tt_elems) {
   if (n_lat <= 0) { set_error("msb_solar_table_sizes: n_lat must be > 0"); return MSB_E_ARG; }
   if (small_elems) *small_elems = (size_t)n_lat * kRows;
-  if (q_elems) *q_elems = (size_t)n_lat * 365 * kQLd;
+  if (q_elems) *q_elems = (size_t)n_lat * 365 * kQLd + MSB_Q_PAD;
   if (tt_elems) *tt_elems = (size_t)n_lat * 365 * kTT;
   return MSB_OK;
 }
@@ -324,5 +324,6 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
   solar_rows_kernel<<<grid, kK1Threads, 0, st>>>(n_lat, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0,
                                                  dv.nstep, *tb);
   MSB_CUDA(cudaGetLastError());
+  MSB_CUDA(cudaMemsetAsync(tb->q + (size_t)n_lat * 365 * kQLd, 0, MSB_Q_PAD * sizeof(double), st));
   return MSB_OK;
 }

@@ -38,7 +38,7 @@ def test_version_defaults_and_error_text():
     assert rc == _lib.E_ARG and b"n_lat" in lib.msb_last_error()
     small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
     assert lib.msb_solar_table_sizes(3, C.byref(small), C.byref(q), C.byref(tt)) == 0
-    assert (small.value, q.value, tt.value) == (3 * 366, 3 * 365 * _lib.Q_LD, 3 * 365 * _lib.TT_TERMS)
+    assert (small.value, q.value, tt.value) == (3 * 366, 3 * 365 * _lib.Q_LD + _lib.Q_PAD, 3 * 365 * _lib.TT_TERMS)
     assert lib.msb_daily_scratch_bytes(1000, 365) % 8 == 0 and lib.msb_daily_scratch_bytes(1000, 365) > 0
     assert lib.msb_mtclim_daily(None, None, None, None, None) == _lib.E_ARG
     assert lib.msb_disaggregate(None, None, None, None, None, None) == _lib.E_ARG

@@ -48,14 +48,15 @@ def test_fp64_building_blocks_accuracy():
     x = np.concatenate([rng.uniform(1e-3, 5e3, 200000), rng.uniform(150.0, 400.0, 100000),
                         10.0 ** rng.uniform(-6, 6, 50000)])
     xd = torch.from_numpy(x).cuda()
-    out = torch.empty((6, x.size), dtype=torch.float64, device="cuda")
+    out = torch.empty((8, x.size), dtype=torch.float64, device="cuda")
     _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     o = out.cpu().numpy()
     assert np.max(np.abs(o[0] * x - 1.0)) < 1e-15
     print('rcp seed max rel err 2^%.1f' % np.log2(np.max(np.abs(o[5] * x - 1.0))))
     assert np.max(np.abs(o[5] * x - 1.0)) < 2.0 ** -18    # the cubic step needs a >= 18-bit seed
-    assert np.max(np.abs(o[2] / np.sqrt(x) - 1.0)) < 1e-15
+    assert np.max(np.abs(o[2] / np.sqrt(x) - 1.0)) < 2e-15
+    assert np.max(np.abs(o[7] / np.sqrt(x) - 1.0)) < 5e-16
     assert np.max(np.abs(o[3] * x / 1.2345678901234567 - 1.0)) < 1e-15
     # exp over the argument range the kernels use
     xe = rng.uniform(-40.0, 40.0, x.size)
@@ -64,6 +65,7 @@ def test_fp64_building_blocks_accuracy():
     torch.cuda.synchronize()
     o = out.cpu().numpy()
     assert np.max(np.abs(o[1] / np.exp(xe) - 1.0)) < 1e-12
+    assert np.max(np.abs(o[6] / np.exp(xe) - 1.0)) < 1e-15
     # svp in kPa over meteorological temperatures (physics.py:124-152)
     t = rng.uniform(-80.0, 60.0, x.size)
     xd.copy_(torch.from_numpy(t))
@@ -91,7 +93,7 @@ def test_solar_tables_against_oracle_table():
     eng.stream.synchronize()
     tb = {k: v.cpu().numpy() for k, v in tbd.items()}
     ulat = eng._ulat
-    q = tb["q"].reshape(n, 365, -1)
+    q = tb["q"][:n * 365 * 2888].reshape(n, 365, 2888)
     rng = np.random.default_rng(3)
     for r, lat in enumerate(ulat):
         trf, dayl, potrad, _ = oracle_lib.solar_geom(0.0, float(lat))
