@@ -209,6 +209,20 @@ __device__ __forceinline__ int first_step_gt(double xk, int ts, double inv_ts) {
   return i;
 }
 
+// L2 prefetch of data a later event / step will load (the streaming stores keep evicting it)
+__device__ __forceinline__ void prefetch_l2(const void *ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+__device__ __forceinline__ void prefetch_l1(const void *ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
+// a load the scheduler must not sink towards its use (issued where it is written)
+__device__ __forceinline__ double load_early(const double *ptr) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(ptr));
+  return v;
+}
+
 // t_t_min of day d: knot of the vapour-pressure interpolant (disaggregate.py:480) = PCHIP knot 2d+2
 __device__ __forceinline__ double vp_knot_x(const Cell &c, int d) { return knot_x(c, 2 * d + 2); }
 
@@ -625,6 +639,13 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         }
         tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
         e_mroll = i + 1 + (kMinPerDay - (sm + ts)) / ts;
+        {   // rows the events of the NEXT output day will load: pull them into L2 a day ahead
+          const size_t op = (size_t)min(md + 3, D - 1) * ld + cell;
+          prefetch_l2(f.t_min + op); prefetch_l2(f.t_max + op); prefetch_l2(a.vp_d + op);
+          prefetch_l2(a.tskc_d + op); prefetch_l2(a.sw_d + op);
+          if (want_prec) prefetch_l2(f.prec + op);
+          if (want_wind) prefetch_l2(f.wind + op);
+        }
       }
       // tiny-step stream reaches the end of its source day / table row (:656-678); the clean
       // switch comes before, the straddle after the day-start row selection (reference order)
@@ -710,6 +731,16 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     // ================= hot path: event-free run [i, i_stop) ===================================
 #pragma unroll 1
     for (; i < i_stop; ++i, x += dx, ooff += ostride) {
+      // -- tiny-step stream: this step's table entry was requested one step ago; request the next
+      //    one now and pull the same position of tomorrow's row into L2 --
+      const double qn = q_pref;
+      ss += C;
+      if (want_sw) {
+        q_pref = load_early(q_cur + ss + C);
+        prefetch_l1(q_cur + ss + 2 * C);
+        prefetch_l2(q_cur + ss + C + kQLd);
+      }
+
       // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
       const double temp = cubic_eval(cub, x);
       const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
@@ -749,12 +780,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         p_carry = 0.0;
       }
 
-      // -- tiny-step stream: shortwave :618-680; the table entry was requested one step ago --
+      // -- shortwave :618-680 --
       double sw = 0.0;
-      ss += C;
       if (want_sw) {
-        const double qn = q_pref;
-        q_pref = q_cur[ss + C];
         sw = fma(rd_cur, qn - q_prev, sw_carry);
         q_prev = qn;
         sw_carry = 0.0;
