@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--workload", default="conus_16th_hourly", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=None, help="truncate the grid (debugging only)")
     ap.add_argument("--days", type=int, default=None, help="truncate the record (debugging only)")
-    ap.add_argument("--tile-days", type=int, default=8)
+    ap.add_argument("--tile-days", type=int, default=32)
     ap.add_argument("--sample-cells", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -288,7 +288,7 @@ def main():
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
     rounds = 3  # ceil(max_iter 24 / 8), daily.cu
-    launches_per_step = 1 + 2 * rounds + 1 + n_tiles
+    launches_per_step = 1 + 2 * rounds + 1 + 2 * n_tiles   # solar, daily passes, (prepare + stream) per tile
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):

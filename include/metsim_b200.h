@@ -118,6 +118,9 @@ typedef struct msb_subdaily {
   int32_t dtype;                     /* 4 = float32 (reference default out_precision), 8 = float64 */
   int64_t ld;
   int32_t day0, day1;                /* produce days [day0, day1); var[] points at step day0*tpd */
+  void *workspace;                   /* device scratch of msb_disagg_workspace_bytes() bytes: the
+                                        per-(cell, day) records of the days around [day0, day1) */
+  size_t workspace_bytes;
 } msb_subdaily;
 
 int msb_version(void);
@@ -141,7 +144,13 @@ int msb_mtclim_daily(const msb_params *p, const msb_forcing *f, const msb_solar_
 /* reads back status/n_iter flags (synchronises the stream); returns MSB_OK or the first error */
 int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 
-/* ---- sub-daily disaggregation: disaggregate.py:34-680, units.py:3-59 ----------------------- */
+/* ---- sub-daily disaggregation: disaggregate.py:34-680, units.py:3-59 -----------------------
+ * A first kernel turns the days around [day0, day1) into per-(cell, day) records (PCHIP knots
+ * with their derivatives, the closed-form precipitation shape, radiation per tiny step); the
+ * streaming kernel then only reads those.  The records live in caller-provided scratch. */
+#define MSB_REC_FIELDS 12
+#define MSB_REC_MARGIN 3
+size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1);
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *daily, const msb_subdaily *out, void *stream);
 

@@ -29,7 +29,8 @@ E_ARG, E_CUDA, E_DTR_NEGATIVE, E_NOT_CONVERGED, E_KNOTS, E_NOMEM = -1, -2, -3, -
 
 EXPORTS = ("msb_version", "msb_last_error", "msb_default_params", "msb_solar_prelude_bytes",
            "msb_solar_table_sizes", "msb_solar_tables_build", "msb_daily_scratch_bytes",
-           "msb_mtclim_daily", "msb_daily_check", "msb_disaggregate", "msb_run_host",
+           "msb_mtclim_daily", "msb_daily_check", "msb_disagg_workspace_bytes", "msb_disaggregate",
+           "msb_run_host",
            "msb_selftest_math")
 
 dp = C.POINTER(C.c_double)
@@ -71,7 +72,8 @@ class Daily(C.Structure):
 class SubDaily(C.Structure):
     _fields_ = [("var", C.c_void_p * N_SUBVARS), ("scale", C.c_double * N_SUBVARS),
                 ("offset", C.c_double * N_SUBVARS), ("dtype", C.c_int32), ("ld", C.c_int64),
-                ("day0", C.c_int32), ("day1", C.c_int32)]
+                ("day0", C.c_int32), ("day1", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class HostRun(C.Structure):
@@ -130,6 +132,8 @@ def lib():
                                    C.POINTER(Daily), C.c_void_p]
     l.msb_daily_check.restype = C.c_int
     l.msb_daily_check.argtypes = [C.POINTER(Forcing), C.POINTER(Daily), C.c_void_p]
+    l.msb_disagg_workspace_bytes.restype = C.c_size_t
+    l.msb_disagg_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
     l.msb_disaggregate.restype = C.c_int
     l.msb_disaggregate.argtypes = [C.POINTER(Params), C.POINTER(Forcing), C.POINTER(SolarTables),
                                    C.POINTER(Daily), C.POINTER(SubDaily), C.c_void_p]

@@ -179,6 +179,8 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   add((size_t)N * 4); add(msb_daily_scratch_bytes(N, D)); add(64);
   const size_t tile_elems = (size_t)tile_days * tpd * N;
   for (int k = 0; k < 2 * n_out; ++k) add(tile_elems * osz);
+  const size_t ws_bytes = sub ? msb_disagg_workspace_bytes(N, 0, tile_days) : 0;
+  add(ws_bytes);
   need += 65536;
 
   std::lock_guard<std::mutex> lock(g_arena.mu);
@@ -208,6 +210,7 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   dl.n_iter = cv.take<int32_t>(N);
   dl.partial = cv.take<double>(msb_daily_scratch_bytes(N, D) / 8 + 1);
   dl.status = cv.take<int32_t>(16);
+  void *d_ws = ws_bytes ? (void *)cv.take<char>(ws_bytes) : nullptr;
   void *d_out[2][MSB_N_SUBVARS];
   for (int b = 0; b < 2; ++b)
     for (int v = 0; v < MSB_N_SUBVARS; ++v)
@@ -301,6 +304,7 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
         so.offset[v] = run->offset[v];
       }
       so.dtype = osz; so.ld = N; so.day0 = d0; so.day1 = d1;
+      so.workspace = d_ws; so.workspace_bytes = ws_bytes;
       MSB_TRY(msb_disaggregate(p, &f, &tb, &dl, &so, s_main));
       MSB_TRYC(cudaEventRecord(ev_k[b], s_main));
       MSB_TRYC(cudaStreamWaitEvent(s_copy, ev_k[b], 0));

@@ -43,7 +43,16 @@ struct DisaggArgs {
   msb_subdaily out;
   int tpd, tile_days;
   unsigned var_mask;   // bit v set = out.var[v] requested
+  double *rec;         // day records [MSB_REC_FIELDS][n_rec][ld], record r = padded day e0 + r
+  int e0, n_rec;       // e runs over [-1, D]: -1 / D are the padded PCHIP ends
 };
+
+// fields of a day record
+enum { kR_XMIN = 0, kR_YMIN, kR_DMIN,   // PCHIP knot at t_Tmin: time, value, derivative
+       kR_XMAX, kR_YMAX, kR_DMAX,       // PCHIP knot at t_Tmax
+       kR_VY,                            // vapour-pressure knot value, kPa (its time is kR_XMIN)
+       kR_PPACK, kR_HSP, kR_HSQ, kR_PF, // PrecDay: packed integers, stepp/2, stepq/2, P/sum
+       kR_RAD };                         // shortwave per tiny step, disaggregate.py:645
 
 // ---- per-thread view of one cell (cold: only the event handler and the set-up read it) --------
 struct Cell {
@@ -161,20 +170,6 @@ __device__ __forceinline__ bool cubic_setup(const Cell &c, int k, Cubic &q, Cubi
   nx.y1 = yc; nx.x2 = xd; nx.y2 = yd; nx.m2 = m2; nx.d1 = d1;
   return has_d;
 }
-// interval k+1 from interval k: one new knot (k+3, which must exist and k >= 0)
-__device__ __forceinline__ void cubic_slide(const Cell &c, int k_new, Cubic &q, CubicNext &nx,
-                                            int32_t *status) {
-  const double xb = q.x1, xc = nx.x2, yb = nx.y1, yc = nx.y2;
-  const double h1 = __dadd_rn(xc, -xb), m1 = nx.m2, d0 = nx.d1;
-  const double xd = knot_x(c, k_new + 2), yd = knot_y(c, k_new + 2);
-  const double h2 = __dadd_rn(xd, -xc);
-  const double m2 = div_nr(__dadd_rn(yd, -yc), h2);
-  if (!(h2 > 0.0)) status[2] = 1;
-  const double d1 = pchip_mid(h1, h2, m1, m2);
-  cubic_coeffs(q, xb, xc, yb, h1, m1, d0, d1);
-  nx.y1 = yc; nx.x2 = xd; nx.y2 = yd; nx.m2 = m2; nx.d1 = d1;
-}
-
 __device__ __forceinline__ double cubic_eval(const Cubic &q, double x) {
   const double s = x - q.x0;
   return fma(fma(fma(q.c0, s, q.c1), s, q.c2), s, q.c3);
@@ -425,11 +420,104 @@ constexpr unsigned kExampleMask = (1u << MSB_V_TEMP) | (1u << MSB_V_PREC) | (1u 
                                   (1u << MSB_V_WIND);
 
 // per-thread shared-memory slots for values that only the event handler touches between events
-enum { kS_Y1 = 0, kS_X2, kS_Y2, kS_M2, kS_D1,   // CubicNext
-       kS_TKN, kS_WDN,                           // tskc / wind of the source day just rolled in
-       kS_ROWTOT,                                // total of the current radiation row (noon event)
-       kS_VPTAIL,                                // forward-fill value of the vapour pressure
+enum { kS_TKN = 0, kS_WDN,   // tskc / wind of the source day just rolled in
+       kS_ROWTOT,            // total of the current radiation row (noon event)
+       kS_VPTAIL,            // forward-fill value of the vapour pressure
        kS_COUNT };
+
+// ---- day records ------------------------------------------------------------------------------
+// Everything an event needs about a (cell, day) -- which the per-cell reference code re-derives
+// from whole-record vectors -- is computed once by a thread-per-(cell, day) kernel and read back
+// by the streaming kernel with single coalesced loads: the PCHIP knots (time, value and the
+// derivative scipy's PchipInterpolator would assign, _cubic.py:279-340), the vapour-pressure knot,
+// the closed-form precipitation shape and the radiation per tiny step.
+__device__ __forceinline__ double pack_prec(const PrecDay &pd) {
+  const unsigned lo = (unsigned)pd.p0 | ((unsigned)pd.nps << 16);
+  const unsigned hi = (unsigned)pd.q0 | ((unsigned)pd.nqs << 16) | (pd.pth != kNever ? 0x80000000u : 0u);
+  return __hiloint2double((int)hi, (int)lo);
+}
+__device__ __forceinline__ void unpack_prec(double w, PrecDay &pd) {
+  const unsigned lo = (unsigned)__double2loint(w), hi = (unsigned)__double2hiint(w);
+  pd.p0 = (int)(lo & 0xffffu); pd.nps = (int)(lo >> 16);
+  pd.q0 = (int)(hi & 0xffffu); pd.nqs = (int)((hi >> 16) & 0x7fffu);
+  pd.pth = (hi & 0x80000000u) ? pd.p0 + pd.nps + 1 : kNever;   // forced 1.0 follows the series
+}
+
+// One thread = one (cell, padded day e): the two knots of the day from the four knots around them
+// (interior: weighted harmonic mean of the neighbouring slopes; record ends: scipy's three-point
+// edge rule, _cubic.py:279-291, :320-333).
+__global__ void __launch_bounds__(128)
+disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (cell >= a.f.n_cells || r >= a.n_rec) return;
+  const msb_params &p = a.p;
+  const msb_forcing &f = a.f;
+  const int D = f.n_days, ts = p.time_step, e = a.e0 + r;
+  Cell c;
+  c.cell = cell; c.D = D; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * D + 4; c.ld = f.ld;
+  const int nk = c.nk;
+  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  c.off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;
+  c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
+  c.frac = p.tmax_daylength_fraction;
+  const int row = f.lat_row[cell];
+  c.rise = a.t.rise_min + (size_t)row * kRows;
+  c.set = a.t.set_min + (size_t)row * kRows;
+  c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
+  c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+  c.t_end = f.t_end;
+  const size_t plane = (size_t)a.n_rec * f.ld;
+  double *out = a.rec + (size_t)r * f.ld + cell;
+
+  // knots j0-1 .. j0+2 (j0 = t_Tmin knot of padded day e); all loads are independent
+  const int j0 = 2 * (e + 1);
+  const int ja = max(j0 - 1, 0), jd = min(j0 + 2, nk - 1);
+  const double xa = knot_x(c, ja), xb = knot_x(c, j0), xc = knot_x(c, j0 + 1), xd = knot_x(c, jd);
+  const double ya = knot_y(c, ja), yb = knot_y(c, j0), yc = knot_y(c, j0 + 1), yd = knot_y(c, jd);
+  const double h1 = __dadd_rn(xc, -xb);
+  const double m1 = div_nr(__dadd_rn(yc, -yb), h1);
+  bool bad = !(h1 > 0.0);
+  double d_min, d_max;
+  if (j0 > 0 && j0 + 1 < nk - 1) {            // both knots interior
+    const double h0 = __dadd_rn(xb, -xa), h2 = __dadd_rn(xd, -xc);
+    const double m0 = div_nr(__dadd_rn(yb, -ya), h0), m2 = div_nr(__dadd_rn(yd, -yc), h2);
+    bad |= !(h0 > 0.0) || !(h2 > 0.0);
+    d_min = pchip_mid(h0, h1, m0, m1);
+    d_max = pchip_mid(h1, h2, m1, m2);
+  } else if (j0 == 0) {                       // first padded day: knot 0 takes the edge rule
+    const double h2 = __dadd_rn(xd, -xc);
+    const double m2 = div_nr(__dadd_rn(yd, -yc), h2);
+    bad |= !(h2 > 0.0);
+    d_min = pchip_edge(h1, h2, m1, m2);
+    d_max = pchip_mid(h1, h2, m1, m2);
+  } else {                                    // last padded day: knot nk-1 takes the edge rule
+    const double h0 = __dadd_rn(xb, -xa);
+    const double m0 = div_nr(__dadd_rn(yb, -ya), h0);
+    bad |= !(h0 > 0.0);
+    d_min = pchip_mid(h0, h1, m0, m1);
+    d_max = pchip_edge(h1, h0, m1, m0);
+  }
+  if (bad) a.status[2] = 1;                   // scipy: `x` must be strictly increasing
+  out[kR_XMIN * plane] = xb;
+  out[kR_YMIN * plane] = yb;
+  out[kR_DMIN * plane] = d_min;
+  out[kR_XMAX * plane] = xc;
+  out[kR_YMAX * plane] = yc;
+  out[kR_DMAX * plane] = d_max;
+  if (e < 0 || e >= D) return;                      // padded ends carry knots only
+  const size_t o = (size_t)e * f.ld + cell;
+  out[kR_VY * plane] = a.vp_d[o] / 1000.0;
+  PrecDay pd;
+  pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
+  if (a.out.var[MSB_V_PREC]) prec_day_setup(p, f, cell, e, f.month[e], pd);
+  out[kR_PPACK * plane] = pack_prec(pd);
+  out[kR_HSP * plane] = pd.hsp;
+  out[kR_HSQ * plane] = pd.hsq;
+  out[kR_PF * plane] = pd.f;
+  const double *dayl = a.t.daylength + (size_t)row * kRows;
+  out[kR_RAD * plane] = (a.sw_d[o] * dayl[f.doy[e] - 1]) * (1.0 / (3600.0 * ((double)ts / 60.0)));
+}
 
 // One thread = one cell x one tile of days.  np.roll by a whole number of minutes (tskc, wind,
 // prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
@@ -492,8 +580,23 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     const unsigned r = (unsigned)(d - win0);
     return r < (unsigned)nwin ? s_month[r] : f.month[d];
   };
+  // day records (disagg_prepare_kernel): field fld of padded day e
+  const size_t plane = (size_t)a.n_rec * (size_t)ld;
+  const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
+  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  auto has_rec = [&](int e) { return (unsigned)(e - a.e0) < (unsigned)a.n_rec; };
+  auto rkx = [&](int j) { return rec((j & 1) ? kR_XMAX : kR_XMIN, (j >> 1) - 1); };
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
-    return (a.sw_d[(size_t)d * ld + cell] * dayl[doy_at(c, d) - 1]) * inv_sw_den;
+    if (has_rec(d)) return rec(kR_RAD, d);
+    return (a.sw_d[(size_t)d * ld + cell] * dayl[doy_at(c, d) - 1]) * inv_sw_den;   // wrapped day
+  };
+  auto prec_of = [&](int d, PrecDay &o) {
+    if (has_rec(d)) {
+      unpack_prec(rec(kR_PPACK, d), o);
+      o.hsp = rec(kR_HSP, d); o.hsq = rec(kR_HSQ, d); o.f = rec(kR_PF, d);
+    } else {
+      prec_day_setup(p, f, cell, d, month_at(d), o);                                  // wrapped day
+    }
   };
   auto q_of = [&](int y) {     // table row y rolled over the table's own 366 rows (:656)
     y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
@@ -527,13 +630,13 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const int qs = off_tiny < 0 ? -1 : 0;
   int sd = wrap(wrap(d_lo + qs) - 1);
   int ss = off_tiny - qs * kTiny + kTiny;
-  int kc = max(0, 2 * (d_lo + 1) - 4);          // PCHIP interval guess (at or left of the answer)
-  bool slide_ok = false;                        // CubicNext slots describe interval kc + 1
-  int vd = 1;                                   // upper knot of the vapour-pressure segment
+  int kc = max(0, 2 * (d_lo + 1) - 4) - 1;      // PCHIP interval: the first event walks right from kc + 1
+  int vd = 0;                                   // upper knot of the vapour-pressure segment (event: from vd + 1)
   bool had_nan = false;
   int e_cub = i_lo, e_day = want_sw ? i_lo : kNever;
   int e_mroll = i_lo, e_mfol = kNever;
   int e_troll = want_sw ? i_lo : kNever;
+  int e_pf = i_lo;
   int e_noon = kNever;
   if (want_sw) {
     const int s0 = ss - kTiny;                  // first window [s0, s0 + C)
@@ -562,6 +665,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         const double x0 = (double)ts * (double)i_lo;
         vd = min(max(d_lo, 1), D - 1);
         while (vd > 1 && !(vp_knot_x(c, vd - 1) < x0)) --vd;
+        --vd;                          // the event handler starts its search at vd + 1
         e_vp = i_lo;
       }
     }
@@ -611,7 +715,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
           const double tk_n = a.tskc_d[on];
           const double wd_n = want_wind ? f.wind[on] : 0.0;
           PrecDay pn = pd;
-          if (want_prec) prec_day_setup(p, f, cell, mdn, month_at(mdn), pn);
+          if (want_prec) prec_of(mdn, pn);
           int pos;                         // minute of the new day where the cumulative sum restarts
           if (sm >= kMinPerDay) {          // clean switch
             sm -= kMinPerDay;
@@ -639,12 +743,16 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         }
         tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
         e_mroll = i + 1 + (kMinPerDay - (sm + ts)) / ts;
-        {   // rows the events of the NEXT output day will load: pull them into L2 a day ahead
-          const size_t op = (size_t)min(md + 3, D - 1) * ld + cell;
-          prefetch_l2(f.t_min + op); prefetch_l2(f.t_max + op); prefetch_l2(a.vp_d + op);
-          prefetch_l2(a.tskc_d + op); prefetch_l2(a.sw_d + op);
-          if (want_prec) prefetch_l2(f.prec + op);
+        {   // what the events of the NEXT output day will load: pull it into L2 a day ahead
+          const int dn = min(md + 3, D - 1);
+          const size_t op = (size_t)dn * ld + cell;
+          prefetch_l2(a.tskc_d + op);
           if (want_wind) prefetch_l2(f.wind + op);
+          if (has_rec(dn)) {
+            const double *rp = rec0 + (long)dn * ld;
+#pragma unroll
+            for (int fld = 0; fld < MSB_REC_FIELDS; ++fld) prefetch_l2(rp + (size_t)fld * plane);
+          }
         }
       }
       // tiny-step stream reaches the end of its source day / table row (:656-678); the clean
@@ -690,40 +798,81 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         e_troll = i + 1 + (kTiny - (ss + C)) / C;
       }
       if (i >= e_vp) {     // vapour-pressure knot crossed (searchsorted side='left')
-        while (vd < D - 1 && vp_knot_x(c, vd) < x) ++vd;
-        const double xh = vp_knot_x(c, vd);
+        int vn = min(vd + 1, D - 1);     // usual case: the next knot is the new upper end
+        double xl = rec(kR_XMIN, vn - 1), yl = rec(kR_VY, vn - 1);
+        double xh = rec(kR_XMIN, vn), yh = rec(kR_VY, vn);
+        while (vn < D - 1 && xh < x) { ++vn; xl = xh; yl = yh; xh = rec(kR_XMIN, vn); yh = rec(kR_VY, vn); }
+        vd = vn;
         if (xh < x) {      // beyond the last knot: forward fill
           yvl = slot[kS_VPTAIL][tid]; vslope = 0.0; v_interior = false; e_vp = kNever;
         } else {
-          xvl = vp_knot_x(c, vd - 1);
-          yvl = a.vp_d[(size_t)(vd - 1) * ld + cell] / 1000.0;
-          const double yh = a.vp_d[(size_t)vd * ld + cell] / 1000.0;
-          vslope = div_nr(yh - yvl, xh - xvl);              // scipy _interpolate.py:513-516
+          xvl = xl; yvl = yl;
+          vslope = div_nr(yh - yl, xh - xl);                // scipy _interpolate.py:513-516
           v_interior = true;
           e_vp = first_step_gt(xh, ts, inv_ts);
         }
       }
       if (i >= e_cub) {    // PCHIP knot crossed (searchsorted side='right')
-        CubicNext nx;
-        const int kn = cubic_walk(c, kc, x);
-        if (slide_ok && kn == kc + 1 && kn + 2 < nk) {
-          nx.y1 = slot[kS_Y1][tid]; nx.x2 = slot[kS_X2][tid]; nx.y2 = slot[kS_Y2][tid];
-          nx.m2 = slot[kS_M2][tid]; nx.d1 = slot[kS_D1][tid];
-          cubic_slide(c, kn, cub, nx, a.status);
-        } else {
-          slide_ok = cubic_setup(c, kn, cub, nx, a.status);
+        int kn = kc + 1;                 // usual case: the next interval; all six loads in flight
+        double x0 = rkx(kn), x1 = rkx(kn + 1);
+        double y0 = rec((kn & 1) ? kR_YMAX : kR_YMIN, (kn >> 1) - 1);
+        double d0 = rec((kn & 1) ? kR_DMAX : kR_DMIN, (kn >> 1) - 1);
+        double y1 = rec((kn & 1) ? kR_YMIN : kR_YMAX, ((kn + 1) >> 1) - 1);
+        double d1 = rec((kn & 1) ? kR_DMIN : kR_DMAX, ((kn + 1) >> 1) - 1);
+        while (kn < nk - 2 && x >= x1) {   // walk right (tile start; several knots inside one step)
+          ++kn;
+          x0 = x1; y0 = y1; d0 = d1;
+          x1 = rkx(kn + 1);
+          y1 = rec((kn & 1) ? kR_YMIN : kR_YMAX, ((kn + 1) >> 1) - 1);
+          d1 = rec((kn & 1) ? kR_DMIN : kR_DMAX, ((kn + 1) >> 1) - 1);
         }
         kc = kn;
-        slot[kS_Y1][tid] = nx.y1; slot[kS_X2][tid] = nx.x2; slot[kS_Y2][tid] = nx.y2;
-        slot[kS_M2][tid] = nx.m2; slot[kS_D1][tid] = nx.d1;
-        e_cub = (kc >= nk - 2) ? kNever : first_step_ge(cub.x1, ts, inv_ts);   // last interval extrapolates
+        // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165)
+        const double inv = rcp_nr(x1 - x0);
+        const double m = (y1 - y0) * inv;
+        const double tt = ((d0 + d1) - 2.0 * m) * inv;
+        cub.x0 = x0; cub.x1 = x1;
+        cub.c0 = tt * inv;
+        cub.c1 = (m - d0) * inv - tt;
+        cub.c2 = d0;
+        cub.c3 = y0;
+        e_cub = (kc >= nk - 2) ? kNever : first_step_ge(x1, ts, inv_ts);   // last interval extrapolates
       }
       if (i == e_noon) {   // this step's window [ss, ss+C) contains tiny step 1440: add the row total
         q_prev -= slot[kS_ROWTOT][tid];
         e_noon += tpd;
       }
+      if (i == e_pf) {     // once per output day (all lanes together): pull what this day's events
+        // will load into L1, so that they wait for an L1 hit instead of an L2 / DRAM round trip
+        for (int j = kc + 1; j <= min(kc + 3, nk - 1); ++j) {
+          const double *rp = rec0 + (long)((j >> 1) - 1) * ld;
+          prefetch_l1(rp + (size_t)((j & 1) ? kR_XMAX : kR_XMIN) * plane);
+          prefetch_l1(rp + (size_t)((j & 1) ? kR_YMAX : kR_YMIN) * plane);
+          prefetch_l1(rp + (size_t)((j & 1) ? kR_DMAX : kR_DMIN) * plane);
+        }
+        for (int v = vd; v <= min(vd + 1, D - 1); ++v) {
+          prefetch_l1(rec0 + (long)v * ld + (size_t)kR_XMIN * plane);
+          prefetch_l1(rec0 + (long)v * ld + (size_t)kR_VY * plane);
+        }
+        const int mdn = (md + 1 == D) ? 0 : md + 1;
+        prefetch_l1(a.tskc_d + (size_t)mdn * ld + cell);
+        if (want_wind) prefetch_l1(f.wind + (size_t)mdn * ld + cell);
+        if (want_prec && has_rec(mdn)) {
+          const double *rp = rec0 + (long)mdn * ld;
+          prefetch_l1(rp + (size_t)kR_PPACK * plane); prefetch_l1(rp + (size_t)kR_HSP * plane);
+          prefetch_l1(rp + (size_t)kR_HSQ * plane); prefetch_l1(rp + (size_t)kR_PF * plane);
+        }
+        if (want_sw) {
+          const int sdn = (sd + 1 == D) ? 0 : sd + 1;
+          if (has_rec(sdn)) prefetch_l1(rec0 + (long)sdn * ld + (size_t)kR_RAD * plane);
+          const double *qn = q_of(doy_at(c, i / tpd) - 1 + qs + 1);
+          const int k2 = ((ss % C) + C) % C;
+          prefetch_l1(qn + k2); prefetch_l1(qn); prefetch_l1(qn + kTiny + 1); prefetch_l1(q_cur + kTiny);
+        }
+        e_pf += tpd;
+      }
       if (want_sw) q_pref = q_cur[ss + C];                  // re-prime the pipelined table load
-      i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), e_mroll));
+      i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), min(e_mroll, e_pf)));
       i_event = max(i_event, i + 1);
     }
     const int i_stop = min(__reduce_min_sync(lanes, i_event), i_hi);
@@ -858,6 +1007,12 @@ extern "C" int msb_selftest_math(int n, const double *x_dev, double *out_dev, vo
   return MSB_OK;
 }
 
+extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
+  if (ld <= 0 || day1 <= day0) return 0;
+  const size_t n_rec = (size_t)(day1 - day0) + 2 * MSB_REC_MARGIN;
+  return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
+}
+
 extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
                                 const msb_solar_tables *t, const msb_daily *daily,
                                 const msb_subdaily *out, void *stream) {
@@ -907,6 +1062,16 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   a.tile_days = tile;
   dim3 grid(cell_blocks, (n_days + tile - 1) / tile);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // day records of the padded days around the range (-1 and D are the padded PCHIP ends)
+  a.e0 = out->day0 - MSB_REC_MARGIN < -1 ? -1 : out->day0 - MSB_REC_MARGIN;
+  const int e1 = out->day1 + MSB_REC_MARGIN > f->n_days + 1 ? f->n_days + 1 : out->day1 + MSB_REC_MARGIN;
+  a.n_rec = e1 - a.e0;
+  a.rec = reinterpret_cast<double *>(out->workspace);
+  if (!out->workspace ||
+      out->workspace_bytes < (size_t)MSB_REC_FIELDS * a.n_rec * (size_t)f->ld * sizeof(double)) {
+    set_error("msb_disaggregate: workspace of msb_disagg_workspace_bytes() bytes is required");
+    return MSB_E_ARG;
+  }
   const bool fast_lw = p->lw_type == MSB_LW_PRATA && p->lw_cloud == MSB_CLOUD_DEARDORFF;
   bool units = false;
   a.var_mask = 0;
@@ -917,6 +1082,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
   const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4;
+  disagg_prepare_kernel<<<dim3(cell_blocks, a.n_rec), 128, 0, st>>>(a);
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
   if (example) MSB_LAUNCH(float, true, false, kVarsExample);   // reference defaults, 8 variables
   else if (out->dtype == 4) {

@@ -77,6 +77,7 @@ class Engine:
         self._t = {}
         self._tables = None
         self._daily = None
+        self._ws = None
         self.n_cells = self.n_days = 0
 
     # ------------------------------------------------------------------ helpers
@@ -235,6 +236,10 @@ class Engine:
                 sd.scale[i], sd.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
             sd.dtype = 4 if out_dtype == torch.float32 else 8
             sd.ld, sd.day0, sd.day1 = n, day0, day1
+            need = self.lib.msb_disagg_workspace_bytes(n, day0, day1)
+            if self._ws is None or self._ws.numel() < need:   # grow-only scratch for the day records
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            sd.workspace, sd.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
             f = self._forcing()
             _lib.check(self.lib.msb_disaggregate(C.byref(self.params), C.byref(f),
                                                  C.byref(self._tables[0]), C.byref(self._daily[0]),
