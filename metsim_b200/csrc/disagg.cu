@@ -235,7 +235,7 @@ __device__ __forceinline__ double svp_kpa(double t, const double *etab) {
 // ptxas re-materialises an fp64 literal as two 32-bit moves at EVERY use (it never keeps an
 // immediate in a register across a loop), which cost ~45 instructions per step.  Values loaded
 // from constant memory are opaque to it, so they are loaded once and stay in (uniform) registers.
-__constant__ double c_hot[10] = {
+__constant__ double c_hot[12] = {
     237.3,                          // svp denominator offset, physics.py:149
     -17.269 * 237.3,                // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
     17.269 - 0.49301845011612494,   // + ln(0.61078): the factor folded into the exponent
@@ -244,13 +244,16 @@ __constant__ double c_hot[10] = {
     0.0027076061740622863,          // ln2/256
     4.618333172514372,              // ln(P_STD/1000): air pressure in kPa, disaggregate.py:401-403
     273.15,                         // KELVIN
-    1.2                             // PRATA, disaggregate.py:557-559
+    1.2,                            // PRATA, disaggregate.py:557-559
+    0.16666666666666666,            // exp polynomial
+    0.375                           // rsqrt step
 };
-struct HotK { double k237, ka, kb, kc2, kc1, inv_l, l, ln_p, kelvin, k12; };
+struct HotK { double k237, ka, kb, kc2, kc1, inv_l, l, ln_p, kelvin, k12, sixth, c375; };
 __device__ __forceinline__ HotK load_hot() {
   HotK k;
   k.k237 = c_hot[0]; k.ka = c_hot[1]; k.kb = c_hot[2]; k.kc2 = c_hot[3]; k.kc1 = c_hot[4];
   k.inv_l = c_hot[5]; k.l = c_hot[6]; k.ln_p = c_hot[7]; k.kelvin = c_hot[8]; k.k12 = c_hot[9];
+  k.sixth = c_hot[10]; k.c375 = c_hot[11];
   return k;
 }
 // exp_tab with its two non-immediate constants taken from HotK
@@ -260,11 +263,19 @@ __device__ __forceinline__ double exp_hot(double x, const double *tab, const Hot
   const int k = __double2loint(kd);
   kd -= kMagic;
   const double r = fma(-kd, K.l, x);
-  const double kSixth = __hiloint2double(0x3fc55555, 0);
-  double p = fma(r, kSixth, 0.5);
+  double p = fma(r, K.sixth, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   return exp_scale(p, k, tab);
+}
+// sqrt_fast with its non-immediate constant taken from HotK
+__device__ __forceinline__ double sqrt_hot(double x, const HotK &K) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double xy = x * y;
+  const double e = fma(-xy, y, 1.0);
+  const double t = fma(e, K.c375, 0.5) * e;
+  return x * fma(y, t, y);
 }
 
 // ---- precipitation: one day's per-minute shape in closed form (disaggregate.py:294-329) ------
@@ -284,13 +295,18 @@ struct PrecDay {
   double hsp, hsq, f;   // stepp/2, stepq/2, P/sum (NaN for a 0/0 day, :327)
 };
 
+// exact int -> double for 0 <= n < 2^31 on the fp64 pipe (I2F.F64 runs on the quarter-rate
+// conversion unit, which the hot loop already loads with its eight F2F and five MUFU per step)
+__device__ __forceinline__ double u2d(int n) {
+  return __hiloint2double(0x43300000, n) - 4503599627370496.0;   // (2^52 + n) - 2^52
+}
 __device__ __forceinline__ double prec_cum(const PrecDay &pd, int m) {
   const int i = min(max(m - pd.p0, 0), pd.nps);
   const int j = min(max(m - pd.q0, 0), pd.nqs);
   const int u = (m >= pd.pth) ? 1 : 0;
   const int tr = i * i - i;   // 2 * sum_{k<i} k
   const int tf = j * j - j;
-  return fma(pd.hsq, (double)tf, fma(pd.hsp, (double)tr, (double)(u + j)));
+  return fma(pd.hsq, u2d(tf), fma(pd.hsp, u2d(tr), u2d(u + j)));
 }
 
 // m = calendar month of day d (1..12)
@@ -413,7 +429,13 @@ __device__ __forceinline__ double longwave(const msb_params &p, double temp_c, d
 
 // variable sets compiled into the kernel: kVarsExample = the 8 variables of
 // examples/example_nc.conf (every pointer known non-NULL, no per-step tests), kVarsAny = runtime
-constexpr int kVarsAny = 0, kVarsExample = 1;
+// The fixed sets come as one kernel (kVarsExample) or as two that split the per-thread state --
+// kVarsThermo (temperature, humidity, pressure, longwave: the fp64-heavy half) and kVarsStreams
+// (precipitation, shortwave, wind: the source-stream half) -- so that each half keeps fewer
+// registers and more warps are resident to cover the 8-cycle dependent DFMA latency.
+constexpr int kVarsAny = 0, kVarsExample = 1, kVarsThermo = 2, kVarsStreams = 3;
+constexpr unsigned kThermoBits = (1u << MSB_V_TEMP) | (1u << MSB_V_LONGWAVE) | (1u << MSB_V_VAPOR_PRESSURE) |
+                                 (1u << MSB_V_REL_HUMID) | (1u << MSB_V_AIR_PRESSURE) | (1u << MSB_V_SPEC_HUMID);
 constexpr unsigned kExampleMask = (1u << MSB_V_TEMP) | (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE) |
                                   (1u << MSB_V_LONGWAVE) | (1u << MSB_V_VAPOR_PRESSURE) |
                                   (1u << MSB_V_REL_HUMID) | (1u << MSB_V_AIR_PRESSURE) |
@@ -523,8 +545,10 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
 // prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
 // is read ts minutes per output step; the stream positions and the current source day live in
 // registers and roll to the next source day once per day (an event).
+constexpr int disagg_min_blocks(int vars) { return vars == kVarsStreams ? 8 : (vars == kVarsThermo ? 5 : 4); }
+
 template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
-__global__ void __launch_bounds__(kDisaggThreads, 4)
+__global__ void __launch_bounds__(kDisaggThreads, disagg_min_blocks(VARS))
 disagg_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[kExpTab];
   __shared__ double slot[kS_COUNT][kDisaggThreads];
@@ -546,11 +570,14 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const int tid = threadIdx.x;
   const int cell = blockIdx.x * blockDim.x + tid;
   if (cell >= f.n_cells || d_lo >= d_hi) return;
-  const unsigned mask = VARS == kVarsExample ? kExampleMask : a.var_mask;
+  const unsigned mask = VARS == kVarsExample ? kExampleMask
+                      : VARS == kVarsThermo ? (kExampleMask & kThermoBits)
+                      : VARS == kVarsStreams ? (kExampleMask & ~kThermoBits) : a.var_mask;
   auto want = [mask](int v) { return (mask >> v) & 1u; };
   const bool want_prec = want(MSB_V_PREC);
-  const bool want_wind = want(MSB_V_WIND) && f.wind != nullptr;
+  const bool want_wind = want(MSB_V_WIND) && (VARS != kVarsAny || f.wind != nullptr);
   const bool want_sw = want(MSB_V_SHORTWAVE);
+  const bool thermo = (mask & kThermoBits) != 0;   // temperature / humidity / pressure / longwave
 
   // ---- cold per-cell constants ----------------------------------------------------------------
   Cell c;
@@ -613,6 +640,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   bool v_interior = false;                                   // clamp to saturation inside the knots
   double tk_cur = 0.0, wd_cur = 0.0;                         // minute stream: tskc, wind
   double tk_a = 0.0, tk_b = 0.0;                             // STEFAN_B * tskc, STEFAN_B * (1 - tskc)
+  OutT wd_o = 0, tk_o = 0;                                   // wind / tskc as they are stored
   const HotK K = load_hot();
   PrecDay pd;                                                // minute stream: precipitation
   pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
@@ -630,10 +658,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const int qs = off_tiny < 0 ? -1 : 0;
   int sd = wrap(wrap(d_lo + qs) - 1);
   int ss = off_tiny - qs * kTiny + kTiny;
+  const double *q_next = q_cur + ss + 2 * C;   // table entry the hot loop requests next (it only
+                                               // advances this pointer; ss is recovered from it)
   int kc = max(0, 2 * (d_lo + 1) - 4) - 1;      // PCHIP interval: the first event walks right from kc + 1
   int vd = 0;                                   // upper knot of the vapour-pressure segment (event: from vd + 1)
   bool had_nan = false;
-  int e_cub = i_lo, e_day = want_sw ? i_lo : kNever;
+  int e_cub = thermo ? i_lo : kNever, e_day = want_sw ? i_lo : kNever;
   int e_mroll = i_lo, e_mfol = kNever;
   int e_troll = want_sw ? i_lo : kNever;
   int e_pf = i_lo;
@@ -645,8 +675,8 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 
   // vapour pressure interpolant: knots (t_t_min[d], vp_daily[d]/1000), NaN outside, the NaN ends
   // filled by pandas bfill / ffill (disaggregate.py:99-101)
-  int e_vp;
-  {
+  int e_vp = kNever;
+  if (thermo) {
     const double xv_first = vp_knot_x(c, 0), xv_last = vp_knot_x(c, D - 1);
     const int i_head = max(first_step_ge(xv_first, ts, inv_ts), 0);   // first step >= x_v[0]
     const int i_tail = first_step_gt(xv_last, ts, inv_ts) - 1;        // last step <= x_v[D-1]
@@ -688,9 +718,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   OutT *const o_sh = reinterpret_cast<OutT *>(a.out.var[MSB_V_SPEC_HUMID]) + obase;
   OutT *const o_tk = reinterpret_cast<OutT *>(a.out.var[MSB_V_TSKC]) + obase;
   OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + obase;
-  auto put = [&](OutT *ptr, int v, double val) {
+  auto conv = [&](int v, double val) {
     if (UNITS) val = fma(val, a.out.scale[v], a.out.offset[v]);
-    __stcs(ptr + ooff, (OutT)val);   // streaming store: outputs are never re-read by this kernel
+    return (OutT)val;
+  };
+  auto put = [&](OutT *ptr, int v, double val) {
+    __stcs(ptr + ooff, conv(v, val));   // streaming store: outputs are never re-read by this kernel
   };
 
   // Lanes of a warp stay in lockstep on the step index (coalesced stores), so the event-free run
@@ -698,12 +731,14 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const unsigned lanes = __activemask();
   int i = i_lo;
   while (i < i_hi) {
+    if (want_sw) ss = (int)(q_next - q_cur) - 2 * C;   // the hot loop only advances the pointer
     if (i == i_event) {
       // ================= event handler (cold): pure state updates =============================
       if (i == e_mfol) {   // step after a straddling roll: tskc / wind settle on the new day
         tk_cur = slot[kS_TKN][tid];
         wd_cur = slot[kS_WDN][tid];
         tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
+        wd_o = conv(MSB_V_WIND, wd_cur); tk_o = conv(MSB_V_TSKC, tk_cur);
         e_mfol = kNever;
       }
       if (i == e_mroll) {  // minute stream reaches the end of its source day (:347-351, :376, :611)
@@ -742,6 +777,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
           }
         }
         tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
+        wd_o = conv(MSB_V_WIND, wd_cur); tk_o = conv(MSB_V_TSKC, tk_cur);
         e_mroll = i + 1 + (kMinPerDay - (sm + ts)) / ts;
         {   // what the events of the NEXT output day will load: pull it into L2 a day ahead
           const int dn = min(md + 3, D - 1);
@@ -797,7 +833,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         }
         e_troll = i + 1 + (kTiny - (ss + C)) / C;
       }
-      if (i >= e_vp) {     // vapour-pressure knot crossed (searchsorted side='left')
+      if (thermo && i >= e_vp) {     // vapour-pressure knot crossed (searchsorted side='left')
         int vn = min(vd + 1, D - 1);     // usual case: the next knot is the new upper end
         double xl = rec(kR_XMIN, vn - 1), yl = rec(kR_VY, vn - 1);
         double xh = rec(kR_XMIN, vn), yh = rec(kR_VY, vn);
@@ -812,7 +848,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
           e_vp = first_step_gt(xh, ts, inv_ts);
         }
       }
-      if (i >= e_cub) {    // PCHIP knot crossed (searchsorted side='right')
+      if (thermo && i >= e_cub) {    // PCHIP knot crossed (searchsorted side='right')
         int kn = kc + 1;                 // usual case: the next interval; all six loads in flight
         double x0 = rkx(kn), x1 = rkx(kn + 1);
         double y0 = rec((kn & 1) ? kR_YMAX : kR_YMIN, (kn >> 1) - 1);
@@ -844,13 +880,13 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
       }
       if (i == e_pf) {     // once per output day (all lanes together): pull what this day's events
         // will load into L1, so that they wait for an L1 hit instead of an L2 / DRAM round trip
-        for (int j = kc + 1; j <= min(kc + 3, nk - 1); ++j) {
+        for (int j = kc + 1; thermo && j <= min(kc + 3, nk - 1); ++j) {
           const double *rp = rec0 + (long)((j >> 1) - 1) * ld;
           prefetch_l1(rp + (size_t)((j & 1) ? kR_XMAX : kR_XMIN) * plane);
           prefetch_l1(rp + (size_t)((j & 1) ? kR_YMAX : kR_YMIN) * plane);
           prefetch_l1(rp + (size_t)((j & 1) ? kR_DMAX : kR_DMIN) * plane);
         }
-        for (int v = vd; v <= min(vd + 1, D - 1); ++v) {
+        for (int v = vd; thermo && v <= min(vd + 1, D - 1); ++v) {
           prefetch_l1(rec0 + (long)v * ld + (size_t)kR_XMIN * plane);
           prefetch_l1(rec0 + (long)v * ld + (size_t)kR_VY * plane);
         }
@@ -871,52 +907,60 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         }
         e_pf += tpd;
       }
-      if (want_sw) q_pref = q_cur[ss + C];                  // re-prime the pipelined table load
+      if (want_sw) {       // re-prime the pipelined table load: this step's entry, pointer to the next
+        q_pref = q_cur[ss + C];
+        q_next = q_cur + ss + 2 * C;
+      }
       i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), min(e_mroll, e_pf)));
       i_event = max(i_event, i + 1);
     }
     const int i_stop = min(__reduce_min_sync(lanes, i_event), i_hi);
 
     // ================= hot path: event-free run [i, i_stop) ===================================
+    const unsigned ooff_stop = ooff + (unsigned)(i_stop - i) * ostride;
+    i = i_stop;
 #pragma unroll 1
-    for (; i < i_stop; ++i, x += dx, ooff += ostride) {
+    for (; ooff != ooff_stop; x += dx, ooff += ostride) {
       // -- tiny-step stream: this step's table entry was requested one step ago; request the next
       //    one now and pull the same position of tomorrow's row into L2 --
       const double qn = q_pref;
-      ss += C;
       if (want_sw) {
-        q_pref = load_early(q_cur + ss + C);
-        prefetch_l1(q_cur + ss + 2 * C);
-        prefetch_l2(q_cur + ss + C + kQLd);
+        const double *q_nn = q_next + C;   // entry of the step after next: to L1 now, loaded next step
+        prefetch_l1(q_nn);
+        prefetch_l2(q_next + kQLd);
+        q_pref = load_early(q_next);
+        q_next = q_nn;
       }
 
-      // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
-      const double temp = cubic_eval(cub, x);
-      const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
-      const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
-      const double es = es0 * (temp < 0.0 ? corr : 1.0);
+      double temp = 0.0, vp = 0.0, rh = 0.0, ap = 0.0, lw = 0.0;
+      if (thermo) {
+        // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
+        temp = cubic_eval(cub, x);
+        const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
+        const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
+        const double es = es0 * (temp < 0.0 ? corr : 1.0);
 
-      // -- vapour pressure (linear, clamped to saturation inside the knots) :480-487 --
-      double vp = fma(x - xvl, vslope, yvl);
-      vp = (v_interior && es < vp) ? es : vp;
+        // -- vapour pressure (linear, clamped to saturation inside the knots) :480-487 --
+        vp = fma(x - xvl, vslope, yvl);
+        vp = (v_interior && es < vp) ? es : vp;
 
-      // -- relative humidity :444-446, air pressure :401-403 --
-      const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);   // 100*1000*vp/(svp in Pa)
-      const double ap = exp_hot(fma(pr_num, rcp_nr(pr_corr + temp), K.ln_p), etab, K);
+        // -- relative humidity :444-446, air pressure :401-403 --
+        rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);   // 100*1000*vp/(svp in Pa)
+        ap = exp_hot(fma(pr_num, rcp_nr(pr_corr + temp), K.ln_p), etab, K);
 
-      // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF inline; tk_a / tk_b carry STEFAN_B) --
-      double lw = 0.0;
-      if (FAST_LW) {
-        if (VARS == kVarsExample || want(MSB_V_LONGWAVE)) {
-          const double at = temp + K.kelvin;
-          const double xx = (465.0 * vp) * rcp_nr(at);             // 46.5 * (10 vp) / T
-          const double ee = exp_hot(-sqrt_fast(fma(3., xx, K.k12)), etab, K);
-          const double e1 = fma(-(1.0 + xx), ee, 1.0);
-          const double t2 = at * at;
-          lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+        // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF inline; tk_a / tk_b carry STEFAN_B) --
+        if (FAST_LW) {
+          if (want(MSB_V_LONGWAVE)) {
+            const double at = temp + K.kelvin;
+            const double xx = (465.0 * vp) * rcp_nr(at);             // 46.5 * (10 vp) / T
+            const double ee = exp_hot(-sqrt_hot(fma(3., xx, K.k12), K), etab, K);
+            const double e1 = fma(-(1.0 + xx), ee, 1.0);
+            const double t2 = at * at;
+            lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+          }
+        } else if (want(MSB_V_LONGWAVE)) {
+          lw = longwave(p, temp, vp, tk_cur);
         }
-      } else if (want(MSB_V_LONGWAVE)) {
-        lw = longwave(p, temp, vp, tk_cur);
       }
 
       // -- minute stream: precipitation :265-352 (tskc / wind are constant between events) --
@@ -937,30 +981,19 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         sw_carry = 0.0;
       }
 
-      if (VARS == kVarsExample) {
-        put(o_temp, MSB_V_TEMP, temp);
-        put(o_vp, MSB_V_VAPOR_PRESSURE, vp);
-        put(o_rh, MSB_V_REL_HUMID, rh);
-        put(o_ap, MSB_V_AIR_PRESSURE, ap);
-        put(o_wd, MSB_V_WIND, wd_cur);
-        put(o_lw, MSB_V_LONGWAVE, lw);
-        put(o_prec, MSB_V_PREC, pr);
-        put(o_sw, MSB_V_SHORTWAVE, sw);
-      } else {
-        if (want(MSB_V_TEMP)) put(o_temp, MSB_V_TEMP, temp);
-        if (want(MSB_V_VAPOR_PRESSURE)) put(o_vp, MSB_V_VAPOR_PRESSURE, vp);
-        if (want(MSB_V_REL_HUMID)) put(o_rh, MSB_V_REL_HUMID, rh);
-        if (want(MSB_V_AIR_PRESSURE)) put(o_ap, MSB_V_AIR_PRESSURE, ap);
-        if (want(MSB_V_TSKC)) put(o_tk, MSB_V_TSKC, tk_cur);
-        if (want_wind) put(o_wd, MSB_V_WIND, wd_cur);
-        if (want(MSB_V_SPEC_HUMID)) {   // specific humidity :423-424
-          const double mix = (kEps * vp) * rcp_nr(ap - vp);
-          put(o_sh, MSB_V_SPEC_HUMID, mix * rcp_nr(1 + mix));
-        }
-        if (want(MSB_V_LONGWAVE)) put(o_lw, MSB_V_LONGWAVE, lw);
-        if (want_prec) put(o_prec, MSB_V_PREC, pr);
-        if (want_sw) put(o_sw, MSB_V_SHORTWAVE, sw);
+      if (want(MSB_V_TEMP)) put(o_temp, MSB_V_TEMP, temp);
+      if (want(MSB_V_VAPOR_PRESSURE)) put(o_vp, MSB_V_VAPOR_PRESSURE, vp);
+      if (want(MSB_V_REL_HUMID)) put(o_rh, MSB_V_REL_HUMID, rh);
+      if (want(MSB_V_AIR_PRESSURE)) put(o_ap, MSB_V_AIR_PRESSURE, ap);
+      if (want(MSB_V_TSKC)) __stcs(o_tk + ooff, tk_o);
+      if (want_wind) __stcs(o_wd + ooff, wd_o);
+      if (want(MSB_V_SPEC_HUMID)) {   // specific humidity :423-424
+        const double mix = (kEps * vp) * rcp_nr(ap - vp);
+        put(o_sh, MSB_V_SPEC_HUMID, mix * rcp_nr(1 + mix));
       }
+      if (want(MSB_V_LONGWAVE)) put(o_lw, MSB_V_LONGWAVE, lw);
+      if (want_prec) put(o_prec, MSB_V_PREC, pr);
+      if (want_sw) put(o_sw, MSB_V_SHORTWAVE, sw);
     }
   }
 
@@ -1084,7 +1117,10 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4;
   disagg_prepare_kernel<<<dim3(cell_blocks, a.n_rec), 128, 0, st>>>(a);
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
-  if (example) MSB_LAUNCH(float, true, false, kVarsExample);   // reference defaults, 8 variables
+  if (example) {   // reference defaults, 8 variables: the thermodynamic half and the stream half
+    MSB_LAUNCH(float, true, false, kVarsThermo);
+    MSB_LAUNCH(float, true, false, kVarsStreams);
+  }
   else if (out->dtype == 4) {
     if (fast_lw) MSB_LAUNCH(float, true, true, kVarsAny); else MSB_LAUNCH(float, false, true, kVarsAny);
   } else {
