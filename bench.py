@@ -287,7 +287,7 @@ def main():
     ring = [{v: torch.empty((tile * tpd, n), dtype=torch.float32, device=dev) for v in OUT_VARS}
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
-    rounds = 3  # ceil(max_iter 24 / 8), daily.cu
+    rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
     launches_per_step = 1 + 2 * rounds + 1 + 2 * n_tiles   # solar, daily passes, (prepare + stream) per tile
     ev = lambda: torch.cuda.Event(enable_timing=True)
 

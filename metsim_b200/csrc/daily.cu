@@ -20,7 +20,7 @@
 
 namespace msb {
 
-constexpr int kEvalsPerRound = 8;
+constexpr int kEvalsPerRound = 6;   // the fixed point needs 4-6 evaluations on realistic forcings
 constexpr int kDailyThreads = 128;
 
 struct DailyLaunch {
@@ -112,6 +112,7 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
   __syncthreads();
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= f.n_cells) return;
+  if (PASS == 1 && k_off > 0 && out.status[3] == 0) return;   // every cell converged earlier
   const int chunk = blockIdx.y;
   const int D = f.n_days;
   const long ld = f.ld;
@@ -187,14 +188,15 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
     if (prec > p.sw_prec_thresh) tf *= p.rain_scalar;
     // day-invariant part of calc_pet (physics.py:62-92)
     const double lhvap = 2.5023e6 - 2430.54 * t_day;
-    const double gamma = kCp * cc.pa / (lhvap * kEps);
+    const double inv_lhvap = rcp_nr(lhvap);
+    const double gamma = (kCp * cc.pa) * (inv_lhvap * (1.0 / kEps));
     const double t1 = t_day + 0.2, t2 = t_day - 0.2;
-    const double sl = (svp_pa(t1, etab) - svp_pa(t2, etab)) / (t1 - t2);
-    const double c1 = 1.26 * (sl / (sl + gamma));
+    const double sl = div_nr(svp_pa(t1, etab) - svp_pa(t2, etab), t1 - t2);
+    const double c1 = 1.26 * div_nr(sl, sl + gamma);
     v.tk = t_min + kKelvin;
     v.base = -0.127 + 1.121 * 1.003 + 0.0006 * dtr;
     v.g = potrad * tf;
-    v.b = ((c1 * 0.72) * daylength / lhvap) / sp80;
+    v.b = (((c1 * 0.72) * daylength) * inv_lhvap) * rcp_nr(sp80);
 
     double tdew = t_min;                                                // mtclim.py:54
     if (PASS == 1) {
@@ -211,7 +213,7 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
       const double vp = svp_pa(tdew, etab);                             // mtclim.py:73-79
       const double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);
       const double sw = potrad * t_tmax * tf;
-      const double pet = ((c1 * (sw * 0.72) * daylength) / lhvap) / 10. * 10.0;
+      const double pet = ((c1 * (sw * 0.72) * daylength) * inv_lhvap) / 10. * 10.0;
       const double tskc = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
       double *const *o_ = out.var;
       if (o_[MSB_D_T_DAY]) o_[MSB_D_T_DAY][o] = t_day;
@@ -237,7 +239,8 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
 
 // while np.sqrt(np.mean((tdew_temp - tdew_old)**2)) > tdew_tol  (mtclim.py:63)
 __global__ void daily_reduce_kernel(msb_params p, int n_cells, int n_days, int n_chunks, int k_off,
-                                    const double *__restrict__ partial, int32_t *n_iter) {
+                                    const double *__restrict__ partial, int32_t *n_iter,
+                                    int32_t *status) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
   if (k_off == 0) n_iter[cell] = 0;
@@ -248,6 +251,7 @@ __global__ void daily_reduce_kernel(msb_params p, int n_cells, int n_days, int n
     const double rms = sqrt(s / (double)n_days);
     if (!(rms > p.tdew_tol)) { n_iter[cell] = k_off + k + 1; return; }
   }
+  atomicAdd(&status[3], 1);   // still iterating: the next round has work to do
 }
 
 }  // namespace msb
@@ -304,9 +308,10 @@ extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
   for (int r = 0; r < rounds; ++r) {
     int k_off = r * kEvalsPerRound;
     daily_kernel<1><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, k_off, 0);
+    MSB_CUDA(cudaMemsetAsync(out->status + 3, 0, sizeof(int32_t), st));   // unconverged-cell count
     daily_reduce_kernel<<<(f->n_cells + 255) / 256, 256, 0, st>>>(*p, f->n_cells, f->n_days,
                                                                   l.n_chunks, k_off, out->partial,
-                                                                  out->n_iter);
+                                                                  out->n_iter, out->status);
   }
   daily_kernel<2><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0,
                                                   rounds * kEvalsPerRound);

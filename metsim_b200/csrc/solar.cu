@@ -100,6 +100,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
                   msb_solar_tables tb) {
   __shared__ double row[kTiny];
   __shared__ double qs[kQLd];
+  double *const etab = qs;   // exp table: lives in qs[] until the prefix scan overwrites it (after a barrier)
   __shared__ double part[kWarps][kTT + 1];
   __shared__ double warp_tot[kWarps];
   __shared__ int s_rise, s_set;
@@ -115,6 +116,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const double kLnTBase = -0.13926206733350766;  // ln(0.87)
 
   for (int j = tid; j < kTiny; j += kK1Threads) row[j] = 0.0;
+  exp_table_init(etab);
   if (tid == 0) { s_rise = -1; s_set = -1; }
   __syncthreads();
 
@@ -126,37 +128,46 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
 #pragma unroll
   for (int m = 0; m <= kTT; ++m) m_loc[m] = 0.0;
 
-  for (int k = tid; k < n; k += kK1Threads) {
-    double h = __dadd_rn(start, __dmul_rn((double)k, dh));
-    double cza = (k == 0) ? cza_first : __dadd_rn(__dmul_rn(cosegeom, cos(h)), sinegeom);
-    double dfa = 0.0;
-    if (cza > 0.0) {
-      dfa = beam * cza;                                  // physics.py:252
-      double am = 1.0 / (cza + 0.0000001);
-      if (am > 2.9) {
-        int ami = (int)(acos(cza) / kRadPerDeg) - 69;
-        ami = min(max(ami, 0), 20);
-        am = c_optam[ami];
-      }
-      m_loc[kTT] += dfa;
-      // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
-      double a = am * kLnTBase;
-      double term = exp(a * MSB_TT_P0) * dfa;
-      m_loc[0] += term;
+  // Each thread walks a contiguous chunk of hour-angle steps: cos(h) comes from one library
+  // sincos at the chunk start and the rotation by dh afterwards (<= 12 steps, error ~1e-15), and
+  // the tiny-step index of step k+1 is carried over as the index of the next step.
+  const int per = (n + kK1Threads - 1) / kK1Threads;
+  const int k_lo = min(tid * per, n), k_hi = min(k_lo + per, n);
+  if (k_lo < k_hi) {
+    const double cd = cos(dh), sd = sin(dh);
+    double ch, sh;
+    sincos(__dadd_rn(start, __dmul_rn((double)k_lo, dh)), &sh, &ch);
+    int ts = tiny_index(__dadd_rn(start, __dmul_rn((double)k_lo, dh)));
+    for (int k = k_lo; k < k_hi; ++k) {
+      const double cza = (k == 0) ? cza_first : __dadd_rn(__dmul_rn(cosegeom, ch), sinegeom);
+      double dfa = 0.0;
+      if (cza > 0.0) {
+        dfa = beam * cza;                                  // physics.py:252
+        double am = rcp_nr(cza + 0.0000001);
+        if (am > 2.9) {
+          int ami = (int)(acos(cza) / kRadPerDeg) - 69;
+          ami = min(max(ami, 0), 20);
+          am = c_optam[ami];
+        }
+        m_loc[kTT] += dfa;
+        // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
+        const double a = am * kLnTBase;
+        double term = exp_acc(a * MSB_TT_P0, etab) * dfa;
+        m_loc[0] += term;
 #pragma unroll
-      for (int m = 1; m < kTT; ++m) {
-        term *= a * (1.0 / (double)m);
-        m_loc[m] += term;
+        for (int m = 1; m < kTT; ++m) {
+          term *= a * (1.0 / (double)m);
+          m_loc[m] += term;
+        }
       }
+      // "assignment, not accumulation" (physics.py:267): the last k mapping to an index wins
+      int ts_next = -1;
+      if (k + 1 < n) ts_next = tiny_index(__dadd_rn(start, __dmul_rn((double)(k + 1), dh)));
+      if (ts_next != ts) row[ts] = dfa;
+      ts = ts_next;
+      const double cn = fma(ch, cd, -(sh * sd)), sn = fma(sh, cd, ch * sd);   // rotate by dh
+      ch = cn; sh = sn;
     }
-    // "assignment, not accumulation" (physics.py:267): the last k mapping to an index wins
-    int ts = tiny_index(h);
-    bool last = (k == n - 1);
-    if (!last) {
-      double hn = __dadd_rn(start, __dmul_rn((double)(k + 1), dh));
-      last = tiny_index(hn) != ts;
-    }
-    if (last) row[ts] = dfa;
   }
 
   // deterministic two-level reduction of the kTT+1 accumulators (fixed shuffle tree, fixed order)
