@@ -288,7 +288,7 @@ def main():
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
     rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
-    launches_per_step = 1 + 2 * rounds + 1 + 2 * n_tiles   # solar, daily passes, (prepare + stream) per tile
+    launches_per_step = 1 + 2 * rounds + 1 + 3 * n_tiles   # solar, daily passes, (prepare + 2 stream kernels) per tile
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):
@@ -412,7 +412,9 @@ def main():
                              % (len(OUT_VARS) * tile * tpd * n * 4 / 1e9, 4 * n_days * n * 8 / 1e9)},
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
                              "disaggregate": float(br[2])},
-            "roofline": {"bound": "hbm", "kernel": "disagg_kernel<float,true>", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + disagg_kernel<thermo> + "
+                                                   "disagg_kernel<streams>, timed together per 32-day call",
+                         "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_cell_timestep": bytes_per_cts,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": float(disagg_ms_per_launch),

@@ -383,6 +383,16 @@ __device__ __noinline__ double prec_fill(const msb_params &p, const msb_forcing 
   return nan("");
 }
 
+// value of the last valid step before step i (what pandas ffill repeats); NaN if there is none
+__device__ __noinline__ double prec_lookback(const msb_params &p, const msb_forcing &f, const Cell &c,
+                                             long i) {
+  for (long j = i - 1; j >= 0; --j) {
+    double v = prec_step_generic(p, f, c, j);
+    if (v == v) return v;
+  }
+  return nan("");
+}
+
 // vapour pressure of ONE step at an end of the interpolant's support: the value pandas
 // back-fills into the leading NaNs (lo = true: knots 0, 1) or forward-fills into the trailing
 // ones (knots D-2, D-1) -- disaggregate.py:480-487, :99-101.
@@ -545,7 +555,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
 // prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
 // is read ts minutes per output step; the stream positions and the current source day live in
 // registers and roll to the next source day once per day (an event).
-constexpr int disagg_min_blocks(int vars) { return vars == kVarsStreams ? 8 : (vars == kVarsThermo ? 5 : 4); }
+constexpr int disagg_min_blocks(int vars) { return vars == kVarsStreams ? 6 : (vars == kVarsThermo ? 5 : 4); }
 
 template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
 __global__ void __launch_bounds__(kDisaggThreads, disagg_min_blocks(VARS))
@@ -645,6 +655,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   PrecDay pd;                                                // minute stream: precipitation
   pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
   double s_prev = 0.0, p_carry = 0.0;
+  double pr = 0.0;                 // precipitation of the previous step (what a NaN day repeats)
+  double p_base = 0.0;             // what every step starts from: 0, or the fill value on a NaN day
+  bool nan_cur = false;            // the current source day is a 0/0 day (disaggregate.py:327)
   double rd_cur = 0.0, q_prev = 0.0, q_pref = 0.0, sw_carry = 0.0;   // tiny-step stream: shortwave
   const double *q_cur = qrow;
 
@@ -662,11 +675,10 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
                                                // advances this pointer; ss is recovered from it)
   int kc = max(0, 2 * (d_lo + 1) - 4) - 1;      // PCHIP interval: the first event walks right from kc + 1
   int vd = 0;                                   // upper knot of the vapour-pressure segment (event: from vd + 1)
-  bool had_nan = false;
+  bool need_fixup = false;                      // leading NaN run: needs the back-fill pass
   int e_cub = thermo ? i_lo : kNever, e_day = want_sw ? i_lo : kNever;
   int e_mroll = i_lo, e_mfol = kNever;
   int e_troll = want_sw ? i_lo : kNever;
-  int e_pf = i_lo;
   int e_noon = kNever;
   if (want_sw) {
     const int s0 = ss - kTiny;                  // first window [s0, s0 + C)
@@ -750,13 +762,26 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
           const double tk_n = a.tskc_d[on];
           const double wd_n = want_wind ? f.wind[on] : 0.0;
           PrecDay pn = pd;
-          if (want_prec) prec_of(mdn, pn);
+          bool nan_new = false;
+          double fill = 0.0;               // pandas ffill: a NaN step repeats the last valid value
+          if (want_prec) {
+            prec_of(mdn, pn);
+            nan_new = !(pn.f == pn.f);
+            if (nan_cur) fill = p_base;                      // already inside a NaN run
+            else if (nan_new) {
+              if (i > i_lo) fill = pr;                       // the previous step of this tile
+              else {                                         // the tile starts at a NaN day: look back
+                fill = prec_lookback(p, f, c, i);
+                if (!(fill == fill)) need_fixup = true;      // nothing valid before: back-fill later
+              }
+            }
+          }
           int pos;                         // minute of the new day where the cumulative sum restarts
           if (sm >= kMinPerDay) {          // clean switch
             sm -= kMinPerDay;
             pos = sm;
             tk_cur = tk_n; wd_cur = wd_n;
-            p_carry = 0.0;
+            p_carry = nan_new ? fill : 0.0;
           } else {                         // straddle: n1 minutes of the old day, n2 of the new one
             const int n2 = sm + ts - kMinPerDay, n1 = ts - n2;
             tk_cur = ((double)n1 * tk_cur + (double)n2 * tk_n) * inv_ts;
@@ -764,32 +789,26 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
             slot[kS_TKN][tid] = tk_n;
             slot[kS_WDN][tid] = wd_n;
             e_mfol = i + 1;
-            if (want_prec)   // old-day part + new-day part; the hot path adds f_new * 0 to it
-              p_carry = pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2);
+            if (want_prec)   // old-day part + new-day part (NaN if either day is); the hot path
+                             // adds f_new * 0 to it
+              p_carry = (nan_cur || nan_new)
+                            ? fill
+                            : pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2);
             pos = n2;
             sm = n2 - ts;                  // the hot path advances it to n2
           }
           md = mdn;
           if (want_prec) {
             pd = pn;
+            if (nan_new) pd.f = 0.0;       // every step of a NaN day is p_base = the fill value
+            p_base = nan_new ? fill : 0.0;
+            nan_cur = nan_new;
             s_prev = prec_cum(pd, pos);
-            had_nan |= !(pd.f == pd.f) || !(p_carry == p_carry);
           }
         }
         tk_a = kStefanB * tk_cur; tk_b = kStefanB * (1.0 - tk_cur);
         wd_o = conv(MSB_V_WIND, wd_cur); tk_o = conv(MSB_V_TSKC, tk_cur);
         e_mroll = i + 1 + (kMinPerDay - (sm + ts)) / ts;
-        {   // what the events of the NEXT output day will load: pull it into L2 a day ahead
-          const int dn = min(md + 3, D - 1);
-          const size_t op = (size_t)dn * ld + cell;
-          prefetch_l2(a.tskc_d + op);
-          if (want_wind) prefetch_l2(f.wind + op);
-          if (has_rec(dn)) {
-            const double *rp = rec0 + (long)dn * ld;
-#pragma unroll
-            for (int fld = 0; fld < MSB_REC_FIELDS; ++fld) prefetch_l2(rp + (size_t)fld * plane);
-          }
-        }
       }
       // tiny-step stream reaches the end of its source day / table row (:656-678); the clean
       // switch comes before, the straddle after the day-start row selection (reference order)
@@ -878,40 +897,11 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         q_prev -= slot[kS_ROWTOT][tid];
         e_noon += tpd;
       }
-      if (i == e_pf) {     // once per output day (all lanes together): pull what this day's events
-        // will load into L1, so that they wait for an L1 hit instead of an L2 / DRAM round trip
-        for (int j = kc + 1; thermo && j <= min(kc + 3, nk - 1); ++j) {
-          const double *rp = rec0 + (long)((j >> 1) - 1) * ld;
-          prefetch_l1(rp + (size_t)((j & 1) ? kR_XMAX : kR_XMIN) * plane);
-          prefetch_l1(rp + (size_t)((j & 1) ? kR_YMAX : kR_YMIN) * plane);
-          prefetch_l1(rp + (size_t)((j & 1) ? kR_DMAX : kR_DMIN) * plane);
-        }
-        for (int v = vd; thermo && v <= min(vd + 1, D - 1); ++v) {
-          prefetch_l1(rec0 + (long)v * ld + (size_t)kR_XMIN * plane);
-          prefetch_l1(rec0 + (long)v * ld + (size_t)kR_VY * plane);
-        }
-        const int mdn = (md + 1 == D) ? 0 : md + 1;
-        prefetch_l1(a.tskc_d + (size_t)mdn * ld + cell);
-        if (want_wind) prefetch_l1(f.wind + (size_t)mdn * ld + cell);
-        if (want_prec && has_rec(mdn)) {
-          const double *rp = rec0 + (long)mdn * ld;
-          prefetch_l1(rp + (size_t)kR_PPACK * plane); prefetch_l1(rp + (size_t)kR_HSP * plane);
-          prefetch_l1(rp + (size_t)kR_HSQ * plane); prefetch_l1(rp + (size_t)kR_PF * plane);
-        }
-        if (want_sw) {
-          const int sdn = (sd + 1 == D) ? 0 : sd + 1;
-          if (has_rec(sdn)) prefetch_l1(rec0 + (long)sdn * ld + (size_t)kR_RAD * plane);
-          const double *qn = q_of(doy_at(c, i / tpd) - 1 + qs + 1);
-          const int k2 = ((ss % C) + C) % C;
-          prefetch_l1(qn + k2); prefetch_l1(qn); prefetch_l1(qn + kTiny + 1); prefetch_l1(q_cur + kTiny);
-        }
-        e_pf += tpd;
-      }
       if (want_sw) {       // re-prime the pipelined table load: this step's entry, pointer to the next
         q_pref = q_cur[ss + C];
         q_next = q_cur + ss + 2 * C;
       }
-      i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), min(e_mroll, e_pf)));
+      i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), e_mroll));
       i_event = max(i_event, i + 1);
     }
     const int i_stop = min(__reduce_min_sync(lanes, i_event), i_hi);
@@ -964,13 +954,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
       }
 
       // -- minute stream: precipitation :265-352 (tskc / wind are constant between events) --
-      double pr = 0.0;
       sm += ts;
       if (want_prec) {
         const double s1 = prec_cum(pd, sm);
         pr = fma(pd.f, s1 - s_prev, p_carry);
         s_prev = s1;
-        p_carry = 0.0;
+        p_carry = p_base;
       }
 
       // -- shortwave :618-680 --
@@ -997,8 +986,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     }
   }
 
-  // ---- NaN precipitation days (0/0 triangles): pandas ffill, then bfill (disaggregate.py:130) --
-  if (want_prec && had_nan) {
+  // ---- a NaN run (0/0 triangle days) that reaches back to the start of the record: pandas ffill
+  //      found nothing, bfill takes the first valid step after it (disaggregate.py:130) --
+  if (want_prec && need_fixup) {
     double last = 0.0;
     bool last_known = false;
     ooff = (unsigned)cell;
