@@ -368,21 +368,6 @@ __device__ __noinline__ double prec_step_generic(const msb_params &p, const msb_
   return v;
 }
 
-// pandas ffill then bfill of one NaN step (disaggregate.py:130)
-__device__ __noinline__ double prec_fill(const msb_params &p, const msb_forcing &f, const Cell &c,
-                                         long i) {
-  const long T = (long)c.D * c.tpd;
-  for (long j = i - 1; j >= 0; --j) {
-    double v = prec_step_generic(p, f, c, j);
-    if (v == v) return v;
-  }
-  for (long j = i + 1; j < T; ++j) {
-    double v = prec_step_generic(p, f, c, j);
-    if (v == v) return v;
-  }
-  return nan("");
-}
-
 // value of the last valid step before step i (what pandas ffill repeats); NaN if there is none
 __device__ __noinline__ double prec_lookback(const msb_params &p, const msb_forcing &f, const Cell &c,
                                              long i) {
@@ -989,15 +974,16 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   // ---- a NaN run (0/0 triangle days) that reaches back to the start of the record: pandas ffill
   //      found nothing, bfill takes the first valid step after it (disaggregate.py:130) --
   if (want_prec && need_fixup) {
-    double last = 0.0;
-    bool last_known = false;
-    ooff = (unsigned)cell;
-    for (int j = i_lo; j < i_hi; ++j, ooff += ostride) {
-      const double v = prec_step_generic(p, f, c, j);
-      if (v == v) { last = v; last_known = true; continue; }
-      if (!last_known) { last = prec_fill(p, f, c, j); last_known = true; }
-      put(o_prec, MSB_V_PREC, last);
+    // every step before this tile is NaN, so the tile opens with the leading NaN run of the
+    // record: find the first valid step after it and write its value over the run
+    double fillv = nan("");
+    int j = i_lo;
+    for (; j < T; ++j) {
+      fillv = prec_step_generic(p, f, c, j);
+      if (fillv == fillv) break;
     }
+    ooff = (unsigned)cell;
+    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) put(o_prec, MSB_V_PREC, fillv);
   }
 }
 
