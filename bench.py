@@ -288,7 +288,7 @@ def main():
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
     rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
-    launches_per_step = 1 + 2 * rounds + 1 + 3 * n_tiles   # solar, daily passes, (prepare + 2 stream kernels) per tile
+    launches_per_step = 2 + 2 * rounds + 1 + 3 * n_tiles   # 2 solar, daily passes, (prepare + 2 stream kernels) per tile
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):

@@ -643,7 +643,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   double pr = 0.0;                 // precipitation of the previous step (what a NaN day repeats)
   double p_base = 0.0;             // what every step starts from: 0, or the fill value on a NaN day
   bool nan_cur = false;            // the current source day is a 0/0 day (disaggregate.py:327)
-  double rd_cur = 0.0, q_prev = 0.0, q_pref = 0.0, sw_carry = 0.0;   // tiny-step stream: shortwave
+  double rd_cur = 0.0, q_prev = 0.0, q_pref = 0.0, q_pref2 = 0.0, sw_carry = 0.0;   // tiny-step stream
   const double *q_cur = qrow;
 
   // ---- cold state: stream positions and the event schedule ------------------------------------
@@ -656,7 +656,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const int qs = off_tiny < 0 ? -1 : 0;
   int sd = wrap(wrap(d_lo + qs) - 1);
   int ss = off_tiny - qs * kTiny + kTiny;
-  const double *q_next = q_cur + ss + 2 * C;   // table entry the hot loop requests next (it only
+  const double *q_next = q_cur + ss + 3 * C;   // table entry the hot loop requests next (it only
                                                // advances this pointer; ss is recovered from it)
   int kc = max(0, 2 * (d_lo + 1) - 4) - 1;      // PCHIP interval: the first event walks right from kc + 1
   int vd = 0;                                   // upper knot of the vapour-pressure segment (event: from vd + 1)
@@ -728,7 +728,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   const unsigned lanes = __activemask();
   int i = i_lo;
   while (i < i_hi) {
-    if (want_sw) ss = (int)(q_next - q_cur) - 2 * C;   // the hot loop only advances the pointer
+    if (want_sw) ss = (int)(q_next - q_cur) - 3 * C;   // the hot loop only advances the pointer
     if (i == i_event) {
       // ================= event handler (cold): pure state updates =============================
       if (i == e_mfol) {   // step after a straddling roll: tskc / wind settle on the new day
@@ -882,9 +882,10 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         q_prev -= slot[kS_ROWTOT][tid];
         e_noon += tpd;
       }
-      if (want_sw) {       // re-prime the pipelined table load: this step's entry, pointer to the next
+      if (want_sw) {       // re-prime the pipelined table loads: the entries of this step and the next
         q_pref = q_cur[ss + C];
-        q_next = q_cur + ss + 2 * C;
+        q_pref2 = q_cur[ss + 2 * C];
+        q_next = q_cur + ss + 3 * C;
       }
       i_event = min(min(min(e_mfol, e_day), min(e_vp, e_cub)), min(min(e_noon, e_troll), e_mroll));
       i_event = max(i_event, i + 1);
@@ -899,12 +900,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
       // -- tiny-step stream: this step's table entry was requested one step ago; request the next
       //    one now and pull the same position of tomorrow's row into L2 --
       const double qn = q_pref;
-      if (want_sw) {
-        const double *q_nn = q_next + C;   // entry of the step after next: to L1 now, loaded next step
-        prefetch_l1(q_nn);
+      if (want_sw) {     // two loads in flight: the entry of the step after next is requested now
+        q_pref = q_pref2;
+        q_pref2 = load_early(q_next);
         prefetch_l2(q_next + kQLd);
-        q_pref = load_early(q_next);
-        q_next = q_nn;
+        q_next += C;
+        prefetch_l1(q_next + C);
       }
 
       double temp = 0.0, vp = 0.0, rh = 0.0, ap = 0.0, lw = 0.0;

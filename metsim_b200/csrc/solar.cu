@@ -100,8 +100,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
                   msb_solar_tables tb) {
   __shared__ double row[kTiny];
   __shared__ double qs[kQLd];
-  double *const etab = qs;   // exp table: lives in qs[] until the prefix scan overwrites it (after a barrier)
-  __shared__ double part[kWarps][kTT + 1];
+  __shared__ double part[kWarps];
   __shared__ double warp_tot[kWarps];
   __shared__ int s_rise, s_set;
 
@@ -113,10 +112,8 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const double cza_first = g_cza0[o];
   const int n = g_nstep[o];
   const double dh = kSwRadDt / kSecPerRad;
-  const double kLnTBase = -0.13926206733350766;  // ln(0.87)
 
   for (int j = tid; j < kTiny; j += kK1Threads) row[j] = 0.0;
-  exp_table_init(etab);
   if (tid == 0) { s_rise = -1; s_set = -1; }
   __syncthreads();
 
@@ -124,9 +121,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
   const double start = -hss;
 
-  double m_loc[kTT + 1];   // Taylor moments of trans**am, [kTT] = sum of dir_flat_topa
-#pragma unroll
-  for (int m = 0; m <= kTT; ++m) m_loc[m] = 0.0;
+  double tot_loc = 0.0;    // sum of dir_flat_topa over this thread's steps
 
   // Each thread walks a contiguous chunk of hour-angle steps: cos(h) comes from one library
   // sincos at the chunk start and the rotation by dh afterwards (<= 12 steps, error ~1e-15), and
@@ -143,22 +138,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
       double dfa = 0.0;
       if (cza > 0.0) {
         dfa = beam * cza;                                  // physics.py:252
-        double am = rcp_nr(cza + 0.0000001);
-        if (am > 2.9) {
-          int ami = (int)(acos(cza) / kRadPerDeg) - 69;
-          ami = min(max(ami, 0), 20);
-          am = c_optam[ami];
-        }
-        m_loc[kTT] += dfa;
-        // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
-        const double a = am * kLnTBase;
-        double term = exp_acc(a * MSB_TT_P0, etab) * dfa;
-        m_loc[0] += term;
-#pragma unroll
-        for (int m = 1; m < kTT; ++m) {
-          term *= a * (1.0 / (double)m);
-          m_loc[m] += term;
-        }
+        tot_loc += dfa;
       }
       // "assignment, not accumulation" (physics.py:267): the last k mapping to an index wins
       int ts_next = -1;
@@ -170,20 +150,14 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
     }
   }
 
-  // deterministic two-level reduction of the kTT+1 accumulators (fixed shuffle tree, fixed order)
-#pragma unroll
-  for (int m = 0; m <= kTT; ++m) {
-    double v = warp_sum(m_loc[m]);
-    if (lane == 0) part[warp][m] = v;
+  // deterministic two-level reduction of the row total (fixed shuffle tree, fixed order)
+  {
+    const double v = warp_sum(tot_loc);
+    if (lane == 0) part[warp] = v;
   }
   __syncthreads();
-  if (tid <= kTT) {
-    double v = 0.0;
-    for (int w = 0; w < kWarps; ++w) v += part[w][tid];
-    part[0][tid] = v;
-  }
-  __syncthreads();
-  const double total = part[0][kTT];
+  double total = 0.0;
+  for (int w = 0; w < kWarps; ++w) total += part[w];
 
   const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
   const bool has_day = daylength != 0.0;
@@ -263,23 +237,94 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
     const double day_tot = (kSecPerDay / kSwRadDt) * (kSwRadDt / 60.0);
     if (rise_m == 0.0) rise_m = day_tot / 6;       // disaggregate.py:179-182
     if (set_m == 0.0) set_m = 4 * day_tot / 6;
-    double potrad = has_day ? total / daylength : 0.0;                      // physics.py:276-280
     size_t s = (size_t)r * kRows + i;
-    tb.daylength[s] = daylength;
-    tb.potrad[s] = potrad;
     tb.rise_min[s] = rise_m;
     tb.set_min[s] = set_m;
     if (i == 364) {  // row 365 copies row 364, physics.py:281-284
-      tb.daylength[s + 1] = daylength;
-      tb.potrad[s + 1] = potrad;
       tb.rise_min[s + 1] = rise_m;
       tb.set_min[s + 1] = set_m;
     }
   }
-  if (tid < kTT) {
-    // tt_max0(p) = sum_trans/sum_flat_potrad (physics.py:275); 0 when there is no daylight
-    double c = (has_day && total > 0.0) ? part[0][tid] / total : 0.0;
-    tb.tt_coef[((size_t)r * 365 + i) * kTT + tid] = c;
+}
+
+// K1b -- one WARP per (latitude, yday): the sums over the hour-angle steps that do not need the
+// row in shared memory -- sum of dir_flat_topa (-> potrad) and the Taylor moments of trans**am
+// in the pressure ratio (-> tt_coef).  Lanes walk contiguous chunks of steps; cos(h) is re-seeded
+// from a library sincos every 16 steps and rotated by dh in between.
+constexpr int kMomWarps = 4;
+__global__ void __launch_bounds__(kMomWarps * 32)
+solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
+                     const double *__restrict__ g_sinegeom, const double *__restrict__ g_hss,
+                     const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
+                     msb_solar_tables tb) {
+  __shared__ double etab[kExpTab];
+  exp_table_init(etab);
+  __syncthreads();
+  const int w = blockIdx.x * kMomWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= n_rows) return;
+  const int i = w % 365, r = w / 365;
+  const double cosegeom = g_cosegeom[w], sinegeom = g_sinegeom[w], hss = g_hss[w];
+  const double cza_first = g_cza0[w];
+  const int n = g_nstep[w];
+  const double dh = kSwRadDt / kSecPerRad;
+  const double kLnTBase = -0.13926206733350766;  // ln(0.87)
+  const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
+  const double start = -hss;
+  const double cd = cos(dh), sd = sin(dh);
+
+  double m_loc[kTT + 1];   // Taylor moments of trans**am, [kTT] = sum of dir_flat_topa
+#pragma unroll
+  for (int m = 0; m <= kTT; ++m) m_loc[m] = 0.0;
+  const int per = (n + 31) / 32;
+  const int k_lo = min(lane * per, n), k_hi = min(k_lo + per, n);
+  double ch = 1.0, sh = 0.0;
+  for (int k = k_lo; k < k_hi; ++k) {
+    if (((k - k_lo) & 15) == 0) sincos(__dadd_rn(start, __dmul_rn((double)k, dh)), &sh, &ch);
+    const double cza = (k == 0) ? cza_first : __dadd_rn(__dmul_rn(cosegeom, ch), sinegeom);
+    if (cza > 0.0) {
+      const double dfa = beam * cza;                       // physics.py:252
+      double am = rcp_nr(cza + 0.0000001);
+      if (am > 2.9) {
+        int ami = (int)(acos(cza) / kRadPerDeg) - 69;
+        ami = min(max(ami, 0), 20);
+        am = c_optam[ami];
+      }
+      m_loc[kTT] += dfa;
+      // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
+      const double a = am * kLnTBase;
+      double term = exp_acc(a * MSB_TT_P0, etab) * dfa;
+      m_loc[0] += term;
+#pragma unroll
+      for (int m = 1; m < kTT; ++m) {
+        term *= a * (1.0 / (double)m);
+        m_loc[m] += term;
+      }
+    }
+    const double cn = fma(ch, cd, -(sh * sd)), sn = fma(sh, cd, ch * sd);   // rotate by dh
+    ch = cn; sh = sn;
+  }
+  // butterfly reduction: every lane ends with the totals (fixed order -> deterministic)
+#pragma unroll
+  for (int m = 0; m <= kTT; ++m)
+    for (int o2 = 16; o2 > 0; o2 >>= 1) m_loc[m] += __shfl_xor_sync(0xffffffffu, m_loc[m], o2);
+  const double total = m_loc[kTT];
+  const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
+  const bool has_day = daylength != 0.0;
+  // tt_max0(p) = sum_trans/sum_flat_potrad (physics.py:275); 0 when there is no daylight
+  double mine = 0.0;
+#pragma unroll
+  for (int m = 0; m < kTT; ++m) mine = (lane == m) ? m_loc[m] : mine;
+  if (lane < kTT) tb.tt_coef[(size_t)w * kTT + lane] = (has_day && total > 0.0) ? mine / total : 0.0;
+  if (lane == 0) {
+    const double potrad = has_day ? total / daylength : 0.0;            // physics.py:276-280
+    const size_t s = (size_t)r * kRows + i;
+    tb.daylength[s] = daylength;
+    tb.potrad[s] = potrad;
+    if (i == 364) {  // row 365 copies row 364, physics.py:281-284
+      tb.daylength[s + 1] = daylength;
+      tb.potrad[s + 1] = potrad;
+    }
   }
 }
 
@@ -334,6 +379,8 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
   unsigned grid = 365u * (unsigned)n_lat;
   solar_rows_kernel<<<grid, kK1Threads, 0, st>>>(n_lat, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0,
                                                  dv.nstep, *tb);
+  solar_moments_kernel<<<(grid + kMomWarps - 1) / kMomWarps, kMomWarps * 32, 0, st>>>(
+      (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, *tb);
   MSB_CUDA(cudaGetLastError());
   MSB_CUDA(cudaMemsetAsync(tb->q + (size_t)n_lat * 365 * kQLd, 0, MSB_Q_PAD * sizeof(double), st));
   return MSB_OK;

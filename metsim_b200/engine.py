@@ -78,6 +78,8 @@ class Engine:
         self._tables = None
         self._daily = None
         self._ws = None
+        self._solar_bufs = None
+        self._solar_done = None
         self.n_cells = self.n_days = 0
 
     # ------------------------------------------------------------------ helpers
@@ -148,25 +150,35 @@ class Engine:
     # ------------------------------------------------------------------ solar tables
     def build_solar(self, n_host_threads: int | None = None):
         n_lat = len(self._ulat)
-        small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
-        _lib.check(self.lib.msb_solar_table_sizes(n_lat, C.byref(small), C.byref(q), C.byref(tt)))
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            opts = dict(dtype=torch.float64, device=self.device)
-            tb = {k: torch.empty(small.value, **opts) for k in ("daylength", "potrad", "rise_min", "set_min")}
-            tb["q"] = torch.empty(q.value, **opts)
-            tb["tt_coef"] = torch.empty(tt.value, **opts)
-            nbytes = self.lib.msb_solar_prelude_bytes(n_lat)
-            host_ws = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            dev_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._solar_bufs is None or self._solar_bufs[0] != n_lat:
+            # device tables + pinned / device prelude workspaces, allocated once per latitude count
+            small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            _lib.check(self.lib.msb_solar_table_sizes(n_lat, C.byref(small), C.byref(q), C.byref(tt)))
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                opts = dict(dtype=torch.float64, device=self.device)
+                tb = {k: torch.empty(small.value, **opts)
+                      for k in ("daylength", "potrad", "rise_min", "set_min")}
+                tb["q"] = torch.empty(q.value, **opts)
+                tb["tt_coef"] = torch.empty(tt.value, **opts)
+                nbytes = self.lib.msb_solar_prelude_bytes(n_lat)
+                host_ws = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                dev_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             st = _lib.SolarTables()
             st.n_lat = n_lat
             for k, v in tb.items():
                 setattr(st, k, self._ptr(v))
-            nthr = n_host_threads or min(os.cpu_count() or 1, 32)
+            self._solar_bufs = (n_lat, st, tb, host_ws, dev_ws)
+        _, st, tb, host_ws, dev_ws = self._solar_bufs
+        nthr = n_host_threads or min(os.cpu_count() or 1, 32)
+        if self._solar_done is not None:
+            self._solar_done.synchronize()   # the previous upload out of the pinned workspace
+        with torch.cuda.device(self.device):
             _lib.check(self.lib.msb_solar_tables_build(
                 n_lat, self._ulat.ctypes.data_as(C.c_void_p), C.c_void_p(host_ws.data_ptr()),
                 C.c_void_p(dev_ws.data_ptr()), C.byref(st), nthr,
                 C.c_void_p(self.stream.cuda_stream)))
+            self._solar_done = torch.cuda.Event()
+            self._solar_done.record(self.stream)
         self._tables = (st, tb, host_ws, dev_ws)
         return tb
 
