@@ -540,7 +540,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
 // prec) or 30 s steps (shortwave) turns every daily series into a contiguous SOURCE STREAM that
 // is read ts minutes per output step; the stream positions and the current source day live in
 // registers and roll to the next source day once per day (an event).
-constexpr int disagg_min_blocks(int vars) { return vars == kVarsStreams ? 6 : (vars == kVarsThermo ? 5 : 4); }
+constexpr int disagg_min_blocks(int vars) { return vars == kVarsStreams ? 6 : (vars == kVarsThermo ? 7 : 4); }
 
 template <typename OutT, bool FAST_LW, bool UNITS, int VARS>
 __global__ void __launch_bounds__(kDisaggThreads, disagg_min_blocks(VARS))

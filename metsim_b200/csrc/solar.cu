@@ -292,13 +292,19 @@ solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
       }
       m_loc[kTT] += dfa;
       // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
+      // four interleaved chains term[m+4] = term[m] * a^4 / ((m+1)(m+2)(m+3)(m+4)): a single chain
+      // of kTT dependent multiplies would expose kTT x 8 cycles of DMUL latency per step
       const double a = am * kLnTBase;
-      double term = exp_acc(a * MSB_TT_P0, etab) * dfa;
-      m_loc[0] += term;
+      const double a2 = a * a, a4 = a2 * a2;
+      double t[4];
+      t[0] = exp_acc(a * MSB_TT_P0, etab) * dfa;
+      t[1] = t[0] * a;
+      t[2] = t[0] * (a2 * 0.5);
+      t[3] = t[1] * (a2 * (1.0 / 6.0));
 #pragma unroll
-      for (int m = 1; m < kTT; ++m) {
-        term *= a * (1.0 / (double)m);
-        m_loc[m] += term;
+      for (int m = 0; m < kTT; ++m) {
+        m_loc[m] += t[m & 3];
+        t[m & 3] *= a4 * (1.0 / ((double)(m + 1) * (double)(m + 2) * (double)(m + 3) * (double)(m + 4)));
       }
     }
     const double cn = fma(ch, cd, -(sh * sd)), sn = fma(sh, cd, ch * sd);   // rotate by dh
