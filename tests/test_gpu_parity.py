@@ -325,3 +325,58 @@ def test_full_size_properties_conus_hourly_slice():
     torch.cuda.synchronize()
     assert torch.equal(part["temp"], full["temp"][2 * 24:5 * 24])
     assert torch.equal(part["prec"], full["prec"][2 * 24:5 * 24])
+
+
+@pytest.mark.parametrize("grid,ts,prec_type,days", [
+    ("conus1/16", 180, "mix", 10),        # BASELINE configs[3] shape (3-hourly, mix), full grid width
+    ("global1/8", 15, "triangle", 3),     # configs[4] shape (15-minute), ~1M cells
+    ("global0.5", 60, "triangle", 334),   # configs[1] grid, January-November (in December the
+                                          # reference's t_pk/dur quirk makes 0/0 days, whose fill
+                                          # does not conserve mass, metsim.py:278-284)
+])
+def test_full_size_properties_other_configs(grid, ts, prec_type, days):
+    """Size-independent properties at BASELINE.json's full grid sizes: precipitation mass per
+    record is conserved by the roll, shortwave energy per record matches the daily totals to a few
+    per cent (with the utc roll the table rows shift independently of the record,
+    disaggregate.py:656, and the wrapped last day lands in the first), relative humidity <= 100, 0 <= vapour pressure, longwave and
+    air pressure inside physical bounds, and the result does not depend on the day-tile split."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    rng = np.random.default_rng(synth.SEED)
+    lat, lon = synth.grid_cells(grid, rng)
+    f = synth.make_forcing_torch(lat, lon, days, "2001-01-01", "cuda")
+    tpd = 1440 // ts
+    eng = Engine(dict(time_step=ts, prec_type=prec_type, utc_offset=True))
+    eng.load(**f)
+    eng.build_solar()
+    dl = eng.daily(want=("shortwave", "daylength"))
+    n = lat.size
+    tile = max(1, min(days, int(2e9 // (n * tpd * 8 * 6))))     # keep the f64 outputs under ~12 GB
+    names = ("prec", "shortwave", "rel_humid", "vapor_pressure", "longwave", "air_pressure")
+    tot_p = torch.zeros(n, dtype=torch.float64, device="cuda")
+    tot_e = torch.zeros(n, dtype=torch.float64, device="cuda")
+    first = None
+    for d0 in range(0, days, tile):
+        d1 = min(days, d0 + tile)
+        out = eng.disaggregate(names, d0, d1, torch.float64)
+        torch.cuda.synchronize()
+        tot_p += out["prec"].sum(0)
+        tot_e += out["shortwave"].sum(0) * (ts * 60.0)
+        assert float(out["rel_humid"].max()) <= 100.0 and float(out["rel_humid"].min()) >= 0.0
+        assert bool((out["vapor_pressure"] >= 0).all())
+        assert 50.0 < float(out["longwave"].min()) and float(out["longwave"].max()) < 700.0
+        assert 40.0 < float(out["air_pressure"].min()) and float(out["air_pressure"].max()) < 110.0
+        if first is None:
+            first = {k: v[: min(tpd, v.shape[0])].clone() for k, v in out.items()}
+        del out
+    eng.check()
+    assert torch.allclose(tot_p, f["prec"].sum(0), rtol=1e-10, atol=1e-9)
+    want_e = (dl["shortwave"] * dl["daylength"]).sum(0)
+    big = want_e > 0.05 * want_e.max()     # polar-night cells: the rows rolled in dominate tiny totals
+    assert float(((tot_e - want_e).abs() / want_e.clamp_min(1.0))[big].max()) < 0.05
+    # a different tile split gives bit-identical values
+    again = eng.disaggregate(names, 0, 1, torch.float64)
+    torch.cuda.synchronize()
+    for k in names:
+        assert torch.equal(again[k][: first[k].shape[0]], first[k]), k
