@@ -66,7 +66,8 @@ __device__ __forceinline__ double svp_pa(double t, const double *etab) {
 
 __device__ __forceinline__ double tdew_step(const DayInv &v, double tdew_old, const double *etab) {
   const double vp = svp_pa(tdew_old, etab);
-  const double t_tmax = fmax(fma(kABase, vp, v.tt_max), 0.0001);
+  const double t_raw = fma(kABase, vp, v.tt_max);
+  const double t_tmax = t_raw > 0.0001 ? t_raw : 0.0001;   // np.maximum; t_raw is never NaN here
   const double r = (v.g * t_tmax) * v.b;
   const double poly = r * fma(r, fma(r, -32.766, 12.312), -1.444);
   return fma(v.tk, fma(1.121, poly, v.base), -kKelvin);
@@ -154,11 +155,14 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
     if (roll) {
       s_prec += prec;
       s_dtr += dtr;
-      seasonal = kDaysPerYear * (s_prec / 90.0);
-      sm_dtr = s_dtr / 30.0;
-      // slide the windows for the next day
-      s_prec -= hist(f.prec, f.st_prec, ld, cell, d - 89);
-      s_dtr -= hist(f.t_max, f.st_t_max, ld, cell, d - 29) - hist(f.t_min, f.st_t_min, ld, cell, d - 29);
+      seasonal = kDaysPerYear * (s_prec * (1.0 / 90.0));
+      sm_dtr = s_dtr * (1.0 / 30.0);
+      // slide the windows for the next day (d is uniform across the block: no divergence)
+      if (d >= 89) s_prec -= f.prec[o - (size_t)89 * ld];
+      else s_prec -= f.st_prec[(size_t)(kState + d - 89) * ld + cell];
+      if (d >= 29) s_dtr -= f.t_max[o - (size_t)29 * ld] - f.t_min[o - (size_t)29 * ld];
+      else s_dtr -= f.st_t_max[(size_t)(kState + d - 29) * ld + cell] -
+                    f.st_t_min[(size_t)(kState + d - 29) * ld + cell];
     } else {
       seasonal = f.given_seasonal_prec[o];
       sm_dtr = f.given_smoothed_dtr[o];
