@@ -69,7 +69,7 @@ typedef struct msb_params {
  * physics.py:177-285: only tt_max0 depends on elevation, everything else on latitude alone). */
 #define MSB_TINY_PER_DAY 2880
 #define MSB_Q_LD 2888        /* row pitch of the signed prefix table: entries 0..2880, [2881]=row total */
-#define MSB_Q_PAD 4096       /* zeroed elements after the last row (the kernel may read one step past a row) */
+#define MSB_Q_PAD 8192       /* zeroed elements after the last row (the kernel may read one step past a row) */
 #define MSB_TT_TERMS 28      /* Taylor terms of tt_max0 in the pressure ratio */
 #define MSB_TT_P0 0.68       /* expansion point of the pressure ratio p = t1**t2 */
 #define MSB_STATE_DAYS 90

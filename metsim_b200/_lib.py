@@ -22,7 +22,7 @@ LW_TYPES = {"default": 0, "tva": 1, "anderson": 2, "brutsaert": 3, "satterlund":
             "prata": 6}
 LW_CLOUD = {"default": 0, "cloud_deardorff": 1}
 Q_LD = 2888
-Q_PAD = 4096
+Q_PAD = 8192
 TT_TERMS = 28
 
 E_ARG, E_CUDA, E_DTR_NEGATIVE, E_NOT_CONVERGED, E_KNOTS, E_NOMEM = -1, -2, -3, -4, -5, -6

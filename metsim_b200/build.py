@@ -33,12 +33,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
+    """``bounds=True`` compiles the debug checks (-DMSB_BOUNDS): every day-record / calendar /
+    table access of the streaming kernels is range-checked on the device (trap or MSB_E_KNOTS)."""
     if not force and not needs_build():
         return OUT
     cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared",
            "-I", INCLUDE, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    if bounds:
+        cmd.insert(1, "-DMSB_BOUNDS")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -48,4 +52,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv or "--bounds" in sys.argv, verbose="--verbose" in sys.argv,
+                bounds="--bounds" in sys.argv))

@@ -68,6 +68,9 @@ struct Cell {
   const double *t_min, *t_max, *st_t_min, *st_t_max, *t_end;
 };
 __device__ __forceinline__ int doy_at(const Cell &c, int d) {
+#ifdef MSB_BOUNDS
+  if ((unsigned)d >= (unsigned)c.D) { asm volatile("trap;"); }
+#endif
   const unsigned r = (unsigned)(d - c.win0);
   return r < (unsigned)c.nwin ? c.sdoy[r] : c.doy[d];
 }
@@ -605,7 +608,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   // day records (disagg_prepare_kernel): field fld of padded day e
   const size_t plane = (size_t)a.n_rec * (size_t)ld;
   const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
-  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  auto rec = [&](int fld, int e) {
+#ifdef MSB_BOUNDS   // debug build (python -m metsim_b200.build --bounds): every record access checked
+    if ((unsigned)(e - a.e0) >= (unsigned)a.n_rec) { a.status[2] = 1; e = a.e0; }
+#endif
+    return rec0[(size_t)fld * plane + (long)e * ld];
+  };
   auto has_rec = [&](int e) { return (unsigned)(e - a.e0) < (unsigned)a.n_rec; };
   auto rkx = [&](int j) { return rec((j & 1) ? kR_XMAX : kR_XMIN, (j >> 1) - 1); };
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
@@ -882,6 +890,10 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         q_prev -= slot[kS_ROWTOT][tid];
         e_noon += tpd;
       }
+#ifdef MSB_BOUNDS
+      if (want_sw && (ss + C < 0 || ss + 3 * C > kQLd + MSB_Q_PAD / 2 || q_cur < qrow ||
+                      q_cur > qrow + (size_t)364 * kQLd)) asm volatile("trap;");
+#endif
       if (want_sw) {       // re-prime the pipelined table loads: the entries of this step and the next
         q_pref = q_cur[ss + C];
         q_pref2 = q_cur[ss + 2 * C];
