@@ -51,7 +51,9 @@ enum {
 enum {
   MSB_D_T_DAY = 0, MSB_D_TFMAX, MSB_D_TSKC, MSB_D_TDEW, MSB_D_VAPOR_PRESSURE, MSB_D_SHORTWAVE,
   MSB_D_PET, MSB_D_DAYLENGTH, MSB_D_POTRAD, MSB_D_TT_MAX, MSB_D_SEASONAL_PREC,
-  MSB_D_SMOOTHED_DTR, MSB_N_DAILYVARS
+  MSB_D_SMOOTHED_DTR,
+  MSB_D_SHORTWAVE_DAILY,   /* daily-output mode: shortwave * daylength / 86400, metsim/metsim.py:779-781 */
+  MSB_N_DAILYVARS
 };
 
 /* the keys of MetSim.params that the hot path reads (metsim/metsim.py:140-171) */

@@ -12,11 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmetsim_b200.so")
 
 N_SUBVARS = 10
-N_DAILYVARS = 12
+N_DAILYVARS = 13
 SUB_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_humid",
             "air_pressure", "spec_humid", "tskc", "wind")
 DAILY_VARS = ("t_day", "tfmax", "tskc", "tdew", "vapor_pressure", "shortwave", "pet",
-              "daylength", "potrad", "tt_max", "seasonal_prec", "smoothed_dtr")
+              "daylength", "potrad", "tt_max", "seasonal_prec", "smoothed_dtr", "shortwave_daily")
 PREC_TYPES = {"uniform": 0, "triangle": 1, "mix": 2}
 LW_TYPES = {"default": 0, "tva": 1, "anderson": 2, "brutsaert": 3, "satterlund": 4, "idso": 5,
             "prata": 6}

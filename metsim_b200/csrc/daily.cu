@@ -232,6 +232,8 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
       if (o_[MSB_D_TT_MAX]) o_[MSB_D_TT_MAX][o] = v.tt_max;
       if (o_[MSB_D_SEASONAL_PREC]) o_[MSB_D_SEASONAL_PREC][o] = seasonal;
       if (o_[MSB_D_SMOOTHED_DTR]) o_[MSB_D_SMOOTHED_DTR][o] = sm_dtr;
+      // daily-output mode: daytime flux -> daily average flux (metsim.py:779-781)
+      if (o_[MSB_D_SHORTWAVE_DAILY]) o_[MSB_D_SHORTWAVE_DAILY][o] = sw * (daylength / kSecPerDay);
     }
   }
   if (PASS == 1) {

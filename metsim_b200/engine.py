@@ -259,11 +259,18 @@ class Engine:
         return res
 
     def run(self, out_vars=DEFAULT_OUT_VARS, out_dtype=torch.float32, units=None, daily_vars=()):
-        """solar tables -> daily -> disaggregate for the whole record; returns tensors."""
+        """solar tables -> daily -> disaggregate for the whole record; returns tensors.
+
+        ``time_step=1440`` is the reference's daily-output mode (metsim/metsim.py:779-792): no
+        disaggregation, and ``res['shortwave']`` is the daily average flux
+        (``shortwave * daylength / 86400``); the other daily columns are under ``res['daily']``."""
         self.build_solar()
-        daily = self.daily(want=daily_vars)
+        daily_mode = self.params.time_step >= 1440
+        daily = self.daily(want=tuple(daily_vars) + (("shortwave_daily",) if daily_mode else ()))
         res = {}
-        if self.params.time_step < 1440:
+        if daily_mode:
+            res["shortwave"] = daily["shortwave_daily"]
+        else:
             res = self.disaggregate(out_vars, 0, self.n_days, out_dtype, units)
         self.check()
         self.stream.synchronize()

@@ -49,7 +49,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Params) == 6 * 4 + 6 * 8
     assert C.sizeof(_lib.SolarTables) == 8 + 6 * 8
     assert C.sizeof(_lib.Forcing) == 16 + 20 * 8
-    assert C.sizeof(_lib.Daily) == (12 + 3) * 8
+    assert C.sizeof(_lib.Daily) == (13 + 3) * 8
     assert C.sizeof(_lib.SubDaily) == 10 * 8 * 3 + 8 + 8 + 8 + 16
 
 

@@ -380,3 +380,20 @@ def test_full_size_properties_other_configs(grid, ts, prec_type, days):
     torch.cuda.synchronize()
     for k in names:
         assert torch.equal(again[k][: first[k].shape[0]], first[k]), k
+
+
+def test_daily_output_mode():
+    """time_step = 1440 (metsim/metsim.py:779-792): no disaggregation; shortwave is converted from
+    the daytime flux to the daily average flux.  Checked against the reference's daily columns."""
+    from metsim_b200.engine import Engine
+    from metsim_b200._lib import DAILY_VARS
+    inputs, params, ref_daily, _, _ = util.load_golden(os.path.join(util.GOLDEN, "synth_daily.npz"))
+    assert int(params["time_step"]) == 1440
+    eng = Engine(params)
+    eng.load(**{k: inputs.get(k) for k in util.INPUT_KEYS})
+    res = eng.run(daily_vars=DAILY_VARS)
+    assert set(res) == {"shortwave", "daily"}
+    want = ref_daily["shortwave"] * ref_daily["daylength"] / 86400.0
+    util.assert_close(res["shortwave"].cpu().numpy(), want, "sw_daily", context="daily mode")
+    for oname, ename in util.DAILY.items():
+        util.assert_close(res["daily"][ename].cpu().numpy(), ref_daily[ename], oname, context="daily mode")
