@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--workload", default="conus_16th_hourly", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=None, help="truncate the grid (debugging only)")
     ap.add_argument("--days", type=int, default=None, help="truncate the record (debugging only)")
-    ap.add_argument("--tile-days", type=int, default=32)
+    ap.add_argument("--tile-days", type=int, default=64)
     ap.add_argument("--sample-cells", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -150,7 +150,7 @@ int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
  * A first kernel turns the days around [day0, day1) into per-(cell, day) records (PCHIP knots
  * with their derivatives, the closed-form precipitation shape, radiation per tiny step); the
  * streaming kernel then only reads those.  The records live in caller-provided scratch. */
-#define MSB_REC_FIELDS 12
+#define MSB_REC_FIELDS 9
 #define MSB_REC_MARGIN 3
 size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1);
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,

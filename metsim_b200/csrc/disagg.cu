@@ -48,9 +48,8 @@ struct DisaggArgs {
 };
 
 // fields of a day record
-enum { kR_XMIN = 0, kR_YMIN, kR_DMIN,   // PCHIP knot at t_Tmin: time, value, derivative
-       kR_XMAX, kR_YMAX, kR_DMAX,       // PCHIP knot at t_Tmax
-       kR_VY,                            // vapour-pressure knot value, kPa (its time is kR_XMIN)
+enum { kR_XMIN = 0, kR_DMIN,            // PCHIP knot at t_Tmin: time, derivative (its value is the
+       kR_XMAX, kR_DMAX,                 //   input t_min / t_max itself); same for the knot at t_Tmax
        kR_PPACK, kR_HSP, kR_HSQ, kR_PF, // PrecDay: packed integers, stepp/2, stepq/2, P/sum
        kR_RAD };                         // shortwave per tiny step, disaggregate.py:645
 
@@ -520,14 +519,11 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   }
   if (bad) a.status[2] = 1;                   // scipy: `x` must be strictly increasing
   out[kR_XMIN * plane] = xb;
-  out[kR_YMIN * plane] = yb;
   out[kR_DMIN * plane] = d_min;
   out[kR_XMAX * plane] = xc;
-  out[kR_YMAX * plane] = yc;
   out[kR_DMAX * plane] = d_max;
   if (e < 0 || e >= D) return;                      // padded ends carry knots only
   const size_t o = (size_t)e * f.ld + cell;
-  out[kR_VY * plane] = a.vp_d[o] / 1000.0;
   PrecDay pd;
   pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
   if (a.out.var[MSB_V_PREC]) prec_day_setup(p, f, cell, e, f.month[e], pd);
@@ -616,6 +612,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   };
   auto has_rec = [&](int e) { return (unsigned)(e - a.e0) < (unsigned)a.n_rec; };
   auto rkx = [&](int j) { return rec((j & 1) ? kR_XMAX : kR_XMIN, (j >> 1) - 1); };
+  auto rky = [&](int j) {      // knot value: the input column, or the padded end (disaggregate.py:242-257)
+    const int e = (j >> 1) - 1;
+    if ((unsigned)e < (unsigned)D) return ((j & 1) ? f.t_max : f.t_min)[(size_t)e * ld + cell];
+    return knot_y(c, j);
+  };
+  auto rvy = [&](int d) { return a.vp_d[(size_t)d * ld + cell] / 1000.0; };   // kPa, :480
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     if (has_rec(d)) return rec(kR_RAD, d);
     return (a.sw_d[(size_t)d * ld + cell] * dayl[doy_at(c, d) - 1]) * inv_sw_den;   // wrapped day
@@ -847,9 +849,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
       }
       if (thermo && i >= e_vp) {     // vapour-pressure knot crossed (searchsorted side='left')
         int vn = min(vd + 1, D - 1);     // usual case: the next knot is the new upper end
-        double xl = rec(kR_XMIN, vn - 1), yl = rec(kR_VY, vn - 1);
-        double xh = rec(kR_XMIN, vn), yh = rec(kR_VY, vn);
-        while (vn < D - 1 && xh < x) { ++vn; xl = xh; yl = yh; xh = rec(kR_XMIN, vn); yh = rec(kR_VY, vn); }
+        double xl = rec(kR_XMIN, vn - 1), yl = rvy(vn - 1);
+        double xh = rec(kR_XMIN, vn), yh = rvy(vn);
+        while (vn < D - 1 && xh < x) { ++vn; xl = xh; yl = yh; xh = rec(kR_XMIN, vn); yh = rvy(vn); }
         vd = vn;
         if (xh < x) {      // beyond the last knot: forward fill
           yvl = slot[kS_VPTAIL][tid]; vslope = 0.0; v_interior = false; e_vp = kNever;
@@ -863,15 +865,15 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
       if (thermo && i >= e_cub) {    // PCHIP knot crossed (searchsorted side='right')
         int kn = kc + 1;                 // usual case: the next interval; all six loads in flight
         double x0 = rkx(kn), x1 = rkx(kn + 1);
-        double y0 = rec((kn & 1) ? kR_YMAX : kR_YMIN, (kn >> 1) - 1);
+        double y0 = rky(kn);
         double d0 = rec((kn & 1) ? kR_DMAX : kR_DMIN, (kn >> 1) - 1);
-        double y1 = rec((kn & 1) ? kR_YMIN : kR_YMAX, ((kn + 1) >> 1) - 1);
+        double y1 = rky(kn + 1);
         double d1 = rec((kn & 1) ? kR_DMIN : kR_DMAX, ((kn + 1) >> 1) - 1);
         while (kn < nk - 2 && x >= x1) {   // walk right (tile start; several knots inside one step)
           ++kn;
           x0 = x1; y0 = y1; d0 = d1;
           x1 = rkx(kn + 1);
-          y1 = rec((kn & 1) ? kR_YMIN : kR_YMAX, ((kn + 1) >> 1) - 1);
+          y1 = rky(kn + 1);
           d1 = rec((kn & 1) ? kR_DMIN : kR_DMAX, ((kn + 1) >> 1) - 1);
         }
         kc = kn;
