@@ -343,9 +343,10 @@ def main():
     peak, peak_src = measured_hbm_peak()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "disagg_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath):   # measured once per round with ncu --set full; scaled to this launch size
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            per_cts = float(json.load(open(tpath))["dram_bytes_per_cell_timestep"])
+            traffic = per_cts * cell_ts_rank / n_tiles
         except Exception:
             traffic = None
 
@@ -413,7 +414,7 @@ def main():
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
                              "disaggregate": float(br[2])},
             "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + disagg_kernel<thermo> + "
-                                                   "disagg_kernel<streams>, timed together per 32-day call",
+                                                   "disagg_kernel<streams>, timed together per call (--tile-days days)",
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_cell_timestep": bytes_per_cts,
