@@ -383,6 +383,7 @@ def main():
         e2e = {"value": world * cell_ts_rank / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(dt.item()) * 1e3, "steps": e_steps,
+               "timer": "host wall clock around the blocking C-ABI call, max over ranks",
                "api": "msb_run_host (C ABI), pinned host inputs, outputs streamed D2H into a pinned "
                       "2-tile host ring (what a streaming netCDF writer would drain)"}
 
