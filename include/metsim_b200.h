@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MSB_VERSION 100
+#define MSB_VERSION 101
 
 enum {
   MSB_OK = 0,
@@ -40,6 +40,9 @@ enum { MSB_PREC_UNIFORM = 0, MSB_PREC_TRIANGLE = 1, MSB_PREC_MIX = 2 };
 enum { MSB_LW_DEFAULT = 0, MSB_LW_TVA = 1, MSB_LW_ANDERSON = 2, MSB_LW_BRUTSAERT = 3,
        MSB_LW_SATTERLUND = 4, MSB_LW_IDSO = 5, MSB_LW_PRATA = 6 };
 enum { MSB_CLOUD_DEFAULT = 0, MSB_CLOUD_DEARDORFF = 1 };
+/* MetSim.methods registry keys (metsim/metsim.py:139): the iterated MTCLIM daily pass, or
+ * 'passthrough' (metsim/methods/passthrough.py:28-46: daily shortwave supplied, one evaluation) */
+enum { MSB_METHOD_MTCLIM = 0, MSB_METHOD_PASSTHROUGH = 1 };
 
 /* sub-daily output variables, metsim/metsim.py:660-666 (out_var_check) */
 enum {
@@ -64,6 +67,9 @@ typedef struct msb_params {
   int32_t lw_type;     /* MSB_LW_* */
   int32_t lw_cloud;    /* MSB_CLOUD_* */
   int32_t max_iter;    /* cap on tdew evaluations (<= 64 supported per call chain) */
+  int32_t method;      /* MSB_METHOD_* */
+  int32_t sw_daylight; /* passthrough only: params['sw_averaging'] == 'daylight'; otherwise the
+                          supplied shortwave is a 24 h mean (disaggregate.py:78-80) */
   double sw_prec_thresh, rain_scalar, tdew_tol, tmax_daylength_fraction, tday_coef, lapse_rate;
 } msb_params;
 
@@ -103,6 +109,10 @@ typedef struct msb_forcing {
    * them from the state / solar tables -- this is the exact contract of the per-cell callable. */
   const double *given_seasonal_prec, *given_smoothed_dtr;   /* [n_days][ld] or NULL (both) */
   const double *given_daylength, *given_potrad, *given_tt_max; /* [n_days][ld] or NULL (all three) */
+  /* 'passthrough' method (methods/passthrough.py:28-46): forcing columns that replace computed
+   * ones.  shortwave is required by that method; the others are optional.  longwave rescales the
+   * sub-daily longwave to the supplied daily mean (disaggregate.py:115-118, :583-589). */
+  const double *given_shortwave, *given_vapor_pressure, *given_tskc, *given_longwave; /* [n_days][ld] */
 } msb_forcing;
 
 typedef struct msb_daily {
@@ -153,6 +163,9 @@ int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 #define MSB_REC_FIELDS 9
 #define MSB_REC_MARGIN 3
 size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1);
+/* the same plus the float64 staging plane [(day1-day0)*tpd][ld] that the longwave rescale of the
+ * passthrough method needs (forcing.given_longwave != NULL and longwave requested) */
+size_t msb_disagg_workspace_bytes_lw(int64_t ld, int day0, int day1, int time_step);
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *daily, const msb_subdaily *out, void *stream);
 
@@ -173,6 +186,7 @@ typedef struct msb_host_run {
   const double *t_min, *t_max, *prec, *wind;
   const double *st_t_min, *st_t_max, *st_prec;
   const double *t_pk12, *dur12, *t_end;
+  const double *given_shortwave, *given_vapor_pressure, *given_tskc, *given_longwave; /* passthrough, or NULL */
   void *out_host[MSB_N_SUBVARS];
   double scale[MSB_N_SUBVARS], offset[MSB_N_SUBVARS];
   int32_t out_dtype;                 /* 4 or 8 */

@@ -21,6 +21,9 @@ PREC_TYPES = {"uniform": 0, "triangle": 1, "mix": 2}
 LW_TYPES = {"default": 0, "tva": 1, "anderson": 2, "brutsaert": 3, "satterlund": 4, "idso": 5,
             "prata": 6}
 LW_CLOUD = {"default": 0, "cloud_deardorff": 1}
+# MetSim.methods keys (metsim/metsim.py:139) and the names this package registers for them
+METHODS = {"mtclim": 0, "mtclim_b200": 0, "passthrough": 1, "passthrough_b200": 1}
+GIVEN_KEYS = ("given_shortwave", "given_vapor_pressure", "given_tskc", "given_longwave")
 Q_LD = 2888
 Q_PAD = 8192
 TT_TERMS = 28
@@ -29,7 +32,8 @@ E_ARG, E_CUDA, E_DTR_NEGATIVE, E_NOT_CONVERGED, E_KNOTS, E_NOMEM = -1, -2, -3, -
 
 EXPORTS = ("msb_version", "msb_last_error", "msb_default_params", "msb_solar_prelude_bytes",
            "msb_solar_table_sizes", "msb_solar_tables_build", "msb_daily_scratch_bytes",
-           "msb_mtclim_daily", "msb_daily_check", "msb_disagg_workspace_bytes", "msb_disaggregate",
+           "msb_mtclim_daily", "msb_daily_check", "msb_disagg_workspace_bytes",
+           "msb_disagg_workspace_bytes_lw", "msb_disaggregate",
            "msb_run_host",
            "msb_selftest_math")
 
@@ -40,6 +44,7 @@ ip = C.POINTER(C.c_int32)
 class Params(C.Structure):
     _fields_ = [("time_step", C.c_int32), ("prec_type", C.c_int32), ("utc_offset", C.c_int32),
                 ("lw_type", C.c_int32), ("lw_cloud", C.c_int32), ("max_iter", C.c_int32),
+                ("method", C.c_int32), ("sw_daylight", C.c_int32),
                 ("sw_prec_thresh", C.c_double), ("rain_scalar", C.c_double),
                 ("tdew_tol", C.c_double), ("tmax_daylength_fraction", C.c_double),
                 ("tday_coef", C.c_double), ("lapse_rate", C.c_double)]
@@ -61,7 +66,9 @@ class Forcing(C.Structure):
                 ("t_pk12", C.c_void_p), ("dur12", C.c_void_p), ("t_end", C.c_void_p),
                 ("given_seasonal_prec", C.c_void_p), ("given_smoothed_dtr", C.c_void_p),
                 ("given_daylength", C.c_void_p), ("given_potrad", C.c_void_p),
-                ("given_tt_max", C.c_void_p)]
+                ("given_tt_max", C.c_void_p),
+                ("given_shortwave", C.c_void_p), ("given_vapor_pressure", C.c_void_p),
+                ("given_tskc", C.c_void_p), ("given_longwave", C.c_void_p)]
 
 
 class Daily(C.Structure):
@@ -84,6 +91,8 @@ class HostRun(C.Structure):
                 ("wind", C.c_void_p),
                 ("st_t_min", C.c_void_p), ("st_t_max", C.c_void_p), ("st_prec", C.c_void_p),
                 ("t_pk12", C.c_void_p), ("dur12", C.c_void_p), ("t_end", C.c_void_p),
+                ("given_shortwave", C.c_void_p), ("given_vapor_pressure", C.c_void_p),
+                ("given_tskc", C.c_void_p), ("given_longwave", C.c_void_p),
                 ("out_host", C.c_void_p * N_SUBVARS), ("scale", C.c_double * N_SUBVARS),
                 ("offset", C.c_double * N_SUBVARS), ("out_dtype", C.c_int32),
                 ("daily_host", C.c_void_p * N_DAILYVARS), ("n_iter_host", C.c_void_p),
@@ -134,6 +143,8 @@ def lib():
     l.msb_daily_check.argtypes = [C.POINTER(Forcing), C.POINTER(Daily), C.c_void_p]
     l.msb_disagg_workspace_bytes.restype = C.c_size_t
     l.msb_disagg_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    l.msb_disagg_workspace_bytes_lw.restype = C.c_size_t
+    l.msb_disagg_workspace_bytes_lw.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int]
     l.msb_disaggregate.restype = C.c_int
     l.msb_disaggregate.argtypes = [C.POINTER(Params), C.POINTER(Forcing), C.POINTER(SolarTables),
                                    C.POINTER(Daily), C.POINTER(SubDaily), C.c_void_p]
@@ -172,6 +183,13 @@ def make_params(user: dict | None = None) -> Params:
             p.lw_cloud = LW_CLOUD[key]
         elif k == "utc_offset":
             p.utc_offset = int(bool(v))
+        elif k == "method":
+            key = str(v).lower()
+            if key not in METHODS:
+                raise KeyError(key)                        # metsim.py:462: self.methods[...]
+            p.method = METHODS[key]
+        elif k == "sw_averaging":
+            p.sw_daylight = int(str(v).lower() == "daylight")   # disaggregate.py:79
         elif k in ("time_step", "max_iter"):
             setattr(p, k, int(v))
         elif k in ("sw_prec_thresh", "rain_scalar", "tdew_tol", "tmax_daylength_fraction",

@@ -99,6 +99,8 @@ extern "C" void msb_default_params(msb_params *p) {
   p->lw_type = MSB_LW_PRATA;
   p->lw_cloud = MSB_CLOUD_DEARDORFF;
   p->max_iter = 24;
+  p->method = MSB_METHOD_MTCLIM;
+  p->sw_daylight = 0;
   p->sw_prec_thresh = 0.0;
   p->rain_scalar = 0.75;
   p->tdew_tol = 1e-6;
@@ -171,6 +173,9 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   auto add = [&](size_t bytes) { need = ((need + 255) & ~(size_t)255) + bytes; };
   add(3 * N * 8); add(N * 4); add(2 * (size_t)D * 4);            // lon/elev(+pad), lat_row, doy/month
   for (int k = 0; k < 4; ++k) add(dn * 8);                       // t_min t_max prec wind
+  const double *given_h[4] = {run->given_shortwave, run->given_vapor_pressure, run->given_tskc,
+                              run->given_longwave};
+  for (int k = 0; k < 4; ++k) if (given_h[k]) add(dn * 8);       // passthrough columns
   for (int k = 0; k < 3; ++k) add(sn * 8);
   add(12 * (size_t)N * 8); add(12 * (size_t)N * 8); add(2 * (size_t)N * 8);
   for (int k = 0; k < 4; ++k) add(small_e * 8);
@@ -179,7 +184,10 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   add((size_t)N * 4); add(msb_daily_scratch_bytes(N, D)); add(64);
   const size_t tile_elems = (size_t)tile_days * tpd * N;
   for (int k = 0; k < 2 * n_out; ++k) add(tile_elems * osz);
-  const size_t ws_bytes = sub ? msb_disagg_workspace_bytes(N, 0, tile_days) : 0;
+  const bool lw_rescale = p->method == MSB_METHOD_PASSTHROUGH && run->given_longwave &&
+                          run->out_host[MSB_V_LONGWAVE];
+  const size_t ws_bytes = !sub ? 0 : lw_rescale ? msb_disagg_workspace_bytes_lw(N, 0, tile_days, ts)
+                                                : msb_disagg_workspace_bytes(N, 0, tile_days);
   add(ws_bytes);
   need += 65536;
 
@@ -191,6 +199,8 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   int32_t *d_row = cv.take<int32_t>(N), *d_doy = cv.take<int32_t>(D), *d_month = cv.take<int32_t>(D);
   double *d_tmin = cv.take<double>(dn), *d_tmax = cv.take<double>(dn), *d_prec = cv.take<double>(dn);
   double *d_wind = run->wind ? cv.take<double>(dn) : nullptr;
+  double *d_given[4];
+  for (int k = 0; k < 4; ++k) d_given[k] = given_h[k] ? cv.take<double>(dn) : nullptr;
   double *d_stmin = cv.take<double>(sn), *d_stmax = cv.take<double>(sn), *d_stprec = cv.take<double>(sn);
   double *d_tpk = run->t_pk12 ? cv.take<double>(12 * (size_t)N) : nullptr;
   double *d_dur = run->dur12 ? cv.take<double>(12 * (size_t)N) : nullptr;
@@ -255,6 +265,7 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   MSB_TRYC(up(d_tmax, run->t_max, dn * 8));
   MSB_TRYC(up(d_prec, run->prec, dn * 8));
   if (d_wind) MSB_TRYC(up(d_wind, run->wind, dn * 8));
+  for (int k = 0; k < 4; ++k) if (d_given[k]) MSB_TRYC(up(d_given[k], given_h[k], dn * 8));
   MSB_TRYC(up(d_stmin, run->st_t_min, sn * 8));
   MSB_TRYC(up(d_stmax, run->st_t_max, sn * 8));
   MSB_TRYC(up(d_stprec, run->st_prec, sn * 8));
@@ -277,6 +288,8 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   f.t_min = d_tmin; f.t_max = d_tmax; f.prec = d_prec; f.wind = d_wind;
   f.st_t_min = d_stmin; f.st_t_max = d_stmax; f.st_prec = d_stprec;
   f.t_pk12 = d_tpk; f.dur12 = d_dur; f.t_end = d_tend;
+  f.given_shortwave = d_given[0]; f.given_vapor_pressure = d_given[1];
+  f.given_tskc = d_given[2]; f.given_longwave = d_given[3];
 
   MSB_TRY(msb_mtclim_daily(p, &f, &tb, &dl, s_main));
   MSB_TRYC(cudaEventRecord(ev[3], s_main));

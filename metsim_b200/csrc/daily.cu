@@ -122,6 +122,8 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
   int n_evals = 0;
   if (PASS == 1) {
     if (k_off > 0 && out.n_iter[cell] != 0) return;  // converged in an earlier round
+  } else if (PASS == 3) {
+    if (chunk == 0) out.n_iter[cell] = 1;            // passthrough: one evaluation, no fixed point
   } else {
     n_evals = out.n_iter[cell];
     if (n_evals == 0) {                               // never converged: flag, use the cap
@@ -213,12 +215,23 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
         tdew = nxt;
       }
     } else {
-      for (int k = 0; k < n_evals; ++k) tdew = tdew_step(v, tdew, etab);
-      const double vp = svp_pa(tdew, etab);                             // mtclim.py:73-79
-      const double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);
-      const double sw = potrad * t_tmax * tf;
+      double vp, sw, tskc = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
+      if (PASS == 3) {
+        // methods/passthrough.py:28-46: shortwave is a forcing; pet, tdew and vapour pressure
+        // follow from it in one evaluation; supplied tskc / vapour pressure columns win
+        sw = f.given_shortwave[o];
+        if (f.given_tskc) tskc = f.given_tskc[o];
+        const double r = sw * v.b;                                      // pet / max(seasonal_prec, 80)
+        const double poly = r * fma(r, fma(r, -32.766, 12.312), -1.444);
+        tdew = fma(v.tk, fma(1.121, poly, v.base), -kKelvin);           // mtclim.py:190-194
+        vp = f.given_vapor_pressure ? f.given_vapor_pressure[o] : svp_pa(tdew, etab);
+      } else {
+        for (int k = 0; k < n_evals; ++k) tdew = tdew_step(v, tdew, etab);
+        vp = svp_pa(tdew, etab);                                        // mtclim.py:73-79
+        const double t_tmax = fmax(v.tt_max + (kABase * vp), 0.0001);
+        sw = potrad * t_tmax * tf;
+      }
       const double pet = ((c1 * (sw * 0.72) * daylength) * inv_lhvap) / 10. * 10.0;
-      const double tskc = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
       double *const *o_ = out.var;
       if (o_[MSB_D_T_DAY]) o_[MSB_D_T_DAY][o] = t_day;
       if (o_[MSB_D_TFMAX]) o_[MSB_D_TFMAX][o] = tf;
@@ -307,6 +320,19 @@ extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DailyLaunch l = daily_launch(f->n_cells, f->n_days);
   dim3 grid((f->n_cells + kDailyThreads - 1) / kDailyThreads, l.n_chunks);
+  if (p->method == MSB_METHOD_PASSTHROUGH) {
+    if (!f->given_shortwave) {
+      set_error("passthrough method: 'shortwave' must be among the forcings");   // passthrough.py:29
+      return MSB_E_ARG;
+    }
+    MSB_CUDA(cudaMemsetAsync(out->status, 0, 4 * sizeof(int32_t), st));
+    daily_kernel<3><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0, 0);
+    MSB_CUDA(cudaGetLastError());
+    return MSB_OK;
+  } else if (p->method != MSB_METHOD_MTCLIM) {
+    set_error("msb_mtclim_daily: unknown method %d", p->method);
+    return MSB_E_ARG;
+  }
   int max_iter = p->max_iter > 0 ? p->max_iter : 24;
   int rounds = (max_iter + kEvalsPerRound - 1) / kEvalsPerRound;
   if (rounds > 8) rounds = 8;

@@ -44,6 +44,9 @@ struct DisaggArgs {
   int tpd, tile_days;
   unsigned var_mask;   // bit v set = out.var[v] requested
   double *rec;         // day records [MSB_REC_FIELDS][n_rec][ld], record r = padded day e0 + r
+  double *lw_raw;      // passthrough with a supplied daily longwave: unscaled float64 longwave
+                       // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL
+  bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
   int e0, n_rec;       // e runs over [-1, D]: -1 / D are the padded PCHIP ends
 };
 
@@ -532,7 +535,8 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   out[kR_HSQ * plane] = pd.hsq;
   out[kR_PF * plane] = pd.f;
   const double *dayl = a.t.daylength + (size_t)row * kRows;
-  out[kR_RAD * plane] = (a.sw_d[o] * dayl[f.doy[e] - 1]) * (1.0 / (3600.0 * ((double)ts / 60.0)));
+  const double dl = a.sw_full_day ? kSecPerDay : dayl[f.doy[e] - 1];
+  out[kR_RAD * plane] = (a.sw_d[o] * dl) * (1.0 / (3600.0 * ((double)ts / 60.0)));
 }
 
 // One thread = one cell x one tile of days.  np.roll by a whole number of minutes (tskc, wind,
@@ -620,7 +624,8 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   auto rvy = [&](int d) { return a.vp_d[(size_t)d * ld + cell] / 1000.0; };   // kPa, :480
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     if (has_rec(d)) return rec(kR_RAD, d);
-    return (a.sw_d[(size_t)d * ld + cell] * dayl[doy_at(c, d) - 1]) * inv_sw_den;   // wrapped day
+    const double dl = a.sw_full_day ? kSecPerDay : dayl[doy_at(c, d) - 1];
+    return (a.sw_d[(size_t)d * ld + cell] * dl) * inv_sw_den;                        // wrapped day
   };
   auto prec_of = [&](int d, PrecDay &o) {
     if (has_rec(d)) {
@@ -980,7 +985,10 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
         const double mix = (kEps * vp) * rcp_nr(ap - vp);
         put(o_sh, MSB_V_SPEC_HUMID, mix * rcp_nr(1 + mix));
       }
-      if (want(MSB_V_LONGWAVE)) put(o_lw, MSB_V_LONGWAVE, lw);
+      if (want(MSB_V_LONGWAVE)) {
+        if (VARS == kVarsAny && a.lw_raw) a.lw_raw[obase + ooff] = lw;   // rescaled by lw_rescale_kernel
+        else put(o_lw, MSB_V_LONGWAVE, lw);
+      }
       if (want_prec) put(o_prec, MSB_V_PREC, pr);
       if (want_sw) put(o_sw, MSB_V_SHORTWAVE, sw);
     }
@@ -999,6 +1007,29 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     }
     ooff = (unsigned)cell;
     for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) put(o_prec, MSB_V_PREC, fillv);
+  }
+}
+
+// disaggregate.py:583-589 (passthrough with a daily longwave forcing): every day of the sub-daily
+// longwave is scaled so that its mean equals the supplied daily value.  One thread = one
+// (cell, day); reads the float64 staging plane the streaming kernel wrote, applies the unit
+// conversion and the output cast.
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+lw_rescale_kernel(const __grid_constant__ DisaggArgs a) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = a.out.day0 + blockIdx.y;
+  if (cell >= a.f.n_cells || d >= a.out.day1) return;
+  const int tpd = a.tpd;
+  const size_t base = (size_t)blockIdx.y * tpd * (size_t)a.out.ld + cell;
+  double s = 0.0;
+  for (int t = 0; t < tpd; ++t) s += a.lw_raw[base + (size_t)t * a.out.ld];
+  const double factor = a.f.given_longwave[(size_t)d * a.f.ld + cell] / (s / (double)tpd);
+  OutT *o = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]);
+  const double sc = a.out.scale[MSB_V_LONGWAVE], of = a.out.offset[MSB_V_LONGWAVE];
+  for (int t = 0; t < tpd; ++t) {
+    const size_t k = base + (size_t)t * a.out.ld;
+    o[k] = (OutT)fma(a.lw_raw[k] * factor, sc, of);
   }
 }
 
@@ -1035,6 +1066,12 @@ extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
   if (ld <= 0 || day1 <= day0) return 0;
   const size_t n_rec = (size_t)(day1 - day0) + 2 * MSB_REC_MARGIN;
   return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
+}
+
+extern "C" size_t msb_disagg_workspace_bytes_lw(int64_t ld, int day0, int day1, int time_step) {
+  if (ld <= 0 || day1 <= day0 || time_step <= 0 || time_step >= kMinPerDay) return 0;
+  const size_t rec = (msb_disagg_workspace_bytes(ld, day0, day1) + 255) & ~(size_t)255;
+  return rec + (size_t)(day1 - day0) * (size_t)(kMinPerDay / time_step) * (size_t)ld * sizeof(double);
 }
 
 extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
@@ -1096,6 +1133,17 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     set_error("msb_disaggregate: workspace of msb_disagg_workspace_bytes() bytes is required");
     return MSB_E_ARG;
   }
+  a.sw_full_day = p->method == MSB_METHOD_PASSTHROUGH && !p->sw_daylight;
+  a.lw_raw = nullptr;
+  if (p->method == MSB_METHOD_PASSTHROUGH && f->given_longwave && out->var[MSB_V_LONGWAVE]) {
+    const size_t rec_bytes = (msb_disagg_workspace_bytes(f->ld, out->day0, out->day1) + 255) & ~(size_t)255;
+    if (out->workspace_bytes < rec_bytes + (size_t)n_days * a.tpd * (size_t)out->ld * sizeof(double)) {
+      set_error("msb_disaggregate: the longwave rescale needs a workspace of "
+                "msb_disagg_workspace_bytes_lw() bytes");
+      return MSB_E_ARG;
+    }
+    a.lw_raw = reinterpret_cast<double *>(reinterpret_cast<char *>(out->workspace) + rec_bytes);
+  }
   const bool fast_lw = p->lw_type == MSB_LW_PRATA && p->lw_cloud == MSB_CLOUD_DEARDORFF;
   bool units = false;
   a.var_mask = 0;
@@ -1105,7 +1153,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     if (out->scale[v] != 1.0 || out->offset[v] != 0.0) units = true;
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
-  const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4;
+  const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4 && !a.lw_raw;
   disagg_prepare_kernel<<<dim3(cell_blocks, a.n_rec), 128, 0, st>>>(a);
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
   if (example) {   // reference defaults, 8 variables: the thermodynamic half and the stream half
@@ -1118,6 +1166,10 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     if (fast_lw) MSB_LAUNCH(double, true, true, kVarsAny); else MSB_LAUNCH(double, false, true, kVarsAny);
   }
 #undef MSB_LAUNCH
+  if (a.lw_raw) {
+    if (out->dtype == 4) lw_rescale_kernel<float><<<dim3(cell_blocks, n_days), 128, 0, st>>>(a);
+    else lw_rescale_kernel<double><<<dim3(cell_blocks, n_days), 128, 0, st>>>(a);
+  }
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }

@@ -106,7 +106,11 @@ class Engine:
 
     # ------------------------------------------------------------------ inputs
     def load(self, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
-             state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None):
+             state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
+             given_shortwave=None, given_vapor_pressure=None, given_tskc=None,
+             given_longwave=None):
+        """``given_*`` are the forcing columns of the 'passthrough' method
+        (metsim/methods/passthrough.py:28-46), daily ``[D][N]``; shortwave is required there."""
         f64, i32 = torch.float64, torch.int32
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             t = self._t
@@ -116,6 +120,9 @@ class Engine:
             t["t_max"] = self._dev(t_max, f64, (d, n))
             t["prec"] = self._dev(prec, f64, (d, n))
             t["wind"] = self._dev(wind, f64, (d, n))
+            for k, v in zip(_lib.GIVEN_KEYS, (given_shortwave, given_vapor_pressure, given_tskc,
+                                              given_longwave)):
+                t[k] = self._dev(v, f64, (d, n))
             for k, v in (("st_t_min", state_t_min), ("st_t_max", state_t_max), ("st_prec", state_prec)):
                 t[k] = self._dev(v, f64, (90, n))
             t["t_pk12"] = self._dev(t_pk12, f64, (12, n))
@@ -143,7 +150,7 @@ class Engine:
         f = _lib.Forcing()
         f.n_cells, f.n_days, f.ld = self.n_cells, self.n_days, self.n_cells
         for name in ("lon", "elev", "lat_row", "doy", "month", "t_min", "t_max", "prec", "wind",
-                     "st_t_min", "st_t_max", "st_prec", "t_pk12", "dur12", "t_end"):
+                     "st_t_min", "st_t_max", "st_prec", "t_pk12", "dur12", "t_end") + _lib.GIVEN_KEYS:
             setattr(f, name, self._ptr(t.get(name)))
         return f
 
@@ -248,7 +255,11 @@ class Engine:
                 sd.scale[i], sd.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
             sd.dtype = 4 if out_dtype == torch.float32 else 8
             sd.ld, sd.day0, sd.day1 = n, day0, day1
-            need = self.lib.msb_disagg_workspace_bytes(n, day0, day1)
+            if (self.params.method == 1 and self._t.get("given_longwave") is not None
+                    and res.get("longwave") is not None):     # longwave rescale staging plane
+                need = self.lib.msb_disagg_workspace_bytes_lw(n, day0, day1, ts)
+            else:
+                need = self.lib.msb_disagg_workspace_bytes(n, day0, day1)
             if self._ws is None or self._ws.numel() < need:   # grow-only scratch for the day records
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             sd.workspace, sd.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
@@ -280,6 +291,7 @@ class Engine:
 
 def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
              state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
+             given_shortwave=None, given_vapor_pressure=None, given_tskc=None, given_longwave=None,
              out_vars=DEFAULT_OUT_VARS, out_dtype=np.float32, units: dict | None = None,
              daily_vars=(), device: int = 0, tile_days: int = 0, out: dict | None = None,
              ring: bool = False, timings: dict | None = None) -> dict:
@@ -296,7 +308,9 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
     arrs = dict(lat=f64(lat), lon=f64(lon), elev=f64(elev), t_min=t_min, t_max=f64(t_max),
                 prec=f64(prec), wind=f64(wind), st_t_min=f64(state_t_min),
                 st_t_max=f64(state_t_max), st_prec=f64(state_prec), t_pk12=f64(t_pk12),
-                dur12=f64(dur12), t_end=f64(t_end))
+                dur12=f64(dur12), t_end=f64(t_end), given_shortwave=f64(given_shortwave),
+                given_vapor_pressure=f64(given_vapor_pressure), given_tskc=f64(given_tskc),
+                given_longwave=f64(given_longwave))
     arrs["doy"] = np.ascontiguousarray(doy, dtype=np.int32)
     arrs["month"] = np.ascontiguousarray(month, dtype=np.int32)
     run = _lib.HostRun()

@@ -25,11 +25,17 @@ _READ_PARAMS = ("tday_coef", "sw_prec_thresh", "rain_scalar", "lw_cloud", "tdew_
 
 def run(df, params: dict):
     """Same contract as metsim/methods/mtclim.py:28-80."""
+    return run_daily(df, params, "mtclim")
+
+
+def run_daily(df, params: dict, method: str, given: dict | None = None):
+    """One cell's daily record through ``msb_mtclim_daily`` (shared with ``passthrough_b200``).
+    ``given`` maps C-ABI forcing names (``given_shortwave`` ...) to df column names."""
     lib = _lib.lib()
     if not torch.cuda.is_available():
-        raise RuntimeError("mtclim_b200.run needs a CUDA device; there is no CPU fallback")
+        raise RuntimeError(f"{method}_b200.run needs a CUDA device; there is no CPU fallback")
     dev = torch.device(params.get("device", "cuda:0"))
-    p = _lib.make_params({k: params[k] for k in _READ_PARAMS if k in params})
+    p = _lib.make_params(dict({k: params[k] for k in _READ_PARAMS if k in params}, method=method))
     n_days = len(df)
     col = lambda name: torch.from_numpy(
         np.array(df[name].values, dtype=np.float64, copy=True).reshape(n_days, 1)).to(dev)
@@ -47,6 +53,9 @@ def run(df, params: dict):
     f.given_daylength = cols["daylength"].data_ptr()
     f.given_potrad = cols["potrad"].data_ptr()
     f.given_tt_max = cols["tt_max"].data_ptr()
+    for cname, dfname in (given or {}).items():
+        cols[cname] = col(dfname)
+        setattr(f, cname, cols[cname].data_ptr())
     out = {k: torch.empty((n_days, 1), dtype=torch.float64, device=dev) for k in ADDED_COLUMNS}
     dl = _lib.Daily()
     for i, k in enumerate(_lib.DAILY_VARS):
@@ -62,5 +71,6 @@ def run(df, params: dict):
                                         C.c_void_p(stream.cuda_stream)))
         _lib.check(lib.msb_daily_check(C.byref(f), C.byref(dl), C.c_void_p(stream.cuda_stream)))
     for k in ADDED_COLUMNS:
-        df[k] = out[k].cpu().numpy()[:, 0]
+        if method == "mtclim" or k not in df:       # passthrough.py:31-45 keeps supplied columns
+            df[k] = out[k].cpu().numpy()[:, 0]
     return df

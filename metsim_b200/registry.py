@@ -7,9 +7,13 @@ file needs: ``method = mtclim_b200``.  ``disaggregate.py`` only special-cases ``
 
 Two levels are offered:
 
-* :func:`register` adds ``'mtclim_b200'`` -> :mod:`metsim_b200.methods.mtclim_b200`, whose
+* :func:`register` adds ``'mtclim_b200'`` -> :mod:`metsim_b200.methods.mtclim_b200` and
+  ``'passthrough_b200'`` -> :mod:`metsim_b200.methods.passthrough_b200`, whose
   ``run(df, params)`` is called per cell by the unmodified driver (daily kernels on the GPU,
-  the reference's own ``disaggregate`` afterwards).
+  the reference's own ``disaggregate`` afterwards; note that ``disaggregate.py:79`` keys its
+  full-day shortwave averaging on the literal name ``'passthrough'``, so with the unmodified
+  driver ``passthrough_b200`` behaves like ``sw_averaging = daylight`` there -- the batched
+  engine implements both modes).
 * :func:`batched_metsim_class` returns a ``MetSim`` subclass whose ``run_slice`` hands the whole
   chunk to the batched engine (solar tables, daily pass and disaggregation all on the GPU).  It
   needs the reference's xarray stack, which is not part of this repo's requirements.
@@ -17,11 +21,12 @@ Two levels are offered:
 from __future__ import annotations
 
 METHOD_NAME = "mtclim_b200"
+PASSTHROUGH_NAME = "passthrough_b200"
 
 
 def register(methods: dict | None = None) -> dict:
     """Insert the method module into ``methods`` (default: ``metsim.metsim.MetSim.methods``)."""
-    from .methods import mtclim_b200
+    from .methods import mtclim_b200, passthrough_b200
     if methods is None:
         try:
             from metsim.metsim import MetSim  # the reference package, if importable
@@ -31,6 +36,7 @@ def register(methods: dict | None = None) -> dict:
                 "explicitly (register(MetSim.methods))") from exc
         methods = MetSim.methods
     methods[METHOD_NAME] = mtclim_b200
+    methods[PASSTHROUGH_NAME] = passthrough_b200
     return methods
 
 
@@ -74,6 +80,9 @@ def batched_metsim_class():
                      doy=times.dayofyear.values, month=times.month.values,
                      t_min=grab(md["t_min"]), t_max=grab(md["t_max"]), prec=grab(md["prec"]),
                      wind=grab(md["wind"]) if "wind" in md else None,
+                     **{"given_" + k: grab(md[k]) for k in
+                        ("shortwave", "vapor_pressure", "tskc", "longwave")
+                        if "passthrough" in str(self.params["method"]) and k in md},
                      state_t_min=grab(st["t_min"]), state_t_max=grab(st["t_max"]),
                      state_prec=grab(st["prec"]), **kw)
             out_vars = list(self.params["out_vars"])

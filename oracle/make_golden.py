@@ -20,6 +20,9 @@ not.  Fixture families:
                    are kept for 9 of the 81 cells.
 * ``synth_*``      seeded synthetic cells sweeping time step, precipitation type, utc offset,
                    long-wave options, hemispheres, a polar cell and a supplied ``t_end``.
+* ``passthrough_*`` the 'passthrough' method (metsim/methods/passthrough.py): supplied daily
+                   shortwave (+ vapour pressure / tskc / longwave), both ``sw_averaging`` modes,
+                   the longwave rescale of disaggregate.py:583-589.
 """
 from __future__ import annotations
 
@@ -54,6 +57,9 @@ def pack(cells, params, outs):
              state_prec=st("state_prec"), t_pk12=st("t_pk12"), dur12=st("dur12"))
     if cells[0].get("t_end") is not None:
         z["t_end"] = st("t_end")
+    for k in ("shortwave", "vapor_pressure", "tskc", "longwave"):   # passthrough forcing columns
+        if cells[0].get(k) is not None:
+            z["given_" + k] = st(k)
     for k, v in params.items():
         z["param_" + k] = np.array(v)
     for k in DAILY:
@@ -151,6 +157,34 @@ def synth():
         print(name, len(cells), "cells x", d, "days")
 
 
+def passthrough():
+    rng = np.random.default_rng(20261020)
+    groups = {
+        "passthrough_hourly_sw_lw": (dict(method="passthrough", time_step=60, prec_type="triangle",
+                                          utc_offset=True), "2002-06-10", 40,
+                                     ("shortwave", "longwave")),
+        "passthrough_3hourly_daylight_all": (dict(method="passthrough", sw_averaging="daylight",
+                                                  time_step=180, prec_type="mix", utc_offset=True),
+                                             "2003-12-15", 35,
+                                             ("shortwave", "vapor_pressure", "tskc", "longwave")),
+        "passthrough_30min_sw_vp": (dict(method="passthrough", time_step=30, prec_type="uniform",
+                                         utc_offset=False, lw_type="idso", lw_cloud="default"),
+                                    "2000-02-20", 20, ("shortwave", "vapor_pressure")),
+    }
+    sites = [(48.3125, -120.5625, 1668.15), (30.03125, -100.03125, 519.0), (-33.9, 151.2, 30.0),
+             (0.25, 0.0, 2200.0), (64.9, 179.9, 410.0), (70.3, -179.75, 5.0), (-54.75, 25.5, 0.0),
+             (41.2, -105.1, 1900.0)]
+    draw = {"shortwave": (20, 350), "vapor_pressure": (200, 1800), "tskc": (0, 1), "longwave": (180, 420)}
+    for name, (params, start, d, given) in groups.items():
+        cells = [synth_cell(rng, la, lo, el, start, d) for la, lo, el in sites]
+        for c in cells:
+            for k in given:
+                c[k] = rng.uniform(*draw[k], d)
+        outs = [rh.run_cell(c, params) for c in cells]
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **pack(cells, params, outs))
+        print(name, len(cells), "cells x", d, "days")
+
+
 def main():
     root = rh.find_reference_root()
     if root is None:
@@ -158,9 +192,11 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     import warnings
     warnings.filterwarnings("ignore")
-    stehekin(root)
-    testdomain(root)
-    synth()
+    if "--passthrough-only" not in sys.argv:
+        stehekin(root)
+        testdomain(root)
+        synth()
+    passthrough()
 
 
 if __name__ == "__main__":

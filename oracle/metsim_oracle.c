@@ -170,6 +170,9 @@ typedef struct {
   double *st_tmin, *st_tmax, *st_prec; /* [90] */
   const double *t_pk12, *dur12;        /* [12] or NULL */
   const double *t_end;                 /* [2] or NULL */
+  /* passthrough method: supplied daily columns [D] (pt_sw != NULL selects the method) */
+  int pt_sw_daylight;
+  const double *pt_sw, *pt_vp, *pt_tskc, *pt_lw;
 } cell_in;
 
 typedef struct {
@@ -266,6 +269,17 @@ static int mtclim_run(const cell_in *c, cell_ws *w) {
     /* tskc mtclim.py:238-256 */
     w->tskc[d] = (p->lw_cloud == MSO_CLOUD_DEARDORFF) ? 1. - tf : sqrt((1. - tf) / 0.65);
   }
+  if (c->pt_sw) { /* methods/passthrough.py:28-46: one evaluation, supplied columns win */
+    for (int d = 0; d < D; ++d) {
+      if (c->pt_tskc) w->tskc[d] = c->pt_tskc[d];
+      w->sw[d] = c->pt_sw[d];
+      w->pet[d] = calc_pet(w->sw[d], w->t_day[d], w->daylength[d], pa) * 10.0;
+      w->tdew[d] = mt_tdew(w->pet[d], c->t_min[d], w->seasonal[d], w->dtr[d]);
+      w->vp[d] = c->pt_vp ? c->pt_vp[d] : svp(w->tdew[d]);
+    }
+    w->n_iter = 1;
+    return 0;
+  }
   for (int d = 0; d < D; ++d) w->tdew_old[d] = c->t_min[d];
   int n_eval = 0;
   for (;;) {
@@ -312,7 +326,8 @@ static void dg_shortwave(const cell_in *c, cell_ws *w, double lon) {
       for (int k = 0; k < chunk; ++k) {
         long it = py_mod((long)(c->doy[d] - 1) * NTINY + (long)t * chunk + k + off, L);
         long ir = py_mod((long)d * NTINY + (long)t * chunk + k + off, LR) / NTINY;
-        double tmp_rad = (w->sw[ir] * w->daylength[ir]) / (3600 * ts_hourly);
+        double dayl = (c->pt_sw && !c->pt_sw_daylight) ? 86400.0 : w->daylength[ir];
+        double tmp_rad = (w->sw[ir] * dayl) / (3600 * ts_hourly);
         acc += w->trf[it] * tmp_rad;
       }
       w->ssw[(size_t)d * tpd + t] = acc;
@@ -588,6 +603,14 @@ static int run_one(const cell_in *c, cell_ws *w) {
   }
   dg_repeat_mean(c, w->tskc, w->stskc, lon);
   for (long i = 0; i < T; ++i) w->lw[i] = dg_longwave(p, w->temp[i], w->svp_[i], w->stskc[i]);
+  if (c->pt_lw) { /* disaggregate.py:583-589: per-day rescale to the supplied daily longwave */
+    for (int d = 0; d < D; ++d) {
+      double m = 0;
+      for (int t = 0; t < tpd; ++t) m += w->lw[(size_t)d * tpd + t];
+      double factor = c->pt_lw[d] / (m / tpd);
+      for (int t = 0; t < tpd; ++t) w->lw[(size_t)d * tpd + t] *= factor;
+    }
+  }
   dg_prec(c, w, lon);
   if (c->wind) dg_repeat_mean(c, c->wind, w->swind, lon);
   /* final frame-wide ffill/bfill, disaggregate.py:130 */
@@ -610,6 +633,7 @@ typedef struct {
   const int *doy, *month;
   const double *t_min, *t_max, *prec, *wind, *st_tmin, *st_tmax, *st_prec, *t_pk12, *dur12, *t_end;
   const mso_outputs *out;
+  const mso_passthrough *pt;
 } job;
 
 static void gather(double *dst, const double *src, int n, int N, int cidx) {
@@ -627,6 +651,7 @@ static void *worker(void *arg) {
   int tpd = ts >= MIN_PER_DAY ? 1 : MIN_PER_DAY / ts;
   cell_ws *w = ws_new(D, tpd);
   double *b_tmin = dalloc(D), *b_tmax = dalloc(D), *b_prec = dalloc(D), *b_wind = dalloc(D);
+  double *b_psw = dalloc(D), *b_pvp = dalloc(D), *b_ptk = dalloc(D), *b_plw = dalloc(D);
   double s_tmin[90], s_tmax[90], s_prec[90], tpk[12], dur[12], tend[2];
   for (int cidx = j->c0; cidx < j->c1; ++cidx) {
     cell_in c;
@@ -646,6 +671,13 @@ static void *worker(void *arg) {
       c.t_pk12 = tpk; c.dur12 = dur;
     }
     if (j->t_end) { gather(tend, j->t_end, 2, N, cidx); c.t_end = tend; }
+    if (j->pt && j->pt->shortwave) {
+      c.pt_sw_daylight = j->pt->sw_daylight;
+      gather(b_psw, j->pt->shortwave, D, N, cidx); c.pt_sw = b_psw;
+      if (j->pt->vapor_pressure) { gather(b_pvp, j->pt->vapor_pressure, D, N, cidx); c.pt_vp = b_pvp; }
+      if (j->pt->tskc) { gather(b_ptk, j->pt->tskc, D, N, cidx); c.pt_tskc = b_ptk; }
+      if (j->pt->longwave) { gather(b_plw, j->pt->longwave, D, N, cidx); c.pt_lw = b_plw; }
+    }
     int rc = run_one(&c, w);
     if (rc) { j->rc = rc; break; }
     const mso_outputs *o = j->out;
@@ -668,6 +700,7 @@ static void *worker(void *arg) {
     }
   }
   free(b_tmin); free(b_tmax); free(b_prec); free(b_wind);
+  free(b_psw); free(b_pvp); free(b_ptk); free(b_plw);
   ws_free(w);
   return NULL;
 }
@@ -677,6 +710,16 @@ int mso_run(const mso_params *p, int n_cells, int n_days, const double *lat, con
             const double *t_max, const double *prec, const double *wind, const double *st_tmin,
             const double *st_tmax, const double *st_prec, const double *t_pk12,
             const double *dur12, const double *t_end, const mso_outputs *out, int n_threads) {
+  return mso_run_pt(p, NULL, n_cells, n_days, lat, lon, elev, doy, month, t_min, t_max, prec, wind,
+                    st_tmin, st_tmax, st_prec, t_pk12, dur12, t_end, out, n_threads);
+}
+
+int mso_run_pt(const mso_params *p, const mso_passthrough *pt, int n_cells, int n_days,
+               const double *lat, const double *lon, const double *elev, const int *doy,
+               const int *month, const double *t_min, const double *t_max, const double *prec,
+               const double *wind, const double *st_tmin, const double *st_tmax,
+               const double *st_prec, const double *t_pk12, const double *dur12,
+               const double *t_end, const mso_outputs *out, int n_threads) {
   if (!p || n_cells <= 0 || n_days < 2 || !out) return -3;
   if (p->time_step <= 0 || MIN_PER_DAY % p->time_step) return -3;
   if (p->prec_type != MSO_PREC_UNIFORM && (!t_pk12 || !dur12)) return -3;
@@ -693,7 +736,7 @@ int mso_run(const mso_params *p, int n_cells, int n_days, const double *lat, con
     j->lat = lat; j->lon = lon; j->elev = elev; j->doy = doy; j->month = month;
     j->t_min = t_min; j->t_max = t_max; j->prec = prec; j->wind = wind;
     j->st_tmin = st_tmin; j->st_tmax = st_tmax; j->st_prec = st_prec;
-    j->t_pk12 = t_pk12; j->dur12 = dur12; j->t_end = t_end; j->out = out;
+    j->t_pk12 = t_pk12; j->dur12 = dur12; j->t_end = t_end; j->out = out; j->pt = pt;
     if (n_threads == 1) worker(j);
     else pthread_create(&th[t], NULL, worker, j);
   }

@@ -101,8 +101,15 @@ def solar_geom(elev: float, lat: float, lr: float = 0.0065):
     return trf, dayl, potrad, ttmax
 
 
+class Passthrough(C.Structure):
+    _fields_ = [("sw_daylight", C.c_int), ("shortwave", C.POINTER(C.c_double)),
+                ("vapor_pressure", C.POINTER(C.c_double)), ("tskc", C.POINTER(C.c_double)),
+                ("longwave", C.POINTER(C.c_double))]
+
+
 def run(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
         state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
+        given_shortwave=None, given_vapor_pressure=None, given_tskc=None, given_longwave=None,
         want=None, n_threads: int | None = None) -> dict:
     """Run the oracle over N cells x D days; arrays are [D][N] (cell fastest).  Returns a dict of
     numpy arrays for every name in ``want`` (default: everything)."""
@@ -131,7 +138,16 @@ def run(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, prec, 
     out.n_iter = res["n_iter"].ctypes.data_as(C.POINTER(C.c_int))
     if n_threads is None:
         n_threads = os.cpu_count() or 1
-    rc = lib().mso_run(C.byref(p), n, d, _dp(lat), _dp(lon), _dp(elev),
+    pt = None
+    if str((params or {}).get("method", "mtclim")).lower() == "passthrough":
+        if given_shortwave is None:
+            raise AssertionError("'shortwave' in df")     # methods/passthrough.py:29
+        gs, gv, gt, gl = (_f64(a, (d, n)) for a in (given_shortwave, given_vapor_pressure,
+                                                      given_tskc, given_longwave))
+        pt = Passthrough(int(str((params or {}).get("sw_averaging", "")).lower() == "daylight"),
+                         _dp(gs), _dp(gv), _dp(gt), _dp(gl))
+    lib().mso_run_pt.restype = C.c_int
+    rc = lib().mso_run_pt(C.byref(p), C.byref(pt) if pt is not None else None, n, d, _dp(lat), _dp(lon), _dp(elev),
                        doy.ctypes.data_as(C.POINTER(C.c_int)),
                        month.ctypes.data_as(C.POINTER(C.c_int)),
                        _dp(t_min), _dp(t_max), _dp(prec), _dp(wind), _dp(st[0]), _dp(st[1]),

@@ -81,6 +81,9 @@ def load_reference(root: str | None = None):
     if not getattr(ns.mtclim.tdew, "_patched", False):
         tdew_copying._patched = True
         ns.mtclim.tdew = tdew_copying
+    # methods/passthrough.py binds mtclim's helpers by name at import time: same read-only fix
+    ns.passthrough = importlib.import_module("metsim.methods.passthrough")
+    ns.passthrough.tdew = tdew_copying
     ns.root = root
     _REF = ns
     return ns
@@ -169,7 +172,13 @@ def run_cell(cell: dict, user_params: dict | None = None, root: str | None = Non
     df["daylength"] = sg["daylength"][yday]
     df["potrad"] = sg["potrad"][yday]
     df["tt_max"] = sg["tt_max0"][yday]
-    df = ref.mtclim.run(df, params)
+    if params["method"] == "passthrough":          # metsim.py:462: methods[params['method']].run
+        for k in ("shortwave", "vapor_pressure", "tskc", "longwave"):
+            if cell.get(k) is not None:
+                df[k] = np.asarray(cell[k], dtype=np.float64)
+        df = ref.passthrough.run(df, params)
+    else:
+        df = ref.mtclim.run(df, params)
 
     out = {"daily": {k: df[k].values.copy() for k in
                      ("t_day", "tfmax", "tskc", "tdew", "vapor_pressure", "shortwave", "pet",
@@ -187,6 +196,8 @@ def run_cell(cell: dict, user_params: dict | None = None, root: str | None = Non
     n_days = d
     n_disagg = n_days * (1440 // ts)
     sub = {}
+    if params["method"] == "passthrough" and params.get("sw_averaging", "") != "daylight":
+        df["daylength"] = 86400.0                  # disaggregate.py:78-80
     sub["shortwave"] = dg.shortwave(df["shortwave"].values, df["daylength"].values,
                                     dates.dayofyear, sg["tiny_rad_fract"], params)
     t_tmin, t_tmax = dg.set_min_max_hour(sg["tiny_rad_fract"], dates.dayofyear - 1,
@@ -199,7 +210,8 @@ def run_cell(cell: dict, user_params: dict | None = None, root: str | None = Non
     sub["air_pressure"] = dg.pressure(sub["temp"], params["elev"], params["lapse_rate"])
     sub["spec_humid"] = dg.specific_humidity(sub["vapor_pressure"], sub["air_pressure"])
     sub["tskc"] = dg.tskc(df["tskc"].values, ts, params)
-    sub["longwave"] = dg.longwave(sub["temp"], sub["vapor_pressure"], sub["tskc"], params, None)
+    daily_lw = df["longwave"] if "longwave" in df else None     # disaggregate.py:115-118
+    sub["longwave"] = dg.longwave(sub["temp"], sub["vapor_pressure"], sub["tskc"], params, daily_lw)
     sub["prec"] = dg.prec(df["prec"], df["t_min"], ts, params, df.get("t_pk"), df.get("dur"))
     if "wind" in df:
         sub["wind"] = dg.wind(df["wind"].values, ts, params)

@@ -68,6 +68,9 @@ def oracle_cell(cell, params):
         kw["t_pk12"], kw["dur12"] = col("t_pk12", 12), col("dur12", 12)
     if cell.get("t_end") is not None:
         kw["t_end"] = np.asarray(cell["t_end"], float).reshape(2, 1)
+    for k in ("shortwave", "vapor_pressure", "tskc", "longwave"):   # passthrough columns
+        if cell.get(k) is not None:
+            kw["given_" + k] = col(k, d)
     return oracle_lib.run(params, n_threads=1, **kw)
 
 
@@ -112,10 +115,27 @@ def main(argv):
                           dict(time_step=120, prec_type="uniform", utc_offset=True, lw_type=lw,
                                lw_cloud=cloud, sw_prec_thresh=0.5, rain_scalar=0.7,
                                tday_coef=0.5, tmax_daylength_fraction=0.6, tdew_tol=1e-8)))
+    # 'passthrough' method (methods/passthrough.py): supplied shortwave, optionally vapour
+    # pressure / tskc / longwave, both sw_averaging modes
+    for i, (la, lo, el) in enumerate(zip(lats[:6], lons[:6], elevs[:6])):
+        cases.append((la, lo, el, "2002-06-10", 40,
+                      dict(method="passthrough", time_step=(60, 180, 30)[i % 3],
+                           prec_type=("uniform", "triangle")[i % 2], utc_offset=bool(i % 2),
+                           sw_averaging=("daylight" if i % 3 == 0 else ""), _given=i)))
     if quick:
-        cases = cases[::5]
+        cases = cases[::5] + cases[-2:]
     for la, lo, el, start, d, prm in cases:
         cell = synth_cell(rng, la, lo, el, start, d)
+        if "_given" in prm:
+            prm = dict(prm)
+            g = prm.pop("_given")
+            cell["shortwave"] = rng.uniform(20, 350, d)
+            if g & 1:
+                cell["vapor_pressure"] = rng.uniform(200, 1800, d)
+            if g & 2:
+                cell["tskc"] = rng.uniform(0, 1, d)
+            if g & 4 or g == 0:
+                cell["longwave"] = rng.uniform(180, 420, d)
         if n % 4 == 1:
             cell["t_end"] = [cell["t_min"][-1] - 1.5, cell["t_max"][-1] + 2.0]
         ok &= compare(cell, prm, worst, f"lat={la} lon={lo} {prm}")

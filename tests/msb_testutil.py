@@ -25,7 +25,8 @@ DAILY = {"t_day": "t_day", "tfmax": "tfmax", "tskc_daily": "tskc", "tdew": "tdew
          "daylength": "daylength", "potrad": "potrad", "tt_max": "tt_max",
          "seasonal_prec": "seasonal_prec", "smoothed_dtr": "smoothed_dtr"}
 INPUT_KEYS = ("lat", "lon", "elev", "doy", "month", "t_min", "t_max", "prec", "wind",
-              "state_t_min", "state_t_max", "state_prec", "t_pk12", "dur12", "t_end")
+              "state_t_min", "state_t_max", "state_prec", "t_pk12", "dur12", "t_end",
+              "given_shortwave", "given_vapor_pressure", "given_tskc", "given_longwave")
 
 
 def relerr(a, b, floor):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_defaults_and_error_text():
     lib = _lib.lib()
-    assert lib.msb_version() == 100
+    assert lib.msb_version() == 101
     p = _lib.make_params({})
     # metsim/metsim.py:140-171
     assert (p.time_step, p.prec_type, p.utc_offset) == (60, 0, 0)
@@ -46,9 +46,9 @@ def test_version_defaults_and_error_text():
 
 def test_struct_layouts_match_header():
     # sizes implied by the header on LP64 (natural alignment)
-    assert C.sizeof(_lib.Params) == 6 * 4 + 6 * 8
+    assert C.sizeof(_lib.Params) == 8 * 4 + 6 * 8
     assert C.sizeof(_lib.SolarTables) == 8 + 6 * 8
-    assert C.sizeof(_lib.Forcing) == 16 + 20 * 8
+    assert C.sizeof(_lib.Forcing) == 16 + 24 * 8
     assert C.sizeof(_lib.Daily) == (13 + 3) * 8
     assert C.sizeof(_lib.SubDaily) == 10 * 8 * 3 + 8 + 8 + 8 + 16
 
@@ -61,3 +61,8 @@ def test_param_translation_errors_match_reference():
         _lib.make_params({"lw_cloud": "bogus"})
     p = _lib.make_params({"prec_type": "MIX", "lw_type": "TVA", "time_step": "180", "utc_offset": True})
     assert (p.prec_type, p.lw_type, p.time_step, p.utc_offset) == (2, 1, 180, 1)
+    assert (p.method, p.sw_daylight) == (0, 0)
+    p = _lib.make_params({"method": "passthrough", "sw_averaging": "daylight"})   # disaggregate.py:79
+    assert (p.method, p.sw_daylight) == (1, 1)
+    with pytest.raises(KeyError):
+        _lib.make_params({"method": "bogus"})       # metsim.py:462: self.methods[params['method']]

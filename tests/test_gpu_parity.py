@@ -285,6 +285,75 @@ def test_registry_method_module_run_df():
                 util.assert_close(df[ename].values, ref_daily[ename][:, c], oname, context=f"run(df) cell {c}")
 
 
+def test_passthrough_method_against_oracle_and_errors():
+    """'passthrough' (metsim/methods/passthrough.py:28-46) on seeded grids against the oracle:
+    supplied shortwave alone and with vapour pressure / tskc / longwave, both sw_averaging modes,
+    f4 outputs with units; the longwave rescale makes every day's mean equal the supplied value
+    (disaggregate.py:583-589); a missing shortwave column raises like the reference's assert."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200._lib import MetsimB200Error
+    from oracle import oracle_lib
+    rng = np.random.default_rng(23)
+    f, params = synth.make_config("conus_16th_hourly", max_cells=300, n_days=45)
+    d, n = f["t_min"].shape
+    cols = dict(given_shortwave=rng.uniform(10, 380, (d, n)), given_vapor_pressure=rng.uniform(150, 2000, (d, n)),
+                given_tskc=rng.uniform(0, 1, (d, n)), given_longwave=rng.uniform(170, 430, (d, n)))
+    for given, over in ((("given_shortwave",), {}),
+                        (("given_shortwave", "given_longwave"), {"sw_averaging": "daylight", "time_step": 180}),
+                        (tuple(cols), {"time_step": 30, "prec_type": "mix"}),
+                        (("given_shortwave", "given_tskc", "given_longwave"),
+                         {"lw_type": "anderson", "lw_cloud": "default", "utc_offset": False})):
+        prm = dict(params, method="passthrough", **over)
+        g = dict(f, **{k: cols[k] for k in given})
+        want = oracle_lib.run(prm, **util.oracle_kwargs(g))
+        got = engine_run(g, prm)
+        compare_to_oracle(got, want, f"passthrough {given} {over}")
+        if "given_longwave" in given:
+            tpd = 1440 // prm["time_step"]
+            np.testing.assert_allclose(got["longwave"].reshape(d, tpd, n).mean(1), cols["given_longwave"], rtol=1e-12)
+            f32 = engine_run(g, prm, out_dtype=torch.float32, units={"longwave": "W m-2", "temp": "K"})
+            np.testing.assert_array_equal(f32["longwave"], got["longwave"].astype(np.float32))
+    with pytest.raises(MetsimB200Error, match="shortwave"):          # passthrough.py:29
+        engine_run(f, dict(params, method="passthrough"))
+
+
+def test_passthrough_run_host_and_registry_module():
+    """msb_run_host with the passthrough columns equals the device path bit for bit, and the
+    registry module passthrough_b200.run(df, params) reproduces the reference's daily columns."""
+    import pandas as pd
+    from metsim_b200 import registry
+    from metsim_b200.engine import run_host
+    from metsim_b200._lib import DAILY_VARS, SUB_VARS
+    from metsim_b200.methods import passthrough_b200
+    path = os.path.join(util.GOLDEN, "passthrough_3hourly_daylight_all.npz")
+    inputs, params, ref_daily, _, _ = util.load_golden(path)
+    ref = engine_run(inputs, params)
+    got = run_host(params, out_vars=SUB_VARS, daily_vars=DAILY_VARS, out_dtype=np.float64, tile_days=4,
+                   **{k: inputs.get(k) for k in util.INPUT_KEYS})
+    for v in SUB_VARS:
+        np.testing.assert_array_equal(got[v], ref[v], err_msg=v)
+    methods = {}
+    registry.register(methods)
+    assert methods["passthrough_b200"] is passthrough_b200
+    for c in (0, 4):
+        df = pd.DataFrame({k: inputs[k][:, c] for k in ("t_min", "t_max", "prec")})
+        for k in ("seasonal_prec", "smoothed_dtr", "daylength", "potrad", "tt_max"):
+            df[k] = ref_daily[k][:, c]
+        df["dtr"] = df["t_max"] - df["t_min"]
+        df["shortwave"] = inputs["given_shortwave"][:, c]
+        df["vapor_pressure"] = inputs["given_vapor_pressure"][:, c]
+        p = dict(params, elev=float(inputs["elev"][c]), lapse_rate=0.0065, tday_coef=0.45,
+                 sw_prec_thresh=0.0, rain_scalar=0.75, lw_cloud="cloud_deardorff", tdew_tol=1e-6)
+        out = passthrough_b200.run(df, p)
+        assert out is df
+        for oname, ename in (("t_day", "t_day"), ("tfmax", "tfmax"), ("pet", "pet"), ("tdew", "tdew")):
+            util.assert_close(df[ename].values, ref_daily[ename][:, c], oname, context=f"passthrough run(df) {c}")
+        np.testing.assert_array_equal(df["vapor_pressure"].values, inputs["given_vapor_pressure"][:, c])
+    with pytest.raises(AssertionError):
+        passthrough_b200.run(pd.DataFrame({"t_min": [1.0]}), {})
+
+
 def test_full_size_properties_conus_hourly_slice():
     """Size-independent properties at the BASELINE grid width (482,560 cells), a few days:
     precipitation mass is conserved per record (roll only moves it), shortwave energy equals the
