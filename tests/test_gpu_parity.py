@@ -157,6 +157,62 @@ def test_cuda_matches_oracle_on_seeded_configs(name, cells, days, over):
     compare_to_oracle(got, want, f"{name} {over}")
 
 
+EXAMPLE_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_humid",
+                "air_pressure", "wind")            # examples/example_nc.conf:3
+
+
+@pytest.mark.parametrize("name,cells,days,over", [
+    ("conus_16th_hourly", 1500, 45, {}),
+    ("conus_16th_hourly", 700, 400, {"start_dec": True}),
+    ("global_half_deg", 900, 30, {}),
+    ("conus_16th_10yr_3h_mix", 500, 60, {}),
+    ("global_8th_30yr_15min", 400, 12, {}),
+    ("conus_16th_hourly", 300, 5, {}),
+    ("conus_16th_hourly", 300, 3, {}),
+], ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(v) or "std")
+def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
+    """The configuration bench.py times: the 8 variables of examples/example_nc.conf, float32
+    outputs, no unit conversion -- the specialised kernels of msb_disaggregate.  Checked against
+    the oracle rounded to float32: the fp64 error (<= 1e-9) can only flip a float32 rounding on a
+    ~1e-9 / 6e-8 fraction of the values, so all but a handful must be bit-equal and none may
+    be off by more than one float32 ulp; precipitation zero / non-zero placement is exact."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    from oracle import oracle_lib
+    f, params = synth.make_config(name, max_cells=cells, n_days=days)
+    if over.get("start_dec"):       # a record that starts in December: NaN days at the head and tail
+        f, params = synth.make_config(name, max_cells=cells, n_days=days)
+        doy, month = synth.calendar_vectors("2001-12-05", days)
+        f["doy"], f["month"] = doy, month
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    eng = Engine(params)
+    eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+    res = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float32)
+    for split in (None, 7):          # whole record in one call, then 7-day calls
+        if split is not None:
+            parts = [eng.disaggregate(EXAMPLE_VARS, d0, min(days, d0 + split), torch.float32)
+                     for d0 in range(0, days, split)]
+            torch.cuda.synchronize()
+            res = {v: torch.cat([p[v] for p in parts]) for v in EXAMPLE_VARS}
+        for v in EXAMPLE_VARS:
+            got = res[v].cpu().numpy()
+            assert got.dtype == np.float32
+            w64 = want[v]
+            w32 = w64.astype(np.float32)
+            same_nan = np.isnan(got) == np.isnan(w32)
+            assert same_nan.all(), v
+            ok = ~np.isnan(w32)
+            neq = got[ok] != w32[ok]
+            ulp = np.spacing(np.abs(w32[ok]).astype(np.float32)).astype(np.float64)
+            err = np.abs(got[ok].astype(np.float64) - w64[ok])
+            floor = util.FLOORS[v]
+            # within float32 rounding of the fp64 value (+ the 1e-9 contract)
+            assert (err <= 0.5000001 * ulp + 1e-9 * np.maximum(np.abs(w64[ok]), floor)).all(), (v, split, float((err / ulp).max()))
+            assert neq.mean() < 2e-4, (v, split, float(neq.mean()))
+        np.testing.assert_array_equal(res["prec"].cpu().numpy() == 0, want["prec"].astype(np.float32) == 0)
+
+
 def test_edge_longitudes_polar_and_wraparound():
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
