@@ -26,6 +26,8 @@
 // lanes' next events (one REDUX per run), so lanes never lose lockstep on the step index.
 // Values that only the handler needs between events live in per-thread shared-memory slots, and
 // the one table load of the hot path is software-pipelined one step ahead.
+#include <cstdlib>
+
 #include "msb_common.cuh"
 
 namespace msb {
@@ -47,6 +49,8 @@ struct DisaggArgs {
   double *lw_raw;      // passthrough with a supplied daily longwave: unscaled float64 longwave
                        // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL
   bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
+  // work range of the interior-day kernels (thermo_knot_kernel, streams_day_kernel)
+  struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)
   int e0, n_rec;       // e runs over [-1, D]: -1 / D are the padded PCHIP ends
 };
 
@@ -1010,6 +1014,428 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   }
 }
 
+
+// ---- interior days of the fast path: knot-aligned thermodynamic kernel ---------------------------
+// Days [2, D-2) of a record are "interior": every PCHIP / vapour-pressure knot a step needs exists
+// in the day records, the vapour-pressure interpolant has no NaN ends there, and the rolled minute
+// stream does not wrap.  For those days the work is cut at the KNOTS instead of at midnight: one
+// thread handles the steps between the t_Tmin knot of day e and the t_Tmin knot of day e+1 -- exactly
+// two PCHIP intervals and one vapour-pressure segment -- so what the event handler of
+// disagg_kernel does under divergence (segment set-up, next-event search) happens here once per
+// (cell, e) with the warp converged and all loads independent.  The step loop runs over the
+// warp's union of step ranges with the lane's own range as a predicate, so stores stay full
+// 128-byte rows.  The first / last two days of a record go through disagg_kernel.
+enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_COUNT };
+
+template <typename OutT>
+__global__ void __launch_bounds__(kDisaggThreads, 7)
+thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
+  __shared__ double etab[kExpTab];
+  __shared__ double slot[kT_COUNT][kDisaggThreads];
+  exp_table_init(etab);
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  const int e_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int e_hi = min(e_lo + a.k.tile, a.k.e1);
+  if (cell >= a.f.n_cells || e_lo >= e_hi) return;
+  const msb_params &p = a.p;
+  const msb_forcing &f = a.f;
+  const int ts = p.time_step;
+  const long ld = f.ld;
+  const double inv_ts = 1.0 / (double)ts;
+  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :611
+  const double elev = f.elev[cell];
+  const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
+  const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
+  const size_t plane = (size_t)a.n_rec * (size_t)ld;
+  const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
+  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  const HotK K = load_hot();
+  const unsigned lanes = __activemask();
+
+  const size_t ostride = (size_t)a.out.ld;
+  const long i_base = (long)a.out.day0 * a.tpd;
+  OutT *const o_temp = reinterpret_cast<OutT *>(a.out.var[MSB_V_TEMP]) + cell;
+  OutT *const o_lw = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]) + cell;
+  OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]) + cell;
+  OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
+  OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
+
+  // knot at t_Tmin of day e (disaggregate.py:198-200) with scipy's derivative, and the daily
+  // vapour pressure in kPa there (:480)
+  double x0 = rec(kR_XMIN, e_lo), d0 = rec(kR_DMIN, e_lo);
+  double y0 = f.t_min[(size_t)e_lo * ld + cell];
+  double v0 = a.vp_d[(size_t)e_lo * ld + cell] / 1000.0;
+  int ia = first_step_ge(x0, ts, inv_ts);
+  // tskc: repeated per minute, rolled by off_min, block mean over ts minutes (:593-615)
+  int i_tk = kNever, tk_day = -4;
+  bool tk_started = false;
+  double tkA = 0.0, tkB = 0.0, tk_a = 0.0, tk_b = 0.0;
+  const double dx = (double)ts;
+
+  for (int e = e_lo; e < e_hi; ++e) {
+    const size_t o0 = (size_t)e * ld + cell, o1 = o0 + ld;
+    const double x1 = rec(kR_XMAX, e), d1 = rec(kR_DMAX, e), y1 = f.t_max[o0];
+    const double x2 = rec(kR_XMIN, e + 1), d2 = rec(kR_DMIN, e + 1), y2 = f.t_min[o1];
+    const double v1 = a.vp_d[o1] / 1000.0;
+    const int ib = first_step_ge(x2, ts, inv_ts);
+    int isw = first_step_ge(x1, ts, inv_ts);
+    // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
+    Cubic cub;
+    {
+      const double inv = rcp_nr(x1 - x0);
+      const double m = (y1 - y0) * inv;
+      const double tt = ((d0 + d1) - 2.0 * m) * inv;
+      cub.x0 = x0; cub.x1 = x1;
+      cub.c0 = tt * inv;
+      cub.c1 = (m - d0) * inv - tt;
+      cub.c2 = d0;
+      cub.c3 = y0;
+    }
+    {
+      const double inv = rcp_nr(x2 - x1);
+      const double m = (y2 - y1) * inv;
+      const double tt = ((d1 + d2) - 2.0 * m) * inv;
+      slot[kT_X0][tid] = x1;
+      slot[kT_C0][tid] = tt * inv;
+      slot[kT_C1][tid] = (m - d1) * inv - tt;
+      slot[kT_C2][tid] = d1;
+      slot[kT_C3][tid] = y1;
+    }
+    const double xvl = x0, yvl = v0;
+    const double vslope = div_nr(v1 - v0, x2 - x0);                  // scipy _interpolate.py:513-516
+    const int ja = max(ia, a.k.i_lo), jb = min(ib, a.k.i_hi);
+    const bool any = ja < jb;
+    if (any && isw <= ja) {          // the range starts beyond the t_Tmax knot
+      cub.x0 = slot[kT_X0][tid]; cub.c0 = slot[kT_C0][tid]; cub.c1 = slot[kT_C1][tid];
+      cub.c2 = slot[kT_C2][tid]; cub.c3 = slot[kT_C3][tid];
+      isw = kNever;
+    }
+    if (any && !tk_started) { i_tk = ja; tk_started = true; }
+    int i_next = min(isw, i_tk);
+    const int lo_w = __reduce_min_sync(lanes, any ? ja : kNever);
+    const int hi_w = __reduce_max_sync(lanes, any ? jb : -kNever);
+    double x = (double)ts * (double)lo_w;
+    size_t ooff = (size_t)((long)lo_w - i_base) * ostride;
+#pragma unroll 1
+    for (int i = lo_w; i < hi_w; ++i, x += dx, ooff += ostride) {
+      if (i < ja || i >= jb) continue;
+      if (i == i_next) {
+        if (i == isw) {              // t_Tmax knot crossed (searchsorted side='right')
+          cub.x0 = slot[kT_X0][tid]; cub.c0 = slot[kT_C0][tid]; cub.c1 = slot[kT_C1][tid];
+          cub.c2 = slot[kT_C2][tid]; cub.c3 = slot[kT_C3][tid];
+          isw = kNever;
+        }
+        if (i == i_tk) {             // source day of the minute stream rolls (:611-614)
+          const int m = i * ts + off_min;         // interior days: 0 < m < (D-1)*1440, no wrap
+          const int dA = m / kMinPerDay, r = m - dA * kMinPerDay;
+          if (dA != tk_day) {
+            tkA = (dA == tk_day + 1) ? tkB : a.tskc_d[(size_t)dA * ld + cell];
+            tkB = a.tskc_d[(size_t)(dA + 1) * ld + cell];   // used a day later
+            tk_day = dA;
+          }
+          const int n2 = r + ts - kMinPerDay;
+          double tk;
+          if (n2 > 0) {              // window straddles the day boundary
+            tk = ((double)(ts - n2) * tkA + (double)n2 * tkB) * inv_ts;
+            i_tk = i + 1;
+          } else {
+            tk = tkA;
+            i_tk = i + (kMinPerDay - r) / ts;
+          }
+          tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
+        }
+        i_next = min(isw, i_tk);
+      }
+      // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
+      const double temp = cubic_eval(cub, x);
+      const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
+      const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
+      const double es = es0 * (temp < 0.0 ? corr : 1.0);
+      // -- vapour pressure (linear, clamped to saturation) :480-487 --
+      double vp = fma(x - xvl, vslope, yvl);
+      vp = es < vp ? es : vp;
+      // -- relative humidity :444-446, air pressure :401-403 --
+      const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);
+      const double ap = exp_hot(fma(pr_num, rcp_nr(pr_corr + temp), K.ln_p), etab, K);
+      // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF; tk_a / tk_b carry STEFAN_B) --
+      const double at = temp + K.kelvin;
+      const double xx = (465.0 * vp) * rcp_nr(at);             // 46.5 * (10 vp) / T
+      const double ee = exp_hot(-sqrt_hot(fma(3., xx, K.k12), K), etab, K);
+      const double e1 = fma(-(1.0 + xx), ee, 1.0);
+      const double t2 = at * at;
+      const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+      __stcs(o_temp + ooff, (OutT)temp);
+      __stcs(o_vp + ooff, (OutT)vp);
+      __stcs(o_rh + ooff, (OutT)rh);
+      __stcs(o_ap + ooff, (OutT)ap);
+      __stcs(o_lw + ooff, (OutT)lw);
+    }
+    x0 = x2; d0 = d2; y0 = y2; v0 = v1; ia = ib;
+  }
+}
+
+// ---- interior days of the fast path: source-stream kernel with a fixed daily schedule -------------
+// Precipitation, wind (minute stream) and shortwave (30 s stream) of the interior days [2, D-2),
+// where neither rolled stream wraps around the record.  Same closed forms as disagg_kernel, but the
+// daily schedule is made explicit: for a given cell the roll of the minute stream, the roll of the
+// 30 s stream and the noon crossing happen at the SAME step of every output day (they depend on
+// the longitude offsets only), so they are four per-cell constants instead of a searched event
+// queue, and what a roll needs about the next source day is fetched at the start of the output
+// day into per-thread shared-memory slots.  The handlers are short, load-free state updates.
+enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_WIND, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
+       kY_ROWTOT_CUR, kY_WD_CUR, kY_COUNT };
+
+template <typename OutT, int MINB>
+__global__ void __launch_bounds__(kDisaggThreads, MINB)
+streams_day_kernel(const __grid_constant__ DisaggArgs a) {
+  __shared__ double slot[kY_COUNT][kDisaggThreads];
+  __shared__ int s_doy[kDayWin];
+  const msb_params &p = a.p;
+  const msb_forcing &f = a.f;
+  const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
+  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
+  const int win0 = max(d_lo - 4, 0), nwin = min(min(d_hi + 4, D) - win0, kDayWin);
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = f.doy[win0 + j];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  if (cell >= f.n_cells || d_lo >= d_hi) return;
+  const long ld = f.ld;
+  const int C = 2 * ts;                                     // tiny steps per output step (:660)
+  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376
+  const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
+  const double *const qrow = a.t.q + (size_t)f.lat_row[cell] * 365 * kQLd;
+  auto q_of = [&](int y) {     // table row y rolled over the table's own 366 rows (:656)
+    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
+    return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
+  };
+  const size_t plane = (size_t)a.n_rec * (size_t)ld;
+  const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
+  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  auto lookback = [&](int i, bool &none) {   // what pandas ffill repeats at step i (cold)
+    Cell c;
+    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
+    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
+    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
+    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+    c.t_end = f.t_end;
+    const double v = prec_lookback(p, f, c, i);
+    if (!(v == v)) none = true;
+    return v;
+  };
+
+  // ---- the cell's daily schedule (steps of the output day at which something happens) ----------
+  // minute stream: output day d reads source day d + mq - 1 up to the roll at step t_s, then
+  // source day d + mq; n2m minutes of the straddling window belong to the new day (0 = clean)
+  const int qm = off_min < 0 ? -1 : 0;
+  const int r0 = off_min - qm * kMinPerDay;                 // [0, 1440)
+  const int mq = r0 == 0 ? qm : qm + 1;
+  const int t_s = r0 == 0 ? 0 : (kMinPerDay - r0) / ts;
+  const int n1m = r0 == 0 ? 0 : kMinPerDay - r0 - t_s * ts;
+  const int n2m = n1m > 0 ? ts - n1m : 0;
+  const int t_f = n1m > 0 ? (t_s + 1 == tpd ? 0 : t_s + 1) : 255;   // wind settles after a straddle
+  // 30 s stream: same for the table row / radiation day
+  const int qs = off_tiny < 0 ? -1 : 0;
+  const int c0 = off_tiny - qs * kTiny;                     // [0, 2880)
+  const int tq = c0 == 0 ? qs : qs + 1;
+  const int t_r = c0 == 0 ? 0 : (kTiny - c0) / C;
+  const int k2 = c0 == 0 ? 0 : (c0 + (t_r + 1) * C - kTiny) % C;        // 0 = clean switch
+  const int t_n = ((c0 <= kNoon ? kNoon : kNoon + kTiny) - c0) / C;     // window that contains noon
+  const unsigned ev = (unsigned)t_s | ((unsigned)t_f << 8) | ((unsigned)t_r << 16) | ((unsigned)t_n << 24);
+  auto next_event = [ev](int t) {      // first scheduled step after t (255 = none left today)
+    unsigned best = 255u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned b = (ev >> (8 * k)) & 255u;
+      if ((int)b > t && b < best) best = b;
+    }
+    return (int)best;
+  };
+
+  // ---- state at the first step of the chunk -----------------------------------------------------
+  const int i_lo = d_lo * tpd;
+  int sm = r0 == 0 ? kMinPerDay : r0;                       // start of the next window in its source day
+  PrecDay pd;
+  {
+    const int md0 = d_lo + mq - 1;
+    unpack_prec(rec(kR_PPACK, md0), pd);
+    pd.hsp = rec(kR_HSP, md0); pd.hsq = rec(kR_HSQ, md0); pd.f = rec(kR_PF, md0);
+    slot[kY_WD_CUR][tid] = f.wind[(size_t)md0 * ld + cell];
+  }
+  OutT wd_o = (OutT)slot[kY_WD_CUR][tid];
+  bool nan_cur = !(pd.f == pd.f), need_fixup = false, settle = false;
+  double p_base = 0.0, pr = 0.0;
+  if (nan_cur && r0 != 0) {            // the chunk opens inside a NaN day
+    p_base = lookback(i_lo, need_fixup);
+    pd.f = 0.0;
+  }
+  if (r0 == 0) nan_cur = false;        // the roll at the first step decides (and looks back itself)
+  double p_carry = p_base;
+  double s_prev = prec_cum(pd, sm);
+  double rd_cur = rec(kR_RAD, d_lo + tq - 1);
+  double q_prev, q_pref, sw_carry = 0.0;
+  const double *q_ptr;                 // table entry the step after next will need
+  {
+    const double *q0 = q_of(s_doy[d_lo - win0] - 1 + tq - 1);
+    const int ss = c0 == 0 ? kTiny : c0;
+    q_prev = q0[ss];
+    q_pref = q0[ss + C];
+    q_ptr = q0 + ss + 2 * C;
+    slot[kY_ROWTOT_CUR][tid] = q0[kTiny + 1];
+  }
+
+  const size_t ostride = (size_t)a.out.ld;
+  size_t ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
+  OutT *const o_prec = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + cell;
+  OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell;
+  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
+  const unsigned lanes = __activemask();
+  const int pf_off = a.k.pf * C;
+
+  for (int d = d_lo; d < d_hi; ++d) {
+    // ---- output day d starts (warp converged): fetch what today's rolls need --------------------
+    {
+      if (settle) {          // a straddle at the last step of yesterday
+        slot[kY_WD_CUR][tid] = slot[kY_WIND][tid];
+        wd_o = (OutT)slot[kY_WIND][tid];
+        settle = false;
+      }
+      const int y = s_doy[d - win0] - 1;
+      const double *qa = q_of(y + tq - 1);
+      if (d > d_lo && c0 != 0 && s_doy[d - win0] != s_doy[d - 1 - win0] + 1) {
+        // the day of year jumped (year boundary): row of the "lo" part of today's windows (:656)
+        q_prev = qa[c0];
+        q_pref = qa[c0 + C];
+        q_ptr = qa + c0 + 2 * C;
+        slot[kY_ROWTOT_CUR][tid] = qa[kTiny + 1];
+      }
+      const double *qb = q_of(y + tq);
+      const int mdn = d + mq, sdn = d + tq;
+      const double w0 = rec(kR_PPACK, mdn), w1 = rec(kR_HSP, mdn), w2 = rec(kR_HSQ, mdn),
+                   w3 = rec(kR_PF, mdn), w4 = f.wind[(size_t)mdn * ld + cell],
+                   w5 = rec(kR_RAD, sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny],
+                   w9 = qb[kTiny + 1];
+      prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
+      slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
+      slot[kY_PF][tid] = w3; slot[kY_WIND][tid] = w4; slot[kY_RAD][tid] = w5;
+      slot[kY_QB0][tid] = w6; slot[kY_QBK][tid] = w7; slot[kY_QAEND][tid] = w8;
+      slot[kY_ROWTOT][tid] = w9;
+    }
+    int t_next = next_event(-1);
+    int t = 0;
+    while (t < tpd) {
+      if (t == t_next) {   // ---- scheduled state updates (cold, lanes with an event at this step) ----
+        if (t == t_f && settle) {   // step after a straddling roll: wind settles on the new day
+          slot[kY_WD_CUR][tid] = slot[kY_WIND][tid];
+          wd_o = (OutT)slot[kY_WIND][tid];
+          settle = false;
+        }
+        if (t == t_s) {      // minute stream reaches the end of its source day (:347-351, :376)
+          PrecDay pn;
+          unpack_prec(slot[kY_PPACK][tid], pn);
+          pn.hsp = slot[kY_HSP][tid]; pn.hsq = slot[kY_HSQ][tid]; pn.f = slot[kY_PF][tid];
+          const double wd_n = slot[kY_WIND][tid];
+          const bool nan_new = !(pn.f == pn.f);
+          double fill = 0.0;               // pandas ffill: a NaN step repeats the last valid value
+          if (nan_cur) fill = p_base;      // already inside a NaN run
+          else if (nan_new) {
+            if (d > d_lo || t > 0) fill = pr;      // the previous step of this chunk
+            else fill = lookback(i_lo, need_fixup); // the chunk starts at a NaN day
+          }
+          int pos;
+          double wd_cur;
+          if (n1m == 0) {                  // clean switch
+            pos = 0;
+            sm = 0;
+            wd_cur = wd_n;
+            p_carry = nan_new ? fill : 0.0;
+          } else {                         // straddle: n1m minutes of the old day, n2m of the new one
+            wd_cur = ((double)n1m * slot[kY_WD_CUR][tid] + (double)n2m * wd_n) * (1.0 / (double)ts);
+            settle = true;
+            p_carry = (nan_cur || nan_new)
+                          ? fill
+                          : pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2m);
+            pos = n2m;
+            sm = n2m - ts;                 // the step advances it to n2m
+          }
+          pd = pn;
+          if (nan_new) pd.f = 0.0;         // every step of a NaN day is p_base = the fill value
+          p_base = nan_new ? fill : 0.0;
+          nan_cur = nan_new;
+          s_prev = prec_cum(pd, pos);
+          slot[kY_WD_CUR][tid] = wd_cur;
+          wd_o = (OutT)wd_cur;
+        }
+        if (t == t_r) {      // 30 s stream reaches the end of its table row / radiation day (:656-678)
+          const double rd_n = slot[kY_RAD][tid];
+          const double *qb = q_of(s_doy[d - win0] - 1 + tq);
+          int ss;
+          if (k2 > 0) {                    // straddle: [ss, 2880) of the old row + [0, k2) of the new
+            const double qk = slot[kY_QBK][tid];
+            sw_carry = fma(rd_n, qk - slot[kY_QB0][tid], rd_cur * (slot[kY_QAEND][tid] - q_prev));
+            q_prev = qk;
+            ss = k2 - C;                   // the step advances it to k2
+          } else {
+            q_prev = slot[kY_QB0][tid];
+            ss = 0;
+          }
+          rd_cur = rd_n;
+          q_pref = qb[ss + C];
+          q_ptr = qb + ss + 2 * C;
+          slot[kY_ROWTOT_CUR][tid] = slot[kY_ROWTOT][tid];
+        }
+        if (t == t_n) q_prev -= slot[kY_ROWTOT_CUR][tid];   // window contains tiny step 1440: + row total
+        t_next = next_event(t);
+      }
+      // ---- event-free run up to the earliest event of any lane of the warp ---------------------
+      const int t_stop = min(__reduce_min_sync(lanes, t_next), tpd);
+#pragma unroll 2
+      for (; t < t_stop; ++t, ooff += ostride) {
+        // step: precipitation :265-352, shortwave :618-680, wind :355-380
+        const double qn = q_pref;
+        q_pref = load_early(q_ptr);
+        if (pf_off) prefetch_l1(q_ptr + pf_off);
+        q_ptr += C;
+        sm += ts;
+        const double s1 = prec_cum(pd, sm);
+        pr = fma(pd.f, s1 - s_prev, p_carry);
+        s_prev = s1;
+        p_carry = p_base;
+        const double sw = fma(rd_cur, qn - q_prev, sw_carry);
+        q_prev = qn;
+        sw_carry = 0.0;
+        __stcs(o_wd + ooff, wd_o);
+        __stcs(o_prec + ooff, (OutT)pr);
+        __stcs(o_sw + ooff, (OutT)sw);
+      }
+    }
+  }
+
+  // a NaN run that reaches back to the start of the record: bfill (disaggregate.py:130)
+  if (need_fixup) {
+    Cell c;
+    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
+    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
+    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
+    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+    c.t_end = f.t_end;
+    const int T = D * tpd, i_hi = d_hi * tpd;
+    double fillv = nan("");
+    int j = i_lo;
+    for (; j < T; ++j) {
+      fillv = prec_step_generic(p, f, c, j);
+      if (fillv == fillv) break;
+    }
+    ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
+    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) __stcs(o_prec + ooff, (OutT)fillv);
+  }
+}
+
 // disaggregate.py:583-589 (passthrough with a daily longwave forcing): every day of the sub-daily
 // longwave is scaled so that its mean equals the supplied daily value.  One thread = one
 // (cell, day); reads the float64 staging plane the streaming kernel wrote, applies the unit
@@ -1066,6 +1492,14 @@ extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
   if (ld <= 0 || day1 <= day0) return 0;
   const size_t n_rec = (size_t)(day1 - day0) + 2 * MSB_REC_MARGIN;
   return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
+}
+
+// tuning knob read once from the environment (experiments only; the defaults are the tuned values)
+static int env_int(const char *name, int dflt, int lo, int hi) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
 }
 
 extern "C" size_t msb_disagg_workspace_bytes_lw(int64_t ld, int day0, int day1, int time_step) {
@@ -1157,8 +1591,52 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   disagg_prepare_kernel<<<dim3(cell_blocks, a.n_rec), 128, 0, st>>>(a);
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
   if (example) {   // reference defaults, 8 variables: the thermodynamic half and the stream half
-    MSB_LAUNCH(float, true, false, kVarsThermo);
-    MSB_LAUNCH(float, true, false, kVarsStreams);
+    // sub-range [s0, s1) of the call through disagg_kernel<VARS> (output pointers shifted)
+    auto launch_old = [&](int vars, int s0, int s1) {
+      if (s0 >= s1) return;
+      DisaggArgs b = a;
+      b.out.day0 = s0; b.out.day1 = s1;
+      for (int v = 0; v < MSB_N_SUBVARS; ++v)
+        if (b.out.var[v])
+          b.out.var[v] = reinterpret_cast<char *>(b.out.var[v]) +
+                         (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * sizeof(float);
+      int tl = a.tile_days;
+      while (tl > 1 && (long)cell_blocks * ((s1 - s0 + tl - 1) / tl) < 148L * 4 * 4) tl >>= 1;
+      b.tile_days = tl;
+      dim3 g(cell_blocks, (s1 - s0 + tl - 1) / tl);
+      if (vars == kVarsThermo) disagg_kernel<float, true, false, kVarsThermo><<<g, kDisaggThreads, 0, st>>>(b);
+      else disagg_kernel<float, true, false, kVarsStreams><<<g, kDisaggThreads, 0, st>>>(b);
+    };
+    // interior days [2, D-2): knot-aligned kernel; the record's first / last two days: disagg_kernel
+    const int D = f->n_days;
+    static const int knot_tile = env_int("MSB_KNOT_TILE", 8, 1, 64);
+    static const int day_tile = env_int("MSB_DAY_TILE", 16, 1, 32);
+    const int a0 = out->day0 > 2 ? out->day0 : 2, b0 = out->day1 < D - 2 ? out->day1 : D - 2;
+    if (a0 < b0) {
+      launch_old(kVarsThermo, out->day0, a0);
+      launch_old(kVarsThermo, b0, out->day1);
+      a.k.i_lo = a0 * a.tpd; a.k.i_hi = b0 * a.tpd;
+      a.k.e0 = a0 - 2 > 0 ? a0 - 2 : 0;
+      a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
+      a.k.tile = knot_tile;
+      dim3 gk(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
+      thermo_knot_kernel<float><<<gk, kDisaggThreads, 0, st>>>(a);
+      launch_old(kVarsStreams, out->day0, a0);
+      launch_old(kVarsStreams, b0, out->day1);
+      a.k.i_lo = a.k.i_hi = 0;
+      a.k.e0 = a0; a.k.e1 = b0;            // streams_day_kernel: output days, 8 per thread
+      a.k.tile = day_tile;
+      static const int day_pf = env_int("MSB_DAY_PF", 4, 0, 16);
+      a.k.pf = day_pf;
+      dim3 gs(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
+      static const int day_minb = env_int("MSB_DAY_MINB", 6, 4, 6);
+      if (day_minb == 6) streams_day_kernel<float, 6><<<gs, kDisaggThreads, 0, st>>>(a);
+      else if (day_minb == 5) streams_day_kernel<float, 5><<<gs, kDisaggThreads, 0, st>>>(a);
+      else streams_day_kernel<float, 4><<<gs, kDisaggThreads, 0, st>>>(a);
+    } else {
+      MSB_LAUNCH(float, true, false, kVarsThermo);
+      MSB_LAUNCH(float, true, false, kVarsStreams);
+    }
   }
   else if (out->dtype == 4) {
     if (fast_lw) MSB_LAUNCH(float, true, true, kVarsAny); else MSB_LAUNCH(float, false, true, kVarsAny);
