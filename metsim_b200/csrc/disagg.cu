@@ -27,6 +27,7 @@
 // Values that only the handler needs between events live in per-thread shared-memory slots, and
 // the one table load of the hot path is software-pipelined one step ahead.
 #include <cstdlib>
+#include <mutex>
 
 #include "msb_common.cuh"
 
@@ -1025,14 +1026,75 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 // (cell, e) with the warp converged and all loads independent.  The step loop runs over the
 // warp's union of step ranges with the lane's own range as a predicate, so stores stay full
 // 128-byte rows.  The first / last two days of a record go through disagg_kernel.
-enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_COUNT };
+enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_COUNT };
 
-template <typename OutT>
-__global__ void __launch_bounds__(kDisaggThreads, 7)
+// 2^(j/2048), j < 2048: the exp table of the knot kernel, built once per device (exp_tables_ready)
+constexpr int kExpBig = 2048;
+__device__ double g_exp2_big[kExpBig];
+__global__ void exp_big_init_kernel() {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < kExpBig) {
+    // 2^(j/2048) with (j << 9) taken off the high word: exp_big() adds (k << 9) as a whole, whose
+    // low 20 bits are exactly j << 9 and whose upper bits are the binary exponent k >> 11
+    const double s = exp2((double)j / (double)kExpBig);
+    g_exp2_big[j] = __hiloint2double(__double2hiint(s) - (j << 9), __double2loint(s));
+  }
+}
+__constant__ double c_knot[10] = {
+    237.3,                          // svp denominator offset, physics.py:149
+    -17.269 * 237.3,                // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
+    17.269 - 0.49301845011612494,   // + ln(0.61078): the factor folded into the exponent
+    .000042, .00972,                // ice correction, physics.py:150-151
+    2954.639443740597,              // 2048/ln2
+    0.00033845077175778578,         // ln2/2048
+    4.618333172514372,              // ln(P_STD/1000): air pressure in kPa, disaggregate.py:401-403
+    273.15,                         // KELVIN
+    1.2                             // PRATA, disaggregate.py:557-559
+};
+struct KnotK { double k237, ka, kb, kc2, kc1, inv_l, l, ln_p, kelvin, k12; };
+__device__ __forceinline__ KnotK load_knot() {
+  KnotK k;
+  k.k237 = c_knot[0]; k.ka = c_knot[1]; k.kb = c_knot[2]; k.kc2 = c_knot[3]; k.kc1 = c_knot[4];
+  k.inv_l = c_knot[5]; k.l = c_knot[6]; k.ln_p = c_knot[7]; k.kelvin = c_knot[8]; k.k12 = c_knot[9];
+  return k;
+}
+// The knot kernel's outputs are only written, never fed back, so its fp64 sequences are cut to
+// what the 1e-9 contract needs with two orders of margin:
+//   1/x      MUFU.RCP64H seed (2^-20) + one second-order step        rel. error < 1e-12
+//   sqrt(x)  MUFU.RSQ64H seed + one second-order step                 rel. error < 4e-13
+//   exp(x)   2048-entry 2^(j/2048) table + quadratic on |r| < 1.7e-4  rel. error < 9e-13
+__device__ __forceinline__ double rcp_2(double x) {
+  const double y = rcp_seed(x);
+  const double e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double sqrt_2(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double xy = x * y;
+  const double e = fma(-xy, y, 1.0);
+  return fma(xy, 0.5 * e, xy);
+}
+__device__ __forceinline__ double exp_big(double x, const double *tab, const KnotK &K) {
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
+  // 2048/ln2 truncated to its high word (an instruction immediate): k may differ by one from
+  // rint(x * 2048/ln2) at a rounding boundary, r = x - k ln2/2048 stays consistent with it
+  double kd = fma(x, __hiloint2double(0x40a71547, 0), kMagic);
+  const int k = __double2loint(kd);
+  kd -= kMagic;
+  const double r = fma(-kd, K.l, x);
+  const double q = fma(r * 0.5, r, r);            // exp(r) - 1 = r + r^2/2 (+ r^3/6 < 9e-13)
+  double s = tab[k & (kExpBig - 1)];
+  s = __hiloint2double(__double2hiint(s) + (k << 9), __double2loint(s));
+  return fma(q, s, s);
+}
+
+template <typename OutT, int MINB>
+__global__ void __launch_bounds__(kDisaggThreads, MINB)
 thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
-  __shared__ double etab[kExpTab];
+  __shared__ double etab[kExpBig];
   __shared__ double slot[kT_COUNT][kDisaggThreads];
-  exp_table_init(etab);
+  for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) etab[j] = g_exp2_big[j];
   __syncthreads();
   const int tid = threadIdx.x;
   const int cell = blockIdx.x * blockDim.x + tid;
@@ -1052,7 +1114,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   const size_t plane = (size_t)a.n_rec * (size_t)ld;
   const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
   auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
-  const HotK K = load_hot();
+  const KnotK K = load_knot();
   const unsigned lanes = __activemask();
 
   const size_t ostride = (size_t)a.out.ld;
@@ -1063,24 +1125,21 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
   OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
 
-  // knot at t_Tmin of day e (disaggregate.py:198-200) with scipy's derivative, and the daily
-  // vapour pressure in kPa there (:480)
-  double x0 = rec(kR_XMIN, e_lo), d0 = rec(kR_DMIN, e_lo);
-  double y0 = f.t_min[(size_t)e_lo * ld + cell];
-  double v0 = a.vp_d[(size_t)e_lo * ld + cell] / 1000.0;
-  int ia = first_step_ge(x0, ts, inv_ts);
   // tskc: repeated per minute, rolled by off_min, block mean over ts minutes (:593-615)
   int i_tk = kNever, tk_day = -4;
   bool tk_started = false;
-  double tkA = 0.0, tkB = 0.0, tk_a = 0.0, tk_b = 0.0;
+  double tk_a = 0.0, tk_b = 0.0;
   const double dx = (double)ts;
 
   for (int e = e_lo; e < e_hi; ++e) {
+    // knots at t_Tmin / t_Tmax of day e and t_Tmin of day e+1 (disaggregate.py:198-200) with
+    // scipy's derivatives, and the daily vapour pressure in kPa at the two t_Tmin knots (:480)
     const size_t o0 = (size_t)e * ld + cell, o1 = o0 + ld;
+    const double x0 = rec(kR_XMIN, e), d0 = rec(kR_DMIN, e), y0 = f.t_min[o0];
     const double x1 = rec(kR_XMAX, e), d1 = rec(kR_DMAX, e), y1 = f.t_max[o0];
     const double x2 = rec(kR_XMIN, e + 1), d2 = rec(kR_DMIN, e + 1), y2 = f.t_min[o1];
-    const double v1 = a.vp_d[o1] / 1000.0;
-    const int ib = first_step_ge(x2, ts, inv_ts);
+    const double v0 = a.vp_d[o0] / 1000.0, v1 = a.vp_d[o1] / 1000.0;
+    const int ia = first_step_ge(x0, ts, inv_ts), ib = first_step_ge(x2, ts, inv_ts);
     int isw = first_step_ge(x1, ts, inv_ts);
     // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
     Cubic cub;
@@ -1132,17 +1191,16 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
           const int m = i * ts + off_min;         // interior days: 0 < m < (D-1)*1440, no wrap
           const int dA = m / kMinPerDay, r = m - dA * kMinPerDay;
           if (dA != tk_day) {
-            tkA = (dA == tk_day + 1) ? tkB : a.tskc_d[(size_t)dA * ld + cell];
-            tkB = a.tskc_d[(size_t)(dA + 1) * ld + cell];   // used a day later
+            slot[kT_TKA][tid] = (dA == tk_day + 1) ? slot[kT_TKB][tid] : a.tskc_d[(size_t)dA * ld + cell];
+            slot[kT_TKB][tid] = a.tskc_d[(size_t)(dA + 1) * ld + cell];   // used a day later
             tk_day = dA;
           }
           const int n2 = r + ts - kMinPerDay;
-          double tk;
+          double tk = slot[kT_TKA][tid];
           if (n2 > 0) {              // window straddles the day boundary
-            tk = ((double)(ts - n2) * tkA + (double)n2 * tkB) * inv_ts;
+            tk = ((double)(ts - n2) * tk + (double)n2 * slot[kT_TKB][tid]) * inv_ts;
             i_tk = i + 1;
           } else {
-            tk = tkA;
             i_tk = i + (kMinPerDay - r) / ts;
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
@@ -1151,19 +1209,20 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       }
       // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
       const double temp = cubic_eval(cub, x);
-      const double es0 = exp_hot(fma(K.ka, rcp_nr(K.k237 + temp), K.kb), etab, K);
+      const double es0 = exp_big(fma(K.ka, rcp_2(K.k237 + temp), K.kb), etab, K);
       const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
       const double es = es0 * (temp < 0.0 ? corr : 1.0);
       // -- vapour pressure (linear, clamped to saturation) :480-487 --
       double vp = fma(x - xvl, vslope, yvl);
       vp = es < vp ? es : vp;
       // -- relative humidity :444-446, air pressure :401-403 --
-      const double rh = fmin(100.0 * (vp * rcp_nr(es)), 100.0);
-      const double ap = exp_hot(fma(pr_num, rcp_nr(pr_corr + temp), K.ln_p), etab, K);
+      const double rh_raw = 100.0 * (vp * rcp_2(es));
+      const double rh = rh_raw > 100.0 ? 100.0 : rh_raw;      // np.minimum; vp, es are finite here
+      const double ap = exp_big(fma(pr_num, rcp_2(pr_corr + temp), K.ln_p), etab, K);
       // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF; tk_a / tk_b carry STEFAN_B) --
       const double at = temp + K.kelvin;
-      const double xx = (465.0 * vp) * rcp_nr(at);             // 46.5 * (10 vp) / T
-      const double ee = exp_hot(-sqrt_hot(fma(3., xx, K.k12), K), etab, K);
+      const double xx = (465.0 * vp) * rcp_2(at);              // 46.5 * (10 vp) / T
+      const double ee = exp_big(-sqrt_2(fma(3., xx, K.k12)), etab, K);
       const double e1 = fma(-(1.0 + xx), ee, 1.0);
       const double t2 = at * at;
       const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
@@ -1173,7 +1232,6 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       __stcs(o_ap + ooff, (OutT)ap);
       __stcs(o_lw + ooff, (OutT)lw);
     }
-    x0 = x2; d0 = d2; y0 = y2; v0 = v1; ia = ib;
   }
 }
 
@@ -1494,6 +1552,23 @@ extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
   return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
 }
 
+// g_exp2_big of the current device, filled on the first call per device (stream-ordered before use)
+static int exp_tables_ready(cudaStream_t st) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  MSB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) { set_error("msb_disaggregate: device index %d out of range", dev); return MSB_E_ARG; }
+  if (!done[dev]) {
+    exp_big_init_kernel<<<kExpBig / 256, 256, 0, st>>>();
+    MSB_CUDA(cudaGetLastError());
+    MSB_CUDA(cudaStreamSynchronize(st));   // later calls may come on other streams
+    done[dev] = true;
+  }
+  return MSB_OK;
+}
+
 // tuning knob read once from the environment (experiments only; the defaults are the tuned values)
 static int env_int(const char *name, int dflt, int lo, int hi) {
   const char *v = getenv(name);
@@ -1613,6 +1688,8 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     static const int day_tile = env_int("MSB_DAY_TILE", 16, 1, 32);
     const int a0 = out->day0 > 2 ? out->day0 : 2, b0 = out->day1 < D - 2 ? out->day1 : D - 2;
     if (a0 < b0) {
+      const int rc_tab = exp_tables_ready(st);
+      if (rc_tab) return rc_tab;
       launch_old(kVarsThermo, out->day0, a0);
       launch_old(kVarsThermo, b0, out->day1);
       a.k.i_lo = a0 * a.tpd; a.k.i_hi = b0 * a.tpd;
@@ -1620,7 +1697,11 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
       a.k.tile = knot_tile;
       dim3 gk(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-      thermo_knot_kernel<float><<<gk, kDisaggThreads, 0, st>>>(a);
+      static const int knot_minb = env_int("MSB_KNOT_MINB", 8, 5, 8);
+      if (knot_minb == 7) thermo_knot_kernel<float, 7><<<gk, kDisaggThreads, 0, st>>>(a);
+      else if (knot_minb == 8) thermo_knot_kernel<float, 8><<<gk, kDisaggThreads, 0, st>>>(a);
+      else if (knot_minb == 6) thermo_knot_kernel<float, 6><<<gk, kDisaggThreads, 0, st>>>(a);
+      else thermo_knot_kernel<float, 5><<<gk, kDisaggThreads, 0, st>>>(a);
       launch_old(kVarsStreams, out->day0, a0);
       launch_old(kVarsStreams, b0, out->day1);
       a.k.i_lo = a.k.i_hi = 0;
