@@ -288,7 +288,16 @@ def main():
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
     rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
-    launches_per_step = 2 + 2 * rounds + 1 + 3 * n_tiles   # 2 solar, daily passes, (prepare + 2 stream kernels) per tile
+    # 2 solar kernels, daily passes (pass 1 + reduce per round, pass 2), and per msb_disaggregate
+    # call: day records + thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2),
+    # plus disagg_kernel<thermo> / <streams> over the first / last two days of the record
+    def disagg_launches(d0, d1):
+        a0, b0 = max(d0, 2), min(d1, n_days - 2)
+        if a0 >= b0:
+            return 3
+        return 3 + (2 if d0 < a0 else 0) + (2 if b0 < d1 else 0)
+    launches_per_step = 2 + 2 * rounds + 1 + sum(
+        disagg_launches(k * tile, min(n_days, (k + 1) * tile)) for k in range(n_tiles))
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(marks=None):
@@ -414,8 +423,9 @@ def main():
                              % (len(OUT_VARS) * tile * tpd * n * 4 / 1e9, 4 * n_days * n * 8 / 1e9)},
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
                              "disaggregate": float(br[2])},
-            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + disagg_kernel<thermo> + "
-                                                   "disagg_kernel<streams>, timed together per call (--tile-days days)",
+            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + thermo_knot_kernel + "
+                                                   "streams_day_kernel (+ disagg_kernel on the record's first / last "
+                                                   "two days), timed together per call (--tile-days days)",
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_cell_timestep": bytes_per_cts,

@@ -169,9 +169,10 @@ size_t msb_disagg_workspace_bytes_lw(int64_t ld, int day0, int day1, int time_st
 int msb_disaggregate(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *daily, const msb_subdaily *out, void *stream);
 
-/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [8][n]
+/* accuracy probe of the library's fp64 divide / exp / sqrt sequences: out_dev is [12][n]
  * (1/x, fast exp(x), fast sqrt(x), 1.2345678901234567/x, svp(x) in kPa, raw reciprocal seed,
- * accurate exp(x), accurate sqrt(x)).  Used by the parity tests. */
+ * accurate exp(x), accurate sqrt(x), remainder(x, 360), and the second-order 1/x, sqrt(x), exp(x)
+ * of the interior-day kernel).  Used by the parity tests. */
 int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream);
 
 /* ---- whole path with HOST buffers (what a reference-side binding calls) ---------------------

@@ -484,7 +484,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const int nk = c.nk;
-  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   c.off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;
   c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
   c.frac = p.tmax_daylength_fraction;
@@ -586,7 +586,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const int nk = 2 * D + 4;
-  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376,:611
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
   c.off_min = off_min;
@@ -1026,7 +1026,7 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 // (cell, e) with the warp converged and all loads independent.  The step loop runs over the
 // warp's union of step ranges with the lane's own range as a predicate, so stores stay full
 // 128-byte rows.  The first / last two days of a record go through disagg_kernel.
-enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_COUNT };
+enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_WDA, kT_WDB, kT_COUNT };
 
 // 2^(j/2048), j < 2048: the exp table of the knot kernel, built once per device (exp_tables_ready)
 constexpr int kExpBig = 2048;
@@ -1106,7 +1106,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   const int ts = p.time_step;
   const long ld = f.ld;
   const double inv_ts = 1.0 / (double)ts;
-  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :611
   const double elev = f.elev[cell];
   const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
@@ -1124,11 +1124,14 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]) + cell;
   OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
   OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
+  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
 
-  // tskc: repeated per minute, rolled by off_min, block mean over ts minutes (:593-615)
+  // tskc and wind: repeated per minute, rolled by off_min, block mean over ts minutes
+  // (:593-615, :355-380); wind rides along here because it shares this stream's roll exactly
   int i_tk = kNever, tk_day = -4;
   bool tk_started = false;
   double tk_a = 0.0, tk_b = 0.0;
+  OutT wd_o = 0;
   const double dx = (double)ts;
 
   for (int e = e_lo; e < e_hi; ++e) {
@@ -1191,19 +1194,26 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
           const int m = i * ts + off_min;         // interior days: 0 < m < (D-1)*1440, no wrap
           const int dA = m / kMinPerDay, r = m - dA * kMinPerDay;
           if (dA != tk_day) {
-            slot[kT_TKA][tid] = (dA == tk_day + 1) ? slot[kT_TKB][tid] : a.tskc_d[(size_t)dA * ld + cell];
-            slot[kT_TKB][tid] = a.tskc_d[(size_t)(dA + 1) * ld + cell];   // used a day later
+            const size_t oA = (size_t)dA * ld + cell;
+            const bool next = dA == tk_day + 1;
+            slot[kT_TKA][tid] = next ? slot[kT_TKB][tid] : a.tskc_d[oA];
+            slot[kT_WDA][tid] = next ? slot[kT_WDB][tid] : f.wind[oA];
+            slot[kT_TKB][tid] = a.tskc_d[oA + ld];   // used a day later
+            slot[kT_WDB][tid] = f.wind[oA + ld];
             tk_day = dA;
           }
           const int n2 = r + ts - kMinPerDay;
-          double tk = slot[kT_TKA][tid];
+          double tk = slot[kT_TKA][tid], wd = slot[kT_WDA][tid];
           if (n2 > 0) {              // window straddles the day boundary
-            tk = ((double)(ts - n2) * tk + (double)n2 * slot[kT_TKB][tid]) * inv_ts;
+            const double w1 = (double)(ts - n2), w2 = (double)n2;
+            tk = (w1 * tk + w2 * slot[kT_TKB][tid]) * inv_ts;
+            wd = (w1 * wd + w2 * slot[kT_WDB][tid]) * inv_ts;
             i_tk = i + 1;
           } else {
             i_tk = i + (kMinPerDay - r) / ts;
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
+          wd_o = (OutT)wd;
         }
         i_next = min(isw, i_tk);
       }
@@ -1231,20 +1241,22 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       __stcs(o_rh + ooff, (OutT)rh);
       __stcs(o_ap + ooff, (OutT)ap);
       __stcs(o_lw + ooff, (OutT)lw);
+      __stcs(o_wd + ooff, wd_o);
     }
   }
 }
 
 // ---- interior days of the fast path: source-stream kernel with a fixed daily schedule -------------
-// Precipitation, wind (minute stream) and shortwave (30 s stream) of the interior days [2, D-2),
+// Precipitation (minute stream) and shortwave (30 s stream) of the interior days [2, D-2) -- wind
+// is written by thermo_knot_kernel, which already follows the minute stream's roll for tskc --
 // where neither rolled stream wraps around the record.  Same closed forms as disagg_kernel, but the
 // daily schedule is made explicit: for a given cell the roll of the minute stream, the roll of the
 // 30 s stream and the noon crossing happen at the SAME step of every output day (they depend on
 // the longitude offsets only), so they are four per-cell constants instead of a searched event
 // queue, and what a roll needs about the next source day is fetched at the start of the output
 // day into per-thread shared-memory slots.  The handlers are short, load-free state updates.
-enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_WIND, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
-       kY_ROWTOT_CUR, kY_WD_CUR, kY_COUNT };
+enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
+       kY_ROWTOT_CUR, kY_COUNT };
 
 template <typename OutT, int MINB>
 __global__ void __launch_bounds__(kDisaggThreads, MINB)
@@ -1264,7 +1276,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   if (cell >= f.n_cells || d_lo >= d_hi) return;
   const long ld = f.ld;
   const int C = 2 * ts;                                     // tiny steps per output step (:660)
-  const double lon = remainder(f.lon[cell], 360.0);                      // disaggregate.py:67
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
   const double *const qrow = a.t.q + (size_t)f.lat_row[cell] * 365 * kQLd;
@@ -1296,7 +1308,6 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   const int t_s = r0 == 0 ? 0 : (kMinPerDay - r0) / ts;
   const int n1m = r0 == 0 ? 0 : kMinPerDay - r0 - t_s * ts;
   const int n2m = n1m > 0 ? ts - n1m : 0;
-  const int t_f = n1m > 0 ? (t_s + 1 == tpd ? 0 : t_s + 1) : 255;   // wind settles after a straddle
   // 30 s stream: same for the table row / radiation day
   const int qs = off_tiny < 0 ? -1 : 0;
   const int c0 = off_tiny - qs * kTiny;                     // [0, 2880)
@@ -1304,11 +1315,11 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   const int t_r = c0 == 0 ? 0 : (kTiny - c0) / C;
   const int k2 = c0 == 0 ? 0 : (c0 + (t_r + 1) * C - kTiny) % C;        // 0 = clean switch
   const int t_n = ((c0 <= kNoon ? kNoon : kNoon + kTiny) - c0) / C;     // window that contains noon
-  const unsigned ev = (unsigned)t_s | ((unsigned)t_f << 8) | ((unsigned)t_r << 16) | ((unsigned)t_n << 24);
+  const unsigned ev = (unsigned)t_s | ((unsigned)t_r << 8) | ((unsigned)t_n << 16);
   auto next_event = [ev](int t) {      // first scheduled step after t (255 = none left today)
     unsigned best = 255u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 3; ++k) {
       const unsigned b = (ev >> (8 * k)) & 255u;
       if ((int)b > t && b < best) best = b;
     }
@@ -1323,10 +1334,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
     const int md0 = d_lo + mq - 1;
     unpack_prec(rec(kR_PPACK, md0), pd);
     pd.hsp = rec(kR_HSP, md0); pd.hsq = rec(kR_HSQ, md0); pd.f = rec(kR_PF, md0);
-    slot[kY_WD_CUR][tid] = f.wind[(size_t)md0 * ld + cell];
   }
-  OutT wd_o = (OutT)slot[kY_WD_CUR][tid];
-  bool nan_cur = !(pd.f == pd.f), need_fixup = false, settle = false;
+  bool nan_cur = !(pd.f == pd.f), need_fixup = false;
   double p_base = 0.0, pr = 0.0;
   if (nan_cur && r0 != 0) {            // the chunk opens inside a NaN day
     p_base = lookback(i_lo, need_fixup);
@@ -1351,18 +1360,12 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   size_t ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
   OutT *const o_prec = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + cell;
   OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell;
-  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
   const unsigned lanes = __activemask();
   const int pf_off = a.k.pf * C;
 
   for (int d = d_lo; d < d_hi; ++d) {
     // ---- output day d starts (warp converged): fetch what today's rolls need --------------------
     {
-      if (settle) {          // a straddle at the last step of yesterday
-        slot[kY_WD_CUR][tid] = slot[kY_WIND][tid];
-        wd_o = (OutT)slot[kY_WIND][tid];
-        settle = false;
-      }
       const int y = s_doy[d - win0] - 1;
       const double *qa = q_of(y + tq - 1);
       if (d > d_lo && c0 != 0 && s_doy[d - win0] != s_doy[d - 1 - win0] + 1) {
@@ -1375,12 +1378,11 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       const double *qb = q_of(y + tq);
       const int mdn = d + mq, sdn = d + tq;
       const double w0 = rec(kR_PPACK, mdn), w1 = rec(kR_HSP, mdn), w2 = rec(kR_HSQ, mdn),
-                   w3 = rec(kR_PF, mdn), w4 = f.wind[(size_t)mdn * ld + cell],
-                   w5 = rec(kR_RAD, sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny],
+                   w3 = rec(kR_PF, mdn), w5 = rec(kR_RAD, sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny],
                    w9 = qb[kTiny + 1];
       prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
       slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
-      slot[kY_PF][tid] = w3; slot[kY_WIND][tid] = w4; slot[kY_RAD][tid] = w5;
+      slot[kY_PF][tid] = w3; slot[kY_RAD][tid] = w5;
       slot[kY_QB0][tid] = w6; slot[kY_QBK][tid] = w7; slot[kY_QAEND][tid] = w8;
       slot[kY_ROWTOT][tid] = w9;
     }
@@ -1388,16 +1390,10 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
     int t = 0;
     while (t < tpd) {
       if (t == t_next) {   // ---- scheduled state updates (cold, lanes with an event at this step) ----
-        if (t == t_f && settle) {   // step after a straddling roll: wind settles on the new day
-          slot[kY_WD_CUR][tid] = slot[kY_WIND][tid];
-          wd_o = (OutT)slot[kY_WIND][tid];
-          settle = false;
-        }
         if (t == t_s) {      // minute stream reaches the end of its source day (:347-351, :376)
           PrecDay pn;
           unpack_prec(slot[kY_PPACK][tid], pn);
           pn.hsp = slot[kY_HSP][tid]; pn.hsq = slot[kY_HSQ][tid]; pn.f = slot[kY_PF][tid];
-          const double wd_n = slot[kY_WIND][tid];
           const bool nan_new = !(pn.f == pn.f);
           double fill = 0.0;               // pandas ffill: a NaN step repeats the last valid value
           if (nan_cur) fill = p_base;      // already inside a NaN run
@@ -1406,15 +1402,11 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
             else fill = lookback(i_lo, need_fixup); // the chunk starts at a NaN day
           }
           int pos;
-          double wd_cur;
           if (n1m == 0) {                  // clean switch
             pos = 0;
             sm = 0;
-            wd_cur = wd_n;
             p_carry = nan_new ? fill : 0.0;
           } else {                         // straddle: n1m minutes of the old day, n2m of the new one
-            wd_cur = ((double)n1m * slot[kY_WD_CUR][tid] + (double)n2m * wd_n) * (1.0 / (double)ts);
-            settle = true;
             p_carry = (nan_cur || nan_new)
                           ? fill
                           : pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2m);
@@ -1426,8 +1418,6 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
           p_base = nan_new ? fill : 0.0;
           nan_cur = nan_new;
           s_prev = prec_cum(pd, pos);
-          slot[kY_WD_CUR][tid] = wd_cur;
-          wd_o = (OutT)wd_cur;
         }
         if (t == t_r) {      // 30 s stream reaches the end of its table row / radiation day (:656-678)
           const double rd_n = slot[kY_RAD][tid];
@@ -1457,7 +1447,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
         // step: precipitation :265-352, shortwave :618-680, wind :355-380
         const double qn = q_pref;
         q_pref = load_early(q_ptr);
-        if (pf_off) prefetch_l1(q_ptr + pf_off);
+        prefetch_l1(q_ptr + pf_off);
         q_ptr += C;
         sm += ts;
         const double s1 = prec_cum(pd, sm);
@@ -1467,7 +1457,6 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
         const double sw = fma(rd_cur, qn - q_prev, sw_carry);
         q_prev = qn;
         sw_carry = 0.0;
-        __stcs(o_wd + ooff, wd_o);
         __stcs(o_prec + ooff, (OutT)pr);
         __stcs(o_sw + ooff, (OutT)sw);
       }
@@ -1520,11 +1509,18 @@ lw_rescale_kernel(const __grid_constant__ DisaggArgs a) {
 // accuracy probe of the hand-written fp64 sequences (tests only touch it through the C ABI)
 __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
   __shared__ double etab[kExpTab];
+  __shared__ double ebig[kExpBig];
   exp_table_init(etab);
+  for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) ebig[j] = g_exp2_big[j];
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
+  const KnotK K = load_knot();
+  out[8 * (size_t)n + i] = wrap_lon(v);
+  out[9 * (size_t)n + i] = rcp_2(v);
+  out[10 * (size_t)n + i] = sqrt_2(v);
+  out[11 * (size_t)n + i] = exp_big(v, ebig, K);
   out[i] = rcp_nr(v);
   out[n + i] = exp_tab(v, etab);
   out[2 * n + i] = sqrt_fast(v);
@@ -1538,19 +1534,6 @@ __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double
 }  // namespace msb
 
 using namespace msb;
-
-extern "C" int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream) {
-  if (n <= 0 || !x_dev || !out_dev) { set_error("msb_selftest_math: bad argument"); return MSB_E_ARG; }
-  math_selftest_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n, x_dev, out_dev);
-  MSB_CUDA(cudaGetLastError());
-  return MSB_OK;
-}
-
-extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
-  if (ld <= 0 || day1 <= day0) return 0;
-  const size_t n_rec = (size_t)(day1 - day0) + 2 * MSB_REC_MARGIN;
-  return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
-}
 
 // g_exp2_big of the current device, filled on the first call per device (stream-ordered before use)
 static int exp_tables_ready(cudaStream_t st) {
@@ -1567,6 +1550,21 @@ static int exp_tables_ready(cudaStream_t st) {
     done[dev] = true;
   }
   return MSB_OK;
+}
+
+extern "C" int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream) {
+  if (n <= 0 || !x_dev || !out_dev) { set_error("msb_selftest_math: bad argument"); return MSB_E_ARG; }
+  const int rc_tab = exp_tables_ready(reinterpret_cast<cudaStream_t>(stream));
+  if (rc_tab) return rc_tab;
+  math_selftest_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n, x_dev, out_dev);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}
+
+extern "C" size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1) {
+  if (ld <= 0 || day1 <= day0) return 0;
+  const size_t n_rec = (size_t)(day1 - day0) + 2 * MSB_REC_MARGIN;
+  return (size_t)MSB_REC_FIELDS * n_rec * (size_t)ld * sizeof(double);
 }
 
 // tuning knob read once from the environment (experiments only; the defaults are the tuned values)

@@ -148,6 +148,18 @@ __device__ __forceinline__ double svp_ref(double t) {
   return s * 1000.0;
 }
 
+// math.remainder(lon, 360) (disaggregate.py:67) for |lon| < 1e9 without the library's bit-serial
+// loop: n = rint(lon / 360) on the IEEE quotient (exact for the ties at odd multiples of 180, which
+// rint then sends to the even n exactly like IEEE remainder), r = lon - 360 n is exact in one fma,
+// and a quotient that rounded across a half-integer is put back by the range fix-up.
+__device__ __forceinline__ double wrap_lon(double lon) {
+  const double n = rint(lon / 360.0);
+  double r = fma(-360.0, n, lon);
+  if (r > 180.0) r -= 360.0;
+  else if (r < -180.0) r += 360.0;
+  return r;
+}
+
 __device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }
 #endif  // __CUDACC__
 

@@ -48,7 +48,7 @@ def test_fp64_building_blocks_accuracy():
     x = np.concatenate([rng.uniform(1e-3, 5e3, 200000), rng.uniform(150.0, 400.0, 100000),
                         10.0 ** rng.uniform(-6, 6, 50000)])
     xd = torch.from_numpy(x).cuda()
-    out = torch.empty((8, x.size), dtype=torch.float64, device="cuda")
+    out = torch.empty((12, x.size), dtype=torch.float64, device="cuda")
     _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
     torch.cuda.synchronize()
     o = out.cpu().numpy()
@@ -58,6 +58,9 @@ def test_fp64_building_blocks_accuracy():
     assert np.max(np.abs(o[2] / np.sqrt(x) - 1.0)) < 2e-15
     assert np.max(np.abs(o[7] / np.sqrt(x) - 1.0)) < 5e-16
     assert np.max(np.abs(o[3] * x / 1.2345678901234567 - 1.0)) < 1e-15
+    # second-order sequences of the interior-day kernel: three orders inside the 1e-9 contract
+    assert np.max(np.abs(o[9] * x - 1.0)) < 1e-11
+    assert np.max(np.abs(o[10] / np.sqrt(x) - 1.0)) < 1e-11
     # exp over the argument range the kernels use
     xe = rng.uniform(-40.0, 40.0, x.size)
     xd.copy_(torch.from_numpy(xe))
@@ -66,6 +69,16 @@ def test_fp64_building_blocks_accuracy():
     o = out.cpu().numpy()
     assert np.max(np.abs(o[1] / np.exp(xe) - 1.0)) < 1e-12
     assert np.max(np.abs(o[6] / np.exp(xe) - 1.0)) < 1e-15
+    assert np.max(np.abs(o[11] / np.exp(xe) - 1.0)) < 2e-12
+    # longitude wrap == math.remainder(lon, 360), bit for bit, including the ties at +-180
+    import math
+    lon = np.concatenate([rng.uniform(-1000.0, 1000.0, x.size - 16),
+                          [180.0, -180.0, 540.0, -540.0, 900.0, 179.99999999999997, -179.99999999999997,
+                           180.00000000000003, 359.9, -359.75, 0.0, 360.0, -360.0, 720.0, 0.125, -67.03125]])
+    xd.copy_(torch.from_numpy(lon))
+    _lib.check(lib.msb_selftest_math(x.size, C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy()[8], np.array([math.remainder(v, 360.0) for v in lon]))
     # svp in kPa over meteorological temperatures (physics.py:124-152)
     t = rng.uniform(-80.0, 60.0, x.size)
     xd.copy_(torch.from_numpy(t))
