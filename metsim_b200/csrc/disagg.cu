@@ -49,6 +49,8 @@ struct DisaggArgs {
   double *rec;         // day records [MSB_REC_FIELDS][n_rec][ld], record r = padded day e0 + r
   double *lw_raw;      // passthrough with a supplied daily longwave: unscaled float64 longwave
                        // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL
+  double inv_sw_den;   // 1 / (3600 * ts / 60), disaggregate.py:645
+  int prep_days;       // padded days per thread of disagg_prepare_kernel
   bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
   // work range of the interior-day kernels (thermo_knot_kernel, streams_day_kernel)
   struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)
@@ -473,14 +475,15 @@ __device__ __forceinline__ void unpack_prec(double w, PrecDay &pd) {
 // One thread = one (cell, padded day e): the two knots of the day from the four knots around them
 // (interior: weighted harmonic mean of the neighbouring slopes; record ends: scipy's three-point
 // edge rule, _cubic.py:279-291, :320-333).
+constexpr int kPrepDays = 8;   // padded days per thread of the record kernel
 __global__ void __launch_bounds__(128)
 disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
-  if (cell >= a.f.n_cells || r >= a.n_rec) return;
+  if (cell >= a.f.n_cells) return;
   const msb_params &p = a.p;
   const msb_forcing &f = a.f;
-  const int D = f.n_days, ts = p.time_step, e = a.e0 + r;
+  const int D = f.n_days, ts = p.time_step;
+  const int r_lo = blockIdx.y * a.prep_days, r_hi = min(r_lo + a.prep_days, a.n_rec);
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const int nk = c.nk;
@@ -495,6 +498,12 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
   c.t_end = f.t_end;
   const size_t plane = (size_t)a.n_rec * f.ld;
+  const double *const dayl = a.t.daylength + (size_t)row * kRows;
+  const double inv_sw_den = a.inv_sw_den;
+  // the per-cell constants above are shared by kPrepDays consecutive padded days
+#pragma unroll 1
+  for (int r = r_lo; r < r_hi; ++r) {
+  const int e = a.e0 + r;
   double *out = a.rec + (size_t)r * f.ld + cell;
 
   // knots j0-1 .. j0+2 (j0 = t_Tmin knot of padded day e); all loads are independent
@@ -530,7 +539,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   out[kR_DMIN * plane] = d_min;
   out[kR_XMAX * plane] = xc;
   out[kR_DMAX * plane] = d_max;
-  if (e < 0 || e >= D) return;                      // padded ends carry knots only
+  if (e < 0 || e >= D) continue;                    // padded ends carry knots only
   const size_t o = (size_t)e * f.ld + cell;
   PrecDay pd;
   pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
@@ -539,9 +548,9 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   out[kR_HSP * plane] = pd.hsp;
   out[kR_HSQ * plane] = pd.hsq;
   out[kR_PF * plane] = pd.f;
-  const double *dayl = a.t.daylength + (size_t)row * kRows;
   const double dl = a.sw_full_day ? kSecPerDay : dayl[f.doy[e] - 1];
-  out[kR_RAD * plane] = (a.sw_d[o] * dl) * (1.0 / (3600.0 * ((double)ts / 60.0)));
+  out[kR_RAD * plane] = (a.sw_d[o] * dl) * inv_sw_den;
+  }
 }
 
 // One thread = one cell x one tile of days.  np.roll by a whole number of minutes (tskc, wind,
@@ -1661,7 +1670,10 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
   const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4 && !a.lw_raw;
-  disagg_prepare_kernel<<<dim3(cell_blocks, a.n_rec), 128, 0, st>>>(a);
+  a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
+  static const int prep_days = env_int("MSB_PREP_DAYS", kPrepDays, 1, 16);
+  a.prep_days = prep_days;
+  disagg_prepare_kernel<<<dim3(cell_blocks, (a.n_rec + prep_days - 1) / prep_days), 128, 0, st>>>(a);
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
   if (example) {   // reference defaults, 8 variables: the thermodynamic half and the stream half
     // sub-range [s0, s1) of the call through disagg_kernel<VARS> (output pointers shifted)
@@ -1710,8 +1722,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       dim3 gs(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
       static const int day_minb = env_int("MSB_DAY_MINB", 6, 4, 6);
       if (day_minb == 6) streams_day_kernel<float, 6><<<gs, kDisaggThreads, 0, st>>>(a);
-      else if (day_minb == 5) streams_day_kernel<float, 5><<<gs, kDisaggThreads, 0, st>>>(a);
-      else streams_day_kernel<float, 4><<<gs, kDisaggThreads, 0, st>>>(a);
+      else streams_day_kernel<float, 5><<<gs, kDisaggThreads, 0, st>>>(a);
     } else {
       MSB_LAUNCH(float, true, false, kVarsThermo);
       MSB_LAUNCH(float, true, false, kVarsStreams);
