@@ -51,6 +51,7 @@ struct DisaggArgs {
                        // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL
   double inv_sw_den;   // 1 / (3600 * ts / 60), disaggregate.py:645
   int prep_days;       // padded days per thread of disagg_prepare_kernel
+  int prep_r0, prep_r1;  // records [prep_r0, prep_r1) are (re)built by this launch
   bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
   // work range of the interior-day kernels (thermo_knot_kernel, streams_day_kernel)
   struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)
@@ -483,7 +484,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   const msb_params &p = a.p;
   const msb_forcing &f = a.f;
   const int D = f.n_days, ts = p.time_step;
-  const int r_lo = blockIdx.y * a.prep_days, r_hi = min(r_lo + a.prep_days, a.n_rec);
+  const int r_lo = a.prep_r0 + blockIdx.y * a.prep_days, r_hi = min(r_lo + a.prep_days, a.prep_r1);
   Cell c;
   c.cell = cell; c.D = D; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * D + 4; c.ld = f.ld;
   const int nk = c.nk;
@@ -1035,18 +1036,20 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 // (cell, e) with the warp converged and all loads independent.  The step loop runs over the
 // warp's union of step ranges with the lane's own range as a predicate, so stores stay full
 // 128-byte rows.  The first / last two days of a record go through disagg_kernel.
-enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_WDA, kT_WDB, kT_COUNT };
+enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_WDA, kT_WDB,
+       kT_KX0, kT_KY0, kT_KD0, kT_KX1, kT_KY1, kT_KM01, kT_COUNT };
 
-// 2^(j/2048), j < 2048: the exp table of the knot kernel, built once per device (exp_tables_ready)
-constexpr int kExpBig = 2048;
+// 2^(j/1024), j < 1024: the exp table of the knot kernel, built once per device (exp_tables_ready)
+constexpr int kExpBig = 1024;
+constexpr int kExpBigShift = 10;   // 20 - log2(kExpBig): where the index bits sit in the high word
 __device__ double g_exp2_big[kExpBig];
 __global__ void exp_big_init_kernel() {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < kExpBig) {
-    // 2^(j/2048) with (j << 9) taken off the high word: exp_big() adds (k << 9) as a whole, whose
-    // low 20 bits are exactly j << 9 and whose upper bits are the binary exponent k >> 11
+    // 2^(j/1024) with (j << 10) taken off the high word: exp_big() adds (k << 10) as a whole, whose
+    // low 20 bits are exactly j << 10 and whose upper bits are the binary exponent k >> 10
     const double s = exp2((double)j / (double)kExpBig);
-    g_exp2_big[j] = __hiloint2double(__double2hiint(s) - (j << 9), __double2loint(s));
+    g_exp2_big[j] = __hiloint2double(__double2hiint(s) - (j << kExpBigShift), __double2loint(s));
   }
 }
 __constant__ double c_knot[10] = {
@@ -1054,8 +1057,8 @@ __constant__ double c_knot[10] = {
     -17.269 * 237.3,                // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
     17.269 - 0.49301845011612494,   // + ln(0.61078): the factor folded into the exponent
     .000042, .00972,                // ice correction, physics.py:150-151
-    2954.639443740597,              // 2048/ln2
-    0.00033845077175778578,         // ln2/2048
+    1477.3197218702985,             // 1024/ln2
+    0.0006769015435155716,          // ln2/1024
     4.618333172514372,              // ln(P_STD/1000): air pressure in kPa, disaggregate.py:401-403
     273.15,                         // KELVIN
     1.2                             // PRATA, disaggregate.py:557-559
@@ -1071,7 +1074,7 @@ __device__ __forceinline__ KnotK load_knot() {
 // what the 1e-9 contract needs with two orders of margin:
 //   1/x      MUFU.RCP64H seed (2^-20) + one second-order step        rel. error < 1e-12
 //   sqrt(x)  MUFU.RSQ64H seed + one second-order step                 rel. error < 4e-13
-//   exp(x)   2048-entry 2^(j/2048) table + quadratic on |r| < 1.7e-4  rel. error < 9e-13
+//   exp(x)   1024-entry 2^(j/1024) table + quadratic on |r| < 3.4e-4  rel. error < 7e-12
 __device__ __forceinline__ double rcp_2(double x) {
   const double y = rcp_seed(x);
   const double e = fma(-x, y, 1.0);
@@ -1086,15 +1089,15 @@ __device__ __forceinline__ double sqrt_2(double x) {
 }
 __device__ __forceinline__ double exp_big(double x, const double *tab, const KnotK &K) {
   const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
-  // 2048/ln2 truncated to its high word (an instruction immediate): k may differ by one from
-  // rint(x * 2048/ln2) at a rounding boundary, r = x - k ln2/2048 stays consistent with it
-  double kd = fma(x, __hiloint2double(0x40a71547, 0), kMagic);
+  // 1024/ln2 truncated to its high word (an instruction immediate): k may differ by one from
+  // rint(x * 1024/ln2) at a rounding boundary, r = x - k ln2/1024 stays consistent with it
+  double kd = fma(x, __hiloint2double(0x40971547, 0), kMagic);
   const int k = __double2loint(kd);
   kd -= kMagic;
   const double r = fma(-kd, K.l, x);
-  const double q = fma(r * 0.5, r, r);            // exp(r) - 1 = r + r^2/2 (+ r^3/6 < 9e-13)
+  const double q = fma(r * 0.5, r, r);            // exp(r) - 1 = r + r^2/2 (+ r^3/6 < 7e-12)
   double s = tab[k & (kExpBig - 1)];
-  s = __hiloint2double(__double2hiint(s) + (k << 9), __double2loint(s));
+  s = __hiloint2double(__double2hiint(s) + (k << kExpBigShift), __double2loint(s));
   return fma(q, s, s);
 }
 
@@ -1103,12 +1106,15 @@ __global__ void __launch_bounds__(kDisaggThreads, MINB)
 thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[kExpBig];
   __shared__ double slot[kT_COUNT][kDisaggThreads];
+  __shared__ int s_doy[kDayWin];
+  const int e_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int e_hi = min(e_lo + a.k.tile, a.k.e1);
+  const int win0 = max(e_lo - 2, 0), nwin = min(min(e_hi + 3, a.f.n_days) - win0, kDayWin);
   for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) etab[j] = g_exp2_big[j];
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = a.f.doy[win0 + j];
   __syncthreads();
   const int tid = threadIdx.x;
   const int cell = blockIdx.x * blockDim.x + tid;
-  const int e_lo = a.k.e0 + blockIdx.y * a.k.tile;
-  const int e_hi = min(e_lo + a.k.tile, a.k.e1);
   if (cell >= a.f.n_cells || e_lo >= e_hi) return;
   const msb_params &p = a.p;
   const msb_forcing &f = a.f;
@@ -1120,9 +1126,22 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   const double elev = f.elev[cell];
   const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
   const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
-  const size_t plane = (size_t)a.n_rec * (size_t)ld;
-  const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
-  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  // the knots of the padded PCHIP sequence (disaggregate.py:236-257) straight from the inputs:
+  // what disagg_prepare_kernel records per (cell, day) is derived here once per (cell, e) with the
+  // warp converged, so the interior days need no record traffic
+  Cell c;
+  c.cell = cell; c.D = f.n_days; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * f.n_days + 4; c.ld = ld;
+  c.off_min = off_min;
+  c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
+  c.frac = p.tmax_daylength_fraction;
+  {
+    const int row = f.lat_row[cell];
+    c.rise = a.t.rise_min + (size_t)row * kRows;
+    c.set = a.t.set_min + (size_t)row * kRows;
+  }
+  c.doy = f.doy; c.sdoy = s_doy; c.win0 = win0; c.nwin = nwin;
+  c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+  c.t_end = f.t_end;
   const KnotK K = load_knot();
   const unsigned lanes = __activemask();
 
@@ -1143,13 +1162,34 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   OutT wd_o = 0;
   const double dx = (double)ts;
 
+  // knots t_Tmax(e-1), t_Tmin(e), t_Tmax(e) of the first e: times, values, slopes and scipy's
+  // derivative at t_Tmin(e) (_cubic.py:320-333); they roll forward through shared-memory slots
+  {
+    const int j0 = 2 * (e_lo + 1);
+    const double xa = knot_x(c, j0 - 1), xb = knot_x(c, j0), xc = knot_x(c, j0 + 1);
+    const double ya = knot_y(c, j0 - 1), yb = knot_y(c, j0), yc = knot_y(c, j0 + 1);
+    const double h0 = __dadd_rn(xb, -xa), h1 = __dadd_rn(xc, -xb);
+    const double m0 = div_nr(__dadd_rn(yb, -ya), h0), m1 = div_nr(__dadd_rn(yc, -yb), h1);
+    if (!(h0 > 0.0) || !(h1 > 0.0)) a.status[2] = 1;      // scipy: `x` must be strictly increasing
+    slot[kT_KX0][tid] = xb; slot[kT_KY0][tid] = yb; slot[kT_KD0][tid] = pchip_mid(h0, h1, m0, m1);
+    slot[kT_KX1][tid] = xc; slot[kT_KY1][tid] = yc; slot[kT_KM01][tid] = m1;
+  }
+
   for (int e = e_lo; e < e_hi; ++e) {
     // knots at t_Tmin / t_Tmax of day e and t_Tmin of day e+1 (disaggregate.py:198-200) with
     // scipy's derivatives, and the daily vapour pressure in kPa at the two t_Tmin knots (:480)
     const size_t o0 = (size_t)e * ld + cell, o1 = o0 + ld;
-    const double x0 = rec(kR_XMIN, e), d0 = rec(kR_DMIN, e), y0 = f.t_min[o0];
-    const double x1 = rec(kR_XMAX, e), d1 = rec(kR_DMAX, e), y1 = f.t_max[o0];
-    const double x2 = rec(kR_XMIN, e + 1), d2 = rec(kR_DMIN, e + 1), y2 = f.t_min[o1];
+    const int j2 = 2 * (e + 2);
+    const double x2 = knot_x(c, j2), x3 = knot_x(c, j2 + 1);
+    const double y2 = knot_y(c, j2), y3 = knot_y(c, j2 + 1);
+    const double x0 = slot[kT_KX0][tid], y0 = slot[kT_KY0][tid], d0 = slot[kT_KD0][tid];
+    const double x1 = slot[kT_KX1][tid], y1 = slot[kT_KY1][tid], m01 = slot[kT_KM01][tid];
+    const double h01 = __dadd_rn(x1, -x0), h12 = __dadd_rn(x2, -x1), h23 = __dadd_rn(x3, -x2);
+    const double m12 = div_nr(__dadd_rn(y2, -y1), h12), m23 = div_nr(__dadd_rn(y3, -y2), h23);
+    if (!(h12 > 0.0) || !(h23 > 0.0)) a.status[2] = 1;
+    const double d1 = pchip_mid(h01, h12, m01, m12), d2 = pchip_mid(h12, h23, m12, m23);
+    slot[kT_KX0][tid] = x2; slot[kT_KY0][tid] = y2; slot[kT_KD0][tid] = d2;
+    slot[kT_KX1][tid] = x3; slot[kT_KY1][tid] = y3; slot[kT_KM01][tid] = m23;
     const double v0 = a.vp_d[o0] / 1000.0, v1 = a.vp_d[o1] / 1000.0;
     const int ia = first_step_ge(x0, ts, inv_ts), ib = first_step_ge(x2, ts, inv_ts);
     int isw = first_step_ge(x1, ts, inv_ts);
@@ -1271,14 +1311,17 @@ template <typename OutT, int MINB>
 __global__ void __launch_bounds__(kDisaggThreads, MINB)
 streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double slot[kY_COUNT][kDisaggThreads];
-  __shared__ int s_doy[kDayWin];
+  __shared__ int s_doy[kDayWin], s_month[kDayWin];
   const msb_params &p = a.p;
   const msb_forcing &f = a.f;
   const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
   const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
   const int d_hi = min(a.k.e1, d_lo + a.k.tile);
   const int win0 = max(d_lo - 4, 0), nwin = min(min(d_hi + 4, D) - win0, kDayWin);
-  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = f.doy[win0 + j];
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+    s_doy[j] = f.doy[win0 + j];
+    s_month[j] = f.month[win0 + j];
+  }
   __syncthreads();
   const int tid = threadIdx.x;
   const int cell = blockIdx.x * blockDim.x + tid;
@@ -1293,9 +1336,13 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
     y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
     return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
   };
-  const size_t plane = (size_t)a.n_rec * (size_t)ld;
-  const double *const rec0 = a.rec + cell - (long)a.e0 * ld;
-  auto rec = [&](int fld, int e) { return rec0[(size_t)fld * plane + (long)e * ld]; };
+  // what disagg_prepare_kernel would put into the record of source day d: done here, once per
+  // (cell, day) with the warp converged, so the interior days need no record traffic at all
+  const double *const dayl = a.t.daylength + (size_t)f.lat_row[cell] * kRows;
+  auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
+    const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
+    return (a.sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
+  };
   auto lookback = [&](int i, bool &none) {   // what pandas ffill repeats at step i (cold)
     Cell c;
     c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
@@ -1341,8 +1388,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   PrecDay pd;
   {
     const int md0 = d_lo + mq - 1;
-    unpack_prec(rec(kR_PPACK, md0), pd);
-    pd.hsp = rec(kR_HSP, md0); pd.hsq = rec(kR_HSQ, md0); pd.f = rec(kR_PF, md0);
+    prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
   }
   bool nan_cur = !(pd.f == pd.f), need_fixup = false;
   double p_base = 0.0, pr = 0.0;
@@ -1353,7 +1399,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   if (r0 == 0) nan_cur = false;        // the roll at the first step decides (and looks back itself)
   double p_carry = p_base;
   double s_prev = prec_cum(pd, sm);
-  double rd_cur = rec(kR_RAD, d_lo + tq - 1);
+  double rd_cur = rad_of(d_lo + tq - 1);
   double q_prev, q_pref, sw_carry = 0.0;
   const double *q_ptr;                 // table entry the step after next will need
   {
@@ -1386,9 +1432,10 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       }
       const double *qb = q_of(y + tq);
       const int mdn = d + mq, sdn = d + tq;
-      const double w0 = rec(kR_PPACK, mdn), w1 = rec(kR_HSP, mdn), w2 = rec(kR_HSQ, mdn),
-                   w3 = rec(kR_PF, mdn), w5 = rec(kR_RAD, sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny],
-                   w9 = qb[kTiny + 1];
+      const double w5 = rad_of(sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny], w9 = qb[kTiny + 1];
+      PrecDay pn;
+      prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
+      const double w0 = pack_prec(pn), w1 = pn.hsp, w2 = pn.hsq, w3 = pn.f;
       prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
       slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
       slot[kY_PF][tid] = w3; slot[kY_RAD][tid] = w5;
@@ -1673,7 +1720,24 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
   static const int prep_days = env_int("MSB_PREP_DAYS", kPrepDays, 1, 16);
   a.prep_days = prep_days;
-  disagg_prepare_kernel<<<dim3(cell_blocks, (a.n_rec + prep_days - 1) / prep_days), 128, 0, st>>>(a);
+  // day records of the padded days [e_a, e_b) (only disagg_kernel reads them)
+  auto launch_prepare = [&](int e_a, int e_b) {
+    a.prep_r0 = (e_a > a.e0 ? e_a : a.e0) - a.e0;
+    a.prep_r1 = (e_b < e1 ? e_b : e1) - a.e0;
+    if (a.prep_r0 >= a.prep_r1) return;
+    disagg_prepare_kernel<<<dim3(cell_blocks, (a.prep_r1 - a.prep_r0 + prep_days - 1) / prep_days), 128, 0, st>>>(a);
+  };
+  {
+    // the fast path sends only the record's first / last two days through disagg_kernel
+    const int D = f->n_days;
+    const int a0 = out->day0 > 2 ? out->day0 : 2, b0 = out->day1 < D - 2 ? out->day1 : D - 2;
+    if (example && a0 < b0) {
+      if (out->day0 < a0) launch_prepare(out->day0 - MSB_REC_MARGIN, a0 + MSB_REC_MARGIN);
+      if (b0 < out->day1) launch_prepare(b0 - MSB_REC_MARGIN, out->day1 + MSB_REC_MARGIN);
+    } else {
+      launch_prepare(a.e0, e1);
+    }
+  }
 #define MSB_LAUNCH(T, F, U, V) disagg_kernel<T, F, U, V><<<grid, kDisaggThreads, 0, st>>>(a)
   if (example) {   // reference defaults, 8 variables: the thermodynamic half and the stream half
     // sub-range [s0, s1) of the call through disagg_kernel<VARS> (output pointers shifted)
