@@ -1758,7 +1758,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     };
     // interior days [2, D-2): knot-aligned kernel; the record's first / last two days: disagg_kernel
     const int D = f->n_days;
-    static const int knot_tile = env_int("MSB_KNOT_TILE", 8, 1, 64);
+    static const int knot_tile = env_int("MSB_KNOT_TILE", 16, 1, 64);
     static const int day_tile = env_int("MSB_DAY_TILE", 16, 1, 32);
     const int a0 = out->day0 > 2 ? out->day0 : 2, b0 = out->day1 < D - 2 ? out->day1 : D - 2;
     if (a0 < b0) {
@@ -1771,7 +1771,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
       a.k.tile = knot_tile;
       dim3 gk(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-      static const int knot_minb = env_int("MSB_KNOT_MINB", 8, 5, 8);
+      static const int knot_minb = env_int("MSB_KNOT_MINB", 7, 5, 8);
       if (knot_minb == 7) thermo_knot_kernel<float, 7><<<gk, kDisaggThreads, 0, st>>>(a);
       else if (knot_minb == 8) thermo_knot_kernel<float, 8><<<gk, kDisaggThreads, 0, st>>>(a);
       else if (knot_minb == 6) thermo_knot_kernel<float, 6><<<gk, kDisaggThreads, 0, st>>>(a);

@@ -14,10 +14,11 @@ not.  Fixture families:
                    three_hourly_48.3125_-120.5625, stored as float32).  state_vic.nc is HDF5 and
                    not readable in this image, so the 90-day state is DECLARED SYNTHETIC: the last
                    90 days of the 1949 record.
-* ``testdomain``   BASELINE config #1: metsim/data/test.nc + domain.nc (81 cells, 31 days, 30 min,
-                   triangle, utc_offset), float32 inputs upcast exactly to float64; state_nc.nc is
-                   HDF5 too, so the state is a declared synthetic one (seeded).  Reference outputs
-                   are kept for 9 of the 81 cells.
+* ``testdomain``   BASELINE config #1 as literally configured by examples/example_nc.conf:
+                   metsim/data/test.nc + domain.nc + the 90-day state of state_nc.nc (81 cells, 31
+                   days, 30 min, triangle, utc_offset), float32 inputs upcast exactly to float64.
+                   state_nc.nc is NetCDF-4 / HDF5; it is read by oracle/mini_hdf5.py (contiguous,
+                   uncompressed datasets).  Reference outputs are kept for 9 of the 81 cells.
 * ``synth_*``      seeded synthetic cells sweeping time step, precipitation type, utc offset,
                    long-wave options, hemispheres, a polar cell and a supplied ``t_end``.
 * ``passthrough_*`` the 'passthrough' method (metsim/methods/passthrough.py): supplied daily
@@ -35,6 +36,7 @@ import pandas as pd
 from scipy.io import netcdf_file
 
 from oracle import reference_harness as rh
+from oracle.mini_hdf5 import read_hdf5
 from oracle.validate_oracle import synth_cell
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
@@ -108,17 +110,18 @@ def testdomain(root):
     frc = netcdf_file(os.path.join(data, "test.nc"), "r", mmap=False)
     dom = netcdf_file(os.path.join(data, "domain.nc"), "r", mmap=False)
     lat, lon = dom.variables["lat"].data.astype(float), dom.variables["lon"].data.astype(float)
-    rng = np.random.default_rng(19500101)
+    state = read_hdf5(os.path.join(data, "state_nc.nc"))      # example_nc.conf:17, [state_vars]
+    assert np.allclose(state["lat"], lat) and np.allclose(state["lon"], lon)
+    assert state["t_min"].shape == (90, 9, 9) and (np.diff(state["time"]) == 1).all()
     cells = []
     for i in range(9):
         for j in range(9):
             g = lambda n: frc.variables[n].data[:, i, j].astype(np.float64)
-            st_tmin = g("Tmin")[:1] + rng.normal(0, 2.5, 90)
             cells.append(dict(lat=lat[i], lon=lon[j], elev=float(dom.variables["elev"].data[i, j]),
                               start="1950-01-01", t_min=g("Tmin"), t_max=g("Tmax"), prec=g("Prec"),
-                              wind=g("wind"), state_t_min=st_tmin,
-                              state_t_max=st_tmin + rng.uniform(3, 15, 90),
-                              state_prec=(rng.random(90) < 0.3) * rng.gamma(0.8, 6, 90),
+                              wind=g("wind"), state_t_min=state["t_min"][:, i, j].copy(),
+                              state_t_max=state["t_max"][:, i, j].copy(),
+                              state_prec=state["prec"][:, i, j].copy(),
                               t_pk12=dom.variables["t_pk"].data[:, i, j].astype(np.float64),
                               dur12=dom.variables["dur"].data[:, i, j].astype(np.float64)))
     params = dict(time_step=30, prec_type="triangle", utc_offset=True)  # examples/example_nc.conf
@@ -192,11 +195,12 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     import warnings
     warnings.filterwarnings("ignore")
-    if "--passthrough-only" not in sys.argv:
-        stehekin(root)
-        testdomain(root)
-        synth()
-    passthrough()
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    steps = dict(stehekin=lambda: stehekin(root), testdomain=lambda: testdomain(root), synth=synth,
+                 passthrough=passthrough)
+    for name, fn in steps.items():
+        if not only or name in only:
+            fn()
 
 
 if __name__ == "__main__":

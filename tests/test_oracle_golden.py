@@ -57,3 +57,22 @@ def test_oracle_rejects_negative_dtr():
     bad["t_max"][5, 2] = bad["t_min"][5, 2] - 1.0
     with pytest.raises(ValueError):
         oracle_lib.run(params, **util.oracle_kwargs(bad))
+
+
+def test_testdomain_golden_carries_the_bundled_state():
+    """BASELINE config #1 literally: the 90-day state of metsim/data/state_nc.nc (constant 10 / 20
+    degC, 3 mm/day) is what the fixture was generated with -- and, where the reference checkout is
+    present, what oracle/mini_hdf5.py reads from the file itself."""
+    inputs, params, *_ = util.load_golden(os.path.join(util.GOLDEN, "testdomain.npz"))
+    assert inputs["state_t_min"].shape == (90, 81)
+    assert (inputs["state_t_min"] == 10.0).all() and (inputs["state_t_max"] == 20.0).all()
+    assert (inputs["state_prec"] == 3.0).all()
+    assert int(params["time_step"]) == 30 and str(params["prec_type"]) == "triangle"
+    path = "/root/reference/metsim/data/state_nc.nc"
+    if os.path.exists(path):
+        from oracle.mini_hdf5 import read_hdf5
+        st = read_hdf5(path)
+        assert set(st) >= {"time", "lat", "lon", "t_min", "t_max", "prec"}
+        np.testing.assert_array_equal(st["t_min"].reshape(90, 81), inputs["state_t_min"])
+        np.testing.assert_array_equal(st["prec"].reshape(90, 81), inputs["state_prec"])
+        np.testing.assert_allclose(st["lat"], np.unique(inputs["lat"]))
