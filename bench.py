@@ -244,7 +244,9 @@ def main():
     ap.add_argument("--workload", default="conus_16th_hourly", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=None, help="truncate the grid (debugging only)")
     ap.add_argument("--days", type=int, default=None, help="truncate the record (debugging only)")
-    ap.add_argument("--tile-days", type=int, default=64)
+    ap.add_argument("--tile-days", type=int, default=None,
+                    help="days per msb_disaggregate call (default: as many as keep one ring slot <= 24 GB, at most 64 "
+                         "for the headline grid)")
     ap.add_argument("--sample-cells", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -283,6 +285,10 @@ def main():
     f = synth.make_forcing_torch(lat, lon, n_days, start, dev, seed=synth.SEED + rank)
     eng = Engine(params, dev)
     eng.load(**f)
+    if args.tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
+        args.tile_days = max(1, int(24.0e9 // (len(OUT_VARS) * tpd * n * 4)))
+        if 7 * n_days * n * 8 > 60e9:       # multi-year records: inputs + daily arrays already fill HBM
+            args.tile_days = min(args.tile_days, 64)
     tile = min(args.tile_days, n_days)
     ring = [{v: torch.empty((tile * tpd, n), dtype=torch.float32, device=dev) for v in OUT_VARS}
             for _ in range(2)]

@@ -1769,7 +1769,10 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       a.k.i_lo = a0 * a.tpd; a.k.i_hi = b0 * a.tpd;
       a.k.e0 = a0 - 2 > 0 ? a0 - 2 : 0;
       a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
+      // small shards: shorter chunks so that the grid still fills the 148 SMs several waves deep
       a.k.tile = knot_tile;
+      while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
+        a.k.tile >>= 1;
       dim3 gk(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
       static const int knot_minb = env_int("MSB_KNOT_MINB", 7, 5, 8);
       if (knot_minb == 7) thermo_knot_kernel<float, 7><<<gk, kDisaggThreads, 0, st>>>(a);
@@ -1781,6 +1784,8 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       a.k.i_lo = a.k.i_hi = 0;
       a.k.e0 = a0; a.k.e1 = b0;            // streams_day_kernel: output days, 8 per thread
       a.k.tile = day_tile;
+      while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 6 * 6)
+        a.k.tile >>= 1;
       static const int day_pf = env_int("MSB_DAY_PF", 4, 0, 16);
       a.k.pf = day_pf;
       dim3 gs(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
