@@ -295,13 +295,13 @@ def main():
     n_tiles = -(-n_days // tile)
     rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
     # 2 solar kernels, daily passes (pass 1 + reduce per round, pass 2), and per msb_disaggregate
-    # call: day records + thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2),
-    # plus disagg_kernel<thermo> / <streams> over the first / last two days of the record
+    # call: thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2), plus day
+    # records + disagg_kernel<thermo> / <streams> over the first / last two days of the record
     def disagg_launches(d0, d1):
         a0, b0 = max(d0, 2), min(d1, n_days - 2)
         if a0 >= b0:
             return 3
-        return 3 + (2 if d0 < a0 else 0) + (2 if b0 < d1 else 0)
+        return 2 + (3 if d0 < a0 else 0) + (3 if b0 < d1 else 0)
     launches_per_step = 2 + 2 * rounds + 1 + sum(
         disagg_launches(k * tile, min(n_days, (k + 1) * tile)) for k in range(n_tiles))
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -403,7 +403,7 @@ def main():
                       "2-tile host ring (what a streaming netCDF writer would drain)"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # reported baseline: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
         res, kind = None, "reference"
         try:

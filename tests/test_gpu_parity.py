@@ -226,6 +226,25 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
         np.testing.assert_array_equal(res["prec"].cpu().numpy() == 0, want["prec"].astype(np.float32) == 0)
 
 
+def test_fast_path_through_run_host_and_tile_independence():
+    """msb_run_host (host buffers, what bench.py's e2e leg and a reference-side binding call) on the
+    default variable set: bit-identical to the device-resident fast path for several tile sizes --
+    the interior-day kernels and the edge-day kernel must agree wherever a tile boundary falls."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine, run_host
+    f, params = synth.make_config("conus_16th_hourly", max_cells=777, n_days=41)
+    eng = Engine(params)
+    eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+    ref = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float32)
+    ref = {v: ref[v].cpu().numpy() for v in EXAMPLE_VARS}
+    kw = {k: f.get(k) for k in util.INPUT_KEYS}
+    for tile in (0, 1, 2, 3, 7, 40, 41):
+        got = run_host(params, out_vars=EXAMPLE_VARS, tile_days=tile, **kw)
+        for v in EXAMPLE_VARS:
+            np.testing.assert_array_equal(got[v], ref[v], err_msg=f"{v} tile={tile}")
+
+
 def test_edge_longitudes_polar_and_wraparound():
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
