@@ -1716,7 +1716,9 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     if (out->scale[v] != 1.0 || out->offset[v] != 0.0) units = true;
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
-  const bool example = a.var_mask == kExampleMask && fast_lw && !units && out->dtype == 4 && !a.lw_raw;
+  // the default variable set (examples/example_nc.conf) without unit conversion: specialised kernels
+  const bool example = a.var_mask == kExampleMask && fast_lw && !units && !a.lw_raw;
+  const bool f4 = out->dtype == 4;
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
   static const int prep_days = env_int("MSB_PREP_DAYS", kPrepDays, 1, 16);
   a.prep_days = prep_days;
@@ -1748,12 +1750,15 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       for (int v = 0; v < MSB_N_SUBVARS; ++v)
         if (b.out.var[v])
           b.out.var[v] = reinterpret_cast<char *>(b.out.var[v]) +
-                         (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * sizeof(float);
+                         (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * (size_t)out->dtype;
       int tl = a.tile_days;
       while (tl > 1 && (long)cell_blocks * ((s1 - s0 + tl - 1) / tl) < 148L * 4 * 4) tl >>= 1;
       b.tile_days = tl;
       dim3 g(cell_blocks, (s1 - s0 + tl - 1) / tl);
-      if (vars == kVarsThermo) disagg_kernel<float, true, false, kVarsThermo><<<g, kDisaggThreads, 0, st>>>(b);
+      if (!f4) {         // float64 outputs: the edge days take the general kernel, all variables at once
+        if (vars == kVarsThermo) disagg_kernel<double, true, true, kVarsAny><<<g, kDisaggThreads, 0, st>>>(b);
+      }
+      else if (vars == kVarsThermo) disagg_kernel<float, true, false, kVarsThermo><<<g, kDisaggThreads, 0, st>>>(b);
       else disagg_kernel<float, true, false, kVarsStreams><<<g, kDisaggThreads, 0, st>>>(b);
     };
     // interior days [2, D-2): knot-aligned kernel; the record's first / last two days: disagg_kernel
@@ -1774,11 +1779,8 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
         a.k.tile >>= 1;
       dim3 gk(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-      static const int knot_minb = env_int("MSB_KNOT_MINB", 7, 5, 8);
-      if (knot_minb == 7) thermo_knot_kernel<float, 7><<<gk, kDisaggThreads, 0, st>>>(a);
-      else if (knot_minb == 8) thermo_knot_kernel<float, 8><<<gk, kDisaggThreads, 0, st>>>(a);
-      else if (knot_minb == 6) thermo_knot_kernel<float, 6><<<gk, kDisaggThreads, 0, st>>>(a);
-      else thermo_knot_kernel<float, 5><<<gk, kDisaggThreads, 0, st>>>(a);
+      if (f4) thermo_knot_kernel<float, 7><<<gk, kDisaggThreads, 0, st>>>(a);
+      else thermo_knot_kernel<double, 7><<<gk, kDisaggThreads, 0, st>>>(a);
       launch_old(kVarsStreams, out->day0, a0);
       launch_old(kVarsStreams, b0, out->day1);
       a.k.i_lo = a.k.i_hi = 0;
@@ -1789,12 +1791,13 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
       static const int day_pf = env_int("MSB_DAY_PF", 4, 0, 16);
       a.k.pf = day_pf;
       dim3 gs(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
-      static const int day_minb = env_int("MSB_DAY_MINB", 6, 4, 6);
-      if (day_minb == 6) streams_day_kernel<float, 6><<<gs, kDisaggThreads, 0, st>>>(a);
-      else streams_day_kernel<float, 5><<<gs, kDisaggThreads, 0, st>>>(a);
-    } else {
+      if (f4) streams_day_kernel<float, 6><<<gs, kDisaggThreads, 0, st>>>(a);
+      else streams_day_kernel<double, 6><<<gs, kDisaggThreads, 0, st>>>(a);
+    } else if (f4) {
       MSB_LAUNCH(float, true, false, kVarsThermo);
       MSB_LAUNCH(float, true, false, kVarsStreams);
+    } else {
+      MSB_LAUNCH(double, true, true, kVarsAny);
     }
   }
   else if (out->dtype == 4) {

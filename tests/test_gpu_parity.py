@@ -224,6 +224,15 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
             assert (err <= 0.5000001 * ulp + 1e-9 * np.maximum(np.abs(w64[ok]), floor)).all(), (v, split, float((err / ulp).max()))
             assert neq.mean() < 2e-4, (v, split, float(neq.mean()))
         np.testing.assert_array_equal(res["prec"].cpu().numpy() == 0, want["prec"].astype(np.float32) == 0)
+    # the same kernels with float64 outputs: the north-star bar itself, 1e-9 on every variable
+    # (this is what pins the second-order exp / rcp / sqrt sequences of the interior-day kernel)
+    res64 = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float64)
+    worst = {v: util.assert_close(res64[v].cpu().numpy(), want[v], v, context=f"fast path f64 {name}")
+             for v in EXAMPLE_VARS}
+    print("fast path f64 worst relative errors:", {k: f"{e:.1e}" for k, e in worst.items()})
+    for v in EXAMPLE_VARS:       # and the float32 outputs are exactly the rounded float64 ones
+        np.testing.assert_array_equal(res[v].cpu().numpy() if split is None else res[v].cpu().numpy(),
+                                      res64[v].cpu().numpy().astype(np.float32), err_msg=v)
 
 
 def test_fast_path_through_run_host_and_tile_independence():
