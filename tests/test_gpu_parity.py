@@ -182,7 +182,10 @@ EXAMPLE_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_
     ("global_8th_30yr_15min", 400, 12, {}),
     ("conus_16th_hourly", 300, 5, {}),
     ("conus_16th_hourly", 300, 3, {}),
-], ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(v) or "std")
+    ("global_half_deg", 400, 16, {"time_step": 360, "prec_type": "mix"}),
+    ("global_half_deg", 400, 9, {"time_step": 20, "utc_offset": False}),
+    ("conus_16th_hourly", 260, 30, {"time_step": 120, "prec_type": "uniform", "tmax_daylength_fraction": 0.5}),
+], ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(f"{k}{x}" for k, x in v.items()) or "std")
 def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
     """The configuration bench.py times: the 8 variables of examples/example_nc.conf, float32
     outputs, no unit conversion -- the specialised kernels of msb_disaggregate.  Checked against
@@ -198,6 +201,7 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
         f, params = synth.make_config(name, max_cells=cells, n_days=days)
         doy, month = synth.calendar_vectors("2001-12-05", days)
         f["doy"], f["month"] = doy, month
+    params.update({k: v for k, v in over.items() if k != "start_dec"})
     want = oracle_lib.run(params, **util.oracle_kwargs(f))
     eng = Engine(params)
     eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
