@@ -12,8 +12,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ("api.cu", "solar.cu", "daily.cu", "disagg.cu")
-HEADERS = ("msb_common.cuh",)
+SOURCES = ("api.cu", "solar.cu", "daily.cu", "disagg.cu", "disagg_event.cu", "disagg_interior.cu")
+HEADERS = ("msb_common.cuh", "disagg_common.cuh")
 OUT = os.path.join(CSRC, "libmetsim_b200.so")
 
 
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> s
     table access of the streaming kernels is range-checked on the device (trap or MSB_E_KNOTS)."""
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [_nvcc(), "-O3", "-std=c++17", "--threads", "0", "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared",
            "-I", INCLUDE, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     if bounds:

@@ -1,0 +1,614 @@
+// The two specialised kernels of the interior days [2, D-2) of a record, default variable set
+// (examples/example_nc.conf: temp, prec, shortwave, longwave, vapor_pressure, rel_humid,
+// air_pressure, wind; no unit conversion), float32 or float64 outputs -- and the accuracy probe
+// of every hand-written fp64 sequence (msb_selftest_math).
+#include <mutex>
+
+#include "disagg_common.cuh"
+
+namespace msb {
+
+// ---- interior days of the fast path: knot-aligned thermodynamic kernel ---------------------------
+// Days [2, D-2) of a record are "interior": every PCHIP / vapour-pressure knot a step needs exists
+// in the day records, the vapour-pressure interpolant has no NaN ends there, and the rolled minute
+// stream does not wrap.  For those days the work is cut at the KNOTS instead of at midnight: one
+// thread handles the steps between the t_Tmin knot of day e and the t_Tmin knot of day e+1 -- exactly
+// two PCHIP intervals and one vapour-pressure segment -- so what the event handler of
+// disagg_kernel does under divergence (segment set-up, next-event search) happens here once per
+// (cell, e) with the warp converged and all loads independent.  The step loop runs over the
+// warp's union of step ranges with the lane's own range as a predicate, so stores stay full
+// 128-byte rows.  The first / last two days of a record go through disagg_kernel.
+enum { kT_C0 = 0, kT_C1, kT_C2, kT_C3, kT_X0, kT_TKA, kT_TKB, kT_WDA, kT_WDB,
+       kT_KX0, kT_KY0, kT_KD0, kT_KX1, kT_KY1, kT_KM01, kT_COUNT };
+
+// 2^(j/1024), j < 1024: the exp table of the knot kernel, built once per device (exp_tables_ready)
+constexpr int kExpBig = 1024;
+constexpr int kExpBigShift = 10;   // 20 - log2(kExpBig): where the index bits sit in the high word
+static __device__ double g_exp2_big[kExpBig];
+__global__ void exp_big_init_kernel() {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < kExpBig) {
+    // 2^(j/1024) with (j << 10) taken off the high word: exp_big() adds (k << 10) as a whole, whose
+    // low 20 bits are exactly j << 10 and whose upper bits are the binary exponent k >> 10
+    const double s = exp2((double)j / (double)kExpBig);
+    g_exp2_big[j] = __hiloint2double(__double2hiint(s) - (j << kExpBigShift), __double2loint(s));
+  }
+}
+static __constant__ double c_knot[10] = {
+    237.3,                          // svp denominator offset, physics.py:149
+    -17.269 * 237.3,                // 17.269*t/(237.3+t) = 17.269 - 17.269*237.3/(237.3+t)
+    17.269 - 0.49301845011612494,   // + ln(0.61078): the factor folded into the exponent
+    .000042, .00972,                // ice correction, physics.py:150-151
+    1477.3197218702985,             // 1024/ln2
+    0.0006769015435155716,          // ln2/1024
+    4.618333172514372,              // ln(P_STD/1000): air pressure in kPa, disaggregate.py:401-403
+    273.15,                         // KELVIN
+    1.2                             // PRATA, disaggregate.py:557-559
+};
+struct KnotK { double k237, ka, kb, kc2, kc1, inv_l, l, ln_p, kelvin, k12; };
+__device__ __forceinline__ KnotK load_knot() {
+  KnotK k;
+  k.k237 = c_knot[0]; k.ka = c_knot[1]; k.kb = c_knot[2]; k.kc2 = c_knot[3]; k.kc1 = c_knot[4];
+  k.inv_l = c_knot[5]; k.l = c_knot[6]; k.ln_p = c_knot[7]; k.kelvin = c_knot[8]; k.k12 = c_knot[9];
+  return k;
+}
+// The knot kernel's outputs are only written, never fed back, so its fp64 sequences are cut to
+// what the 1e-9 contract needs with two orders of margin:
+//   1/x      MUFU.RCP64H seed (2^-20) + one second-order step        rel. error < 1e-12
+//   sqrt(x)  MUFU.RSQ64H seed + one second-order step                 rel. error < 4e-13
+//   exp(x)   1024-entry 2^(j/1024) table + quadratic on |r| < 3.4e-4  rel. error < 7e-12
+__device__ __forceinline__ double rcp_2(double x) {
+  const double y = rcp_seed(x);
+  const double e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double sqrt_2(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double xy = x * y;
+  const double e = fma(-xy, y, 1.0);
+  return fma(xy, 0.5 * e, xy);
+}
+__device__ __forceinline__ double exp_big(double x, const double *tab, const KnotK &K) {
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
+  // 1024/ln2 truncated to its high word (an instruction immediate): k may differ by one from
+  // rint(x * 1024/ln2) at a rounding boundary, r = x - k ln2/1024 stays consistent with it
+  double kd = fma(x, __hiloint2double(0x40971547, 0), kMagic);
+  const int k = __double2loint(kd);
+  kd -= kMagic;
+  const double r = fma(-kd, K.l, x);
+  const double q = fma(r * 0.5, r, r);            // exp(r) - 1 = r + r^2/2 (+ r^3/6 < 7e-12)
+  double s = tab[k & (kExpBig - 1)];
+  s = __hiloint2double(__double2hiint(s) + (k << kExpBigShift), __double2loint(s));
+  return fma(q, s, s);
+}
+
+template <typename OutT, int MINB>
+__global__ void __launch_bounds__(kDisaggThreads, MINB)
+thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
+  __shared__ double etab[kExpBig];
+  __shared__ double slot[kT_COUNT][kDisaggThreads];
+  __shared__ int s_doy[kDayWin];
+  const int e_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int e_hi = min(e_lo + a.k.tile, a.k.e1);
+  const int win0 = max(e_lo - 2, 0), nwin = min(min(e_hi + 3, a.f.n_days) - win0, kDayWin);
+  for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) etab[j] = g_exp2_big[j];
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = a.f.doy[win0 + j];
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  if (cell >= a.f.n_cells || e_lo >= e_hi) return;
+  const msb_params &p = a.p;
+  const msb_forcing &f = a.f;
+  const int ts = p.time_step;
+  const long ld = f.ld;
+  const double inv_ts = 1.0 / (double)ts;
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
+  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :611
+  const double elev = f.elev[cell];
+  const double pr_num = -(elev * kGStd) / kRDry;            // pressure :401-402
+  const double pr_corr = kKelvin + 0.5 * elev * -p.lapse_rate;
+  // the knots of the padded PCHIP sequence (disaggregate.py:236-257) straight from the inputs:
+  // what disagg_prepare_kernel records per (cell, day) is derived here once per (cell, e) with the
+  // warp converged, so the interior days need no record traffic
+  Cell c;
+  c.cell = cell; c.D = f.n_days; c.ts = ts; c.tpd = a.tpd; c.nk = 2 * f.n_days + 4; c.ld = ld;
+  c.off_min = off_min;
+  c.utc_min = p.utc_offset ? (double)(int)(((lon - 0.0) / kDegPerRev) * kMinPerDay) : 0.0;  // :186
+  c.frac = p.tmax_daylength_fraction;
+  {
+    const int row = f.lat_row[cell];
+    c.rise = a.t.rise_min + (size_t)row * kRows;
+    c.set = a.t.set_min + (size_t)row * kRows;
+  }
+  c.doy = f.doy; c.sdoy = s_doy; c.win0 = win0; c.nwin = nwin;
+  c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+  c.t_end = f.t_end;
+  const KnotK K = load_knot();
+  const unsigned lanes = __activemask();
+
+  const size_t ostride = (size_t)a.out.ld;
+  const long i_base = (long)a.out.day0 * a.tpd;
+  OutT *const o_temp = reinterpret_cast<OutT *>(a.out.var[MSB_V_TEMP]) + cell;
+  OutT *const o_lw = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]) + cell;
+  OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]) + cell;
+  OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
+  OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
+  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
+
+  // tskc and wind: repeated per minute, rolled by off_min, block mean over ts minutes
+  // (:593-615, :355-380); wind rides along here because it shares this stream's roll exactly
+  int i_tk = kNever, tk_day = -4;
+  bool tk_started = false;
+  double tk_a = 0.0, tk_b = 0.0;
+  OutT wd_o = 0;
+  const double dx = (double)ts;
+
+  // knots t_Tmax(e-1), t_Tmin(e), t_Tmax(e) of the first e: times, values, slopes and scipy's
+  // derivative at t_Tmin(e) (_cubic.py:320-333); they roll forward through shared-memory slots
+  {
+    const int j0 = 2 * (e_lo + 1);
+    const double xa = knot_x(c, j0 - 1), xb = knot_x(c, j0), xc = knot_x(c, j0 + 1);
+    const double ya = knot_y(c, j0 - 1), yb = knot_y(c, j0), yc = knot_y(c, j0 + 1);
+    const double h0 = __dadd_rn(xb, -xa), h1 = __dadd_rn(xc, -xb);
+    const double m0 = div_nr(__dadd_rn(yb, -ya), h0), m1 = div_nr(__dadd_rn(yc, -yb), h1);
+    if (!(h0 > 0.0) || !(h1 > 0.0)) a.status[2] = 1;      // scipy: `x` must be strictly increasing
+    slot[kT_KX0][tid] = xb; slot[kT_KY0][tid] = yb; slot[kT_KD0][tid] = pchip_mid(h0, h1, m0, m1);
+    slot[kT_KX1][tid] = xc; slot[kT_KY1][tid] = yc; slot[kT_KM01][tid] = m1;
+  }
+
+  for (int e = e_lo; e < e_hi; ++e) {
+    // knots at t_Tmin / t_Tmax of day e and t_Tmin of day e+1 (disaggregate.py:198-200) with
+    // scipy's derivatives, and the daily vapour pressure in kPa at the two t_Tmin knots (:480)
+    const size_t o0 = (size_t)e * ld + cell, o1 = o0 + ld;
+    const int j2 = 2 * (e + 2);
+    const double x2 = knot_x(c, j2), x3 = knot_x(c, j2 + 1);
+    const double y2 = knot_y(c, j2), y3 = knot_y(c, j2 + 1);
+    const double x0 = slot[kT_KX0][tid], y0 = slot[kT_KY0][tid], d0 = slot[kT_KD0][tid];
+    const double x1 = slot[kT_KX1][tid], y1 = slot[kT_KY1][tid], m01 = slot[kT_KM01][tid];
+    const double h01 = __dadd_rn(x1, -x0), h12 = __dadd_rn(x2, -x1), h23 = __dadd_rn(x3, -x2);
+    const double m12 = div_nr(__dadd_rn(y2, -y1), h12), m23 = div_nr(__dadd_rn(y3, -y2), h23);
+    if (!(h12 > 0.0) || !(h23 > 0.0)) a.status[2] = 1;
+    const double d1 = pchip_mid(h01, h12, m01, m12), d2 = pchip_mid(h12, h23, m12, m23);
+    slot[kT_KX0][tid] = x2; slot[kT_KY0][tid] = y2; slot[kT_KD0][tid] = d2;
+    slot[kT_KX1][tid] = x3; slot[kT_KY1][tid] = y3; slot[kT_KM01][tid] = m23;
+    const double v0 = a.vp_d[o0] / 1000.0, v1 = a.vp_d[o1] / 1000.0;
+    const int ia = first_step_ge(x0, ts, inv_ts), ib = first_step_ge(x2, ts, inv_ts);
+    int isw = first_step_ge(x1, ts, inv_ts);
+    // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
+    Cubic cub;
+    {
+      const double inv = rcp_nr(x1 - x0);
+      const double m = (y1 - y0) * inv;
+      const double tt = ((d0 + d1) - 2.0 * m) * inv;
+      cub.x0 = x0; cub.x1 = x1;
+      cub.c0 = tt * inv;
+      cub.c1 = (m - d0) * inv - tt;
+      cub.c2 = d0;
+      cub.c3 = y0;
+    }
+    {
+      const double inv = rcp_nr(x2 - x1);
+      const double m = (y2 - y1) * inv;
+      const double tt = ((d1 + d2) - 2.0 * m) * inv;
+      slot[kT_X0][tid] = x1;
+      slot[kT_C0][tid] = tt * inv;
+      slot[kT_C1][tid] = (m - d1) * inv - tt;
+      slot[kT_C2][tid] = d1;
+      slot[kT_C3][tid] = y1;
+    }
+    const double xvl = x0, yvl = v0;
+    const double vslope = div_nr(v1 - v0, x2 - x0);                  // scipy _interpolate.py:513-516
+    const int ja = max(ia, a.k.i_lo), jb = min(ib, a.k.i_hi);
+    const bool any = ja < jb;
+    if (any && isw <= ja) {          // the range starts beyond the t_Tmax knot
+      cub.x0 = slot[kT_X0][tid]; cub.c0 = slot[kT_C0][tid]; cub.c1 = slot[kT_C1][tid];
+      cub.c2 = slot[kT_C2][tid]; cub.c3 = slot[kT_C3][tid];
+      isw = kNever;
+    }
+    if (any && !tk_started) { i_tk = ja; tk_started = true; }
+    int i_next = min(isw, i_tk);
+    const int lo_w = __reduce_min_sync(lanes, any ? ja : kNever);
+    const int hi_w = __reduce_max_sync(lanes, any ? jb : -kNever);
+    double x = (double)ts * (double)lo_w;
+    size_t ooff = (size_t)((long)lo_w - i_base) * ostride;
+#pragma unroll 1
+    for (int i = lo_w; i < hi_w; ++i, x += dx, ooff += ostride) {
+      if (i < ja || i >= jb) continue;
+      if (i == i_next) {
+        if (i == isw) {              // t_Tmax knot crossed (searchsorted side='right')
+          cub.x0 = slot[kT_X0][tid]; cub.c0 = slot[kT_C0][tid]; cub.c1 = slot[kT_C1][tid];
+          cub.c2 = slot[kT_C2][tid]; cub.c3 = slot[kT_C3][tid];
+          isw = kNever;
+        }
+        if (i == i_tk) {             // source day of the minute stream rolls (:611-614)
+          const int m = i * ts + off_min;         // interior days: 0 < m < (D-1)*1440, no wrap
+          const int dA = m / kMinPerDay, r = m - dA * kMinPerDay;
+          if (dA != tk_day) {
+            const size_t oA = (size_t)dA * ld + cell;
+            const bool next = dA == tk_day + 1;
+            slot[kT_TKA][tid] = next ? slot[kT_TKB][tid] : a.tskc_d[oA];
+            slot[kT_WDA][tid] = next ? slot[kT_WDB][tid] : f.wind[oA];
+            slot[kT_TKB][tid] = a.tskc_d[oA + ld];   // used a day later
+            slot[kT_WDB][tid] = f.wind[oA + ld];
+            tk_day = dA;
+          }
+          const int n2 = r + ts - kMinPerDay;
+          double tk = slot[kT_TKA][tid], wd = slot[kT_WDA][tid];
+          if (n2 > 0) {              // window straddles the day boundary
+            const double w1 = (double)(ts - n2), w2 = (double)n2;
+            tk = (w1 * tk + w2 * slot[kT_TKB][tid]) * inv_ts;
+            wd = (w1 * wd + w2 * slot[kT_WDB][tid]) * inv_ts;
+            i_tk = i + 1;
+          } else {
+            i_tk = i + (kMinPerDay - r) / ts;
+          }
+          tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
+          wd_o = (OutT)wd;
+        }
+        i_next = min(isw, i_tk);
+      }
+      // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
+      const double temp = cubic_eval(cub, x);
+      const double es0 = exp_big(fma(K.ka, rcp_2(K.k237 + temp), K.kb), etab, K);
+      const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
+      const double es = es0 * (temp < 0.0 ? corr : 1.0);
+      // -- vapour pressure (linear, clamped to saturation) :480-487 --
+      double vp = fma(x - xvl, vslope, yvl);
+      vp = es < vp ? es : vp;
+      // -- relative humidity :444-446, air pressure :401-403 --
+      const double rh_raw = 100.0 * (vp * rcp_2(es));
+      const double rh = rh_raw > 100.0 ? 100.0 : rh_raw;      // np.minimum; vp, es are finite here
+      const double ap = exp_big(fma(pr_num, rcp_2(pr_corr + temp), K.ln_p), etab, K);
+      // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF; tk_a / tk_b carry STEFAN_B) --
+      const double at = temp + K.kelvin;
+      const double xx = (465.0 * vp) * rcp_2(at);              // 46.5 * (10 vp) / T
+      const double ee = exp_big(-sqrt_2(fma(3., xx, K.k12)), etab, K);
+      const double e1 = fma(-(1.0 + xx), ee, 1.0);
+      const double t2 = at * at;
+      const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+      __stcs(o_temp + ooff, (OutT)temp);
+      __stcs(o_vp + ooff, (OutT)vp);
+      __stcs(o_rh + ooff, (OutT)rh);
+      __stcs(o_ap + ooff, (OutT)ap);
+      __stcs(o_lw + ooff, (OutT)lw);
+      __stcs(o_wd + ooff, wd_o);
+    }
+  }
+}
+
+// ---- interior days of the fast path: source-stream kernel with a fixed daily schedule -------------
+// Precipitation (minute stream) and shortwave (30 s stream) of the interior days [2, D-2) -- wind
+// is written by thermo_knot_kernel, which already follows the minute stream's roll for tskc --
+// where neither rolled stream wraps around the record.  Same closed forms as disagg_kernel, but the
+// daily schedule is made explicit: for a given cell the roll of the minute stream, the roll of the
+// 30 s stream and the noon crossing happen at the SAME step of every output day (they depend on
+// the longitude offsets only), so they are four per-cell constants instead of a searched event
+// queue, and what a roll needs about the next source day is fetched at the start of the output
+// day into per-thread shared-memory slots.  The handlers are short, load-free state updates.
+enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
+       kY_ROWTOT_CUR, kY_COUNT };
+
+template <typename OutT, int MINB>
+__global__ void __launch_bounds__(kDisaggThreads, MINB)
+streams_day_kernel(const __grid_constant__ DisaggArgs a) {
+  __shared__ double slot[kY_COUNT][kDisaggThreads];
+  __shared__ int s_doy[kDayWin], s_month[kDayWin];
+  const msb_params &p = a.p;
+  const msb_forcing &f = a.f;
+  const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
+  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
+  const int win0 = max(d_lo - 4, 0), nwin = min(min(d_hi + 4, D) - win0, kDayWin);
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+    s_doy[j] = f.doy[win0 + j];
+    s_month[j] = f.month[win0 + j];
+  }
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  if (cell >= f.n_cells || d_lo >= d_hi) return;
+  const long ld = f.ld;
+  const int C = 2 * ts;                                     // tiny steps per output step (:660)
+  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
+  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376
+  const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
+  const double *const qrow = a.t.q + (size_t)f.lat_row[cell] * 365 * kQLd;
+  auto q_of = [&](int y) {     // table row y rolled over the table's own 366 rows (:656)
+    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
+    return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
+  };
+  // what disagg_prepare_kernel would put into the record of source day d: done here, once per
+  // (cell, day) with the warp converged, so the interior days need no record traffic at all
+  const double *const dayl = a.t.daylength + (size_t)f.lat_row[cell] * kRows;
+  auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
+    const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
+    return (a.sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
+  };
+  auto lookback = [&](int i, bool &none) {   // what pandas ffill repeats at step i (cold)
+    Cell c;
+    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
+    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
+    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
+    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+    c.t_end = f.t_end;
+    const double v = prec_lookback(p, f, c, i);
+    if (!(v == v)) none = true;
+    return v;
+  };
+
+  // ---- the cell's daily schedule (steps of the output day at which something happens) ----------
+  // minute stream: output day d reads source day d + mq - 1 up to the roll at step t_s, then
+  // source day d + mq; n2m minutes of the straddling window belong to the new day (0 = clean)
+  const int qm = off_min < 0 ? -1 : 0;
+  const int r0 = off_min - qm * kMinPerDay;                 // [0, 1440)
+  const int mq = r0 == 0 ? qm : qm + 1;
+  const int t_s = r0 == 0 ? 0 : (kMinPerDay - r0) / ts;
+  const int n1m = r0 == 0 ? 0 : kMinPerDay - r0 - t_s * ts;
+  const int n2m = n1m > 0 ? ts - n1m : 0;
+  // 30 s stream: same for the table row / radiation day
+  const int qs = off_tiny < 0 ? -1 : 0;
+  const int c0 = off_tiny - qs * kTiny;                     // [0, 2880)
+  const int tq = c0 == 0 ? qs : qs + 1;
+  const int t_r = c0 == 0 ? 0 : (kTiny - c0) / C;
+  const int k2 = c0 == 0 ? 0 : (c0 + (t_r + 1) * C - kTiny) % C;        // 0 = clean switch
+  const int t_n = ((c0 <= kNoon ? kNoon : kNoon + kTiny) - c0) / C;     // window that contains noon
+  const unsigned ev = (unsigned)t_s | ((unsigned)t_r << 8) | ((unsigned)t_n << 16);
+  auto next_event = [ev](int t) {      // first scheduled step after t (255 = none left today)
+    unsigned best = 255u;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned b = (ev >> (8 * k)) & 255u;
+      if ((int)b > t && b < best) best = b;
+    }
+    return (int)best;
+  };
+
+  // ---- state at the first step of the chunk -----------------------------------------------------
+  const int i_lo = d_lo * tpd;
+  int sm = r0 == 0 ? kMinPerDay : r0;                       // start of the next window in its source day
+  PrecDay pd;
+  {
+    const int md0 = d_lo + mq - 1;
+    prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
+  }
+  bool nan_cur = !(pd.f == pd.f), need_fixup = false;
+  double p_base = 0.0, pr = 0.0;
+  if (nan_cur && r0 != 0) {            // the chunk opens inside a NaN day
+    p_base = lookback(i_lo, need_fixup);
+    pd.f = 0.0;
+  }
+  if (r0 == 0) nan_cur = false;        // the roll at the first step decides (and looks back itself)
+  double p_carry = p_base;
+  double s_prev = prec_cum(pd, sm);
+  double rd_cur = rad_of(d_lo + tq - 1);
+  double q_prev, q_pref, sw_carry = 0.0;
+  const double *q_ptr;                 // table entry the step after next will need
+  {
+    const double *q0 = q_of(s_doy[d_lo - win0] - 1 + tq - 1);
+    const int ss = c0 == 0 ? kTiny : c0;
+    q_prev = q0[ss];
+    q_pref = q0[ss + C];
+    q_ptr = q0 + ss + 2 * C;
+    slot[kY_ROWTOT_CUR][tid] = q0[kTiny + 1];
+  }
+
+  const size_t ostride = (size_t)a.out.ld;
+  size_t ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
+  OutT *const o_prec = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + cell;
+  OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell;
+  const unsigned lanes = __activemask();
+  const int pf_off = a.k.pf * C;
+
+  for (int d = d_lo; d < d_hi; ++d) {
+    // ---- output day d starts (warp converged): fetch what today's rolls need --------------------
+    {
+      const int y = s_doy[d - win0] - 1;
+      const double *qa = q_of(y + tq - 1);
+      if (d > d_lo && c0 != 0 && s_doy[d - win0] != s_doy[d - 1 - win0] + 1) {
+        // the day of year jumped (year boundary): row of the "lo" part of today's windows (:656)
+        q_prev = qa[c0];
+        q_pref = qa[c0 + C];
+        q_ptr = qa + c0 + 2 * C;
+        slot[kY_ROWTOT_CUR][tid] = qa[kTiny + 1];
+      }
+      const double *qb = q_of(y + tq);
+      const int mdn = d + mq, sdn = d + tq;
+      const double w5 = rad_of(sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny], w9 = qb[kTiny + 1];
+      PrecDay pn;
+      prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
+      const double w0 = pack_prec(pn), w1 = pn.hsp, w2 = pn.hsq, w3 = pn.f;
+      prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
+      slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
+      slot[kY_PF][tid] = w3; slot[kY_RAD][tid] = w5;
+      slot[kY_QB0][tid] = w6; slot[kY_QBK][tid] = w7; slot[kY_QAEND][tid] = w8;
+      slot[kY_ROWTOT][tid] = w9;
+    }
+    int t_next = next_event(-1);
+    int t = 0;
+    while (t < tpd) {
+      if (t == t_next) {   // ---- scheduled state updates (cold, lanes with an event at this step) ----
+        if (t == t_s) {      // minute stream reaches the end of its source day (:347-351, :376)
+          PrecDay pn;
+          unpack_prec(slot[kY_PPACK][tid], pn);
+          pn.hsp = slot[kY_HSP][tid]; pn.hsq = slot[kY_HSQ][tid]; pn.f = slot[kY_PF][tid];
+          const bool nan_new = !(pn.f == pn.f);
+          double fill = 0.0;               // pandas ffill: a NaN step repeats the last valid value
+          if (nan_cur) fill = p_base;      // already inside a NaN run
+          else if (nan_new) {
+            if (d > d_lo || t > 0) fill = pr;      // the previous step of this chunk
+            else fill = lookback(i_lo, need_fixup); // the chunk starts at a NaN day
+          }
+          int pos;
+          if (n1m == 0) {                  // clean switch
+            pos = 0;
+            sm = 0;
+            p_carry = nan_new ? fill : 0.0;
+          } else {                         // straddle: n1m minutes of the old day, n2m of the new one
+            p_carry = (nan_cur || nan_new)
+                          ? fill
+                          : pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2m);
+            pos = n2m;
+            sm = n2m - ts;                 // the step advances it to n2m
+          }
+          pd = pn;
+          if (nan_new) pd.f = 0.0;         // every step of a NaN day is p_base = the fill value
+          p_base = nan_new ? fill : 0.0;
+          nan_cur = nan_new;
+          s_prev = prec_cum(pd, pos);
+        }
+        if (t == t_r) {      // 30 s stream reaches the end of its table row / radiation day (:656-678)
+          const double rd_n = slot[kY_RAD][tid];
+          const double *qb = q_of(s_doy[d - win0] - 1 + tq);
+          int ss;
+          if (k2 > 0) {                    // straddle: [ss, 2880) of the old row + [0, k2) of the new
+            const double qk = slot[kY_QBK][tid];
+            sw_carry = fma(rd_n, qk - slot[kY_QB0][tid], rd_cur * (slot[kY_QAEND][tid] - q_prev));
+            q_prev = qk;
+            ss = k2 - C;                   // the step advances it to k2
+          } else {
+            q_prev = slot[kY_QB0][tid];
+            ss = 0;
+          }
+          rd_cur = rd_n;
+          q_pref = qb[ss + C];
+          q_ptr = qb + ss + 2 * C;
+          slot[kY_ROWTOT_CUR][tid] = slot[kY_ROWTOT][tid];
+        }
+        if (t == t_n) q_prev -= slot[kY_ROWTOT_CUR][tid];   // window contains tiny step 1440: + row total
+        t_next = next_event(t);
+      }
+      // ---- event-free run up to the earliest event of any lane of the warp ---------------------
+      const int t_stop = min(__reduce_min_sync(lanes, t_next), tpd);
+#pragma unroll 2
+      for (; t < t_stop; ++t, ooff += ostride) {
+        // step: precipitation :265-352, shortwave :618-680, wind :355-380
+        const double qn = q_pref;
+        q_pref = load_early(q_ptr);
+        prefetch_l1(q_ptr + pf_off);
+        q_ptr += C;
+        sm += ts;
+        const double s1 = prec_cum(pd, sm);
+        pr = fma(pd.f, s1 - s_prev, p_carry);
+        s_prev = s1;
+        p_carry = p_base;
+        const double sw = fma(rd_cur, qn - q_prev, sw_carry);
+        q_prev = qn;
+        sw_carry = 0.0;
+        __stcs(o_prec + ooff, (OutT)pr);
+        __stcs(o_sw + ooff, (OutT)sw);
+      }
+    }
+  }
+
+  // a NaN run that reaches back to the start of the record: bfill (disaggregate.py:130)
+  if (need_fixup) {
+    Cell c;
+    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
+    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
+    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
+    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
+    c.t_end = f.t_end;
+    const int T = D * tpd, i_hi = d_hi * tpd;
+    double fillv = nan("");
+    int j = i_lo;
+    for (; j < T; ++j) {
+      fillv = prec_step_generic(p, f, c, j);
+      if (fillv == fillv) break;
+    }
+    ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
+    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) __stcs(o_prec + ooff, (OutT)fillv);
+  }
+}
+
+// accuracy probe of the hand-written fp64 sequences (tests only touch it through the C ABI)
+__global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
+  __shared__ double etab[kExpTab];
+  __shared__ double ebig[kExpBig];
+  exp_table_init(etab);
+  for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) ebig[j] = g_exp2_big[j];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  const KnotK K = load_knot();
+  out[8 * (size_t)n + i] = wrap_lon(v);
+  out[9 * (size_t)n + i] = rcp_2(v);
+  out[10 * (size_t)n + i] = sqrt_2(v);
+  out[11 * (size_t)n + i] = exp_big(v, ebig, K);
+  out[i] = rcp_nr(v);
+  out[n + i] = exp_tab(v, etab);
+  out[2 * n + i] = sqrt_fast(v);
+  out[3 * n + i] = div_nr(1.2345678901234567, v);
+  out[4 * n + i] = svp_kpa(v, etab);
+  out[5 * n + i] = rcp_seed(v);
+  out[6 * n + i] = exp_acc(v, etab);
+  out[7 * n + i] = sqrt_nr(v);
+}
+
+// g_exp2_big of the current device, filled on the first call per device (stream-ordered before use)
+int exp_tables_ready(cudaStream_t st) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  MSB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) { set_error("msb_disaggregate: device index %d out of range", dev); return MSB_E_ARG; }
+  if (!done[dev]) {
+    exp_big_init_kernel<<<kExpBig / 256, 256, 0, st>>>();
+    MSB_CUDA(cudaGetLastError());
+    MSB_CUDA(cudaStreamSynchronize(st));   // later calls may come on other streams
+    done[dev] = true;
+  }
+  return MSB_OK;
+}
+
+int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
+  const int D = a.f.n_days;
+  static const int knot_tile = env_int("MSB_KNOT_TILE", 16, 1, 64);
+  const int rc_tab = exp_tables_ready(st);
+  if (rc_tab) return rc_tab;
+  // knot-days e whose steps can fall into [a0, b0): t_Tmin(e) lies within (-1080, 2160) minutes
+  // of midnight of day e
+  a.k.i_lo = a0 * a.tpd; a.k.i_hi = b0 * a.tpd;
+  a.k.e0 = a0 - 2 > 0 ? a0 - 2 : 0;
+  a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
+  // small shards: shorter chunks so that the grid still fills the 148 SMs several waves deep
+  a.k.tile = knot_tile;
+  while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
+    a.k.tile >>= 1;
+  const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
+  if (a.out.dtype == 4) thermo_knot_kernel<float, 7><<<grid, kDisaggThreads, 0, st>>>(a);
+  else thermo_knot_kernel<double, 7><<<grid, kDisaggThreads, 0, st>>>(a);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}
+
+int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
+  static const int day_tile = env_int("MSB_DAY_TILE", 16, 1, 32);
+  static const int day_pf = env_int("MSB_DAY_PF", 4, 0, 16);
+  a.k.i_lo = a.k.i_hi = 0;
+  a.k.e0 = a0; a.k.e1 = b0;            // output days, day_tile per thread
+  a.k.tile = day_tile;
+  while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 6 * 6)
+    a.k.tile >>= 1;
+  a.k.pf = day_pf;
+  const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
+  if (a.out.dtype == 4) streams_day_kernel<float, 6><<<grid, kDisaggThreads, 0, st>>>(a);
+  else streams_day_kernel<double, 6><<<grid, kDisaggThreads, 0, st>>>(a);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" int msb_selftest_math(int n, const double *x_dev, double *out_dev, void *stream) {
+  if (n <= 0 || !x_dev || !out_dev) { set_error("msb_selftest_math: bad argument"); return MSB_E_ARG; }
+  const int rc_tab = exp_tables_ready(reinterpret_cast<cudaStream_t>(stream));
+  if (rc_tab) return rc_tab;
+  math_selftest_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n, x_dev, out_dev);
+  MSB_CUDA(cudaGetLastError());
+  return MSB_OK;
+}
