@@ -39,6 +39,8 @@ WORKLOADS = {
     "conus_16th_hourly": "CONUS 1/16 deg, 482,560 cells, 365 d daily -> hourly, triangle precip",
     "global_half_deg": "global 0.5 deg land (~67k cells), 365 d daily -> hourly, triangle precip",
     "conus_16th_10yr_3h_mix": "CONUS 1/16 deg, 3652 d daily -> 3-hourly, mix precip",
+    "global_8th_30yr_15min": "global 1/8 deg land (~1M cells), 10957 d daily -> 15-minute, triangle precip "
+                             "(BASELINE configs[4]: run it with --gpus 8 --shard)",
 }
 METRIC = "cell-timesteps/sec (daily sim + hourly disagg)"
 UNIT = "cell-timesteps/s"
@@ -248,6 +250,9 @@ def main():
                     help="days per msb_disaggregate call (default: as many as keep one ring slot <= 24 GB, at most 64 "
                          "for the headline grid)")
     ap.add_argument("--sample-cells", type=int, default=None)
+    ap.add_argument("--shard", action="store_true",
+                    help="strong scaling: the ranks share ONE domain, each takes a contiguous cell range "
+                         "(metsim_b200.shard.cell_range); default is one full domain per rank (weak)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
@@ -278,11 +283,17 @@ def main():
     if args.cells:
         idx = np.linspace(0, lat.size - 1, args.cells).astype(np.int64)
         lat, lon = lat[idx], lon[idx]
+    n_domain = lat.size
+    if args.shard and world > 1:      # latitude bands: contiguous ranges of the row-major enumeration
+        from metsim_b200.shard import cell_range
+        lo, hi = cell_range(n_domain, rank, world)
+        lat, lon = lat[lo:hi], lon[lo:hi]
     n = lat.size
     tpd = 1440 // ts
     params = dict(time_step=ts, prec_type=prec_type, utc_offset=True)
     # every rank owns a shard of the same shape (different seed = different part of the domain)
     f = synth.make_forcing_torch(lat, lon, n_days, start, dev, seed=synth.SEED + rank)
+    torch.cuda.empty_cache()
     eng = Engine(params, dev)
     eng.load(**f)
     if args.tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
@@ -349,7 +360,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     cell_ts_rank = n * n_days * tpd
-    value = world * cell_ts_rank / (ms_per_step * 1e-3)
+    strong = args.shard and world > 1
+    total_cell_ts = n_domain * n_days * tpd if strong else world * cell_ts_rank
+    value = total_cell_ts / (ms_per_step * 1e-3)
     br = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(3)] for m in marks]).mean(0)
     disagg_ms_per_launch = br[2] / n_tiles
     bytes_per_cts = algorithmic_bytes_per_cell_ts(tpd, len(OUT_VARS))
@@ -395,7 +408,7 @@ def main():
                                             "wind", "state_t_min", "state_t_max", "state_prec",
                                             "t_pk12", "dur12")) + n * 4
         d2h = len(OUT_VARS) * n_days * tpd * n * 4
-        e2e = {"value": world * cell_ts_rank / float(dt.item()), "unit": UNIT,
+        e2e = {"value": total_cell_ts / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": float(dt.item()) * 1e3, "steps": e_steps,
                "timer": "host wall clock around the blocking C-ABI call, max over ranks",
@@ -420,11 +433,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload],
                        "cells_per_gpu": int(n), "n_days": int(n_days), "time_step_min": ts,
                        "prec_type": prec_type, "utc_offset": True, "out_vars": list(OUT_VARS),
-                       "out_precision": "f4", "tile_days": tile, "sharding": f"cell-chunks x{world}, no collective",
+                       "out_precision": "f4", "tile_days": tile,
+                       "sharding": (f"one domain of {n_domain} cells cut into {world} contiguous cell ranges, no collective"
+                                    if strong else f"cell-chunks x{world}, no collective"),
                        "l2": "each tile writes %.1f GB (>> 126 MB L2) into a 2-tile ring; inputs %.1f GB"
                              % (len(OUT_VARS) * tile * tpd * n * 4 / 1e9, 4 * n_days * n * 8 / 1e9)},
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),

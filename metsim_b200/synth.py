@@ -124,12 +124,23 @@ def make_forcing_torch(lat, lon, n_days: int, start: str, device, seed: int = SE
         eps = torch.randn(n, generator=g, device=device, dtype=f64) * 3.0
         noise = eps if d == 0 else 0.7 * noise + innov * eps
         t_min_all[d] = base_lat + seas[d] * sign + noise
-    t_max_all = t_min_all + (2.0 + 16.0 * rnd(total, n))
-    wet = rnd(total, n) < 0.3
     # gamma(0.8, 6) via torch.distributions is CPU-seeded; use -log(U)*scale*U^(1/k) (Ahrens-Dieter
     # boost of an exponential) which has the right shape and support for a synthetic field
-    prec_all = torch.where(wet, -torch.log(rnd(total, n).clamp_min(1e-300)) * 6.0
-                           * rnd(total, n).pow(1.0 / 0.8), torch.zeros((), dtype=f64, device=device))
+    if total * n <= (1 << 28):
+        t_max_all = t_min_all + (2.0 + 16.0 * rnd(total, n))
+        wet = rnd(total, n) < 0.3
+        prec_all = torch.where(wet, -torch.log(rnd(total, n).clamp_min(1e-300)) * 6.0
+                               * rnd(total, n).pow(1.0 / 0.8), torch.zeros((), dtype=f64, device=device))
+    else:   # multi-decade records: the same process filled in blocks of days (bounded temporaries)
+        t_max_all = torch.empty_like(t_min_all)
+        prec_all = torch.empty_like(t_min_all)
+        for d0 in range(0, total, 256):
+            d1 = min(total, d0 + 256)
+            t_max_all[d0:d1] = t_min_all[d0:d1] + (2.0 + 16.0 * rnd(d1 - d0, n))
+            wet = rnd(d1 - d0, n) < 0.3
+            prec_all[d0:d1] = torch.where(wet, -torch.log(rnd(d1 - d0, n).clamp_min(1e-300)) * 6.0
+                                          * rnd(d1 - d0, n).pow(1.0 / 0.8),
+                                          torch.zeros((), dtype=f64, device=device))
     elev = (-(torch.log(rnd(n).clamp_min(1e-300)) + torch.log(rnd(n).clamp_min(1e-300))) * 400.0
             ).clamp(0.0, 4500.0)  # gamma(2, 400) = sum of two exponentials
     out = dict(lat=lat_t, lon=lon_t, elev=elev,
@@ -140,5 +151,11 @@ def make_forcing_torch(lat, lon, n_days: int, start: str, device, seed: int = SE
                state_prec=prec_all[:90].contiguous(),
                t_pk12=300.0 + 840.0 * rnd(12, n), dur12=120.0 + 600.0 * rnd(12, n))
     if wind:
-        out["wind"] = 0.5 + 7.5 * rnd(n_days, n)
+        if n_days * n <= (1 << 28):
+            out["wind"] = 0.5 + 7.5 * rnd(n_days, n)
+        else:
+            out["wind"] = torch.empty((n_days, n), dtype=f64, device=device)
+            for d0 in range(0, n_days, 256):
+                d1 = min(n_days, d0 + 256)
+                out["wind"][d0:d1] = 0.5 + 7.5 * rnd(d1 - d0, n)
     return out
