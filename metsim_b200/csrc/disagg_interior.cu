@@ -225,6 +225,9 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
           const int m = i * ts + off_min;         // interior days: 0 < m < (D-1)*1440, no wrap
           const int dA = m / kMinPerDay, r = m - dA * kMinPerDay;
           if (dA != tk_day) {
+#ifdef MSB_BOUNDS
+            if (dA < 0 || dA + 1 >= f.n_days || m < 0) asm volatile("trap;");
+#endif
             const size_t oA = (size_t)dA * ld + cell;
             const bool next = dA == tk_day + 1;
             slot[kT_TKA][tid] = next ? slot[kT_TKB][tid] : a.tskc_d[oA];
@@ -318,10 +321,18 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
     y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
     return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
   };
+#ifdef MSB_BOUNDS   // debug build (python -m metsim_b200.build --bounds): window / table accesses checked
+#define MSB_CHECK_WIN(d) do { if ((unsigned)((d) - win0) >= (unsigned)nwin) asm volatile("trap;"); } while (0)
+#define MSB_CHECK_Q(ptr) do { if ((ptr) < qrow || (ptr) >= qrow + (size_t)365 * kQLd + MSB_Q_PAD / 2) asm volatile("trap;"); } while (0)
+#else
+#define MSB_CHECK_WIN(d) do { } while (0)
+#define MSB_CHECK_Q(ptr) do { } while (0)
+#endif
   // what disagg_prepare_kernel would put into the record of source day d: done here, once per
   // (cell, day) with the warp converged, so the interior days need no record traffic at all
   const double *const dayl = a.t.daylength + (size_t)f.lat_row[cell] * kRows;
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
+    MSB_CHECK_WIN(d);
     const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
     return (a.sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
   };
@@ -370,6 +381,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   PrecDay pd;
   {
     const int md0 = d_lo + mq - 1;
+    MSB_CHECK_WIN(md0);
     prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
   }
   bool nan_cur = !(pd.f == pd.f), need_fixup = false;
@@ -416,6 +428,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       const int mdn = d + mq, sdn = d + tq;
       const double w5 = rad_of(sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny], w9 = qb[kTiny + 1];
       PrecDay pn;
+      MSB_CHECK_WIN(mdn); MSB_CHECK_WIN(d); MSB_CHECK_WIN(d - 1 + (d == d_lo));
       prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
       const double w0 = pack_prec(pn), w1 = pn.hsp, w2 = pn.hsq, w3 = pn.f;
       prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
@@ -484,6 +497,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       for (; t < t_stop; ++t, ooff += ostride) {
         // step: precipitation :265-352, shortwave :618-680, wind :355-380
         const double qn = q_pref;
+        MSB_CHECK_Q(q_ptr);
         q_pref = load_early(q_ptr);
         prefetch_l1(q_ptr + pf_off);
         q_ptr += C;
