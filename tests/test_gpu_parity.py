@@ -497,6 +497,39 @@ def test_full_size_properties_conus_hourly_slice():
     assert torch.equal(part["prec"], full["prec"][2 * 24:5 * 24])
 
 
+def test_fast_path_full_width_against_general_path_and_properties():
+    """The specialised interior-day kernels at the BASELINE grid width (482,560 cells, 9 days): every
+    variable agrees with the event-driven general kernel (float64) to float32 rounding, precipitation
+    mass per record is conserved, relative humidity <= 100, and 3-day calls give the same bits."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    rng = np.random.default_rng(synth.SEED)
+    lat, lon = synth.grid_cells("conus1/16", rng)
+    d = 9
+    f = synth.make_forcing_torch(lat, lon, d, "2001-03-28", "cuda")
+    eng = Engine(dict(time_step=60, prec_type="triangle", utc_offset=True))
+    eng.load(**f)
+    eng.build_solar()
+    eng.daily(want=())
+    fast = eng.disaggregate(EXAMPLE_VARS, 0, d, torch.float32)                       # specialised path
+    gen = eng.disaggregate(EXAMPLE_VARS + ("tskc",), 0, d, torch.float64)            # general path
+    eng.check()
+    torch.cuda.synchronize()
+    for v in EXAMPLE_VARS:
+        a, b = fast[v], gen[v].to(torch.float32)
+        neq = (a != b)
+        assert float(neq.double().mean()) < 1e-3, v
+        scale = b.abs().clamp_min(util.FLOORS[v])
+        assert float(((a - b).abs() / scale).max()) < 3e-7, v
+    assert torch.allclose(fast["prec"].double().sum(0), f["prec"].sum(0), rtol=2e-6, atol=1e-5)
+    assert float(fast["rel_humid"].max()) <= 100.0
+    parts = [eng.disaggregate(EXAMPLE_VARS, d0, min(d, d0 + 3), torch.float32) for d0 in range(0, d, 3)]
+    torch.cuda.synchronize()
+    for v in EXAMPLE_VARS:
+        assert torch.equal(torch.cat([p[v] for p in parts]), fast[v]), v
+
+
 @pytest.mark.parametrize("grid,ts,prec_type,days", [
     ("conus1/16", 180, "mix", 10),        # BASELINE configs[3] shape (3-hourly, mix), full grid width
     ("global1/8", 15, "triangle", 3),     # configs[4] shape (15-minute), ~1M cells
