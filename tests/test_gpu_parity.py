@@ -185,6 +185,8 @@ EXAMPLE_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_
     ("global_half_deg", 400, 16, {"time_step": 360, "prec_type": "mix"}),
     ("global_half_deg", 400, 9, {"time_step": 20, "utc_offset": False}),
     ("conus_16th_hourly", 260, 30, {"time_step": 120, "prec_type": "uniform", "tmax_daylength_fraction": 0.5}),
+    ("edge", None, 20, {"time_step": 60, "t_end": True}),      # polar rows, |lon| = 180, lon outside [-180, 180]
+    ("edge", None, 12, {"time_step": 180, "prec_type": "mix"}),
 ], ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(f"{k}{x}" for k, x in v.items()) or "std")
 def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
     """The configuration bench.py times: the 8 variables of examples/example_nc.conf, float32
@@ -196,12 +198,19 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
     from metsim_b200 import synth
     from metsim_b200.engine import Engine
     from oracle import oracle_lib
-    f, params = synth.make_config(name, max_cells=cells, n_days=days)
-    if over.get("start_dec"):       # a record that starts in December: NaN days at the head and tail
+    if name == "edge":
+        lat = np.array([89.5, -89.5, 66.6, 0.0, 45.0, 45.0, 45.0, 45.0, 78.2, -71.0, 30.0, 30.0] * 3)
+        lon = np.array([10.0, -10.0, 180.0, -180.0, 359.9, 540.0, -359.75, 0.125, -179.99, 179.99, 0.0, -105.0] * 3)
+        f = synth.make_forcing(lat, lon, days, "2000-12-20", np.random.default_rng(31))
+        params = dict(time_step=60, prec_type="triangle", utc_offset=True)
+        if over.get("t_end"):
+            f["t_end"] = np.stack([f["t_min"][-1] - 1.5, f["t_max"][-1] + 2.0])
+    else:
         f, params = synth.make_config(name, max_cells=cells, n_days=days)
+    if over.get("start_dec"):       # a record that starts in December: NaN days at the head and tail
         doy, month = synth.calendar_vectors("2001-12-05", days)
         f["doy"], f["month"] = doy, month
-    params.update({k: v for k, v in over.items() if k != "start_dec"})
+    params.update({k: v for k, v in over.items() if k not in ("start_dec", "t_end")})
     want = oracle_lib.run(params, **util.oracle_kwargs(f))
     eng = Engine(params)
     eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
@@ -226,7 +235,10 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
             floor = util.FLOORS[v]
             # within float32 rounding of the fp64 value (+ the 1e-9 contract)
             assert (err <= 0.5000001 * ulp + 1e-9 * np.maximum(np.abs(w64[ok]), floor)).all(), (v, split, float((err / ulp).max()))
-            assert neq.mean() < 2e-4, (v, split, float(neq.mean()))
+            # (values far below the floor are rounding noise of sums that are mathematically zero --
+            #  polar night, the first tiny step after sunrise -- and are left out of the count)
+            sig = np.abs(w64[ok]) >= 1e-3 * floor
+            assert neq[sig].sum() <= max(3, 2e-4 * sig.sum()), (v, split, int(neq[sig].sum()), int(sig.sum()))
         np.testing.assert_array_equal(res["prec"].cpu().numpy() == 0, want["prec"].astype(np.float32) == 0)
     # the same kernels with float64 outputs: the north-star bar itself, 1e-9 on every variable
     # (this is what pins the second-order exp / rcp / sqrt sequences of the interior-day kernel)
