@@ -444,6 +444,8 @@ def main():
                              % (len(OUT_VARS) * tile * tpd * n * 4 / 1e9, 4 * n_days * n * 8 / 1e9)},
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
                              "disaggregate": float(br[2])},
+            # the metric with and without the (time-independent) solar-geometry set-up
+            "value_excl_solar_tables": total_cell_ts / max(1e-9, (ms_per_step - float(br[0])) * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + thermo_knot_kernel + "
                                                    "streams_day_kernel (+ disagg_kernel on the record's first / last "
                                                    "two days), timed together per call (--tile-days days)",
