@@ -157,9 +157,12 @@ int msb_mtclim_daily(const msb_params *p, const msb_forcing *f, const msb_solar_
 int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 
 /* ---- sub-daily disaggregation: disaggregate.py:34-680, units.py:3-59 -----------------------
- * A first kernel turns the days around [day0, day1) into per-(cell, day) records (PCHIP knots
- * with their derivatives, the closed-form precipitation shape, radiation per tiny step); the
- * streaming kernel then only reads those.  The records live in caller-provided scratch. */
+ * Days [2, D-2) of a record with the default variable set (examples/example_nc.conf) and no unit
+ * conversion go through two specialised kernels that need no scratch.  Everything else -- the
+ * record's first / last two days, other variable sets, unit conversion -- goes through an
+ * event-driven kernel that reads per-(cell, day) records (PCHIP knots with their derivatives, the
+ * closed-form precipitation shape, radiation per tiny step) built by a first kernel in
+ * caller-provided scratch.  Results do not depend on how a record is cut into calls. */
 #define MSB_REC_FIELDS 9
 #define MSB_REC_MARGIN 3
 size_t msb_disagg_workspace_bytes(int64_t ld, int day0, int day1);
