@@ -199,6 +199,14 @@ typedef struct msb_host_run {
   int32_t tile_days;                 /* 0 = choose */
   int32_t out_is_ring;               /* !=0: out_host[v] holds only 2*tile_days*tpd steps and is
                                         reused as a ring (a streaming writer drains it) */
+  /* Optional consumer hook (the streaming writer of metsim/metsim.py:363-454): called on the calling
+   * thread once per output tile, in order, after the tile's device-to-host copies have completed,
+   * while the NEXT tile is already computing / copying.  The tile holds days [day0, day1); with
+   * out_is_ring its steps start at slot*tile_days*tpd of every out_host[v] (slot = tile & 1) and the
+   * slot is not overwritten before the callback returns; without it slot = -1 and the steps are at
+   * their final position day0*tpd.  A non-zero return aborts the run (MSB_E_ARG). */
+  int32_t (*on_tile)(void *user, int32_t tile, int32_t day0, int32_t day1, int32_t slot);
+  void *user;
   double ms_solar, ms_h2d, ms_daily, ms_disagg_total; /* filled on return (CUDA events) */
 } msb_host_run;
 int msb_run_host(const msb_params *p, msb_host_run *run);

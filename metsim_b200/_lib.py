@@ -97,8 +97,13 @@ class HostRun(C.Structure):
                 ("offset", C.c_double * N_SUBVARS), ("out_dtype", C.c_int32),
                 ("daily_host", C.c_void_p * N_DAILYVARS), ("n_iter_host", C.c_void_p),
                 ("tile_days", C.c_int32), ("out_is_ring", C.c_int32),
+                ("on_tile", C.c_void_p), ("user", C.c_void_p),
                 ("ms_solar", C.c_double), ("ms_h2d", C.c_double), ("ms_daily", C.c_double),
                 ("ms_disagg_total", C.c_double)]
+
+
+# int32_t (*on_tile)(void *user, int32_t tile, int32_t day0, int32_t day1, int32_t slot)
+ON_TILE = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32)
 
 
 class MetsimB200Error(RuntimeError):

@@ -305,6 +305,18 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   // ---- tiled disaggregation with double-buffered D2H ----
   if (sub && n_out > 0) {
     int n_tiles = (D + tile_days - 1) / tile_days;
+    // hand a finished tile to the consumer: its D2H is complete, the next tile is in flight
+    auto deliver = [&](int k) -> int {
+      if (!run->on_tile) return MSB_OK;
+      cudaError_t e = cudaEventSynchronize(ev_c[k & 1]);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(tile copied)");
+      const int d0 = k * tile_days, d1 = d0 + tile_days < D ? d0 + tile_days : D;
+      if (run->on_tile(run->user, k, d0, d1, run->out_is_ring ? (k & 1) : -1) != 0) {
+        set_error("msb_run_host: on_tile callback failed at tile %d", k);
+        return MSB_E_ARG;
+      }
+      return MSB_OK;
+    };
     for (int k = 0; k < n_tiles; ++k) {
       const int b = k & 1;
       const int d0 = k * tile_days, d1 = d0 + tile_days < D ? d0 + tile_days : D;
@@ -329,7 +341,11 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
         MSB_TRYC(cudaMemcpyAsync(dst, d_out[b][v], steps * (size_t)N * osz, cudaMemcpyDeviceToHost, s_copy));
       }
       MSB_TRYC(cudaEventRecord(ev_c[b], s_copy));
+      // the previous tile goes to the consumer while this one computes; its host slot is the one
+      // tile k + 1 will overwrite, and that copy is only enqueued after the callback has returned
+      if (k >= 1) MSB_TRY(deliver(k - 1));
     }
+    MSB_TRY(deliver(n_tiles - 1));
   }
   MSB_TRYC(cudaEventRecord(ev[4], s_main));
   MSB_TRYC(cudaStreamSynchronize(s_main));

@@ -294,10 +294,15 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
              given_shortwave=None, given_vapor_pressure=None, given_tskc=None, given_longwave=None,
              out_vars=DEFAULT_OUT_VARS, out_dtype=np.float32, units: dict | None = None,
              daily_vars=(), device: int = 0, tile_days: int = 0, out: dict | None = None,
-             ring: bool = False, timings: dict | None = None) -> dict:
+             ring: bool = False, timings: dict | None = None, on_tile=None) -> dict:
     """Whole path with HOST (numpy) buffers through ``msb_run_host``: the call a reference-side
     binding makes in place of the cell loop of ``MetSim.run_slice`` (metsim/metsim.py:477-493).
-    Host-to-device and device-to-host copies happen inside."""
+    Host-to-device and device-to-host copies happen inside.
+
+    ``on_tile(tile, day0, day1, slot)`` is the consumer hook of a streaming writer: called once per
+    output tile, in order, when the tile's rows are in host memory and while the next tile is
+    already computing (``slot`` is the ring slot with ``ring=True``, else -1).  An exception
+    raised inside it aborts the run and is re-raised here."""
     lib = _lib.lib()
     p = _lib.make_params(params)
     ts = p.time_step
@@ -342,7 +347,21 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
             run.daily_host[i] = None
     n_iter = np.zeros(n, dtype=np.int32)
     run.n_iter_host = n_iter.ctypes.data_as(C.c_void_p)
-    _lib.check(lib.msb_run_host(C.byref(p), C.byref(run)))
+    failure = []
+    if on_tile is not None:
+        def _cb(_user, tile, day0, day1, slot):
+            try:
+                on_tile(int(tile), int(day0), int(day1), int(slot))
+                return 0
+            except BaseException as exc:       # must not propagate through the C frame
+                failure.append(exc)
+                return 1
+        cb = _lib.ON_TILE(_cb)                  # keep the thunk alive for the duration of the call
+        run.on_tile = C.cast(cb, C.c_void_p)
+    rc = lib.msb_run_host(C.byref(p), C.byref(run))
+    if failure:
+        raise failure[0]
+    _lib.check(rc)
     daily["n_iter"] = n_iter
     res["daily"] = daily
     if timings is not None:

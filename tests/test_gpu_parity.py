@@ -270,6 +270,63 @@ def test_fast_path_through_run_host_and_tile_independence():
             np.testing.assert_array_equal(got[v], ref[v], err_msg=f"{v} tile={tile}")
 
 
+def test_streaming_writer_through_on_tile_hook(tmp_path):
+    """msb_run_host's on_tile consumer hook + the NetCDF-3 writer (metsim/metsim.py:363-454 in
+    streaming form): outputs go through a 2-slot pinned host ring, every finished tile is scattered
+    into (time, lat, lon) and written while the next one computes; the file, read back with scipy,
+    equals the whole-record result bit for bit, NaN outside the mask.  An exception raised by the
+    consumer aborts the run and surfaces unchanged."""
+    from scipy.io import netcdf_file
+    from metsim_b200 import synth
+    from metsim_b200.engine import run_host
+    from metsim_b200.ncwriter import NC3Writer
+    rng = np.random.default_rng(17)
+    lats = 40.03125 + np.arange(12) / 16.0
+    lons = -110.96875 + np.arange(40) / 16.0
+    mask = rng.random((lats.size, lons.size)) < 0.7
+    la, lo = np.meshgrid(lats, lons, indexing="ij")
+    days, ts, tile = 23, 60, 4
+    tpd = 1440 // ts
+    f = synth.make_forcing(la[mask], lo[mask], days, "2001-05-01", rng)
+    params = dict(time_step=ts, prec_type="triangle", utc_offset=True)
+    kw = {k: f.get(k) for k in util.INPUT_KEYS}
+    n = int(mask.sum())
+    ref = run_host(params, out_vars=EXAMPLE_VARS, **kw)                       # whole record in host memory
+    ring = {v: np.empty((2 * tile * tpd, n), dtype=np.float32) for v in EXAMPLE_VARS}
+    path = os.path.join(tmp_path, "forcing.nc")
+    seen = []
+    with NC3Writer(path, n_steps=days * tpd, lat=lats, lon=lons, cell_index=np.flatnonzero(mask.ravel()),
+                   variables={v: {"units": "-"} for v in EXAMPLE_VARS},
+                   time_values=np.arange(days * tpd) * float(ts), time_units="minutes since 2001-05-01") as w:
+        write = w.tile_consumer(ring, tile, tpd, ring=True)
+
+        def on_tile(k, d0, d1, slot):
+            seen.append((k, d0, d1, slot))
+            write(k, d0, d1, slot)
+        run_host(params, out_vars=EXAMPLE_VARS, tile_days=tile, out=ring, ring=True, on_tile=on_tile, **kw)
+        assert all(c == days * tpd for c in w.steps_written.values())
+    assert seen == [(k, k * tile, min(days, (k + 1) * tile), k & 1) for k in range(-(-days // tile))]
+    nc = netcdf_file(path, "r", mmap=False)
+    idx = np.flatnonzero(mask.ravel())
+    for v in EXAMPLE_VARS:
+        got = nc.variables[v].data.reshape(days * tpd, -1)
+        np.testing.assert_array_equal(got[:, idx], ref[v], err_msg=v)
+        assert np.isnan(np.delete(got, idx, axis=1)).all()
+    nc.close()
+
+    class Boom(RuntimeError):
+        pass
+
+    def bad(k, d0, d1, slot):
+        if k == 2:
+            raise Boom("disk full")
+    with pytest.raises(Boom):
+        run_host(params, out_vars=("temp",), tile_days=tile, on_tile=bad, **kw)
+    # the library is usable afterwards
+    again = run_host(params, out_vars=("temp",), **kw)
+    np.testing.assert_array_equal(again["temp"], ref["temp"])
+
+
 def test_edge_longitudes_polar_and_wraparound():
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
