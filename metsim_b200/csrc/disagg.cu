@@ -82,9 +82,14 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     if (out->scale[v] != 1.0 || out->offset[v] != 0.0) units = true;
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
-  // the default variable set (examples/example_nc.conf) without unit conversion: specialised kernels
-  const bool example = a.var_mask == kExampleMask && fast_lw && !units && !a.lw_raw;
+  // Any subset of the default variable set (examples/example_nc.conf) without unit conversion takes
+  // the specialised kernels on the interior days; `full` is that set itself at float32, for which
+  // the edge days have the two compile-time halves of disagg_kernel as well.
+  const bool example = (a.var_mask & ~kExampleMask) == 0 && fast_lw && !units && !a.lw_raw;
   const bool f4 = out->dtype == 4;
+  const bool full = example && a.var_mask == kExampleMask && f4;
+  const unsigned knot_bits = kThermoBits | (1u << MSB_V_WIND);            // thermo_knot_kernel's outputs
+  const unsigned day_bits = (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE);  // streams_day_kernel's
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
   const int D = f->n_days;
   // interior days [a0, b0) of this call: every knot exists, no NaN ends, no wrapped stream
@@ -106,17 +111,17 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
         if (b.out.var[v])
           b.out.var[v] = reinterpret_cast<char *>(b.out.var[v]) +
                          (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * (size_t)out->dtype;
-      if (!f4) return launch_event_kernel(b, kEvAnyF8, true, cell_blocks, st);
+      if (!full) return launch_event_kernel(b, f4 ? kEvAnyF4 : kEvAnyF8, true, cell_blocks, st);
       r = launch_event_kernel(b, kEvThermoF4, true, cell_blocks, st);
       return r != MSB_OK ? r : launch_event_kernel(b, kEvStreamsF4, true, cell_blocks, st);
     };
     MSB_TRY(launch_edge(out->day0, a0));
     MSB_TRY(launch_edge(b0, out->day1));
-    MSB_TRY(launch_interior_thermo(a, a0, b0, cell_blocks, st));
-    MSB_TRY(launch_interior_streams(a, a0, b0, cell_blocks, st));
+    if (a.var_mask & knot_bits) MSB_TRY(launch_interior_thermo(a, a0, b0, cell_blocks, st));
+    if (a.var_mask & day_bits) MSB_TRY(launch_interior_streams(a, a0, b0, cell_blocks, st));
   } else {
     MSB_TRY(launch_day_records(a, a.e0, e1, e1, cell_blocks, st));
-    if (example && f4) {   // too short for interior days: the thermodynamic half and the stream half
+    if (full) {            // too short for interior days: the thermodynamic half and the stream half
       MSB_TRY(launch_event_kernel(a, kEvThermoF4, true, cell_blocks, st));
       MSB_TRY(launch_event_kernel(a, kEvStreamsF4, true, cell_blocks, st));
     } else {

@@ -83,7 +83,9 @@ __device__ __forceinline__ double exp_big(double x, const double *tab, const Kno
   return fma(q, s, s);
 }
 
-template <typename OutT, int MINB>
+// MASKED = false: the whole default variable set, every store unconditional (the benchmarked
+// instantiation); true: any subset of it, stores under the request mask.
+template <typename OutT, int MINB, bool MASKED>
 __global__ void __launch_bounds__(kDisaggThreads, MINB)
 thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double etab[kExpBig];
@@ -126,6 +128,12 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   c.t_end = f.t_end;
   const KnotK K = load_knot();
   const unsigned lanes = __activemask();
+  // any subset of the default variable set: a variable that was not requested is computed (the
+  // others depend on it) but not stored
+  const unsigned vm = MASKED ? a.var_mask : kExampleMask;
+  const bool w_temp = (vm >> MSB_V_TEMP) & 1u, w_vp = (vm >> MSB_V_VAPOR_PRESSURE) & 1u,
+             w_rh = (vm >> MSB_V_REL_HUMID) & 1u, w_ap = (vm >> MSB_V_AIR_PRESSURE) & 1u,
+             w_lw = (vm >> MSB_V_LONGWAVE) & 1u, w_wd = (vm >> MSB_V_WIND) & 1u;
 
   const size_t ostride = (size_t)a.out.ld;
   const long i_base = (long)a.out.day0 * a.tpd;
@@ -231,9 +239,9 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
             const size_t oA = (size_t)dA * ld + cell;
             const bool next = dA == tk_day + 1;
             slot[kT_TKA][tid] = next ? slot[kT_TKB][tid] : a.tskc_d[oA];
-            slot[kT_WDA][tid] = next ? slot[kT_WDB][tid] : f.wind[oA];
+            slot[kT_WDA][tid] = next ? slot[kT_WDB][tid] : (w_wd ? f.wind[oA] : 0.0);
             slot[kT_TKB][tid] = a.tskc_d[oA + ld];   // used a day later
-            slot[kT_WDB][tid] = f.wind[oA + ld];
+            slot[kT_WDB][tid] = w_wd ? f.wind[oA + ld] : 0.0;
             tk_day = dA;
           }
           const int n2 = r + ts - kMinPerDay;
@@ -270,12 +278,12 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       const double e1 = fma(-(1.0 + xx), ee, 1.0);
       const double t2 = at * at;
       const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
-      __stcs(o_temp + ooff, (OutT)temp);
-      __stcs(o_vp + ooff, (OutT)vp);
-      __stcs(o_rh + ooff, (OutT)rh);
-      __stcs(o_ap + ooff, (OutT)ap);
-      __stcs(o_lw + ooff, (OutT)lw);
-      __stcs(o_wd + ooff, wd_o);
+      if (w_temp) __stcs(o_temp + ooff, (OutT)temp);
+      if (w_vp) __stcs(o_vp + ooff, (OutT)vp);
+      if (w_rh) __stcs(o_rh + ooff, (OutT)rh);
+      if (w_ap) __stcs(o_ap + ooff, (OutT)ap);
+      if (w_lw) __stcs(o_lw + ooff, (OutT)lw);
+      if (w_wd) __stcs(o_wd + ooff, wd_o);
     }
   }
 }
@@ -292,7 +300,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
 enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
        kY_ROWTOT_CUR, kY_COUNT };
 
-template <typename OutT, int MINB>
+template <typename OutT, int MINB, bool MASKED>
 __global__ void __launch_bounds__(kDisaggThreads, MINB)
 streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ double slot[kY_COUNT][kDisaggThreads];
@@ -313,6 +321,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   if (cell >= f.n_cells || d_lo >= d_hi) return;
   const long ld = f.ld;
   const int C = 2 * ts;                                     // tiny steps per output step (:660)
+  const bool w_prec = !MASKED || ((a.var_mask >> MSB_V_PREC) & 1u);
+  const bool w_sw = !MASKED || ((a.var_mask >> MSB_V_SHORTWAVE) & 1u);
   const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
@@ -382,7 +392,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   {
     const int md0 = d_lo + mq - 1;
     MSB_CHECK_WIN(md0);
-    prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
+    pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
+    if (w_prec) prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
   }
   bool nan_cur = !(pd.f == pd.f), need_fixup = false;
   double p_base = 0.0, pr = 0.0;
@@ -429,7 +440,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       const double w5 = rad_of(sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny], w9 = qb[kTiny + 1];
       PrecDay pn;
       MSB_CHECK_WIN(mdn); MSB_CHECK_WIN(d); MSB_CHECK_WIN(d - 1 + (d == d_lo));
-      prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
+      pn.p0 = pn.nps = pn.q0 = pn.nqs = 0; pn.pth = kNever; pn.hsp = pn.hsq = pn.f = 0.0;
+      if (w_prec) prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
       const double w0 = pack_prec(pn), w1 = pn.hsp, w2 = pn.hsq, w3 = pn.f;
       prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
       slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
@@ -509,8 +521,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
         const double sw = fma(rd_cur, qn - q_prev, sw_carry);
         q_prev = qn;
         sw_carry = 0.0;
-        __stcs(o_prec + ooff, (OutT)pr);
-        __stcs(o_sw + ooff, (OutT)sw);
+        if (w_prec) __stcs(o_prec + ooff, (OutT)pr);
+        if (w_sw) __stcs(o_sw + ooff, (OutT)sw);
       }
     }
   }
@@ -592,8 +604,14 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-  if (a.out.dtype == 4) thermo_knot_kernel<float, 7><<<grid, kDisaggThreads, 0, st>>>(a);
-  else thermo_knot_kernel<double, 7><<<grid, kDisaggThreads, 0, st>>>(a);
+  const bool masked = a.var_mask != kExampleMask;
+  if (a.out.dtype == 4) {
+    if (masked) thermo_knot_kernel<float, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else thermo_knot_kernel<float, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
+  } else {
+    if (masked) thermo_knot_kernel<double, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else thermo_knot_kernel<double, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
+  }
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }
@@ -608,8 +626,15 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
     a.k.tile >>= 1;
   a.k.pf = day_pf;
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
-  if (a.out.dtype == 4) streams_day_kernel<float, 6><<<grid, kDisaggThreads, 0, st>>>(a);
-  else streams_day_kernel<double, 6><<<grid, kDisaggThreads, 0, st>>>(a);
+  const bool masked = (a.var_mask & ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE))) !=
+                      ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE));
+  if (a.out.dtype == 4) {
+    if (masked) streams_day_kernel<float, 6, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else streams_day_kernel<float, 6, false><<<grid, kDisaggThreads, 0, st>>>(a);
+  } else {
+    if (masked) streams_day_kernel<double, 6, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else streams_day_kernel<double, 6, false><<<grid, kDisaggThreads, 0, st>>>(a);
+  }
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }

@@ -251,6 +251,42 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
                                       res64[v].cpu().numpy().astype(np.float32), err_msg=v)
 
 
+@pytest.mark.parametrize("subset", [
+    ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_humid"),   # MetSim.params default out_vars
+    ("temp",), ("prec", "shortwave"), ("wind", "longwave"), ("air_pressure", "rel_humid", "prec"),
+    ("shortwave",), ("vapor_pressure", "wind"),
+], ids=lambda v: "+".join(v))
+def test_fast_path_variable_subsets(subset):
+    """Any subset of the default variable set takes the specialised kernels (a variable that was
+    not requested is simply not stored): same bits as in the full-set run, float32 and float64,
+    and the float64 values within 1e-9 of the oracle.  Triangle precipitation without t_pk12 /
+    dur12 is fine as long as prec is not requested; without a wind forcing wind is skipped."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    from oracle import oracle_lib
+    f, params = synth.make_config("conus_16th_hourly", max_cells=333, n_days=21)
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    eng = Engine(params)
+    eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+    full32 = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float32)
+    full64 = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float64)
+    g = dict(f)
+    if "prec" not in subset:
+        g.pop("t_pk12"); g.pop("dur12")
+    if "wind" not in subset:
+        g.pop("wind")
+    sub_eng = Engine(params)
+    sub_eng.load(**{k: g.get(k) for k in util.INPUT_KEYS})
+    for dtype, full in ((torch.float32, full32), (torch.float64, full64)):
+        got = sub_eng.run(out_vars=subset, out_dtype=dtype)
+        assert set(got) - {"daily"} == set(subset)
+        for v in subset:
+            assert torch.equal(got[v], full[v]), (v, dtype)
+            if dtype == torch.float64:
+                util.assert_close(got[v].cpu().numpy(), want[v], v, context=f"subset {subset}")
+
+
 def test_fast_path_through_run_host_and_tile_independence():
     """msb_run_host (host buffers, what bench.py's e2e leg and a reference-side binding call) on the
     default variable set: bit-identical to the device-resident fast path for several tile sizes --
