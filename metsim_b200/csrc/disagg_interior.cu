@@ -133,7 +133,8 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   const unsigned vm = MASKED ? a.var_mask : kExampleMask;
   const bool w_temp = (vm >> MSB_V_TEMP) & 1u, w_vp = (vm >> MSB_V_VAPOR_PRESSURE) & 1u,
              w_rh = (vm >> MSB_V_REL_HUMID) & 1u, w_ap = (vm >> MSB_V_AIR_PRESSURE) & 1u,
-             w_lw = (vm >> MSB_V_LONGWAVE) & 1u, w_wd = (vm >> MSB_V_WIND) & 1u;
+             w_lw = (vm >> MSB_V_LONGWAVE) & 1u, w_wd = (vm >> MSB_V_WIND) & 1u,
+             w_sh = (vm >> MSB_V_SPEC_HUMID) & 1u, w_tk = (vm >> MSB_V_TSKC) & 1u;   // MASKED only
 
   const size_t ostride = (size_t)a.out.ld;
   const long i_base = (long)a.out.day0 * a.tpd;
@@ -143,13 +144,15 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
   OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
   OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
+  OutT *const o_sh = reinterpret_cast<OutT *>(a.out.var[MSB_V_SPEC_HUMID]) + cell;
+  OutT *const o_tk = reinterpret_cast<OutT *>(a.out.var[MSB_V_TSKC]) + cell;
 
   // tskc and wind: repeated per minute, rolled by off_min, block mean over ts minutes
   // (:593-615, :355-380); wind rides along here because it shares this stream's roll exactly
   int i_tk = kNever, tk_day = -4;
   bool tk_started = false;
   double tk_a = 0.0, tk_b = 0.0;
-  OutT wd_o = 0;
+  OutT wd_o = 0, tk_o = 0;
   const double dx = (double)ts;
 
   // knots t_Tmax(e-1), t_Tmin(e), t_Tmax(e) of the first e: times, values, slopes and scipy's
@@ -256,6 +259,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
           wd_o = (OutT)wd;
+          tk_o = (OutT)tk;
         }
         i_next = min(isw, i_tk);
       }
@@ -284,6 +288,13 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       if (w_ap) __stcs(o_ap + ooff, (OutT)ap);
       if (w_lw) __stcs(o_lw + ooff, (OutT)lw);
       if (w_wd) __stcs(o_wd + ooff, wd_o);
+      if (MASKED) {             // the two variables outside the default set
+        if (w_tk) __stcs(o_tk + ooff, tk_o);
+        if (w_sh) {             // specific humidity :423-424
+          const double mix = (kEps * vp) * rcp_2(ap - vp);
+          __stcs(o_sh + ooff, (OutT)(mix * rcp_2(1.0 + mix)));
+        }
+      }
     }
   }
 }

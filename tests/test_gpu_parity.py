@@ -15,6 +15,18 @@ import msb_testutil as util
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "event"])
+def disagg_path(request, monkeypatch):
+    """Both disaggregation paths: "auto" = the specialised interior-day kernels wherever they apply
+    (+ the event-driven kernel on the record's edge days), "event" = the event-driven kernel for
+    every day (MSB_DISAGG_PATH, read by msb_disaggregate on every call)."""
+    if request.param == "event":
+        monkeypatch.setenv("MSB_DISAGG_PATH", "event")
+    else:
+        monkeypatch.delenv("MSB_DISAGG_PATH", raising=False)
+    return request.param
+
+
 def engine_run(inputs, params, out_dtype=None, units=None):
     import torch
     from metsim_b200.engine import Engine
@@ -133,7 +145,7 @@ def test_solar_tables_against_oracle_table():
 
 
 @pytest.mark.parametrize("path", util.golden_files(), ids=lambda p: os.path.basename(p)[:-4])
-def test_cuda_matches_reference_golden(path):
+def test_cuda_matches_reference_golden(path, disagg_path):
     inputs, params, ref_daily, ref_sub, extra = util.load_golden(path)
     got = engine_run(inputs, params)
     cells = extra.get("ref_cells")
@@ -160,7 +172,7 @@ CASES = [
 
 @pytest.mark.parametrize("name,cells,days,over", CASES,
                          ids=[f"{c[0]}-{c[1]}x{c[2]}-{i}" for i, c in enumerate(CASES)])
-def test_cuda_matches_oracle_on_seeded_configs(name, cells, days, over):
+def test_cuda_matches_oracle_on_seeded_configs(name, cells, days, over, disagg_path):
     from metsim_b200 import synth
     from oracle import oracle_lib
     f, params = synth.make_config(name, max_cells=cells, n_days=days)
@@ -363,7 +375,7 @@ def test_streaming_writer_through_on_tile_hook(tmp_path):
     np.testing.assert_array_equal(again["temp"], ref["temp"])
 
 
-def test_edge_longitudes_polar_and_wraparound():
+def test_edge_longitudes_polar_and_wraparound(disagg_path):
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
     from oracle import oracle_lib
@@ -379,7 +391,7 @@ def test_edge_longitudes_polar_and_wraparound():
             compare_to_oracle(got, want, f"edge d={d} ts={ts} {pt}")
 
 
-def test_precipitation_nan_days_and_fill():
+def test_precipitation_nan_days_and_fill(disagg_path):
     """Degenerate triangle days (0/0 -> NaN day, disaggregate.py:327) in runs, at the start and at
     the end of the record, with the ffill/bfill of disaggregate.py:130."""
     from metsim_b200 import synth
@@ -430,7 +442,7 @@ def test_run_host_equals_device_path_and_tiling():
         np.testing.assert_array_equal(ring["temp"][slot:slot + (d1 - d0) * tpd], ref["temp"][d0 * tpd:d1 * tpd])
 
 
-def test_float32_outputs_and_unit_conversion():
+def test_float32_outputs_and_unit_conversion(monkeypatch):
     """out_precision f4 (reference default, metsim.py:154) and the converters of units.py."""
     import torch
     from metsim_b200 import synth
@@ -439,6 +451,10 @@ def test_float32_outputs_and_unit_conversion():
     f32 = engine_run(f, params, out_dtype=torch.float32)
     for v in util.SUB:
         np.testing.assert_array_equal(f32[v], base[v].astype(np.float32), err_msg=v)
+    # unit conversion is fused into the stores of the event-driven kernel: compare it with the same
+    # kernel's unconverted output, to the last bit of the conversion
+    monkeypatch.setenv("MSB_DISAGG_PATH", "event")
+    base = engine_run(f, params)
     units = {"temp": "K", "prec": "mm s-1", "vapor_pressure": "hPa", "air_pressure": "Pa",
              "tskc": "%", "rel_humid": "fraction"}
     conv = engine_run(f, params, units=units)
@@ -491,7 +507,7 @@ def test_registry_method_module_run_df():
                 util.assert_close(df[ename].values, ref_daily[ename][:, c], oname, context=f"run(df) cell {c}")
 
 
-def test_passthrough_method_against_oracle_and_errors():
+def test_passthrough_method_against_oracle_and_errors(disagg_path):
     """'passthrough' (metsim/methods/passthrough.py:28-46) on seeded grids against the oracle:
     supplied shortwave alone and with vapour pressure / tskc / longwave, both sw_averaging modes,
     f4 outputs with units; the longwave rescale makes every day's mean equal the supplied value
