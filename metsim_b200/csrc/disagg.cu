@@ -82,15 +82,16 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     if (out->scale[v] != 1.0 || out->offset[v] != 0.0) units = true;
   }
   if (!a.var_mask) { set_error("msb_disaggregate: no output variable requested"); return MSB_E_ARG; }
-  // Without unit conversion (and with the default PRATA + CLOUD_DEARDORFF longwave) every variable
-  // set takes the specialised kernels on the interior days; `full` is the default set
-  // (examples/example_nc.conf) at float32, which has unconditional-store instantiations and, for the
-  // edge days, the two compile-time halves of disagg_kernel.  MSB_DISAGG_PATH=event forces the
+  a.units = units;
+  // With the default PRATA + CLOUD_DEARDORFF longwave every variable set, with or without unit
+  // conversion, takes the specialised kernels on the interior days; `full` is the default set
+  // (examples/example_nc.conf) at float32 without conversion, which has unconditional-store
+  // instantiations and, for the edge days, the two compile-time halves of disagg_kernel.  MSB_DISAGG_PATH=event forces the
   // event-driven kernel for every day (the parity tests use it to keep both paths covered).
   const char *force = getenv("MSB_DISAGG_PATH");
-  const bool example = fast_lw && !units && !a.lw_raw && !(force && force[0] == 'e');
+  const bool example = fast_lw && !a.lw_raw && !(force && force[0] == 'e');
   const bool f4 = out->dtype == 4;
-  const bool full = example && a.var_mask == kExampleMask && f4;
+  const bool full = example && a.var_mask == kExampleMask && f4 && !units;
   const unsigned knot_bits = kThermoBits | (1u << MSB_V_WIND) | (1u << MSB_V_TSKC);   // thermo_knot_kernel's outputs
   const unsigned day_bits = (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE);  // streams_day_kernel's
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));

@@ -42,6 +42,7 @@ struct DisaggArgs {
   msb_subdaily out;
   int tpd, tile_days;
   unsigned var_mask;   // bit v set = out.var[v] requested
+  bool units;          // some requested variable has scale != 1 or offset != 0
   double *rec;         // day records [MSB_REC_FIELDS][n_rec][ld], record r = padded day e0 + r
   double *lw_raw;      // passthrough with a supplied daily longwave: unscaled float64 longwave
                        // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL

@@ -154,6 +154,12 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   double tk_a = 0.0, tk_b = 0.0;
   OutT wd_o = 0, tk_o = 0;
   const double dx = (double)ts;
+  // unit conversion (metsim/units.py:3-59) fused into the stores of the MASKED instantiation;
+  // scale 1 / offset 0 leave the value bit-identical
+  auto conv = [&](int v, double val) {
+    if (MASKED) val = fma(val, a.out.scale[v], a.out.offset[v]);
+    return (OutT)val;
+  };
 
   // knots t_Tmax(e-1), t_Tmin(e), t_Tmax(e) of the first e: times, values, slopes and scipy's
   // derivative at t_Tmin(e) (_cubic.py:320-333); they roll forward through shared-memory slots
@@ -258,8 +264,8 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
             i_tk = i + (kMinPerDay - r) / ts;
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
-          wd_o = (OutT)wd;
-          tk_o = (OutT)tk;
+          wd_o = conv(MSB_V_WIND, wd);
+          tk_o = conv(MSB_V_TSKC, tk);
         }
         i_next = min(isw, i_tk);
       }
@@ -282,17 +288,17 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       const double e1 = fma(-(1.0 + xx), ee, 1.0);
       const double t2 = at * at;
       const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
-      if (w_temp) __stcs(o_temp + ooff, (OutT)temp);
-      if (w_vp) __stcs(o_vp + ooff, (OutT)vp);
-      if (w_rh) __stcs(o_rh + ooff, (OutT)rh);
-      if (w_ap) __stcs(o_ap + ooff, (OutT)ap);
-      if (w_lw) __stcs(o_lw + ooff, (OutT)lw);
+      if (w_temp) __stcs(o_temp + ooff, conv(MSB_V_TEMP, temp));
+      if (w_vp) __stcs(o_vp + ooff, conv(MSB_V_VAPOR_PRESSURE, vp));
+      if (w_rh) __stcs(o_rh + ooff, conv(MSB_V_REL_HUMID, rh));
+      if (w_ap) __stcs(o_ap + ooff, conv(MSB_V_AIR_PRESSURE, ap));
+      if (w_lw) __stcs(o_lw + ooff, conv(MSB_V_LONGWAVE, lw));
       if (w_wd) __stcs(o_wd + ooff, wd_o);
       if (MASKED) {             // the two variables outside the default set
         if (w_tk) __stcs(o_tk + ooff, tk_o);
         if (w_sh) {             // specific humidity :423-424
           const double mix = (kEps * vp) * rcp_2(ap - vp);
-          __stcs(o_sh + ooff, (OutT)(mix * rcp_2(1.0 + mix)));
+          __stcs(o_sh + ooff, conv(MSB_V_SPEC_HUMID, mix * rcp_2(1.0 + mix)));
         }
       }
     }
@@ -433,6 +439,10 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell;
   const unsigned lanes = __activemask();
   const int pf_off = a.k.pf * C;
+  auto conv = [&](int v, double val) {     // unit conversion, MASKED instantiation only
+    if (MASKED) val = fma(val, a.out.scale[v], a.out.offset[v]);
+    return (OutT)val;
+  };
 
   for (int d = d_lo; d < d_hi; ++d) {
     // ---- output day d starts (warp converged): fetch what today's rolls need --------------------
@@ -532,8 +542,8 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
         const double sw = fma(rd_cur, qn - q_prev, sw_carry);
         q_prev = qn;
         sw_carry = 0.0;
-        if (w_prec) __stcs(o_prec + ooff, (OutT)pr);
-        if (w_sw) __stcs(o_sw + ooff, (OutT)sw);
+        if (w_prec) __stcs(o_prec + ooff, conv(MSB_V_PREC, pr));
+        if (w_sw) __stcs(o_sw + ooff, conv(MSB_V_SHORTWAVE, sw));
       }
     }
   }
@@ -554,7 +564,7 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
       if (fillv == fillv) break;
     }
     ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
-    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) __stcs(o_prec + ooff, (OutT)fillv);
+    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) __stcs(o_prec + ooff, conv(MSB_V_PREC, fillv));
   }
 }
 
@@ -615,7 +625,7 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-  const bool masked = a.var_mask != kExampleMask;
+  const bool masked = a.var_mask != kExampleMask || a.units;
   if (a.out.dtype == 4) {
     if (masked) thermo_knot_kernel<float, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
     else thermo_knot_kernel<float, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
@@ -637,8 +647,8 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
     a.k.tile >>= 1;
   a.k.pf = day_pf;
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
-  const bool masked = (a.var_mask & ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE))) !=
-                      ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE));
+  const bool masked = a.units || (a.var_mask & ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE))) !=
+                                     ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE));
   if (a.out.dtype == 4) {
     if (masked) streams_day_kernel<float, 6, true><<<grid, kDisaggThreads, 0, st>>>(a);
     else streams_day_kernel<float, 6, false><<<grid, kDisaggThreads, 0, st>>>(a);

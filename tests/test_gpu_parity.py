@@ -442,8 +442,9 @@ def test_run_host_equals_device_path_and_tiling():
         np.testing.assert_array_equal(ring["temp"][slot:slot + (d1 - d0) * tpd], ref["temp"][d0 * tpd:d1 * tpd])
 
 
-def test_float32_outputs_and_unit_conversion(monkeypatch):
-    """out_precision f4 (reference default, metsim.py:154) and the converters of units.py."""
+def test_float32_outputs_and_unit_conversion(disagg_path):
+    """out_precision f4 (reference default, metsim.py:154) and the converters of units.py, fused
+    into the stores of both disaggregation paths."""
     import torch
     from metsim_b200 import synth
     f, params = synth.make_config("global_half_deg", max_cells=128, n_days=20)
@@ -451,10 +452,6 @@ def test_float32_outputs_and_unit_conversion(monkeypatch):
     f32 = engine_run(f, params, out_dtype=torch.float32)
     for v in util.SUB:
         np.testing.assert_array_equal(f32[v], base[v].astype(np.float32), err_msg=v)
-    # unit conversion is fused into the stores of the event-driven kernel: compare it with the same
-    # kernel's unconverted output, to the last bit of the conversion
-    monkeypatch.setenv("MSB_DISAGG_PATH", "event")
-    base = engine_run(f, params)
     units = {"temp": "K", "prec": "mm s-1", "vapor_pressure": "hPa", "air_pressure": "Pa",
              "tskc": "%", "rel_humid": "fraction"}
     conv = engine_run(f, params, units=units)
