@@ -83,6 +83,15 @@ __device__ __forceinline__ double exp_big(double x, const double *tab, const Kno
   return fma(q, s, s);
 }
 
+// smallest step index i with ts*i >= xk, for the knot times around interior days (|xk| < 2^31 minutes):
+// ceil of the rounded quotient is within one of the answer, the products ts*i are exact integers
+__device__ __forceinline__ int first_step_ge_fast(double xk, int ts, double inv_ts) {
+  int i = (int)ceil(xk * inv_ts);
+  if ((double)(ts * i) < xk) ++i;
+  else if ((double)(ts * (i - 1)) >= xk) --i;
+  return i;
+}
+
 // MASKED = false: the whole default variable set, every store unconditional (the benchmarked
 // instantiation); true: any subset of it, stores under the request mask.
 template <typename OutT, int MINB, bool MASKED>
@@ -190,8 +199,8 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     slot[kT_KX0][tid] = x2; slot[kT_KY0][tid] = y2; slot[kT_KD0][tid] = d2;
     slot[kT_KX1][tid] = x3; slot[kT_KY1][tid] = y3; slot[kT_KM01][tid] = m23;
     const double v0 = a.vp_d[o0] / 1000.0, v1 = a.vp_d[o1] / 1000.0;
-    const int ia = first_step_ge(x0, ts, inv_ts), ib = first_step_ge(x2, ts, inv_ts);
-    int isw = first_step_ge(x1, ts, inv_ts);
+    const int ia = first_step_ge_fast(x0, ts, inv_ts), ib = first_step_ge_fast(x2, ts, inv_ts);
+    int isw = first_step_ge_fast(x1, ts, inv_ts);
     // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
     Cubic cub;
     {
