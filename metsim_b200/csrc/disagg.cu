@@ -62,6 +62,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     set_error("msb_disaggregate: workspace of msb_disagg_workspace_bytes() bytes is required");
     return MSB_E_ARG;
   }
+  a.fill[0] = a.fill[1] = a.fill[2] = a.fill[3] = 0;   // no valid records yet (launch_day_records)
   a.sw_full_day = p->method == MSB_METHOD_PASSTHROUGH && !p->sw_daylight;
   a.lw_raw = nullptr;
   if (p->method == MSB_METHOD_PASSTHROUGH && f->given_longwave && out->var[MSB_V_LONGWAVE]) {

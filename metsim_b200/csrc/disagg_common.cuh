@@ -49,6 +49,8 @@ struct DisaggArgs {
   double inv_sw_den;   // 1 / (3600 * ts / 60), disaggregate.py:645
   int prep_days;       // padded days per thread of disagg_prepare_kernel
   int prep_r0, prep_r1;  // records [prep_r0, prep_r1) are (re)built by this launch
+  int fill[4];           // padded days whose records are valid: [fill[0], fill[1]) and [fill[2], fill[3])
+                         // (the specialised path only builds the records around the edge days)
   bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
   // work range of the interior-day kernels (thermo_knot_kernel, streams_day_kernel)
   struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)

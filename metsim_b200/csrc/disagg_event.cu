@@ -267,7 +267,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
 #endif
     return rec0[(size_t)fld * plane + (long)e * ld];
   };
-  auto has_rec = [&](int e) { return (unsigned)(e - a.e0) < (unsigned)a.n_rec; };
+  auto has_rec = [&](int e) {   // a valid record exists for padded day e (else: derive it on the spot)
+    return (e >= a.fill[0] && e < a.fill[1]) || (e >= a.fill[2] && e < a.fill[3]);
+  };
   auto rkx = [&](int j) { return rec((j & 1) ? kR_XMAX : kR_XMIN, (j >> 1) - 1); };
   auto rky = [&](int j) {      // knot value: the input column, or the padded end (disaggregate.py:242-257)
     const int e = (j >> 1) - 1;
@@ -693,6 +695,10 @@ int launch_day_records(DisaggArgs &a, int e_a, int e_b, int e1, int cell_blocks,
   a.prep_r0 = (e_a > a.e0 ? e_a : a.e0) - a.e0;
   a.prep_r1 = (e_b < e1 ? e_b : e1) - a.e0;
   if (a.prep_r0 >= a.prep_r1) return MSB_OK;
+  // remember what is valid: disagg_kernel derives a (wrapped) day without a record on the spot
+  const int slot = (a.fill[0] >= a.fill[1]) ? 0 : 2;
+  a.fill[slot] = a.e0 + a.prep_r0;
+  a.fill[slot + 1] = a.e0 + a.prep_r1;
   disagg_prepare_kernel<<<dim3(cell_blocks, (a.prep_r1 - a.prep_r0 + prep_days - 1) / prep_days), 128, 0, st>>>(a);
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;

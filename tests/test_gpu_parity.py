@@ -375,6 +375,43 @@ def test_streaming_writer_through_on_tile_hook(tmp_path):
     np.testing.assert_array_equal(again["temp"], ref["temp"])
 
 
+def test_seeded_fuzz_small_records_against_oracle(disagg_path):
+    """Forty seeded random small shards: record lengths 2..13 days (so that the interior range is
+    empty, one day, or a few days, and every call boundary falls somewhere else), random time step,
+    precipitation type, utc offset, start date, call length, latitudes from pole to pole and
+    longitudes from -360 to 540.  All ten variables, float64, against the oracle at 1e-9; the
+    record is produced in calls of a random length and must not depend on it."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200._lib import DAILY_VARS, SUB_VARS
+    from metsim_b200.engine import Engine
+    from oracle import oracle_lib
+    rng = np.random.default_rng(20261020)
+    for case in range(40):
+        n = int(rng.integers(33, 97))
+        days = int(rng.integers(2, 14))
+        ts = int(rng.choice([15, 20, 30, 60, 90, 120, 180, 240, 360]))
+        lat = np.sort(rng.uniform(-89.9, 89.9, n))
+        lon = rng.uniform(-360.0, 540.0, n)
+        start = str(np.datetime64("1999-01-01") + int(rng.integers(0, 3000)))
+        f = synth.make_forcing(lat, lon, days, start, rng)
+        params = dict(time_step=ts, prec_type=str(rng.choice(["uniform", "triangle", "mix"])),
+                      utc_offset=bool(rng.integers(0, 2)))
+        want = oracle_lib.run(params, **util.oracle_kwargs(f))
+        eng = Engine(params)
+        eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+        eng.build_solar()
+        daily = eng.daily(want=DAILY_VARS)
+        call = int(rng.integers(1, days + 1))
+        parts = [eng.disaggregate(SUB_VARS, d0, min(days, d0 + call), torch.float64)
+                 for d0 in range(0, days, call)]
+        eng.check()
+        torch.cuda.synchronize()
+        got = {v: torch.cat([p[v] for p in parts]).cpu().numpy() for v in SUB_VARS}
+        got["daily"] = {k: v.cpu().numpy() for k, v in daily.items()}
+        compare_to_oracle(got, want, f"fuzz case {case}: n={n} days={days} ts={ts} {params} call={call} start={start}")
+
+
 def test_edge_longitudes_polar_and_wraparound(disagg_path):
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
