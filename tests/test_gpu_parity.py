@@ -412,6 +412,65 @@ def test_seeded_fuzz_small_records_against_oracle(disagg_path):
         compare_to_oracle(got, want, f"fuzz case {case}: n={n} days={days} ts={ts} {params} call={call} start={start}")
 
 
+def test_seeded_fuzz_host_path_subsets_units_and_tiles():
+    """Forty seeded random requests through msb_run_host (host buffers, random tile length):
+    random variable subsets, float32 / float64, random unit conversions, mtclim or passthrough
+    (with random supplied columns), optional t_end.  Every request must equal the oracle (float64:
+    1e-9; float32: within rounding) -- whatever mix of specialised and event-driven kernels and
+    whatever tile boundaries it ends up with."""
+    from metsim_b200 import synth
+    from metsim_b200._lib import SUB_VARS
+    from metsim_b200.engine import run_host, unit_scale_offset
+    from oracle import oracle_lib
+    rng = np.random.default_rng(777)
+    unit_choices = {"temp": ["C", "K"], "prec": ["mm timestep-1", "mm h-1", "mm s-1"],
+                    "vapor_pressure": ["Pa", "hPa", "kPa"], "air_pressure": ["kPa", "hPa", "Pa"],
+                    "tskc": ["fraction", "%"], "rel_humid": ["%", "fraction"]}
+    for case in range(40):
+        n = int(rng.integers(33, 80))
+        days = int(rng.integers(3, 16))
+        ts = int(rng.choice([30, 60, 120, 180, 360]))
+        lat = np.sort(rng.uniform(-75.0, 80.0, n))
+        lon = rng.uniform(-180.0, 180.0, n)
+        start = str(np.datetime64("2000-01-01") + int(rng.integers(0, 2500)))
+        f = synth.make_forcing(lat, lon, days, start, rng)
+        params = dict(time_step=ts, prec_type=str(rng.choice(["uniform", "triangle", "mix"])),
+                      utc_offset=bool(rng.integers(0, 2)))
+        if rng.random() < 0.3:
+            params["method"] = "passthrough"
+            f["given_shortwave"] = rng.uniform(10, 380, (days, n))
+            if rng.random() < 0.5:
+                f["given_vapor_pressure"] = rng.uniform(150, 2000, (days, n))
+            if rng.random() < 0.5:
+                f["given_longwave"] = rng.uniform(170, 430, (days, n))
+            if rng.random() < 0.5:
+                params["sw_averaging"] = "daylight"
+        if rng.random() < 0.3:
+            f["t_end"] = np.stack([f["t_min"][-1] - 1.5, f["t_max"][-1] + 2.0])
+        k = int(rng.integers(1, len(SUB_VARS) + 1))
+        subset = tuple(sorted(rng.choice(SUB_VARS, size=k, replace=False).tolist(), key=SUB_VARS.index))
+        units = {v: str(rng.choice(unit_choices[v])) for v in subset if v in unit_choices and rng.random() < 0.4}
+        dtype = np.float32 if rng.random() < 0.5 else np.float64
+        tile = int(rng.integers(0, days + 2))
+        ctx = f"host fuzz {case}: n={n} days={days} ts={ts} {params} subset={subset} units={units} {dtype.__name__} tile={tile}"
+        want = oracle_lib.run(params, **util.oracle_kwargs(f))
+        got = run_host(params, out_vars=subset, out_dtype=dtype, units=units, tile_days=tile,
+                       **{k2: f.get(k2) for k2 in util.INPUT_KEYS})
+        assert set(got) - {"daily"} == set(subset), ctx
+        for v in subset:
+            sc, of = unit_scale_offset(v, units.get(v), ts)
+            w = want[v] * sc + of
+            if dtype == np.float64:
+                e = util.relerr(got[v], w, util.FLOORS[v] * abs(sc))
+                assert e <= 2e-9, f"{ctx}: {v} relative error {e:.3e}"
+            else:
+                ok = ~np.isnan(w)
+                assert (np.isnan(got[v]) == ~ok).all(), ctx
+                ulp = np.spacing(np.abs(w[ok]).astype(np.float32)).astype(np.float64)
+                err = np.abs(got[v][ok].astype(np.float64) - w[ok])
+                assert (err <= 0.5000001 * ulp + 2e-9 * np.maximum(np.abs(w[ok]), util.FLOORS[v] * abs(sc))).all(), (ctx, v)
+
+
 def test_edge_longitudes_polar_and_wraparound(disagg_path):
     """lon outside [-180,180], |lon| = 180, polar day/night latitudes, 2-day record."""
     from metsim_b200 import synth
