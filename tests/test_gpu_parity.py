@@ -197,6 +197,7 @@ EXAMPLE_VARS = ("temp", "prec", "shortwave", "longwave", "vapor_pressure", "rel_
     ("global_half_deg", 400, 16, {"time_step": 360, "prec_type": "mix"}),
     ("global_half_deg", 400, 9, {"time_step": 20, "utc_offset": False}),
     ("conus_16th_hourly", 260, 30, {"time_step": 120, "prec_type": "uniform", "tmax_daylength_fraction": 0.5}),
+    ("global_half_deg", 500, 40, {"start": "2000-12-10"}),    # day of year 366 -> 1 inside the interior days
     ("edge", None, 20, {"time_step": 60, "t_end": True}),      # polar rows, |lon| = 180, lon outside [-180, 180]
     ("edge", None, 12, {"time_step": 180, "prec_type": "mix"}),
 ], ids=lambda v: str(v) if not isinstance(v, dict) else "-".join(f"{k}{x}" for k, x in v.items()) or "std")
@@ -219,10 +220,10 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
             f["t_end"] = np.stack([f["t_min"][-1] - 1.5, f["t_max"][-1] + 2.0])
     else:
         f, params = synth.make_config(name, max_cells=cells, n_days=days)
-    if over.get("start_dec"):       # a record that starts in December: NaN days at the head and tail
-        doy, month = synth.calendar_vectors("2001-12-05", days)
+    if over.get("start_dec") or over.get("start"):   # e.g. a record that starts in December: NaN days at the head and tail
+        doy, month = synth.calendar_vectors(over.get("start", "2001-12-05"), days)
         f["doy"], f["month"] = doy, month
-    params.update({k: v for k, v in over.items() if k not in ("start_dec", "t_end")})
+    params.update({k: v for k, v in over.items() if k not in ("start_dec", "t_end", "start")})
     want = oracle_lib.run(params, **util.oracle_kwargs(f))
     eng = Engine(params)
     eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
