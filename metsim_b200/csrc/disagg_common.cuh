@@ -43,6 +43,7 @@ struct DisaggArgs {
   int tpd, tile_days;
   unsigned var_mask;   // bit v set = out.var[v] requested
   bool units;          // some requested variable has scale != 1 or offset != 0
+  bool fast_lw;        // lw_type PRATA + lw_cloud CLOUD_DEARDORFF (the defaults): inlined sequence
   double *rec;         // day records [MSB_REC_FIELDS][n_rec][ld], record r = padded day e0 + r
   double *lw_raw;      // passthrough with a supplied daily longwave: unscaled float64 longwave
                        // [(day1-day0)*tpd][out.ld] for the rescale pass, else NULL
@@ -373,6 +374,31 @@ __device__ __forceinline__ void unpack_prec(double w, PrecDay &pd) {
   pd.p0 = (int)(lo & 0xffffu); pd.nps = (int)(lo >> 16);
   pd.q0 = (int)(hi & 0xffffu); pd.nqs = (int)((hi >> 16) & 0x7fffu);
   pd.pth = (hi & 0x80000000u) ? pd.p0 + pd.nps + 1 : kNever;   // forced 1.0 follows the series
+}
+
+// disaggregate.py:491-590 without the daily_lw rescale (mtclim method): every lw_type / lw_cloud
+// option with library math (the default PRATA + CLOUD_DEARDORFF pair is inlined in the hot loop)
+__device__ __forceinline__ double longwave(const msb_params &p, double temp_c, double vp_kpa,
+                                           double tskc) {
+  const double air_temp = temp_c + kKelvin;
+  const double vp = vp_kpa * 10;
+  double e;
+  switch (p.lw_type) {
+    case MSB_LW_ANDERSON: e = 0.68 + 0.036 * sqrt(vp); break;
+    case MSB_LW_BRUTSAERT: e = 1.24 * pow(vp / air_temp, 0.14285714); break;
+    case MSB_LW_SATTERLUND: e = 1.08 * (1 - exp(-1 * pow(vp, (air_temp / 2016)))); break;
+    case MSB_LW_IDSO: e = 0.7 + 5.95e-5 * vp * exp(1500 / air_temp); break;
+    case MSB_LW_PRATA: {
+      const double x = 46.5 * vp / air_temp;
+      e = (1 - (1 + x) * exp(-sqrt((1.2 + 3. * x))));
+      break;
+    }
+    default: e = 0.74 + 0.0049 * vp; break;
+  }
+  const double emis = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? tskc + (1 - tskc) * e
+                                                          : (1.0 + (0.17 * (tskc * tskc))) * e;
+  const double t2 = air_temp * air_temp;
+  return emis * kStefanB * (t2 * t2);
 }
 
 // ---- launch plumbing (host) --------------------------------------------------------------------

@@ -80,31 +80,6 @@ static __device__ __noinline__ double vp_endpoint(const Cell &c, const double *v
   return fmin(v, svp_kpa(tt, etab));
 }
 
-// disaggregate.py:491-590 without the daily_lw rescale (mtclim method): every lw_type / lw_cloud
-// option with library math (the default PRATA + CLOUD_DEARDORFF pair is inlined in the hot loop)
-__device__ __forceinline__ double longwave(const msb_params &p, double temp_c, double vp_kpa,
-                                           double tskc) {
-  const double air_temp = temp_c + kKelvin;
-  const double vp = vp_kpa * 10;
-  double e;
-  switch (p.lw_type) {
-    case MSB_LW_ANDERSON: e = 0.68 + 0.036 * sqrt(vp); break;
-    case MSB_LW_BRUTSAERT: e = 1.24 * pow(vp / air_temp, 0.14285714); break;
-    case MSB_LW_SATTERLUND: e = 1.08 * (1 - exp(-1 * pow(vp, (air_temp / 2016)))); break;
-    case MSB_LW_IDSO: e = 0.7 + 5.95e-5 * vp * exp(1500 / air_temp); break;
-    case MSB_LW_PRATA: {
-      const double x = 46.5 * vp / air_temp;
-      e = (1 - (1 + x) * exp(-sqrt((1.2 + 3. * x))));
-      break;
-    }
-    default: e = 0.74 + 0.0049 * vp; break;
-  }
-  const double emis = (p.lw_cloud == MSB_CLOUD_DEARDORFF) ? tskc + (1 - tskc) * e
-                                                          : (1.0 + (0.17 * (tskc * tskc))) * e;
-  const double t2 = air_temp * air_temp;
-  return emis * kStefanB * (t2 * t2);
-}
-
 // per-thread shared-memory slots for values that only the event handler touches between events
 enum { kS_TKN = 0, kS_WDN,   // tskc / wind of the source day just rolled in
        kS_ROWTOT,            // total of the current radiation row (noon event)

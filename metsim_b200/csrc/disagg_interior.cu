@@ -160,7 +160,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   // (:593-615, :355-380); wind rides along here because it shares this stream's roll exactly
   int i_tk = kNever, tk_day = -4;
   bool tk_started = false;
-  double tk_a = 0.0, tk_b = 0.0;
+  double tk_a = 0.0, tk_b = 0.0, tk_cur = 0.0;   // tk_cur: MASKED with a non-default longwave option
   OutT wd_o = 0, tk_o = 0;
   const double dx = (double)ts;
   // unit conversion (metsim/units.py:3-59) fused into the stores of the MASKED instantiation;
@@ -273,6 +273,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
             i_tk = i + (kMinPerDay - r) / ts;
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
+          if (MASKED) tk_cur = tk;
           wd_o = conv(MSB_V_WIND, wd);
           tk_o = conv(MSB_V_TSKC, tk);
         }
@@ -296,7 +297,8 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       const double ee = exp_big(-sqrt_2(fma(3., xx, K.k12)), etab, K);
       const double e1 = fma(-(1.0 + xx), ee, 1.0);
       const double t2 = at * at;
-      const double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+      double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
+      if (MASKED && !a.fast_lw) lw = longwave(p, temp, vp, tk_cur);   // the other lw_type / lw_cloud options
       if (w_temp) __stcs(o_temp + ooff, conv(MSB_V_TEMP, temp));
       if (w_vp) __stcs(o_vp + ooff, conv(MSB_V_VAPOR_PRESSURE, vp));
       if (w_rh) __stcs(o_rh + ooff, conv(MSB_V_REL_HUMID, rh));
@@ -634,7 +636,7 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-  const bool masked = a.var_mask != kExampleMask || a.units;
+  const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw;
   if (a.out.dtype == 4) {
     if (masked) thermo_knot_kernel<float, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
     else thermo_knot_kernel<float, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
