@@ -157,8 +157,8 @@ int msb_mtclim_daily(const msb_params *p, const msb_forcing *f, const msb_solar_
 int msb_daily_check(const msb_forcing *f, const msb_daily *out, void *stream);
 
 /* ---- sub-daily disaggregation: disaggregate.py:34-680, units.py:3-59 -----------------------
- * Days [2, D-2) of a record go through two specialised kernels that need no scratch.  Everything
- * else -- the record's first / last two days, the passthrough longwave rescale -- goes through an
+ * Days [2, D-2) of a record go through two specialised kernels that need no scratch.  The
+ * record's first / last two days go through an
  * event-driven kernel that reads per-(cell, day) records (PCHIP knots with their derivatives, the
  * closed-form precipitation shape, radiation per tiny step) built by a first kernel in
  * caller-provided scratch.  Results do not depend on how a record is cut into calls. */

@@ -86,14 +86,14 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   a.units = units;
   a.fast_lw = fast_lw;
   // Every variable set, with or without unit conversion, with any longwave option, takes the
-  // specialised kernels on the interior days (all but the passthrough longwave rescale); `full` is the default set
+  // specialised kernels on the interior days; `full` is the default set
   // (examples/example_nc.conf) at float32 without conversion, which has unconditional-store
   // instantiations and, for the edge days, the two compile-time halves of disagg_kernel.  MSB_DISAGG_PATH=event forces the
   // event-driven kernel for every day (the parity tests use it to keep both paths covered).
   const char *force = getenv("MSB_DISAGG_PATH");
-  const bool example = !a.lw_raw && !(force && force[0] == 'e');
+  const bool example = !(force && force[0] == 'e');
   const bool f4 = out->dtype == 4;
-  const bool full = example && a.var_mask == kExampleMask && f4 && !units && fast_lw;
+  const bool full = example && a.var_mask == kExampleMask && f4 && !units && fast_lw && !a.lw_raw;
   const unsigned knot_bits = kThermoBits | (1u << MSB_V_WIND) | (1u << MSB_V_TSKC);   // thermo_knot_kernel's outputs
   const unsigned day_bits = (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE);  // streams_day_kernel's
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
@@ -117,6 +117,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
         if (b.out.var[v])
           b.out.var[v] = reinterpret_cast<char *>(b.out.var[v]) +
                          (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * (size_t)out->dtype;
+      if (b.lw_raw) b.lw_raw += (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld;
       if (!full) return launch_event_kernel(b, f4 ? kEvAnyF4 : kEvAnyF8, fast_lw, cell_blocks, st);
       r = launch_event_kernel(b, kEvThermoF4, true, cell_blocks, st);
       return r != MSB_OK ? r : launch_event_kernel(b, kEvStreamsF4, true, cell_blocks, st);

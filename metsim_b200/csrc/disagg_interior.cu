@@ -303,7 +303,10 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       if (w_vp) __stcs(o_vp + ooff, conv(MSB_V_VAPOR_PRESSURE, vp));
       if (w_rh) __stcs(o_rh + ooff, conv(MSB_V_REL_HUMID, rh));
       if (w_ap) __stcs(o_ap + ooff, conv(MSB_V_AIR_PRESSURE, ap));
-      if (w_lw) __stcs(o_lw + ooff, conv(MSB_V_LONGWAVE, lw));
+      if (w_lw) {
+        if (MASKED && a.lw_raw) a.lw_raw[ooff + cell] = lw;    // passthrough: rescaled by lw_rescale_kernel
+        else __stcs(o_lw + ooff, conv(MSB_V_LONGWAVE, lw));
+      }
       if (w_wd) __stcs(o_wd + ooff, wd_o);
       if (MASKED) {             // the two variables outside the default set
         if (w_tk) __stcs(o_tk + ooff, tk_o);
@@ -636,7 +639,7 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
-  const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw;
+  const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw || a.lw_raw;
   if (a.out.dtype == 4) {
     if (masked) thermo_knot_kernel<float, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
     else thermo_knot_kernel<float, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
