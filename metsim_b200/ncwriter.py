@@ -123,6 +123,9 @@ class NC3Writer:
                 self.vars[vname] = (begin, np.dtype(be))
         self.steps_written = {v: 0 for v in self.vars}
         self._grid = {}
+        # every grid cell active and in grid order (e.g. CONUS 1/16 deg): no scatter needed
+        self._dense = (self.cell_index.size == self.n_grid and
+                       bool((self.cell_index == np.arange(self.n_grid)).all()))
 
     def write_steps(self, name: str, step0: int, block) -> None:
         """Scatter ``block[steps][cells]`` to ``(steps, lat, lon)`` (NaN elsewhere) and write it at
@@ -132,6 +135,11 @@ class NC3Writer:
         steps = block.shape[0]
         if block.shape[1] != self.cell_index.size or step0 < 0 or step0 + steps > self.n_steps:
             raise ValueError("block does not fit the file")
+        if self._dense:                   # byte-swapped copy of the block, written as it is
+            os.pwrite(self.fd, np.ascontiguousarray(block, dtype=be).data,
+                      begin + step0 * self.n_grid * be.itemsize)
+            self.steps_written[name] += steps
+            return
         key = (steps, be)
         grid = self._grid.get(key)
         if grid is None:                  # reused scatter buffer, NaN where no cell maps

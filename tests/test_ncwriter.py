@@ -53,3 +53,16 @@ def test_writer_rejects_misfit_blocks(tmp_path):
     w.close()
     with pytest.raises(ValueError):
         NC3Writer(os.path.join(tmp_path, "y.nc"), n_steps=1, lat=[0.0], lon=[0.0], cell_index=[5], variables={})
+
+
+def test_dense_grid_fast_path(tmp_path):
+    lat, lon = np.arange(3.0), np.arange(4.0)
+    data = np.arange(5 * 12, dtype=np.float32).reshape(5, 12)
+    path = os.path.join(tmp_path, "d.nc")
+    with NC3Writer(path, n_steps=5, lat=lat, lon=lon, cell_index=np.arange(12), variables={"wind": {}}) as w:
+        assert w._dense
+        w.write_steps("wind", 2, data[2:5])
+        w.write_steps("wind", 0, data[0:2])
+    nc = netcdf_file(path, "r", mmap=False)
+    np.testing.assert_array_equal(nc.variables["wind"].data.reshape(5, 12), data)
+    nc.close()
