@@ -388,7 +388,7 @@ def test_seeded_fuzz_small_records_against_oracle(disagg_path):
     from metsim_b200.engine import Engine
     from oracle import oracle_lib
     rng = np.random.default_rng(20261020)
-    for case in range(40):
+    for case in range(int(os.environ.get("MSB_FUZZ_CASES", "40"))):   # more cases: a longer one-off hunt
         n = int(rng.integers(33, 97))
         days = int(rng.integers(2, 14))
         ts = int(rng.choice([15, 20, 30, 60, 90, 120, 180, 240, 360]))
@@ -427,7 +427,7 @@ def test_seeded_fuzz_host_path_subsets_units_and_tiles():
     unit_choices = {"temp": ["C", "K"], "prec": ["mm timestep-1", "mm h-1", "mm s-1"],
                     "vapor_pressure": ["Pa", "hPa", "kPa"], "air_pressure": ["kPa", "hPa", "Pa"],
                     "tskc": ["fraction", "%"], "rel_humid": ["%", "fraction"]}
-    for case in range(40):
+    for case in range(int(os.environ.get("MSB_FUZZ_CASES", "40"))):
         n = int(rng.integers(33, 80))
         days = int(rng.integers(3, 16))
         ts = int(rng.choice([30, 60, 120, 180, 360]))
