@@ -356,7 +356,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)
     ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    rank_ms = [total_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(every, ms)
+        rank_ms = [float(t.item()) / args.steps for t in every]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     cell_ts_rank = n * n_days * tpd
@@ -445,6 +449,7 @@ def main():
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
                              "disaggregate": float(br[2])},
             # the metric with and without the (time-independent) solar-geometry set-up
+            "rank_ms_per_step": rank_ms,      # device time of every rank (value uses the maximum)
             "value_excl_solar_tables": total_cell_ts / max(1e-9, (ms_per_step - float(br[0])) * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + thermo_knot_kernel + "
                                                    "streams_day_kernel (+ disagg_kernel on the record's first / last "
