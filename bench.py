@@ -253,6 +253,8 @@ def main():
     ap.add_argument("--shard", action="store_true",
                     help="strong scaling: the ranks share ONE domain, each takes a contiguous cell range "
                          "(metsim_b200.shard.cell_range); default is one full domain per rank (weak)")
+    ap.add_argument("--emulate-shard", default=None, metavar="R/W",
+                    help="debugging: on ONE GPU, take the cell range rank R of W would get with --shard")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
@@ -284,6 +286,12 @@ def main():
         idx = np.linspace(0, lat.size - 1, args.cells).astype(np.int64)
         lat, lon = lat[idx], lon[idx]
     n_domain = lat.size
+    if args.emulate_shard and world == 1:
+        from metsim_b200.shard import cell_range
+        r_, w_ = (int(x) for x in args.emulate_shard.split("/"))
+        lo, hi = cell_range(n_domain, r_, w_)
+        lat, lon = lat[lo:hi], lon[lo:hi]
+        n_domain = lat.size
     if args.shard and world > 1:      # latitude bands: contiguous ranges of the row-major enumeration
         from metsim_b200.shard import cell_range
         lo, hi = cell_range(n_domain, rank, world)
@@ -301,7 +309,8 @@ def main():
         if 7 * n_days * n * 8 > 60e9:       # multi-year records: inputs + daily arrays already fill HBM
             args.tile_days = min(args.tile_days, 64)
     tile = min(args.tile_days, n_days)
-    ring = [{v: torch.empty((tile * tpd, n), dtype=torch.float32, device=dev) for v in OUT_VARS}
+    ld_pad = (n + 31) // 32 * 32      # rows on 128-byte boundaries, as Engine.disaggregate allocates them
+    ring = [{v: torch.empty((tile * tpd, ld_pad), dtype=torch.float32, device=dev)[:, :n] for v in OUT_VARS}
             for _ in range(2)]
     n_tiles = -(-n_days // tile)
     rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu

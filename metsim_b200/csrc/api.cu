@@ -182,11 +182,14 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
   add(q_e * 8); add(tt_e * 8); add(prelude);
   for (int k = 0; k < MSB_N_DAILYVARS; ++k) add(dn * 8);
   add((size_t)N * 4); add(msb_daily_scratch_bytes(N, D)); add(64);
-  const size_t tile_elems = (size_t)tile_days * tpd * N;
+  // device output tiles with rows on 128-byte boundaries (leading dimension padded to 32 cells):
+  // warp-wide stores then never share a sector with the neighbouring row
+  const size_t ld_out = ((size_t)N + 31) / 32 * 32;
+  const size_t tile_elems = (size_t)tile_days * tpd * ld_out;
   for (int k = 0; k < 2 * n_out; ++k) add(tile_elems * osz);
   const bool lw_rescale = p->method == MSB_METHOD_PASSTHROUGH && run->given_longwave &&
                           run->out_host[MSB_V_LONGWAVE];
-  const size_t ws_bytes = !sub ? 0 : lw_rescale ? msb_disagg_workspace_bytes_lw(N, 0, tile_days, ts)
+  const size_t ws_bytes = !sub ? 0 : lw_rescale ? msb_disagg_workspace_bytes_lw((int64_t)ld_out, 0, tile_days, ts)
                                                 : msb_disagg_workspace_bytes(N, 0, tile_days);
   add(ws_bytes);
   need += 65536;
@@ -328,7 +331,7 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
         so.scale[v] = run->scale[v];
         so.offset[v] = run->offset[v];
       }
-      so.dtype = osz; so.ld = N; so.day0 = d0; so.day1 = d1;
+      so.dtype = osz; so.ld = (int64_t)ld_out; so.day0 = d0; so.day1 = d1;
       so.workspace = d_ws; so.workspace_bytes = ws_bytes;
       MSB_TRY(msb_disaggregate(p, &f, &tb, &dl, &so, s_main));
       MSB_TRYC(cudaEventRecord(ev_k[b], s_main));
@@ -338,7 +341,8 @@ extern "C" int msb_run_host(const msb_params *p, msb_host_run *run) {
         if (!d_out[b][v]) continue;
         size_t host_step0 = run->out_is_ring ? (size_t)b * tile_days * tpd : (size_t)d0 * tpd;
         char *dst = reinterpret_cast<char *>(run->out_host[v]) + host_step0 * (size_t)N * osz;
-        MSB_TRYC(cudaMemcpyAsync(dst, d_out[b][v], steps * (size_t)N * osz, cudaMemcpyDeviceToHost, s_copy));
+        MSB_TRYC(cudaMemcpy2DAsync(dst, (size_t)N * osz, d_out[b][v], ld_out * osz, (size_t)N * osz, steps,
+                                   cudaMemcpyDeviceToHost, s_copy));
       }
       MSB_TRYC(cudaEventRecord(ev_c[b], s_copy));
       // the previous tile goes to the consumer while this one computes; its host slot is the one

@@ -238,6 +238,11 @@ class Engine:
         steps = (day1 - day0) * self.tpd
         n = self.n_cells
         res = {}
+        # Rows of the [step][cell] outputs start on 128-byte boundaries: the leading dimension is
+        # padded to a multiple of 32 cells and the caller gets [:, :n] views.  (With ld = n and a
+        # cell count that is not a multiple of 8, every warp-wide store is split across sectors
+        # that the neighbouring row also writes -- measured 1.5x slower on a 125,684-cell shard.)
+        ld_out = (n + 31) // 32 * 32
         sd = _lib.SubDaily()
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             for i, v in enumerate(SUB_VARS):
@@ -248,16 +253,22 @@ class Engine:
                 if out is not None and v in out:
                     tns = out[v]
                     assert tns.dtype == out_dtype and tns.shape[0] >= steps and tns.shape[1] == n
+                    assert tns.stride(1) == 1, "output rows must be contiguous"
+                    if res and tns.stride(0) != ld_out:
+                        raise ValueError("all preallocated outputs must share one row stride")
+                    ld_out = tns.stride(0)
                 else:
-                    tns = torch.empty((steps, n), dtype=out_dtype, device=self.device)
+                    tns = torch.empty((steps, ld_out), dtype=out_dtype, device=self.device)[:, :n]
+                    if tns.stride(0) != ld_out:     # mixing with preallocated outputs of another stride
+                        raise ValueError("all outputs must share one row stride")
                 res[v] = tns
                 sd.var[i] = tns.data_ptr()
                 sd.scale[i], sd.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
             sd.dtype = 4 if out_dtype == torch.float32 else 8
-            sd.ld, sd.day0, sd.day1 = n, day0, day1
+            sd.ld, sd.day0, sd.day1 = ld_out, day0, day1
             if (self.params.method == 1 and self._t.get("given_longwave") is not None
                     and res.get("longwave") is not None):     # longwave rescale staging plane
-                need = self.lib.msb_disagg_workspace_bytes_lw(n, day0, day1, ts)
+                need = self.lib.msb_disagg_workspace_bytes_lw(max(n, ld_out), day0, day1, ts)
             else:
                 need = self.lib.msb_disagg_workspace_bytes(n, day0, day1)
             if self._ws is None or self._ws.numel() < need:   # grow-only scratch for the day records
