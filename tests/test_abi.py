@@ -66,3 +66,26 @@ def test_param_translation_errors_match_reference():
     assert (p.method, p.sw_daylight) == (1, 1)
     with pytest.raises(KeyError):
         _lib.make_params({"method": "bogus"})       # metsim.py:462: self.methods[params['method']]
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of every struct of include/metsim_b200.h as gcc lays them out, against the
+    ctypes mirrors in metsim_b200/_lib.py (catches any drift between the header and the binding)."""
+    import subprocess
+    pairs = {"msb_params": _lib.Params, "msb_solar_tables": _lib.SolarTables, "msb_forcing": _lib.Forcing,
+             "msb_daily": _lib.Daily, "msb_subdaily": _lib.SubDaily, "msb_host_run": _lib.HostRun}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "metsim_b200.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = os.path.join(tmp_path, "layout.c")
+    exe = os.path.join(tmp_path, "layout")
+    open(src, "w").write("\n".join(lines))
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for cname, ct in pairs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
