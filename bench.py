@@ -14,8 +14,16 @@ domain grows with N ("weak").
 
 Prints ONE JSON line (rank 0).  ``value`` is measured with inputs resident in HBM; ``e2e`` is the
 same metric through msb_run_host with pinned HOST buffers, H2D/D2H inside the timed region.
-``--impl reference`` times the CPU restatement of the reference (oracle/, kind "port") on all host
-cores on a bounded sample of the same workload.
+``--impl reference`` times the reference's OWN Python functions (the unmodified hot-path modules of
+``baseline/_ref``, kind "reference") in a process pool over all host cores on a bounded sample of
+the same workload; the C port's figure (oracle/, kind "port") is reported beside it and is the
+fall-back when the reference install is absent.
+
+Beyond the contract keys the line carries: ``verify`` (a sample of cells of one extra full pass, same
+launch geometry as the timed ones, checked against the oracle after the timed region), ``strong``
+(N > 1: ONE domain cut into contiguous cell ranges, the north_star's partition, run after the weak
+pass in the same process), ``d2h_ceiling`` (bare pinned device-to-host copies on all ranks at once:
+what the box can deliver to host memory, the yardstick of ``e2e``).
 """
 from __future__ import annotations
 
@@ -176,7 +184,7 @@ def reference_python_run(workload, n_days, cores, sample_cells, steps=1, warmup=
     if root is None:
         return None
     if sample_cells is None:
-        sample_cells = 8 * cores                      # ~0.14 s per cell-year hourly per core
+        sample_cells = max(256, 8 * cores)            # BASELINE.md plan B: >= 256 cells; ~0.14 s per cell-year per core
     f, params = synth.make_config(workload, max_cells=sample_cells, n_days=n_days)
     start = synth.CONFIGS[workload][2]
     d, n = f["t_min"].shape
@@ -236,7 +244,225 @@ def run_reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's threads (and so the first-touch placement of its pinned buffers) to the CPUs
+    nearest to its GPU.  Without it eight ranks place their host rings wherever the allocator
+    likes and the device-to-host streams cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as exc:
+        sys.stderr.write(f"rank affinity not set: {exc!r}\n")
+    return None
+
+
+def verify_against_oracle(eng, f, params, step_tiles, ring, n_days, tpd, sample=512, seed=1):
+    """One extra full pass with the SAME Engine, tile length and launch geometry as the timed ones;
+    ``sample`` random cell columns of every variable and every step are pulled off the device ring
+    and compared with the oracle run on those cells' inputs (checker only, after the timed region).
+    float32 outputs must sit within float32 rounding of the oracle's float64 value plus the 1e-9
+    contract; the tdew evaluation counts must be equal."""
+    import torch
+    from oracle import oracle_lib
+    n = eng.n_cells
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(n, size=min(sample, n), replace=False))
+    idx_t = torch.as_tensor(idx, device=eng.device)
+    got = {v: [] for v in OUT_VARS}
+    eng.build_solar()
+    daily = eng.daily(want=())
+    for k, (d0, d1) in enumerate(step_tiles):
+        res = eng.disaggregate(OUT_VARS, d0, d1, torch.float32, out=ring[k & 1])
+        for v in OUT_VARS:
+            got[v].append(res[v][:(d1 - d0) * tpd].index_select(1, idx_t).cpu())
+    eng.check()
+    n_iter = daily["n_iter"].index_select(0, idx_t).cpu().numpy()
+    cpu = lambda t: t.index_select(-1, idx_t).cpu().numpy() if t.dim() else t.cpu().numpy()
+    kw = {k: cpu(f[k]) for k in ("lat", "lon", "elev", "t_min", "t_max", "prec", "wind", "state_t_min",
+                                 "state_t_max", "state_prec", "t_pk12", "dur12")}
+    kw["doy"], kw["month"] = f["doy"].cpu().numpy(), f["month"].cpu().numpy()
+    want = oracle_lib.run(params, want=OUT_VARS, **kw)
+    floors = {"temp": 1.0, "prec": 1e-3, "shortwave": 1e-2, "longwave": 1.0, "vapor_pressure": 1e-3,
+              "rel_humid": 1e-1, "air_pressure": 1.0, "wind": 1e-2}
+    worst_rel, beyond, values = 0.0, 0, 0
+    for v in OUT_VARS:
+        g = torch.cat(got[v]).numpy().astype(np.float64)
+        w = want[v]
+        ulp = np.spacing(np.abs(w).astype(np.float32)).astype(np.float64)
+        err = np.abs(g - w)
+        scale = np.maximum(np.abs(w), floors[v])
+        worst_rel = max(worst_rel, float(np.nanmax(err / scale)))
+        beyond += int(np.sum(~(err <= 0.5000001 * ulp + 1e-9 * scale)))
+        values += g.size
+    zero_equal = bool(np.array_equal(torch.cat(got["prec"]).numpy() == 0, want["prec"].astype(np.float32) == 0))
+    return {"cells": int(idx.size), "values": int(values), "worst_rel": worst_rel,
+            "beyond_f4_rounding_plus_1e-9": beyond, "n_iter_equal": bool(np.array_equal(n_iter, want["n_iter"])),
+            "n_iter_hist": np.bincount(want["n_iter"]).tolist(), "prec_zero_placement_equal": zero_equal,
+            "checked": "one extra full pass, same Engine / tile length / launch geometry as the timed steps; "
+                       "float32 outputs vs the oracle's float64 (bound: half a float32 ulp + 1e-9)"}
+
+
+def d2h_ceiling(dev, world, nbytes=2 << 30, reps=3):
+    """Bare cudaMemcpyAsync device-to-host of one pinned buffer per rank, all ranks at once."""
+    import torch
+    import torch.distributed as dist
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del src, dst
+    return reps * nbytes * world / float(t.item()) / 1e9
+
+
 # ------------------------------------------------------------------------------------------
+class DevicePass:
+    """One shard on this rank's GPU: inputs resident in HBM, the timed step, its launch count."""
+
+    def __init__(self, args, dev, lat, lon, n_days, start, ts, prec_type, seed, tile_days=None):
+        import torch
+        from metsim_b200 import synth
+        from metsim_b200.engine import Engine
+        self.torch, self.dev = torch, dev
+        self.n, self.n_days, self.ts, self.tpd = int(lat.size), n_days, ts, 1440 // ts
+        self.params = dict(time_step=ts, prec_type=prec_type, utc_offset=True)
+        self.f = synth.make_forcing_torch(lat, lon, n_days, start, dev, seed=seed)
+        torch.cuda.empty_cache()
+        self.eng = Engine(self.params, dev)
+        self.eng.load(**self.f)
+        n, tpd = self.n, self.tpd
+        if tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
+            tile_days = max(1, int(24.0e9 // (len(OUT_VARS) * tpd * n * 4)))
+            if 7 * n_days * n * 8 > 60e9:       # multi-year records: inputs + daily arrays already fill HBM
+                tile_days = min(tile_days, 64)
+                self.eng.single_pass_budget = 0  # ... and leave no room for candidate planes
+        self.tile = tile = min(tile_days, n_days)
+        ld_pad = (n + 31) // 32 * 32      # rows on 128-byte boundaries, as Engine.disaggregate allocates them
+        self.ring = [{v: torch.empty((tile * tpd, ld_pad), dtype=torch.float32, device=dev)[:, :n]
+                      for v in OUT_VARS} for _ in range(2)]
+        self.tiles = [(d0, min(n_days, d0 + tile)) for d0 in range(0, n_days, tile)]
+        # kernels of mine per step: 2 solar kernels; daily single pass = fused + reduce, then for the
+        # replay list 3 x (pass 1 + reduce) + pass 2 (they exit at once when the list is empty) -- the
+        # two-pass form is 4 x (pass 1 + reduce) + pass 2, the same count; per msb_disaggregate call
+        # thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2), plus day records +
+        # disagg_kernel<thermo> / <streams> over the first / last two days of the record
+        def disagg_launches(d0, d1):
+            a0, b0 = max(d0, 2), min(d1, n_days - 2)
+            if a0 >= b0:
+                return 3
+            return 2 + (3 if d0 < a0 else 0) + (3 if b0 < d1 else 0)
+        self.launches_per_step = 2 + 9 + sum(disagg_launches(*t) for t in self.tiles)
+
+    def step(self, marks=None):
+        torch, eng = self.torch, self.eng
+        s = eng.stream
+        if marks is not None:
+            marks[0].record(s)
+        eng.build_solar()
+        if marks is not None:
+            marks[1].record(s)
+        eng.daily(want=())
+        if marks is not None:
+            marks[2].record(s)
+        for k, (d0, d1) in enumerate(self.tiles):
+            eng.disaggregate(OUT_VARS, d0, d1, torch.float32, out=self.ring[k & 1])
+        if marks is not None:
+            marks[3].record(s)
+
+    def timed(self, steps, warmup, barrier, sampler=None):
+        """(ms per step of this rank, breakdown [solar, daily, disagg] in ms)"""
+        torch, eng = self.torch, self.eng
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        for _ in range(max(3, warmup)):
+            self.step()
+        eng.check()
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        marks = [[ev() for _ in range(4)] for _ in range(steps)]
+        t0, t1 = ev(), ev()
+        t0.record(eng.stream)
+        for k in range(steps):
+            self.step(marks[k])
+        t1.record(eng.stream)
+        barrier()
+        ms = t0.elapsed_time(t1) / steps
+        br = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(3)] for m in marks]).mean(0)
+        return ms, br
+
+    def release(self):
+        self.ring = None
+        self.eng = None
+        self.f = None
+        self.torch.cuda.empty_cache()
+
+
+def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, consume=True):
+    """The same step through msb_run_host_ctx (C ABI) with pinned HOST buffers: H2D of the inputs and
+    D2H of every output tile inside the timed region, every tile handed to a consumer (the native
+    thread pool of csrc/sink.cu: reads every row, scatters / byte-swaps it into its staging --
+    what the streaming NetCDF writer does short of the disk) while the next tile computes."""
+    import torch
+    from metsim_b200.engine import HostContext, run_host
+    from metsim_b200.ncwriter import NativeSink
+    pin = lambda t: t.cpu().pin_memory().numpy()
+    host = {k: pin(v) for k, v in dp_f.items()}
+    tile_e2e = max(1, min(n_days, int((2 << 30) // max(1, len(OUT_VARS) * tpd * n * 4))))
+    hring = {v: torch.empty((2 * tile_e2e * tpd, n), dtype=torch.float32).pin_memory().numpy()
+             for v in OUT_VARS}
+    kw = dict(lat=host["lat"], lon=host["lon"], elev=host["elev"], doy=host["doy"],
+              month=host["month"], t_min=host["t_min"], t_max=host["t_max"], prec=host["prec"],
+              wind=host["wind"], state_t_min=host["state_t_min"], state_t_max=host["state_t_max"],
+              state_prec=host["state_prec"], t_pk12=host["t_pk12"], dur12=host["dur12"])
+    n_thr = max(2, min(16, (len(os.sched_getaffinity(0)) or 2) // 2))
+    sink = NativeSink(n_cells=n, elem_bytes=4, byteswap=True, n_threads=n_thr, fd=-1) if consume else None
+    consumed = [0]
+
+    def on_tile(k, d0, d1, slot):
+        rows = (d1 - d0) * tpd
+        for v in OUT_VARS:
+            sink.write(hring[v][slot * tile_e2e * tpd: slot * tile_e2e * tpd + rows])
+            consumed[0] += rows * n * 4
+    ctx = HostContext(local)
+    call = lambda: run_host(params, out_vars=OUT_VARS, tile_days=tile_e2e, out=hring, ring=True, ctx=ctx,
+                            on_tile=on_tile if consume else None, **kw)
+    call()  # warm-up: arena allocation, page faults
+    barrier()
+    consumed[0] = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    barrier()
+    dt = reduce_max((time.perf_counter() - t0) / steps)
+    ctx.close()
+    if sink is not None:
+        sink.close()
+    h2d = sum(host[k].nbytes for k in ("lon", "elev", "doy", "month", "t_min", "t_max", "prec",
+                                        "wind", "state_t_min", "state_t_max", "state_prec",
+                                        "t_pk12", "dur12")) + n * 4
+    d2h = len(OUT_VARS) * n_days * tpd * n * 4
+    return dt, int(h2d), int(d2h), int(consumed[0] // max(1, steps)), n_thr, tile_e2e
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -251,21 +477,26 @@ def main():
                          "for the headline grid)")
     ap.add_argument("--sample-cells", type=int, default=None)
     ap.add_argument("--shard", action="store_true",
-                    help="strong scaling: the ranks share ONE domain, each takes a contiguous cell range "
-                         "(metsim_b200.shard.cell_range); default is one full domain per rank (weak)")
+                    help="make the strong-scaling partition the HEADLINE: the ranks share ONE domain, each takes a "
+                         "contiguous cell range (metsim_b200.shard.cell_range).  Default: one full domain per rank "
+                         "(weak) as the headline, the partitioned domain reported beside it under 'strong'")
     ap.add_argument("--emulate-shard", default=None, metavar="R/W",
                     help="debugging: on ONE GPU, take the cell range rank R of W would get with --shard")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-consumer", action="store_true", help="e2e without the native tile consumer")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--verify-cells", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch
     import torch.distributed as dist
-    from metsim_b200 import synth
-    from metsim_b200.engine import Engine, run_host
+    from metsim_b200 import build as msb_build, synth
+    from metsim_b200.shard import cell_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -274,73 +505,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    grid, n_days, start, ts, prec_type = synth.CONFIGS[args.workload]
-    n_days = args.days or n_days
-    rng = np.random.default_rng(synth.SEED)
-    lat, lon = synth.grid_cells(grid, rng)
-    if args.cells:
-        idx = np.linspace(0, lat.size - 1, args.cells).astype(np.int64)
-        lat, lon = lat[idx], lon[idx]
-    n_domain = lat.size
-    if args.emulate_shard and world == 1:
-        from metsim_b200.shard import cell_range
-        r_, w_ = (int(x) for x in args.emulate_shard.split("/"))
-        lo, hi = cell_range(n_domain, r_, w_)
-        lat, lon = lat[lo:hi], lon[lo:hi]
-        n_domain = lat.size
-    if args.shard and world > 1:      # latitude bands: contiguous ranges of the row-major enumeration
-        from metsim_b200.shard import cell_range
-        lo, hi = cell_range(n_domain, rank, world)
-        lat, lon = lat[lo:hi], lon[lo:hi]
-    n = lat.size
-    tpd = 1440 // ts
-    params = dict(time_step=ts, prec_type=prec_type, utc_offset=True)
-    # every rank owns a shard of the same shape (different seed = different part of the domain)
-    f = synth.make_forcing_torch(lat, lon, n_days, start, dev, seed=synth.SEED + rank)
-    torch.cuda.empty_cache()
-    eng = Engine(params, dev)
-    eng.load(**f)
-    if args.tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
-        args.tile_days = max(1, int(24.0e9 // (len(OUT_VARS) * tpd * n * 4)))
-        if 7 * n_days * n * 8 > 60e9:       # multi-year records: inputs + daily arrays already fill HBM
-            args.tile_days = min(args.tile_days, 64)
-    tile = min(args.tile_days, n_days)
-    ld_pad = (n + 31) // 32 * 32      # rows on 128-byte boundaries, as Engine.disaggregate allocates them
-    ring = [{v: torch.empty((tile * tpd, ld_pad), dtype=torch.float32, device=dev)[:, :n] for v in OUT_VARS}
-            for _ in range(2)]
-    n_tiles = -(-n_days // tile)
-    rounds = 4  # ceil(max_iter 24 / 6 evaluations per round), daily.cu
-    # 2 solar kernels, daily passes (pass 1 + reduce per round, pass 2), and per msb_disaggregate
-    # call: thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2), plus day
-    # records + disagg_kernel<thermo> / <streams> over the first / last two days of the record
-    def disagg_launches(d0, d1):
-        a0, b0 = max(d0, 2), min(d1, n_days - 2)
-        if a0 >= b0:
-            return 3
-        return 2 + (3 if d0 < a0 else 0) + (3 if b0 < d1 else 0)
-    launches_per_step = 2 + 2 * rounds + 1 + sum(
-        disagg_launches(k * tile, min(n_days, (k + 1) * tile)) for k in range(n_tiles))
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def step(marks=None):
-        s = eng.stream
-        if marks is not None:
-            marks[0].record(s)
-        eng.build_solar()
-        if marks is not None:
-            marks[1].record(s)
-        eng.daily(want=())
-        if marks is not None:
-            marks[2].record(s)
-        for k in range(n_tiles):
-            d0, d1 = k * tile, min(n_days, (k + 1) * tile)
-            eng.disaggregate(OUT_VARS, d0, d1, torch.float32, out=ring[k & 1])
-        if marks is not None:
-            marks[3].record(s)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -348,85 +516,138 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    eng.check()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    marks = [[ev() for _ in range(4)] for _ in range(args.steps)]
-    t_start, t_end = ev(), ev()
-    t_start.record(eng.stream)
-    for k in range(args.steps):
-        step(marks[k])
-    t_end.record(eng.stream)
-    barrier()
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        return [float(e.item()) for e in every]
+
+    grid, n_days, start, ts, prec_type = synth.CONFIGS[args.workload]
+    n_days = args.days or n_days
+    rng = np.random.default_rng(synth.SEED)
+    lat_all, lon_all = synth.grid_cells(grid, rng)
+    if args.cells:
+        idx = np.linspace(0, lat_all.size - 1, args.cells).astype(np.int64)
+        lat_all, lon_all = lat_all[idx], lon_all[idx]
+    if args.emulate_shard and world == 1:
+        r_, w_ = (int(x) for x in args.emulate_shard.split("/"))
+        lo, hi = cell_range(lat_all.size, r_, w_)
+        lat_all, lon_all = lat_all[lo:hi], lon_all[lo:hi]
+    n_domain = lat_all.size
+    tpd = 1440 // ts
+    headline_strong = args.shard and world > 1
+    if headline_strong:      # latitude bands: contiguous ranges of the row-major enumeration
+        lo, hi = cell_range(n_domain, rank, world)
+        lat, lon = lat_all[lo:hi], lon_all[lo:hi]
+    else:
+        lat, lon = lat_all, lon_all
+
+    # ---- headline pass: every rank owns a shard (different seed = different part of a larger domain)
+    dp = DevicePass(args, dev, lat, lon, n_days, start, ts, prec_type, synth.SEED + rank, args.tile_days)
+    n, tile = dp.n, dp.tile
+    sampler = ClockSampler(local) if rank == 0 else None
+    my_ms, br = dp.timed(args.steps, args.warmup, barrier, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = t_start.elapsed_time(t_end)
-    ms = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    rank_ms = [total_ms / args.steps]
-    if world > 1:
-        every = [torch.zeros_like(ms) for _ in range(world)]
-        dist.all_gather(every, ms)
-        rank_ms = [float(t.item()) / args.steps for t in every]
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
+    rank_ms = gather(my_ms)
+    ms_per_step = max(rank_ms)
     cell_ts_rank = n * n_days * tpd
-    strong = args.shard and world > 1
-    total_cell_ts = n_domain * n_days * tpd if strong else world * cell_ts_rank
+    total_cell_ts = n_domain * n_days * tpd if headline_strong else world * cell_ts_rank
     value = total_cell_ts / (ms_per_step * 1e-3)
-    br = np.array([[m[i].elapsed_time(m[i + 1]) for i in range(3)] for m in marks]).mean(0)
+    n_tiles = len(dp.tiles)
     disagg_ms_per_launch = br[2] / n_tiles
     bytes_per_cts = algorithmic_bytes_per_cell_ts(tpd, len(OUT_VARS))
     bytes_per_launch = bytes_per_cts * cell_ts_rank / n_tiles
     achieved = bytes_per_launch / (disagg_ms_per_launch * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
-    traffic = None
+    # DRAM traffic of the call from the committed ncu capture -- only if it was taken from THIS build
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "disagg_traffic.json")
-    if os.path.exists(tpath):   # measured once per round with ncu --set full; scaled to this launch size
+    src_hash = msb_build.source_hash()
+    if os.path.exists(tpath):
         try:
-            per_cts = float(json.load(open(tpath))["dram_bytes_per_cell_timestep"])
-            traffic = per_cts * cell_ts_rank / n_tiles
-        except Exception:
-            traffic = None
+            tj = json.load(open(tpath))
+            if tj.get("source_hash") == src_hash:
+                traffic = float(tj["dram_bytes_per_cell_timestep"]) * cell_ts_rank / n_tiles
+            else:
+                traffic_note = (f"profiles/disagg_traffic.json was captured from sources {tj.get('source_hash')}, "
+                                f"this build is {src_hash}: not reported")
+        except Exception as exc:
+            traffic_note = f"profiles/disagg_traffic.json unreadable: {exc!r}"
+
+    # ---- parity of the timed configuration (checker only; after the timed region) ----
+    verify = None
+    if not args.no_verify and rank == 0:
+        try:
+            verify = verify_against_oracle(dp.eng, dp.f, dp.params, dp.tiles, dp.ring, n_days, tpd,
+                                           sample=args.verify_cells)
+        except Exception as exc:
+            verify = {"error": repr(exc)}
+    barrier()
 
     # ---- end to end through the C ABI with pinned host buffers ----
-    e2e = None
+    e2e, ceiling = None, None
+    launches_per_step = dp.launches_per_step
     if not args.no_e2e:
-        pin = lambda t: t.cpu().pin_memory().numpy()
-        host = {k: pin(v) for k, v in f.items()}
-        tile_e2e = max(1, min(n_days, int((2 << 30) // max(1, len(OUT_VARS) * tpd * n * 4))))
-        hring = {v: torch.empty((2 * tile_e2e * tpd, n), dtype=torch.float32).pin_memory().numpy()
-                 for v in OUT_VARS}
-        kw = dict(lat=host["lat"], lon=host["lon"], elev=host["elev"], doy=host["doy"],
-                  month=host["month"], t_min=host["t_min"], t_max=host["t_max"], prec=host["prec"],
-                  wind=host["wind"], state_t_min=host["state_t_min"], state_t_max=host["state_t_max"],
-                  state_prec=host["state_prec"], t_pk12=host["t_pk12"], dur12=host["dur12"])
-        e_steps = args.e2e_steps or max(1, min(args.steps, 3))
-        del ring
+        f_keep, params_keep = dp.f, dp.params
+        dp.ring = None
         torch.cuda.empty_cache()
-        call = lambda: run_host(params, out_vars=OUT_VARS, device=local, tile_days=tile_e2e,
-                                out=hring, ring=True, **kw)
-        call()  # warm-up: arena allocation, page faults
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            call()
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = sum(host[k].nbytes for k in ("lon", "elev", "doy", "month", "t_min", "t_max", "prec",
-                                            "wind", "state_t_min", "state_t_max", "state_prec",
-                                            "t_pk12", "dur12")) + n * 4
-        d2h = len(OUT_VARS) * n_days * tpd * n * 4
-        e2e = {"value": total_cell_ts / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": float(dt.item()) * 1e3, "steps": e_steps,
+        ceiling = d2h_ceiling(dev, world)
+        e_steps = args.e2e_steps or max(1, min(args.steps, 3))
+        dt, h2d, d2h, consumed, n_thr, tile_e2e = e2e_pass(f_keep, params_keep, n, n_days, tpd, local, e_steps,
+                                                           barrier, reduce_max, consume=not args.no_consumer)
+        e2e = {"value": total_cell_ts / dt, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": e_steps,
+               "d2h_gbs_all_ranks": world * d2h / dt / 1e9,
+               "d2h_ceiling_gbs_all_ranks": ceiling,
+               "fraction_of_d2h_ceiling": (world * d2h / dt / 1e9) / ceiling if ceiling else None,
+               "consumer": (f"native sink (csrc/sink.cu), {n_thr} threads per rank: every tile read, byte-swapped "
+                            f"and scattered into staging while the next tile computes; {consumed} bytes per step"
+                            if not args.no_consumer else "none"),
+               "tile_days": tile_e2e, "rank_cpu_affinity": affinity,
                "timer": "host wall clock around the blocking C-ABI call, max over ranks",
-               "api": "msb_run_host (C ABI), pinned host inputs, outputs streamed D2H into a pinned "
-                      "2-tile host ring (what a streaming netCDF writer would drain)"}
+               "api": "msb_run_host_ctx (C ABI), pinned host inputs, outputs streamed D2H into a pinned "
+                      "2-tile host ring and handed to the consumer tile by tile"}
+    dp.release()
+
+    # ---- the north_star's partition: ONE domain cut into contiguous cell ranges (N > 1) ----
+    strong = None
+    if world > 1 and not headline_strong and not args.no_strong:
+        lo, hi = cell_range(n_domain, rank, world)
+        sp = DevicePass(args, dev, lat_all[lo:hi], lon_all[lo:hi], n_days, start, ts, prec_type,
+                        synth.SEED + 100 + rank, None)
+        s_ms, s_br = sp.timed(args.steps, args.warmup, barrier)
+        s_rank = gather(s_ms)
+        s_max = max(s_rank)
+        dom_cts = n_domain * n_days * tpd
+        strong = {"value": dom_cts / (s_max * 1e-3), "unit": UNIT, "ms_per_step": s_max,
+                  "rank_ms_per_step": s_rank, "cells_per_gpu": int(hi - lo), "tile_days": sp.tile,
+                  # one GPU running the whole domain = this run's own weak pass (same domain size per rank)
+                  "efficiency_vs_n1": (ms_per_step / s_max) / world,
+                  "n1_ms_per_step_used": ms_per_step,
+                  "sharding": f"one domain of {n_domain} cells cut into {world} contiguous cell ranges, no collective"}
+        if not args.no_e2e:
+            e_steps = args.e2e_steps or max(1, min(args.steps, 3))
+            f_keep, params_keep = sp.f, sp.params
+            sp.ring = None
+            torch.cuda.empty_cache()
+            dt, h2d, d2h, consumed, n_thr, tile_e2e = e2e_pass(f_keep, params_keep, sp.n, n_days, tpd, local,
+                                                               e_steps, barrier, reduce_max,
+                                                               consume=not args.no_consumer)
+            d2h_all = sum(gather(d2h))
+            strong["e2e"] = {"value": dom_cts / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                             "d2h_gbs_all_ranks": d2h_all / dt / 1e9,
+                             "fraction_of_d2h_ceiling": (d2h_all / dt / 1e9) / ceiling if ceiling else None,
+                             "efficiency_vs_n1": (e2e["ms_per_step"] / (dt * 1e3)) / world if e2e else None}
+        sp.release()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:      # reported baseline: rank 0 at N = 1 only
@@ -446,13 +667,16 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if headline_strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload],
                        "cells_per_gpu": int(n), "n_days": int(n_days), "time_step_min": ts,
                        "prec_type": prec_type, "utc_offset": True, "out_vars": list(OUT_VARS),
                        "out_precision": "f4", "tile_days": tile,
+                       "launch_geometry": "library defaults: 16 knot-days / 16 output days per thread, daily chunks of "
+                                          "ceil(n_days / (2^21 / cells + 1)) days, single-pass daily form",
                        "sharding": (f"one domain of {n_domain} cells cut into {world} contiguous cell ranges, no collective"
-                                    if strong else f"cell-chunks x{world}, no collective"),
+                                    if headline_strong else f"cell-chunks x{world}, no collective"),
                        "l2": "each tile writes %.1f GB (>> 126 MB L2) into a 2-tile ring; inputs %.1f GB"
                              % (len(OUT_VARS) * tile * tpd * n * 4 / 1e9, 4 * n_days * n * 8 / 1e9)},
             "breakdown_ms": {"solar_tables": float(br[0]), "daily_mtclim": float(br[1]),
@@ -460,16 +684,20 @@ def main():
             # the metric with and without the (time-independent) solar-geometry set-up
             "rank_ms_per_step": rank_ms,      # device time of every rank (value uses the maximum)
             "value_excl_solar_tables": total_cell_ts / max(1e-9, (ms_per_step - float(br[0])) * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = disagg_prepare_kernel + thermo_knot_kernel + "
-                                                   "streams_day_kernel (+ disagg_kernel on the record's first / last "
+            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = thermo_knot_kernel + streams_day_kernel (+ "
+                                                   "disagg_prepare_kernel and disagg_kernel on the record's first / last "
                                                    "two days), timed together per call (--tile-days days)",
                          "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_cell_timestep": bytes_per_cts,
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "algorithmic_bytes_per_cell_timestep": bytes_per_cts,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": float(disagg_ms_per_launch),
                          "whole_step_frac": bytes_per_cts * cell_ts_rank / (ms_per_step * 1e-3) / 1e9 / peak},
+            "verify": verify, "strong": strong,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
+            "build": {"library": "metsim_b200/csrc/libmetsim_b200.so", "source_hash": src_hash,
+                      "built_from_these_sources": msb_build.built_hash() == src_hash},
         }
         print(json.dumps(line))
     if world > 1:

@@ -7,9 +7,11 @@
  * Conventions
  *   - every array is cell-fastest: daily [D][ld], sub-daily [D*tpd][ld], state [90][ld],
  *     monthly [12][ld]; "ld" (leading dimension, in elements) >= n_cells.
- *   - `msb_dev_*` arguments are DEVICE pointers owned by the caller; `stream` is a cudaStream_t
- *     passed as void* (0 = default stream).  Nothing is allocated behind the caller's back except
- *     inside msb_run_host(), which owns its device buffers for the duration of the call.
+ *   - pointers inside msb_forcing / msb_daily / msb_subdaily / msb_solar_tables are DEVICE
+ *     pointers owned by the caller; `stream` is a cudaStream_t passed as void* (0 = default
+ *     stream).  Those entry points allocate nothing, keep no state between calls and only enqueue
+ *     work on `stream`: they are thread-safe per stream.  msb_run_host_ctx() takes HOST buffers and
+ *     uses the device arena of a caller-owned msb_host_ctx.
  *   - every function returns 0 on success, <0 on error (MSB_E_*); msb_last_error() gives the text.
  *     Errors mirror the reference's exceptions (e.g. t_max < t_min -> MSB_E_DTR_NEGATIVE,
  *     metsim/metsim.py:612-614).  There is no CPU fallback anywhere in this library.
@@ -24,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MSB_VERSION 101
+#define MSB_VERSION 200
 
 enum {
   MSB_OK = 0,
@@ -73,6 +75,24 @@ typedef struct msb_params {
   double sw_prec_thresh, rain_scalar, tdew_tol, tmax_daylength_fraction, tday_coef, lapse_rate;
 } msb_params;
 
+/* Launch-geometry / path overrides, embedded in msb_daily, msb_subdaily and msb_host_run.
+ * Every field: 0 = let the library choose (what bench.py times on the full grids).  On a small
+ * shard the library shortens the work per thread so that the grid still fills the GPU; the parity
+ * tests pin the values of the benchmarked configuration instead, so that the oracle comparisons
+ * run exactly the geometry the performance number is earned with.  Nothing here changes results
+ * beyond floating-point summation order (daily_chunk_len: partial sums of the tdew stop rule). */
+typedef struct msb_tuning {
+  int32_t daily_chunk_len;  /* days per thread of the daily pass */
+  int32_t daily_two_pass;   /* != 0: two-pass daily form even when candidate planes are supplied */
+  int32_t knot_tile;        /* knot-days per thread of the interior thermodynamic kernel, used as given */
+  int32_t day_tile;         /* output days per thread of the interior stream kernel, used as given */
+  int32_t disagg_path;      /* 0 = specialised interior-day kernels + event kernel on the edge days,
+                               1 = event-driven kernel for every day */
+  int32_t day_prefetch;     /* L1 prefetch distance of the table stream in steps (0 = default 4, -1 = off) */
+  int32_t prep_days;        /* padded days per thread of the day-record kernel */
+  int32_t reserved;
+} msb_tuning;
+
 /* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of
  * physics.py:177-285: only tt_max0 depends on elevation, everything else on latitude alone). */
 #define MSB_TINY_PER_DAY 2880
@@ -115,12 +135,30 @@ typedef struct msb_forcing {
   const double *given_shortwave, *given_vapor_pressure, *given_tskc, *given_longwave; /* [n_days][ld] */
 } msb_forcing;
 
+#define MSB_DAILY_CAND 3      /* candidate evaluation counts kept by the single-pass daily form */
+#define MSB_DAILY_CAND_K0 4   /* ... after 4, 5 and 6 evaluations of the tdew map */
 typedef struct msb_daily {
   double *var[MSB_N_DAILYVARS];      /* [n_days][ld] each; TSKC, VAPOR_PRESSURE, SHORTWAVE are
-                                        required by the disaggregation, the rest may be NULL */
+                                        required by the disaggregation, the rest may be NULL
+                                        (VAPOR_PRESSURE / SHORTWAVE may be NULL when `cand` is given) */
   int32_t *n_iter;                   /* [n_cells] tdew evaluations used (0 = not converged) */
   double *partial;                   /* scratch, msb_daily_scratch_bytes() */
   int32_t *status;                   /* [4] device error flags (dtr<0, knots, ...) */
+  /* Single-pass form of the tdew fixed point (optional).  The number of evaluations n* of a cell is
+   * only known once the RMS over its whole record is (mtclim.py:63).  With `cand` the daily kernel
+   * runs the evaluations once, keeps vapour pressure and shortwave after MSB_DAILY_CAND_K0 ..
+   * MSB_DAILY_CAND_K0 + MSB_DAILY_CAND - 1 evaluations in candidate planes and msb_disaggregate reads
+   * the plane cand_sel[cell] = n* - MSB_DAILY_CAND_K0 picks; the (rare) cells outside that window are
+   * finished by a compacted replay into plane 0.  Used when cand != NULL, the method is mtclim, no
+   * given_* column replaces a computed one and no daily variable beyond TSKC is requested; otherwise
+   * the two-pass form fills var[] as before.
+   *   cand      [2*MSB_DAILY_CAND][n_days][ld]: plane 2j = vapour pressure, 2j+1 = shortwave
+   *   cand_sel  [n_cells] plane index per cell (written by msb_mtclim_daily)
+   *   cand_list [n_cells + 1] scratch: count, then the cells finished by the replay */
+  double *cand;
+  int32_t *cand_sel;
+  int32_t *cand_list;
+  msb_tuning tune;
 } msb_daily;
 
 typedef struct msb_subdaily {
@@ -133,6 +171,7 @@ typedef struct msb_subdaily {
   void *workspace;                   /* device scratch of msb_disagg_workspace_bytes() bytes: the
                                         per-(cell, day) records of the days around [day0, day1) */
   size_t workspace_bytes;
+  msb_tuning tune;
 } msb_subdaily;
 
 int msb_version(void);
@@ -151,6 +190,10 @@ int msb_solar_tables_build(int n_lat, const double *lat_deg_host, void *host_ws,
 
 /* ---- daily MTCLIM: mtclim.py:28-80 (run), metsim.py:589-618 (rolling means) ---------------- */
 size_t msb_daily_scratch_bytes(int n_cells, int n_days);
+/* the same for a pinned msb_tuning.daily_chunk_len (0 = the library's choice, as above) */
+size_t msb_daily_scratch_bytes_chunk(int n_cells, int n_days, int daily_chunk_len);
+/* 1 when msb_mtclim_daily would take the single-pass form for these arguments, else 0 */
+int msb_daily_single_pass(const msb_params *p, const msb_forcing *f, const msb_daily *out);
 int msb_mtclim_daily(const msb_params *p, const msb_forcing *f, const msb_solar_tables *t,
                      const msb_daily *out, void *stream);
 /* reads back status/n_iter flags (synchronises the stream); returns MSB_OK or the first error */
@@ -207,8 +250,52 @@ typedef struct msb_host_run {
   int32_t (*on_tile)(void *user, int32_t tile, int32_t day0, int32_t day1, int32_t slot);
   void *user;
   double ms_solar, ms_h2d, ms_daily, ms_disagg_total; /* filled on return (CUDA events) */
+  msb_tuning tune;                   /* all zero = the library's choices */
 } msb_host_run;
+
+/* Caller-owned context of the host-buffer path: the device arena (grow-only, reused from call to
+ * call), the pinned staging of the solar prelude, a compute and a copy stream and their events, all
+ * on one device.  The library keeps NO process-wide mutable state: two contexts -- on the same
+ * device or on different ones -- run concurrently from two threads (the reference drives its cell
+ * loop from a thread pool, scheduler='threading', metsim/metsim.py:63,195); calls on ONE context
+ * are serialised by it.  Every call returns with nothing of the context still in flight, on
+ * success and on error alike. */
+typedef struct msb_host_ctx msb_host_ctx;
+int msb_host_ctx_create(int device, msb_host_ctx **ctx);
+void msb_host_ctx_destroy(msb_host_ctx *ctx);
+size_t msb_host_ctx_device_bytes(const msb_host_ctx *ctx);   /* current size of the device arena */
+/* workspace-size query: device / pinned bytes a context holds after running `run` */
+int msb_run_host_bytes(const msb_params *p, const msb_host_run *run, size_t *device_bytes,
+                       size_t *pinned_bytes);
+int msb_run_host_ctx(msb_host_ctx *ctx, const msb_params *p, msb_host_run *run);
+/* convenience: a context created for this one call on run->device and destroyed afterwards */
 int msb_run_host(const msb_params *p, msb_host_run *run);
+
+/* ---- native consumer of output tiles (host threads; metsim/metsim.py:363-454, :581-586) ------
+ * The reference scatters every cell's series into NaN-filled (time, lat, lon) arrays and writes them
+ * through xarray / netCDF4.  A sink does that for the rows of one output variable as they arrive in
+ * host memory from msb_run_host_ctx()'s on_tile hook: scatter [step][cell] -> [step][n_grid] (NaN where
+ * no cell maps), optional byte swap to the big-endian order of the classic NetCDF format, pwrite()
+ * at the given file offset -- on a pool of threads, each with its own staging buffer, so that a tile
+ * is consumed at memory speed while the next one is being copied.  Host code only. */
+typedef struct msb_sink msb_sink;
+typedef struct msb_sink_desc {
+  int32_t n_cells;            /* cells per row of the source */
+  int32_t elem_bytes;         /* 4 (float32) or 8 (float64) */
+  int64_t n_grid;             /* lat * lon positions per step in the file, >= n_cells */
+  const int64_t *cell_index;  /* [n_cells] grid position of every cell; NULL = identity (n_grid == n_cells) */
+  int32_t byteswap;           /* != 0: big-endian in the file */
+  int32_t n_threads;          /* 0 = all hardware threads */
+  int32_t fd;                 /* open file descriptor to pwrite() to; -1 = no file (scatter + swap only) */
+  int32_t reserved;
+} msb_sink_desc;
+int msb_sink_create(const msb_sink_desc *desc, msb_sink **sink);
+/* rows [0, n_steps) of src ([n_steps][n_cells]) -> file_offset (bytes; where the first row's grid
+ * starts).  Returns when everything has been handed to the kernel's page cache. */
+int msb_sink_write(msb_sink *sink, const void *src, int64_t n_steps, int64_t file_offset);
+uint64_t msb_sink_checksum(const msb_sink *sink);      /* sum of the raw bit patterns consumed so far */
+uint64_t msb_sink_bytes_written(const msb_sink *sink);
+void msb_sink_destroy(msb_sink *sink);
 
 #ifdef __cplusplus
 }

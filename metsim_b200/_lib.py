@@ -30,11 +30,18 @@ TT_TERMS = 28
 
 E_ARG, E_CUDA, E_DTR_NEGATIVE, E_NOT_CONVERGED, E_KNOTS, E_NOMEM = -1, -2, -3, -4, -5, -6
 
+DAILY_CAND = 3          # MSB_DAILY_CAND: candidate planes of the single-pass daily form
+DAILY_CAND_K0 = 4       # MSB_DAILY_CAND_K0
+
 EXPORTS = ("msb_version", "msb_last_error", "msb_default_params", "msb_solar_prelude_bytes",
            "msb_solar_table_sizes", "msb_solar_tables_build", "msb_daily_scratch_bytes",
+           "msb_daily_scratch_bytes_chunk", "msb_daily_single_pass",
            "msb_mtclim_daily", "msb_daily_check", "msb_disagg_workspace_bytes",
            "msb_disagg_workspace_bytes_lw", "msb_disaggregate",
-           "msb_run_host",
+           "msb_host_ctx_create", "msb_host_ctx_destroy", "msb_host_ctx_device_bytes",
+           "msb_run_host_bytes", "msb_run_host_ctx", "msb_run_host",
+           "msb_sink_create", "msb_sink_write", "msb_sink_checksum", "msb_sink_bytes_written",
+           "msb_sink_destroy",
            "msb_selftest_math")
 
 dp = C.POINTER(C.c_double)
@@ -48,6 +55,40 @@ class Params(C.Structure):
                 ("sw_prec_thresh", C.c_double), ("rain_scalar", C.c_double),
                 ("tdew_tol", C.c_double), ("tmax_daylength_fraction", C.c_double),
                 ("tday_coef", C.c_double), ("lapse_rate", C.c_double)]
+
+
+class Tuning(C.Structure):
+    """msb_tuning: launch-geometry / path overrides, 0 = the library's choice."""
+    _fields_ = [("daily_chunk_len", C.c_int32), ("daily_two_pass", C.c_int32),
+                ("knot_tile", C.c_int32), ("day_tile", C.c_int32), ("disagg_path", C.c_int32),
+                ("day_prefetch", C.c_int32), ("prep_days", C.c_int32), ("reserved", C.c_int32)]
+
+
+TUNING_KEYS = tuple(n for n, _ in Tuning._fields_ if n != "reserved")
+# environment spellings of the same knobs (read here, in Python, once per Engine / run_host call --
+# the C library itself never looks at the environment)
+_TUNING_ENV = {"MSB_DAILY_CHUNK": "daily_chunk_len", "MSB_DAILY_TWO_PASS": "daily_two_pass",
+               "MSB_KNOT_TILE": "knot_tile", "MSB_DAY_TILE": "day_tile", "MSB_DAY_PF": "day_prefetch",
+               "MSB_PREP_DAYS": "prep_days"}
+
+
+def make_tuning(user: dict | None = None) -> Tuning:
+    """``user`` keys are the msb_tuning field names (``disagg_path`` also takes 'event' / 'auto').
+    Unset fields fall back to the MSB_* environment variables, then to 0 (library default)."""
+    t = Tuning()
+    for env, field in _TUNING_ENV.items():
+        v = os.environ.get(env)
+        if v:
+            setattr(t, field, int(v))
+    if os.environ.get("MSB_DISAGG_PATH", "").startswith("e"):
+        t.disagg_path = 1
+    for k, v in (user or {}).items():
+        if k not in TUNING_KEYS:
+            raise KeyError(f"unknown tuning key {k!r}")
+        if k == "disagg_path" and isinstance(v, str):
+            v = 1 if v.startswith("e") else 0
+        setattr(t, k, int(v))
+    return t
 
 
 class SolarTables(C.Structure):
@@ -73,14 +114,16 @@ class Forcing(C.Structure):
 
 class Daily(C.Structure):
     _fields_ = [("var", C.c_void_p * N_DAILYVARS), ("n_iter", C.c_void_p),
-                ("partial", C.c_void_p), ("status", C.c_void_p)]
+                ("partial", C.c_void_p), ("status", C.c_void_p),
+                ("cand", C.c_void_p), ("cand_sel", C.c_void_p), ("cand_list", C.c_void_p),
+                ("tune", Tuning)]
 
 
 class SubDaily(C.Structure):
     _fields_ = [("var", C.c_void_p * N_SUBVARS), ("scale", C.c_double * N_SUBVARS),
                 ("offset", C.c_double * N_SUBVARS), ("dtype", C.c_int32), ("ld", C.c_int64),
                 ("day0", C.c_int32), ("day1", C.c_int32),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("tune", Tuning)]
 
 
 class HostRun(C.Structure):
@@ -99,7 +142,13 @@ class HostRun(C.Structure):
                 ("tile_days", C.c_int32), ("out_is_ring", C.c_int32),
                 ("on_tile", C.c_void_p), ("user", C.c_void_p),
                 ("ms_solar", C.c_double), ("ms_h2d", C.c_double), ("ms_daily", C.c_double),
-                ("ms_disagg_total", C.c_double)]
+                ("ms_disagg_total", C.c_double), ("tune", Tuning)]
+
+
+class SinkDesc(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("elem_bytes", C.c_int32), ("n_grid", C.c_int64),
+                ("cell_index", C.c_void_p), ("byteswap", C.c_int32), ("n_threads", C.c_int32),
+                ("fd", C.c_int32), ("reserved", C.c_int32)]
 
 
 # int32_t (*on_tile)(void *user, int32_t tile, int32_t day0, int32_t day1, int32_t slot)
@@ -153,8 +202,33 @@ def lib():
     l.msb_disaggregate.restype = C.c_int
     l.msb_disaggregate.argtypes = [C.POINTER(Params), C.POINTER(Forcing), C.POINTER(SolarTables),
                                    C.POINTER(Daily), C.POINTER(SubDaily), C.c_void_p]
+    l.msb_daily_scratch_bytes_chunk.restype = C.c_size_t
+    l.msb_daily_scratch_bytes_chunk.argtypes = [C.c_int, C.c_int, C.c_int]
+    l.msb_daily_single_pass.restype = C.c_int
+    l.msb_daily_single_pass.argtypes = [C.POINTER(Params), C.POINTER(Forcing), C.POINTER(Daily)]
     l.msb_run_host.restype = C.c_int
     l.msb_run_host.argtypes = [C.POINTER(Params), C.POINTER(HostRun)]
+    l.msb_host_ctx_create.restype = C.c_int
+    l.msb_host_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    l.msb_host_ctx_destroy.restype = None
+    l.msb_host_ctx_destroy.argtypes = [C.c_void_p]
+    l.msb_host_ctx_device_bytes.restype = C.c_size_t
+    l.msb_host_ctx_device_bytes.argtypes = [C.c_void_p]
+    l.msb_run_host_bytes.restype = C.c_int
+    l.msb_run_host_bytes.argtypes = [C.POINTER(Params), C.POINTER(HostRun), C.POINTER(C.c_size_t),
+                                     C.POINTER(C.c_size_t)]
+    l.msb_run_host_ctx.restype = C.c_int
+    l.msb_run_host_ctx.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(HostRun)]
+    l.msb_sink_create.restype = C.c_int
+    l.msb_sink_create.argtypes = [C.POINTER(SinkDesc), C.POINTER(C.c_void_p)]
+    l.msb_sink_write.restype = C.c_int
+    l.msb_sink_write.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    l.msb_sink_checksum.restype = C.c_uint64
+    l.msb_sink_checksum.argtypes = [C.c_void_p]
+    l.msb_sink_bytes_written.restype = C.c_uint64
+    l.msb_sink_bytes_written.argtypes = [C.c_void_p]
+    l.msb_sink_destroy.restype = None
+    l.msb_sink_destroy.argtypes = [C.c_void_p]
     l.msb_selftest_math.restype = C.c_int
     l.msb_selftest_math.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = l

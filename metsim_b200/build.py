@@ -4,6 +4,7 @@
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,7 +13,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ("api.cu", "solar.cu", "daily.cu", "disagg.cu", "disagg_event.cu", "disagg_interior.cu")
+SOURCES = ("api.cu", "solar.cu", "daily.cu", "disagg.cu", "disagg_event.cu", "disagg_interior.cu",
+           "sink.cu")
 HEADERS = ("msb_common.cuh", "disagg_common.cuh")
 OUT = os.path.join(CSRC, "libmetsim_b200.so")
 
@@ -24,13 +26,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+FLAGS = ("-O3", "-std=c++17", "--threads", "0", "-gencode", "arch=compute_100a,code=sm_100a",
+         "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared")
+STAMP = OUT + ".sha"      # hash of the sources the library was built from (travels with the .so)
+
+
+def source_hash(extra: tuple = ()) -> str:
+    """sha256 over every source, header and compiler flag that goes into the library (12 hex digits)."""
+    h = hashlib.sha256()
+    for path in [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(INCLUDE, "metsim_b200.h")]:
+        h.update(os.path.basename(path).encode())
+        h.update(open(path, "rb").read())
+    h.update(" ".join(FLAGS + tuple(extra)).encode())
+    return h.hexdigest()[:12]
+
+
+def built_hash() -> str | None:
+    """Hash recorded when the present .so was compiled (None: no library, or one of unknown origin)."""
+    if os.path.exists(OUT) and os.path.exists(STAMP):
+        return open(STAMP).read().strip()
+    return None
+
+
 def needs_build() -> bool:
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [
-        os.path.join(INCLUDE, "metsim_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    """By content, not by mtime: a shipped .so is reused only if it was built from exactly these
+    sources and flags."""
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> str:
@@ -38,9 +59,9 @@ def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> s
     table access of the streaming kernels is range-checked on the device (trap or MSB_E_KNOTS)."""
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc(), "-O3", "-std=c++17", "--threads", "0", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared",
-           "-I", INCLUDE, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *FLAGS, "-I", INCLUDE, "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    if os.path.exists(STAMP):
+        os.remove(STAMP)
     if bounds:
         cmd.insert(1, "-DMSB_BOUNDS")
     if verbose:
@@ -48,6 +69,8 @@ def build(force: bool = False, verbose: bool = False, bounds: bool = False) -> s
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    with open(STAMP, "w") as fh:          # a debug build never passes for the product library
+        fh.write(source_hash(("-DMSB_BOUNDS",) if bounds else ()) + "\n")
     return OUT
 
 

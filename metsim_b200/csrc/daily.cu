@@ -14,6 +14,15 @@
 //           reference's while-loop would;
 //   pass 2  replays n* evaluations and writes the daily outputs.
 // No per-iteration state ever touches HBM.
+//
+// Single-pass form (msb_daily.cand != NULL, the benchmarked configuration): what the
+// disaggregation needs from the daily pass is tskc (independent of n*), vapour pressure and
+// shortwave.  n* is 4, 5 or 6 on almost every cell, and evaluation k+1 starts by computing exactly
+// vp(tdew_k) and sw(tdew_k) -- so daily_fused_kernel runs six evaluations ONCE, stores the three
+// candidate (vp, sw) pairs and the stop-rule partials, the reduce kernel turns n* into a plane
+// index per cell, and msb_disaggregate reads that plane.  The replay (7.4 of 13 ms on CONUS) and
+// its second read of the inputs disappear; cells with n* outside the window are appended to a list
+// and finished by the two-pass kernels running over that list only.
 #include <cstring>
 
 #include "msb_common.cuh"
@@ -27,7 +36,13 @@ struct DailyLaunch {
   int chunk_len, n_chunks;
 };
 
-static DailyLaunch daily_launch(int n_cells, int n_days) {
+static DailyLaunch daily_launch(int n_cells, int n_days, int forced_chunk_len = 0) {
+  DailyLaunch l;
+  if (forced_chunk_len > 0) {   // msb_tuning.daily_chunk_len: the tests pin the benchmarked geometry
+    l.chunk_len = forced_chunk_len < n_days ? forced_chunk_len : n_days;
+    l.n_chunks = (n_days + l.chunk_len - 1) / l.chunk_len;
+    return l;
+  }
   // aim for >= ~2M threads, chunks of at least 8 days
   long want = (2L << 20) / (n_cells > 0 ? n_cells : 1) + 1;
   long max_chunks = (n_days + 7) / 8;
@@ -35,7 +50,6 @@ static DailyLaunch daily_launch(int n_cells, int n_days) {
   if (nc > max_chunks) nc = max_chunks;
   if (nc > 64) nc = 64;
   if (nc < 1) nc = 1;
-  DailyLaunch l;
   l.chunk_len = (int)((n_days + nc - 1) / nc);
   l.n_chunks = (n_days + l.chunk_len - 1) / l.chunk_len;
   return l;
@@ -107,11 +121,16 @@ __device__ __forceinline__ double hist(const double *cur, const double *st, long
 template <int PASS>
 __global__ void __launch_bounds__(kDailyThreads)
 daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int chunk_len,
-             int k_off, int max_evals) {
+             int k_off, int max_evals, const int32_t *__restrict__ list) {
   __shared__ double etab[kExpTab];
   exp_table_init(etab);
   __syncthreads();
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  // list != NULL: the cells the single-pass form could not finish (list[0] of them, from list[1])
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (list) {
+    if (cell >= list[0]) return;
+    cell = list[1 + cell];
+  }
   if (cell >= f.n_cells) return;
   if (PASS == 1 && k_off > 0 && out.status[3] == 0) return;   // every cell converged earlier
   const int chunk = blockIdx.y;
@@ -130,6 +149,7 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
       n_evals = max_evals;
       out.status[1] = 1;
     }
+    if (list && chunk == 0) out.cand_sel[cell] = 0;   // the replay writes candidate plane 0
   }
   const CellConst cc = cell_const(p, f, t, cell);
 
@@ -259,8 +279,12 @@ daily_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int
 // while np.sqrt(np.mean((tdew_temp - tdew_old)**2)) > tdew_tol  (mtclim.py:63)
 __global__ void daily_reduce_kernel(msb_params p, int n_cells, int n_days, int n_chunks, int k_off,
                                     const double *__restrict__ partial, int32_t *n_iter,
-                                    int32_t *status) {
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+                                    int32_t *status, const int32_t *__restrict__ list) {
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (list) {
+    if (cell >= list[0]) return;
+    cell = list[1 + cell];
+  }
   if (cell >= n_cells) return;
   if (k_off == 0) n_iter[cell] = 0;
   else if (n_iter[cell] != 0) return;
@@ -273,14 +297,175 @@ __global__ void daily_reduce_kernel(msb_params p, int n_cells, int n_days, int n
   atomicAdd(&status[3], 1);   // still iterating: the next round has work to do
 }
 
+
+// ---- single-pass form -----------------------------------------------------------------------
+// One thread = (cell, chunk of days), as above, for the product configuration only (mtclim
+// method, rolling means from the state, solar tables, no extra daily outputs).  Differences from
+// daily_kernel<1>: the 30-day temperature-range window lives in a per-thread shared-memory ring
+// (no second read of t_min / t_max rows), and the (vp, sw) pairs after 4, 5 and 6 evaluations go
+// to the candidate planes together with tskc.
+constexpr int kDtrWin = 30;
+__global__ void __launch_bounds__(kDailyThreads)
+daily_fused_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily out, int chunk_len) {
+  __shared__ double etab[kExpTab];
+  __shared__ double ring[kDtrWin][kDailyThreads];
+  exp_table_init(etab);
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int cell = blockIdx.x * blockDim.x + tid;
+  if (cell >= f.n_cells) return;
+  const int chunk = blockIdx.y;
+  const int D = f.n_days;
+  const long ld = f.ld;
+  const int d_lo = chunk * chunk_len;
+  const int d_hi = min(D, d_lo + chunk_len);
+  const CellConst cc = cell_const(p, f, t, cell);
+
+  // rolling windows (metsim.py:601-616): sums over the 89 / 29 days before d_lo, the ring holds
+  // the temperature ranges of days d-29 .. d-1 at slot (day mod 30)
+  double s_prec = 0.0, s_dtr = 0.0;
+  for (int k = d_lo - 89; k < d_lo; ++k) s_prec += hist(f.prec, f.st_prec, ld, cell, k);
+  int slot = (d_lo + 1) % kDtrWin;      // slot of day d_lo - 29
+  for (int k = d_lo - 29; k < d_lo; ++k) {
+    const double v = hist(f.t_max, f.st_t_max, ld, cell, k) - hist(f.t_min, f.st_t_min, ld, cell, k);
+    s_dtr += v;
+    ring[slot][tid] = v;
+    slot = slot + 1 == kDtrWin ? 0 : slot + 1;
+  }
+  // slot now names day d_lo: (d_lo + 1 + 29) mod 30
+
+  double acc[kEvalsPerRound];
+#pragma unroll
+  for (int k = 0; k < kEvalsPerRound; ++k) acc[k] = 0.0;
+  const size_t plane = (size_t)D * (size_t)ld;
+  double *const o_tskc = out.var[MSB_D_TSKC];
+  double *const o_cand = out.cand;
+  const bool deardorff = p.lw_cloud == MSB_CLOUD_DEARDORFF;
+
+  for (int d = d_lo; d < d_hi; ++d) {
+    const size_t o = (size_t)d * ld + cell;
+    DayInv v;
+    const double t_min = f.t_min[o], t_max = f.t_max[o], prec = f.prec[o];
+    // the value leaving the 90-day window (d is uniform across the block: no divergence)
+    const double prec_out = d >= 89 ? f.prec[o - (size_t)89 * ld]
+                                    : f.st_prec[(size_t)(kState + d - 89) * ld + cell];
+    const double dtr = t_max - t_min;
+    if (dtr < 0.0) out.status[0] = 1;                   // ValueError, metsim.py:612-614
+    s_prec += prec;
+    s_dtr += dtr;
+    const double seasonal = kDaysPerYear * (s_prec * (1.0 / 90.0));
+    const double sm_dtr = s_dtr * (1.0 / 30.0);
+    s_prec -= prec_out;
+    {   // day d-29 leaves the 30-day window; its slot is the one after day d's
+      const int nxt = slot + 1 == kDtrWin ? 0 : slot + 1;
+      ring[slot][tid] = dtr;
+      s_dtr -= ring[nxt][tid];
+      slot = nxt;
+    }
+    const double sp80 = seasonal < 80.0 ? 80.0 : seasonal;   // mtclim.py:187-188
+    const int y = f.doy[d] - 1;
+    const double daylength = cc.dayl[y];
+    const double potrad = cc.potrad[y];
+    {   // tt_max0(p): Horner in (p - p0), coefficients per (latitude, yday)
+      const double *c = cc.tt + (size_t)min(y, 364) * kTT;
+      double s = c[kTT - 1];
+#pragma unroll
+      for (int m = kTT - 2; m >= 0; --m) s = fma(s, cc.px, c[m]);
+      v.tt_max = s;
+    }
+    const double t_mean = (t_min + t_max) / 2;                          // mtclim.py:103-104
+    const double t_day = ((t_max - t_mean) * p.tday_coef) + t_mean;
+    const double bb = kB0 + kB1 * exp_acc(-kB2 * sm_dtr, etab);        // mtclim.py:129-133
+    double tf = 1.0 - 0.9 * exp_acc(-bb * (dtr * sqrt_nr(fmax(dtr, 1e-300))), etab);  // dtr**1.5
+    if (prec > p.sw_prec_thresh) tf *= p.rain_scalar;
+    // day-invariant part of calc_pet (physics.py:62-92)
+    const double lhvap = 2.5023e6 - 2430.54 * t_day;
+    const double inv_lhvap = rcp_nr(lhvap);
+    const double gamma = (kCp * cc.pa) * (inv_lhvap * (1.0 / kEps));
+    const double t1 = t_day + 0.2, t2 = t_day - 0.2;
+    const double sl = div_nr(svp_pa(t1, etab) - svp_pa(t2, etab), t1 - t2);
+    const double c1 = 1.26 * div_nr(sl, sl + gamma);
+    v.tk = t_min + kKelvin;
+    v.base = -0.127 + 1.121 * 1.003 + 0.0006 * dtr;
+    v.g = potrad * tf;
+    v.b = (((c1 * 0.72) * daylength) * inv_lhvap) * rcp_nr(sp80);
+    o_tskc[o] = deardorff ? 1. - tf : sqrt((1. - tf) / 0.65);           // mtclim.py:238-256
+
+    double tdew = t_min;                                                // mtclim.py:54
+#pragma unroll
+    for (int k = 0; k <= kEvalsPerRound; ++k) {
+      // evaluation k+1 of the loop body (mtclim.py:65-71) opens with vp and sw of tdew_k -- the
+      // daily outputs of a cell that stops after k evaluations (mtclim.py:73-79)
+      const double vp = svp_pa(tdew, etab);
+      const double t_raw = fma(kABase, vp, v.tt_max);
+      const double t_tmax = t_raw > 0.0001 ? t_raw : 0.0001;
+      const double sw = v.g * t_tmax;
+      if (k >= MSB_DAILY_CAND_K0) {
+        const int j = k - MSB_DAILY_CAND_K0;
+        __stcs(o_cand + (size_t)(2 * j) * plane + o, vp);
+        __stcs(o_cand + (size_t)(2 * j + 1) * plane + o, sw);
+      }
+      if (k < kEvalsPerRound) {
+        const double r = sw * v.b;
+        const double poly = r * fma(r, fma(r, -32.766, 12.312), -1.444);
+        const double nxt = fma(v.tk, fma(1.121, poly, v.base), -kKelvin);
+        const double df = nxt - tdew;
+        acc[k] = fma(df, df, acc[k]);
+        tdew = nxt;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kEvalsPerRound; ++k)
+    out.partial[((size_t)chunk * kEvalsPerRound + k) * f.n_cells + cell] = acc[k];
+}
+
+// the stop rule for every cell after the single pass: n* inside the candidate window picks the
+// plane, anything else (n* <= 3, or more than 6 evaluations needed) goes onto the replay list
+__global__ void daily_fused_reduce_kernel(msb_params p, int n_cells, int n_days, int n_chunks,
+                                          const double *__restrict__ partial, int32_t *n_iter,
+                                          int32_t *status, int32_t *sel, int32_t *list) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= n_cells) return;
+  int n = 0;
+  for (int k = 0; k < kEvalsPerRound; ++k) {
+    double s = 0.0;
+    for (int c = 0; c < n_chunks; ++c) s += partial[((size_t)c * kEvalsPerRound + k) * n_cells + cell];
+    const double rms = sqrt(s / (double)n_days);
+    if (!(rms > p.tdew_tol)) { n = k + 1; break; }
+  }
+  n_iter[cell] = n;
+  const int j = n - MSB_DAILY_CAND_K0;
+  if (j >= 0 && j < MSB_DAILY_CAND) {
+    sel[cell] = j;
+  } else {
+    sel[cell] = 0;
+    list[1 + atomicAdd(&list[0], 1)] = cell;
+    if (n == 0) atomicAdd(&status[3], 1);   // still iterating: the next round has work to do
+  }
+}
+
 }  // namespace msb
 
 using namespace msb;
 
-extern "C" size_t msb_daily_scratch_bytes(int n_cells, int n_days) {
+extern "C" size_t msb_daily_scratch_bytes_chunk(int n_cells, int n_days, int daily_chunk_len) {
   if (n_cells <= 0 || n_days <= 0) return 0;
-  DailyLaunch l = daily_launch(n_cells, n_days);
+  DailyLaunch l = daily_launch(n_cells, n_days, daily_chunk_len);
   return (size_t)l.n_chunks * kEvalsPerRound * (size_t)n_cells * sizeof(double);
+}
+extern "C" size_t msb_daily_scratch_bytes(int n_cells, int n_days) {
+  return msb_daily_scratch_bytes_chunk(n_cells, n_days, 0);
+}
+
+extern "C" int msb_daily_single_pass(const msb_params *p, const msb_forcing *f, const msb_daily *out) {
+  if (!p || !f || !out) return 0;
+  if (!out->cand || !out->cand_sel || !out->cand_list || out->tune.daily_two_pass) return 0;
+  if (p->method != MSB_METHOD_MTCLIM || f->given_seasonal_prec || f->given_daylength) return 0;
+  if (!out->var[MSB_D_TSKC]) return 0;
+  for (int k = 0; k < MSB_N_DAILYVARS; ++k)   // the single pass writes tskc and the candidate planes only
+    if (k != MSB_D_TSKC && out->var[k]) return 0;
+  return 1;
 }
 
 static int check_forcing(const msb_forcing *f, const char *who) {
@@ -318,7 +503,7 @@ extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
   }
   if (!(p->lapse_rate != 0.0)) { set_error("msb_mtclim_daily: lapse_rate must be non-zero"); return MSB_E_ARG; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DailyLaunch l = daily_launch(f->n_cells, f->n_days);
+  DailyLaunch l = daily_launch(f->n_cells, f->n_days, out->tune.daily_chunk_len);
   dim3 grid((f->n_cells + kDailyThreads - 1) / kDailyThreads, l.n_chunks);
   if (p->method == MSB_METHOD_PASSTHROUGH) {
     if (!f->given_shortwave) {
@@ -326,7 +511,7 @@ extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
       return MSB_E_ARG;
     }
     MSB_CUDA(cudaMemsetAsync(out->status, 0, 4 * sizeof(int32_t), st));
-    daily_kernel<3><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0, 0);
+    daily_kernel<3><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0, 0, nullptr);
     MSB_CUDA(cudaGetLastError());
     return MSB_OK;
   } else if (p->method != MSB_METHOD_MTCLIM) {
@@ -337,16 +522,41 @@ extern "C" int msb_mtclim_daily(const msb_params *p, const msb_forcing *f,
   int rounds = (max_iter + kEvalsPerRound - 1) / kEvalsPerRound;
   if (rounds > 8) rounds = 8;
   MSB_CUDA(cudaMemsetAsync(out->status, 0, 4 * sizeof(int32_t), st));
+  const int rgrid = (f->n_cells + 255) / 256;
+  if (msb_daily_single_pass(p, f, out)) {
+    // six evaluations once; candidate planes + stop-rule partials; plane index per cell
+    MSB_CUDA(cudaMemsetAsync(out->cand_list, 0, sizeof(int32_t), st));
+    daily_fused_kernel<<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len);
+    daily_fused_reduce_kernel<<<rgrid, 256, 0, st>>>(*p, f->n_cells, f->n_days, l.n_chunks, out->partial,
+                                                     out->n_iter, out->status, out->cand_sel,
+                                                     out->cand_list);
+    // the cells outside the candidate window (normally none or a few): further rounds for those
+    // that need more than six evaluations, then the replay into candidate plane 0
+    for (int r = 1; r < rounds; ++r) {
+      int k_off = r * kEvalsPerRound;
+      daily_kernel<1><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, k_off, 0, out->cand_list);
+      MSB_CUDA(cudaMemsetAsync(out->status + 3, 0, sizeof(int32_t), st));
+      daily_reduce_kernel<<<rgrid, 256, 0, st>>>(*p, f->n_cells, f->n_days, l.n_chunks, k_off,
+                                                 out->partial, out->n_iter, out->status, out->cand_list);
+    }
+    msb_daily replay = *out;
+    for (int k = 0; k < MSB_N_DAILYVARS; ++k) replay.var[k] = nullptr;   // tskc is already final
+    replay.var[MSB_D_VAPOR_PRESSURE] = out->cand;
+    replay.var[MSB_D_SHORTWAVE] = out->cand + (size_t)f->n_days * (size_t)f->ld;
+    daily_kernel<2><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, replay, l.chunk_len, 0,
+                                                    rounds * kEvalsPerRound, out->cand_list);
+    MSB_CUDA(cudaGetLastError());
+    return MSB_OK;
+  }
   for (int r = 0; r < rounds; ++r) {
     int k_off = r * kEvalsPerRound;
-    daily_kernel<1><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, k_off, 0);
+    daily_kernel<1><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, k_off, 0, nullptr);
     MSB_CUDA(cudaMemsetAsync(out->status + 3, 0, sizeof(int32_t), st));   // unconverged-cell count
-    daily_reduce_kernel<<<(f->n_cells + 255) / 256, 256, 0, st>>>(*p, f->n_cells, f->n_days,
-                                                                  l.n_chunks, k_off, out->partial,
-                                                                  out->n_iter, out->status);
+    daily_reduce_kernel<<<rgrid, 256, 0, st>>>(*p, f->n_cells, f->n_days, l.n_chunks, k_off, out->partial,
+                                               out->n_iter, out->status, nullptr);
   }
   daily_kernel<2><<<grid, kDailyThreads, 0, st>>>(*p, *f, *t, *out, l.chunk_len, 0,
-                                                  rounds * kEvalsPerRound);
+                                                  rounds * kEvalsPerRound, nullptr);
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }

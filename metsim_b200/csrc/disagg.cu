@@ -41,12 +41,19 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   }
   const double *vp = daily->var[MSB_D_VAPOR_PRESSURE], *sw = daily->var[MSB_D_SHORTWAVE],
                *tk = daily->var[MSB_D_TSKC];
+  const bool single = msb_daily_single_pass(p, f, daily) != 0;   // candidate planes instead (daily.cu)
+  if (single) {
+    vp = daily->cand;
+    sw = daily->cand + (size_t)f->n_days * (size_t)f->ld;
+  }
   if (!vp || !sw || !tk || !daily->status) {
     set_error("msb_disaggregate: daily vapor_pressure / shortwave / tskc / status are required");
     return MSB_E_ARG;
   }
   DisaggArgs a;
   a.p = *p; a.f = *f; a.t = *t; a.vp_d = vp; a.sw_d = sw; a.tskc_d = tk; a.status = daily->status;
+  a.cand_sel = single ? daily->cand_sel : nullptr;
+  a.cand_stride = single ? 2 * (size_t)f->n_days * (size_t)f->ld : 0;
   a.out = *out;
   a.tpd = kMinPerDay / ts;
   const int n_days = out->day1 - out->day0;
@@ -88,10 +95,10 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   // Every variable set, with or without unit conversion, with any longwave option, takes the
   // specialised kernels on the interior days; `full` is the default set
   // (examples/example_nc.conf) at float32 without conversion, which has unconditional-store
-  // instantiations and, for the edge days, the two compile-time halves of disagg_kernel.  MSB_DISAGG_PATH=event forces the
-  // event-driven kernel for every day (the parity tests use it to keep both paths covered).
-  const char *force = getenv("MSB_DISAGG_PATH");
-  const bool example = !(force && force[0] == 'e');
+  // instantiations and, for the edge days, the two compile-time halves of disagg_kernel.
+  // msb_tuning.disagg_path = 1 forces the event-driven kernel for every day (the parity tests use it
+  // to keep both paths covered).
+  const bool example = out->tune.disagg_path != 1;
   const bool f4 = out->dtype == 4;
   const bool full = example && a.var_mask == kExampleMask && f4 && !units && fast_lw && !a.lw_raw;
   const unsigned knot_bits = kThermoBits | (1u << MSB_V_WIND) | (1u << MSB_V_TSKC);   // thermo_knot_kernel's outputs

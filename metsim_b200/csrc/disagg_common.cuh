@@ -22,7 +22,6 @@
 //   disagg_event.cu     day records + the event-driven kernel (any variable set, any day)
 //   disagg_interior.cu  the two specialised kernels of the interior days [2, D-2)
 #pragma once
-#include <cstdlib>
 
 #include "msb_common.cuh"
 
@@ -38,6 +37,8 @@ struct DisaggArgs {
   msb_forcing f;
   msb_solar_tables t;
   const double *vp_d, *sw_d, *tskc_d;  // daily [D][ld] from the MTCLIM pass
+  const int32_t *cand_sel;             // single-pass daily form: vp_d / sw_d are candidate plane 0 and
+  size_t cand_stride;                  //   a cell reads plane cand_sel[cell], cand_stride elements apart
   int32_t *status;
   msb_subdaily out;
   int tpd, tile_days;
@@ -57,6 +58,11 @@ struct DisaggArgs {
   struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)
   int e0, n_rec;       // e runs over [-1, D]: -1 / D are the padded PCHIP ends
 };
+
+// the cell's daily vapour pressure / shortwave column base (msb_daily.cand, daily.cu)
+__device__ __forceinline__ const double *daily_plane(const DisaggArgs &a, const double *plane0, int cell) {
+  return a.cand_sel ? plane0 + (size_t)a.cand_sel[cell] * a.cand_stride : plane0;
+}
 
 // fields of a day record
 enum { kR_XMIN = 0, kR_DMIN,            // PCHIP knot at t_Tmin: time, derivative (its value is the
@@ -402,14 +408,6 @@ __device__ __forceinline__ double longwave(const msb_params &p, double temp_c, d
 }
 
 // ---- launch plumbing (host) --------------------------------------------------------------------
-// tuning knob read once from the environment (experiments only; the defaults are the tuned values)
-inline int env_int(const char *name, int dflt, int lo, int hi) {
-  const char *v = getenv(name);
-  if (!v || !*v) return dflt;
-  const int x = atoi(v);
-  return x < lo ? lo : (x > hi ? hi : x);
-}
-
 // disagg_event.cu
 enum EventKernel { kEvThermoF4, kEvStreamsF4, kEvAnyF4, kEvAnyF8 };
 // day records of the padded days [e_a, e_b) clipped to [a.e0, e1) (only disagg_kernel reads them)

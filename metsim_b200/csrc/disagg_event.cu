@@ -163,7 +163,7 @@ disagg_prepare_kernel(const __grid_constant__ DisaggArgs a) {
   out[kR_HSQ * plane] = pd.hsq;
   out[kR_PF * plane] = pd.f;
   const double dl = a.sw_full_day ? kSecPerDay : dayl[f.doy[e] - 1];
-  out[kR_RAD * plane] = (a.sw_d[o] * dl) * inv_sw_den;
+  out[kR_RAD * plane] = (daily_plane(a, a.sw_d, cell)[o] * dl) * inv_sw_den;
   }
 }
 
@@ -251,11 +251,12 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     if ((unsigned)e < (unsigned)D) return ((j & 1) ? f.t_max : f.t_min)[(size_t)e * ld + cell];
     return knot_y(c, j);
   };
-  auto rvy = [&](int d) { return a.vp_d[(size_t)d * ld + cell] / 1000.0; };   // kPa, :480
+  const double *const vp_d = daily_plane(a, a.vp_d, cell), *const sw_d = daily_plane(a, a.sw_d, cell);
+  auto rvy = [&](int d) { return vp_d[(size_t)d * ld + cell] / 1000.0; };   // kPa, :480
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     if (has_rec(d)) return rec(kR_RAD, d);
     const double dl = a.sw_full_day ? kSecPerDay : dayl[doy_at(c, d) - 1];
-    return (a.sw_d[(size_t)d * ld + cell] * dl) * inv_sw_den;                        // wrapped day
+    return (sw_d[(size_t)d * ld + cell] * dl) * inv_sw_den;                        // wrapped day
   };
   auto prec_of = [&](int d, PrecDay &o) {
     if (has_rec(d)) {
@@ -327,9 +328,9 @@ disagg_kernel(const __grid_constant__ DisaggArgs a) {
     if (all_nan) {
       yvl = nan(""); e_vp = kNever;
     } else {
-      if (i_hi - 1 > i_tail) vp_tail = vp_endpoint(c, a.vp_d, i_tail, false, etab, a.status);
+      if (i_hi - 1 > i_tail) vp_tail = vp_endpoint(c, vp_d, i_tail, false, etab, a.status);
       if (i_lo < i_head) {             // head: constant until the first in-range step
-        yvl = vp_endpoint(c, a.vp_d, i_head, true, etab, a.status);
+        yvl = vp_endpoint(c, vp_d, i_head, true, etab, a.status);
         e_vp = i_head;
       } else if (i_lo > i_tail) {      // tail
         yvl = vp_tail; e_vp = kNever;
@@ -665,7 +666,8 @@ lw_rescale_kernel(const __grid_constant__ DisaggArgs a) {
 }
 
 int launch_day_records(DisaggArgs &a, int e_a, int e_b, int e1, int cell_blocks, cudaStream_t st) {
-  static const int prep_days = env_int("MSB_PREP_DAYS", kPrepDays, 1, 16);
+  const int prep_days = a.out.tune.prep_days > 0 ? (a.out.tune.prep_days < 16 ? a.out.tune.prep_days : 16)
+                                                 : kPrepDays;
   a.prep_days = prep_days;
   a.prep_r0 = (e_a > a.e0 ? e_a : a.e0) - a.e0;
   a.prep_r1 = (e_b < e1 ? e_b : e1) - a.e0;

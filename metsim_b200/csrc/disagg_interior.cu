@@ -137,6 +137,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   c.t_end = f.t_end;
   const KnotK K = load_knot();
   const unsigned lanes = __activemask();
+  const double *const vp_d = daily_plane(a, a.vp_d, cell);
   // any subset of the default variable set: a variable that was not requested is computed (the
   // others depend on it) but not stored
   const unsigned vm = MASKED ? a.var_mask : kExampleMask;
@@ -198,7 +199,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     const double d1 = pchip_mid(h01, h12, m01, m12), d2 = pchip_mid(h12, h23, m12, m23);
     slot[kT_KX0][tid] = x2; slot[kT_KY0][tid] = y2; slot[kT_KD0][tid] = d2;
     slot[kT_KX1][tid] = x3; slot[kT_KY1][tid] = y3; slot[kT_KM01][tid] = m23;
-    const double v0 = a.vp_d[o0] / 1000.0, v1 = a.vp_d[o1] / 1000.0;
+    const double v0 = vp_d[o0] / 1000.0, v1 = vp_d[o1] / 1000.0;
     const int ia = first_step_ge_fast(x0, ts, inv_ts), ib = first_step_ge_fast(x2, ts, inv_ts);
     int isw = first_step_ge_fast(x1, ts, inv_ts);
     // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
@@ -372,10 +373,11 @@ streams_day_kernel(const __grid_constant__ DisaggArgs a) {
   // what disagg_prepare_kernel would put into the record of source day d: done here, once per
   // (cell, day) with the warp converged, so the interior days need no record traffic at all
   const double *const dayl = a.t.daylength + (size_t)f.lat_row[cell] * kRows;
+  const double *const sw_d = daily_plane(a, a.sw_d, cell);
   auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
     MSB_CHECK_WIN(d);
     const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
-    return (a.sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
+    return (sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
   };
   auto lookback = [&](int i, bool &none) {   // what pandas ffill repeats at step i (cold)
     Cell c;
@@ -624,9 +626,10 @@ int exp_tables_ready(cudaStream_t st) {
   return MSB_OK;
 }
 
+constexpr int kKnotTile = 16, kDayTile = 16;   // knot-days / output days per thread on full-size grids
+
 int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
   const int D = a.f.n_days;
-  static const int knot_tile = env_int("MSB_KNOT_TILE", 16, 1, 64);
   const int rc_tab = exp_tables_ready(st);
   if (rc_tab) return rc_tab;
   // knot-days e whose steps can fall into [a0, b0): t_Tmin(e) lies within (-1080, 2160) minutes
@@ -634,10 +637,12 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   a.k.i_lo = a0 * a.tpd; a.k.i_hi = b0 * a.tpd;
   a.k.e0 = a0 - 2 > 0 ? a0 - 2 : 0;
   a.k.e1 = (b0 < D - 2 ? b0 : D - 2) + 1;
-  // small shards: shorter chunks so that the grid still fills the 148 SMs several waves deep
-  a.k.tile = knot_tile;
+  // small shards: shorter chunks so that the grid still fills the 148 SMs several waves deep;
+  // msb_tuning.knot_tile pins the value (the parity tests run the benchmarked 16 on small shards)
+  a.k.tile = kKnotTile;
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
+  if (a.out.tune.knot_tile > 0) a.k.tile = a.out.tune.knot_tile < kDayWin - 8 ? a.out.tune.knot_tile : kDayWin - 8;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
   const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw || a.lw_raw;
   if (a.out.dtype == 4) {
@@ -652,14 +657,14 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
 }
 
 int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
-  static const int day_tile = env_int("MSB_DAY_TILE", 16, 1, 32);
-  static const int day_pf = env_int("MSB_DAY_PF", 4, 0, 16);
   a.k.i_lo = a.k.i_hi = 0;
   a.k.e0 = a0; a.k.e1 = b0;            // output days, day_tile per thread
-  a.k.tile = day_tile;
+  a.k.tile = kDayTile;
   while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 6 * 6)
     a.k.tile >>= 1;
-  a.k.pf = day_pf;
+  if (a.out.tune.day_tile > 0) a.k.tile = a.out.tune.day_tile < kDayWin - 8 ? a.out.tune.day_tile : kDayWin - 8;
+  a.k.pf = a.out.tune.day_prefetch > 0 ? (a.out.tune.day_prefetch < 16 ? a.out.tune.day_prefetch : 16)
+                                       : (a.out.tune.day_prefetch < 0 ? 0 : 4);
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
   const bool masked = a.units || (a.var_mask & ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE))) !=
                                      ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE));

@@ -16,6 +16,7 @@
 //    coefficients of tt_max0 in the pressure ratio p (so the per-cell part is a Horner chain).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <thread>
 #include <vector>
 
@@ -70,6 +71,27 @@ static void prelude_rows(const double *lat_deg, int r0, int r1, PreludeView v) {
   }
 }
 
+// Class boundaries of the OPTAM lookup for solar_moments_kernel: for j < 20 the largest double c
+// with int(acos(c) / RAD_PER_DEG) >= 70 + j, by bisection over the (ordered) bit patterns of the
+// positive doubles with this libm's acos.  acos is decreasing, so the predicate is monotone.
+static void optam_thresholds(double *c32) {
+  for (int j = 0; j < 32; ++j) c32[j] = -1.0;
+  for (int j = 0; j < 20; ++j) {
+    auto pred = [j](double c) { return (int)(std::acos(c) / kRadPerDeg) >= 70 + j; };
+    double lo_d = 0.0, hi_d = 0.5;                 // pred(0) holds (90 deg), pred(0.5) fails (60 deg)
+    uint64_t lo, hi;
+    std::memcpy(&lo, &lo_d, 8);
+    std::memcpy(&hi, &hi_d, 8);
+    while (hi - lo > 1) {
+      const uint64_t mid = lo + (hi - lo) / 2;
+      double m;
+      std::memcpy(&m, &mid, 8);
+      if (pred(m)) lo = mid; else hi = mid;
+    }
+    std::memcpy(&c32[j], &lo, 8);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 256;
 constexpr int kChunk = 12;                       // 240 active scan threads x 12 = 2880
@@ -78,10 +100,18 @@ __constant__ double c_optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.3
                                    6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
 
 __device__ __forceinline__ int tiny_index(double h) {
-  // physics.py:264-266, evaluated without contraction
-  double v = __ddiv_rn(__dadd_rn(43200.0, __dmul_rn(h, kSecPerRad)), kSwRadDt);
-  v = fmin(fmax(v, 0.0), (double)(kTiny - 1));
-  return (int)v;
+  // physics.py:264-266: int(min(max((43200 + h*SEC_PER_RAD)/30, 0), 2879)) with x = 43200 + h*SEC_PER_RAD
+  // evaluated without contraction.  The IEEE quotient fl(x/30) never rounds up across an integer m
+  // (x < 30m implies x <= 30m - ulp(30m-) and ulp(30m-) >= 16 ulp(m-), so x/30 <= m - 0.53 ulp(m-)),
+  // hence int(fl(x/30)) == floor(x/30) exactly, which needs no division: n = rint(x/30) up to one
+  // unit, r = x - 30n in one exactly-signed fma, and r < 0 steps back.
+  const double x = __dadd_rn(43200.0, __dmul_rn(h, kSecPerRad));
+  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
+  double nd = fma(x, 1.0 / 30.0, kMagic);
+  int n = __double2loint(nd);
+  nd -= kMagic;
+  if (fma(-30.0, nd, x) < 0.0) --n;
+  return min(max(n, 0), kTiny - 1);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -252,13 +282,21 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
 // in the pressure ratio (-> tt_coef).  Lanes walk contiguous chunks of steps; cos(h) is re-seeded
 // from a library sincos every 16 steps and rotated by dh in between.
 constexpr int kMomWarps = 4;
+// zenith-angle class boundaries of the OPTAM lookup (physics.py:255-258) as cosines: entry j is the
+// largest double c with int(acos(c) / RAD_PER_DEG) >= 70 + j under the HOST's libm -- the one the
+// reference runs on -- found by bisection in optam_thresholds(); padded to 32 with -1 (never met)
+struct OptamThr { double c[32]; };
 __global__ void __launch_bounds__(kMomWarps * 32)
 solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
                      const double *__restrict__ g_sinegeom, const double *__restrict__ g_hss,
                      const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
-                     msb_solar_tables tb) {
+                     msb_solar_tables tb, const __grid_constant__ OptamThr thr) {
   __shared__ double etab[kExpTab];
+  __shared__ double s_thr[32];
+  __shared__ double s_optam[21];
   exp_table_init(etab);
+  if (threadIdx.x < 32) s_thr[threadIdx.x] = thr.c[threadIdx.x];
+  if (threadIdx.x < 21) s_optam[threadIdx.x] = c_optam[threadIdx.x];
   __syncthreads();
   const int w = blockIdx.x * kMomWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -286,25 +324,31 @@ solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
       const double dfa = beam * cza;                       // physics.py:252
       double am = rcp_nr(cza + 0.0000001);
       if (am > 2.9) {
-        int ami = (int)(acos(cza) / kRadPerDeg) - 69;
-        ami = min(max(ami, 0), 20);
-        am = c_optam[ami];
+        // ami = min(max(int(acos(cza)/RAD_PER_DEG) - 69, 0), 20) = number of class boundaries at or
+        // above cza (they descend): branch-free binary search, no acos
+        int ami = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1)
+          if (cza <= s_thr[ami + st - 1]) ami += st;
+        am = s_optam[ami];
       }
       m_loc[kTT] += dfa;
       // trans**am = exp(am*p*ln(TBASE)); expand in (p - p0): sum_m dfa*e^{a p0} a^m/m! (p-p0)^m
       // four interleaved chains term[m+4] = term[m] * a^4 / ((m+1)(m+2)(m+3)(m+4)): a single chain
       // of kTT dependent multiplies would expose kTT x 8 cycles of DMUL latency per step
+      // the power sums sum dfa e^{a p0} a^m are accumulated raw (one multiply and one add per
+      // term); the 1/m! go on once per row after the reduction
       const double a = am * kLnTBase;
       const double a2 = a * a, a4 = a2 * a2;
       double t[4];
       t[0] = exp_acc(a * MSB_TT_P0, etab) * dfa;
       t[1] = t[0] * a;
-      t[2] = t[0] * (a2 * 0.5);
-      t[3] = t[1] * (a2 * (1.0 / 6.0));
+      t[2] = t[0] * a2;
+      t[3] = t[1] * a2;
 #pragma unroll
       for (int m = 0; m < kTT; ++m) {
         m_loc[m] += t[m & 3];
-        t[m & 3] *= a4 * (1.0 / ((double)(m + 1) * (double)(m + 2) * (double)(m + 3) * (double)(m + 4)));
+        t[m & 3] *= a4;
       }
     }
     const double cn = fma(ch, cd, -(sh * sd)), sn = fma(sh, cd, ch * sd);   // rotate by dh
@@ -318,9 +362,12 @@ solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
   const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
   const bool has_day = daylength != 0.0;
   // tt_max0(p) = sum_trans/sum_flat_potrad (physics.py:275); 0 when there is no daylight
-  double mine = 0.0;
+  double mine = 0.0, inv_fact = 1.0;
 #pragma unroll
-  for (int m = 0; m < kTT; ++m) mine = (lane == m) ? m_loc[m] : mine;
+  for (int m = 0; m < kTT; ++m) {
+    if (m > 0) inv_fact *= 1.0 / (double)m;      // compile-time 1/m!
+    mine = (lane == m) ? m_loc[m] * inv_fact : mine;
+  }
   if (lane < kTT) tb.tt_coef[(size_t)w * kTT + lane] = (has_day && total > 0.0) ? mine / total : 0.0;
   if (lane == 0) {
     const double potrad = has_day ? total / daylength : 0.0;            // physics.py:276-280
@@ -385,8 +432,10 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
   unsigned grid = 365u * (unsigned)n_lat;
   solar_rows_kernel<<<grid, kK1Threads, 0, st>>>(n_lat, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0,
                                                  dv.nstep, *tb);
+  OptamThr thr;
+  optam_thresholds(thr.c);
   solar_moments_kernel<<<(grid + kMomWarps - 1) / kMomWarps, kMomWarps * 32, 0, st>>>(
-      (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, *tb);
+      (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, *tb, thr);
   MSB_CUDA(cudaGetLastError());
   MSB_CUDA(cudaMemsetAsync(tb->q + (size_t)n_lat * 365 * kQLd, 0, MSB_Q_PAD * sizeof(double), st));
   return MSB_OK;

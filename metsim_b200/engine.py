@@ -66,13 +66,19 @@ class Engine:
     be numpy arrays (copied through pinned memory) or CUDA tensors (used in place).
     """
 
-    def __init__(self, params: dict | None = None, device: str | int | torch.device = "cuda:0"):
+    def __init__(self, params: dict | None = None, device: str | int | torch.device = "cuda:0",
+                 tuning: dict | None = None):
+        """``tuning``: msb_tuning overrides (``_lib.TUNING_KEYS``; tests pin the benchmarked launch
+        geometry with it); unset keys fall back to the MSB_* environment variables, then to the
+        library's own choice."""
         if not torch.cuda.is_available():
             raise RuntimeError("metsim_b200 needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.lib()
         self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         self.user_params = dict(params or {})
         self.params = _lib.make_params(self.user_params)
+        self.tuning = _lib.make_tuning(tuning)
+        self.single_pass_budget = 24 << 30    # bytes of candidate planes the single-pass daily form may take
         self.stream = torch.cuda.Stream(device=self.device)
         self._t = {}
         self._tables = None
@@ -190,29 +196,69 @@ class Engine:
         return tb
 
     # ------------------------------------------------------------------ daily MTCLIM
-    def daily(self, want=DAILY_VARS):
+    def daily(self, want=DAILY_VARS, single_pass: bool | None = None):
+        """Daily MTCLIM pass.  ``want`` names the daily columns to return.  When nothing beyond
+        ``tskc`` is wanted (what the disaggregation alone needs) the single-pass form of
+        ``csrc/daily.cu`` runs: candidate planes of vapour pressure / shortwave after 4, 5, 6
+        evaluations instead of a replay; ``single_pass=False`` forces the two-pass form."""
         if self._tables is None:
             self.build_solar()
         st = self._tables[0]
         n, d = self.n_cells, self.n_days
-        need = {"tskc", "vapor_pressure", "shortwave"} | set(want)
+        want = set(want)
+        cand_bytes = 2 * _lib.DAILY_CAND * d * n * 8
+        single = (want <= {"tskc"} and self.params.method == 0 and not self.tuning.daily_two_pass
+                  and self.params.time_step < 1440 and cand_bytes <= self.single_pass_budget)
+        if single_pass is not None:
+            if single_pass and not single:
+                raise ValueError("the single-pass daily form needs method mtclim, a sub-daily time step, "
+                                 "no daily column beyond tskc and candidate planes within the budget")
+            single = bool(single_pass)
+        need = ({"tskc"} if single else {"tskc", "vapor_pressure", "shortwave"}) | want
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            out = {k: torch.empty((d, n), dtype=torch.float64, device=self.device)
-                   for k in DAILY_VARS if k in need}
-            n_iter = torch.zeros(n, dtype=torch.int32, device=self.device)
-            scratch = torch.empty(self.lib.msb_daily_scratch_bytes(n, d) // 8 + 1,
-                                  dtype=torch.float64, device=self.device)
-            status = torch.zeros(4, dtype=torch.int32, device=self.device)
+            if (single and self._daily is not None and self._daily[0].cand
+                    and self._daily[4] == (d, n)):
+                out = dict(self._daily[1])                  # reuse the planes of the previous call
+                n_iter, scratch, status = out.pop("n_iter"), self._daily[2], self._daily[3]
+                cand, sel, lst = self._daily[5]
+            else:
+                self._daily = None
+                out = {k: torch.empty((d, n), dtype=torch.float64, device=self.device)
+                       for k in DAILY_VARS if k in need}
+                n_iter = torch.zeros(n, dtype=torch.int32, device=self.device)
+                nbytes = self.lib.msb_daily_scratch_bytes_chunk(n, d, self.tuning.daily_chunk_len)
+                scratch = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=self.device)
+                status = torch.zeros(4, dtype=torch.int32, device=self.device)
+                cand = sel = lst = None
+                if single:
+                    cand = torch.empty((2 * _lib.DAILY_CAND, d, n), dtype=torch.float64, device=self.device)
+                    sel = torch.zeros(n, dtype=torch.int32, device=self.device)
+                    lst = torch.zeros(n + 1, dtype=torch.int32, device=self.device)
             dl = _lib.Daily()
             for i, k in enumerate(DAILY_VARS):
                 dl.var[i] = out[k].data_ptr() if k in out else None
             dl.n_iter, dl.partial, dl.status = (self._ptr(n_iter), self._ptr(scratch), self._ptr(status))
+            dl.cand, dl.cand_sel, dl.cand_list = self._ptr(cand), self._ptr(sel), self._ptr(lst)
+            dl.tune = self.tuning
             f = self._forcing()
+            assert bool(self.lib.msb_daily_single_pass(C.byref(self.params), C.byref(f), C.byref(dl))) == single
             _lib.check(self.lib.msb_mtclim_daily(C.byref(self.params), C.byref(f), C.byref(st),
                                                  C.byref(dl), C.c_void_p(self.stream.cuda_stream)))
         out["n_iter"] = n_iter
-        self._daily = (dl, out, scratch, status)
+        self._daily = (dl, out, scratch, status, (d, n), (cand, sel, lst))
         return out
+
+    def daily_for_disagg(self):
+        """The daily vapour pressure and shortwave the disaggregation reads, as ``[D][N]`` tensors
+        (gathered from the candidate planes when the single-pass form ran)."""
+        dl, out, _, _, _, (cand, sel, _) = self._daily
+        if cand is None:
+            return out["vapor_pressure"], out["shortwave"]
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            idx = (2 * sel.long())[None, None, :].expand(1, cand.shape[1], -1)
+            vp = torch.gather(cand, 0, idx)[0]
+            sw = torch.gather(cand, 0, idx + 1)[0]
+        return vp, sw
 
     def check(self):
         """Synchronise and raise what the reference would have raised (ValueError for t_max<t_min)."""
@@ -274,6 +320,7 @@ class Engine:
             if self._ws is None or self._ws.numel() < need:   # grow-only scratch for the day records
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             sd.workspace, sd.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+            sd.tune = self.tuning
             f = self._forcing()
             _lib.check(self.lib.msb_disaggregate(C.byref(self.params), C.byref(f),
                                                  C.byref(self._tables[0]), C.byref(self._daily[0]),
@@ -288,7 +335,8 @@ class Engine:
         (``shortwave * daylength / 86400``); the other daily columns are under ``res['daily']``."""
         self.build_solar()
         daily_mode = self.params.time_step >= 1440
-        daily = self.daily(want=tuple(daily_vars) + (("shortwave_daily",) if daily_mode else ()))
+        daily = self.daily(want=tuple(daily_vars) + (("shortwave_daily", "vapor_pressure", "shortwave")
+                                                     if daily_mode else ()))
         res = {}
         if daily_mode:
             res["shortwave"] = daily["shortwave_daily"]
@@ -300,12 +348,47 @@ class Engine:
         return res
 
 
+class HostContext:
+    """Caller-owned ``msb_host_ctx`` (include/metsim_b200.h): the device arena, pinned staging,
+    streams and events of the host-buffer path on one device.  Contexts are independent -- two
+    threads with a context each run concurrently; calls on one context are serialised by it."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.lib()
+        self.device = int(device)
+        h = C.c_void_p()
+        _lib.check(self.lib.msb_host_ctx_create(self.device, C.byref(h)))
+        self.handle = h
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.msb_host_ctx_device_bytes(self.handle)) if self.handle else 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.msb_host_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
              state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
              given_shortwave=None, given_vapor_pressure=None, given_tskc=None, given_longwave=None,
              out_vars=DEFAULT_OUT_VARS, out_dtype=np.float32, units: dict | None = None,
              daily_vars=(), device: int = 0, tile_days: int = 0, out: dict | None = None,
-             ring: bool = False, timings: dict | None = None, on_tile=None) -> dict:
+             ring: bool = False, timings: dict | None = None, on_tile=None,
+             ctx: HostContext | None = None, tuning: dict | None = None) -> dict:
     """Whole path with HOST (numpy) buffers through ``msb_run_host``: the call a reference-side
     binding makes in place of the cell loop of ``MetSim.run_slice`` (metsim/metsim.py:477-493).
     Host-to-device and device-to-host copies happen inside.
@@ -313,7 +396,10 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
     ``on_tile(tile, day0, day1, slot)`` is the consumer hook of a streaming writer: called once per
     output tile, in order, when the tile's rows are in host memory and while the next tile is
     already computing (``slot`` is the ring slot with ``ring=True``, else -1).  An exception
-    raised inside it aborts the run and is re-raised here."""
+    raised inside it aborts the run and is re-raised here.
+
+    ``ctx``: a :class:`HostContext` to run in (its device wins over ``device``; the arena is reused
+    from call to call); without one a context is created for this call and destroyed afterwards."""
     lib = _lib.lib()
     p = _lib.make_params(params)
     ts = p.time_step
@@ -329,8 +415,19 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
                 given_longwave=f64(given_longwave))
     arrs["doy"] = np.ascontiguousarray(doy, dtype=np.int32)
     arrs["month"] = np.ascontiguousarray(month, dtype=np.int32)
+    # the C ABI takes bare pointers: every shape is checked here, before any of them is taken
+    want_shape = {"lat": (n,), "lon": (n,), "elev": (n,), "doy": (d,), "month": (d,),
+                  "st_t_min": (90, n), "st_t_max": (90, n), "st_prec": (90, n),
+                  "t_pk12": (12, n), "dur12": (12, n), "t_end": (2, n)}
+    for k, a in arrs.items():
+        if a is not None and a.shape != want_shape.get(k, (d, n)):
+            raise ValueError(f"run_host: {k} has shape {a.shape}, expected {want_shape.get(k, (d, n))}")
+    for k in ("lat", "lon", "elev", "t_max", "prec", "st_t_min", "st_t_max", "st_prec"):
+        if arrs[k] is None:
+            raise ValueError(f"run_host: {k} is required")
     run = _lib.HostRun()
-    run.n_cells, run.n_days, run.device = n, d, device
+    run.n_cells, run.n_days, run.device = n, d, (ctx.device if ctx is not None else device)
+    run.tune = _lib.make_tuning(tuning)
     for k, a in arrs.items():
         setattr(run, k, None if a is None else a.ctypes.data_as(C.c_void_p))
     res = {}
@@ -344,8 +441,18 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
             run.out_host[i] = None
             continue
         if out is not None and v in out:
-            res[v] = out[v]
+            o = out[v]
+            rows = 2 * int(tile_days) * tpd if ring else d * tpd
+            if (not isinstance(o, np.ndarray) or o.dtype != odt or o.ndim != 2 or o.shape[1] != n
+                    or o.shape[0] < rows or not o.flags.c_contiguous or not o.flags.writeable):
+                raise ValueError(f"run_host: out[{v!r}] must be a writeable C-contiguous {odt} array of "
+                                 f"shape (>= {rows}, {n})")
+            if ring and int(tile_days) <= 0:
+                raise ValueError("run_host: ring=True needs an explicit tile_days")
+            res[v] = o
         else:
+            if ring:
+                raise ValueError(f"run_host: ring=True needs a preallocated out[{v!r}]")
             res[v] = np.empty((d * tpd, n), dtype=odt)
         run.out_host[i] = res[v].ctypes.data_as(C.c_void_p)
         run.scale[i], run.offset[i] = unit_scale_offset(v, (units or {}).get(v), ts)
@@ -369,7 +476,10 @@ def run_host(params: dict | None, *, lat, lon, elev, doy, month, t_min, t_max, p
                 return 1
         cb = _lib.ON_TILE(_cb)                  # keep the thunk alive for the duration of the call
         run.on_tile = C.cast(cb, C.c_void_p)
-    rc = lib.msb_run_host(C.byref(p), C.byref(run))
+    if ctx is not None:
+        rc = lib.msb_run_host_ctx(ctx.handle, C.byref(p), C.byref(run))
+    else:
+        rc = lib.msb_run_host(C.byref(p), C.byref(run))
     if failure:
         raise failure[0]
     _lib.check(rc)

@@ -14,7 +14,9 @@ import numpy as np
 # per-cell arrays ([N]) and cell-fastest 2-D arrays ([rows][N]) of the engine's input dict
 CELL_KEYS = ("lat", "lon", "elev")
 ROWS_BY_CELL_KEYS = ("t_min", "t_max", "prec", "wind", "state_t_min", "state_t_max", "state_prec",
-                     "t_pk12", "dur12", "t_end")
+                     "t_pk12", "dur12", "t_end",
+                     # forcing columns of the 'passthrough' method (methods/passthrough.py:28-46)
+                     "given_shortwave", "given_vapor_pressure", "given_tskc", "given_longwave")
 SHARED_KEYS = ("doy", "month")
 
 
@@ -47,7 +49,14 @@ def shard_inputs(inputs: dict, rank: int, world: int, align: int = 32) -> dict:
             out[k] = v[lo:hi]
         elif k in ROWS_BY_CELL_KEYS:
             out[k] = v[:, lo:hi]
+        elif k in SHARED_KEYS:
+            out[k] = v
         else:
+            # an unknown key must not reach a rank at full domain width by accident
+            shape = tuple(getattr(v, "shape", ()))
+            if len(shape) >= 1 and shape[-1] == n and n > 1:
+                raise KeyError(f"shard_inputs: do not know how to slice {k!r} of shape {shape}; "
+                               "add it to CELL_KEYS / ROWS_BY_CELL_KEYS")
             out[k] = v
     return out
 

@@ -27,11 +27,11 @@ def disagg_path(request, monkeypatch):
     return request.param
 
 
-def engine_run(inputs, params, out_dtype=None, units=None):
+def engine_run(inputs, params, out_dtype=None, units=None, tuning=None):
     import torch
     from metsim_b200.engine import Engine
     from metsim_b200._lib import DAILY_VARS, SUB_VARS
-    eng = Engine(params)
+    eng = Engine(params, tuning=tuning)
     eng.load(**{k: inputs.get(k) for k in util.INPUT_KEYS})
     res = eng.run(out_vars=SUB_VARS, out_dtype=out_dtype or torch.float64, units=units,
                   daily_vars=DAILY_VARS)
@@ -228,6 +228,8 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
     eng = Engine(params)
     eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
     res = eng.run(out_vars=EXAMPLE_VARS, out_dtype=torch.float32)
+    # (no daily column requested: this is the single-pass daily form, candidate planes and all)
+    np.testing.assert_array_equal(res["daily"]["n_iter"].cpu().numpy(), want["n_iter"])
     for split in (None, 7):          # whole record in one call, then 7-day calls
         if split is not None:
             parts = [eng.disaggregate(EXAMPLE_VARS, d0, min(days, d0 + split), torch.float32)
@@ -262,6 +264,130 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
     for v in EXAMPLE_VARS:       # and the float32 outputs are exactly the rounded float64 ones
         np.testing.assert_array_equal(res[v].cpu().numpy() if split is None else res[v].cpu().numpy(),
                                       res64[v].cpu().numpy().astype(np.float32), err_msg=v)
+
+
+# ---- the launch geometry bench.py times, and the record lengths of BASELINE configs[3] / [4] ------
+# bench.py's shards are large enough that the library keeps its full work per thread: 16 knot-days /
+# 16 output days per thread in the interior kernels and day chunks of 73 (CONUS year), 731 (CONUS
+# decade) and 645 days (30-year global shard) in the daily pass.  Small shards would shorten all of
+# these; msb_tuning pins them, so the oracle comparisons below run what the benchmark runs.
+BENCH_GEOMETRY = dict(knot_tile=16, day_tile=16, daily_chunk_len=73)
+
+
+def run_both_daily_forms(f, params, tuning, want, ctx, sub_vars, day_ranges=None, out_dtype=None):
+    """Single-pass daily form (candidate planes, what bench.py times) and the two-pass form, each
+    followed by the disaggregation of ``day_ranges`` (default: the whole record) in float64:
+    n_iter EQUAL to the oracle's, every value within 1e-9."""
+    import torch
+    from metsim_b200._lib import DAILY_VARS
+    from metsim_b200.engine import Engine
+    days = f["t_min"].shape[0]
+    tpd = 1440 // params["time_step"]
+    day_ranges = day_ranges or [(0, days)]
+    worst = {}
+    for form in ("single", "two-pass"):
+        eng = Engine(params, tuning=tuning)
+        eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+        eng.build_solar()
+        if form == "single":
+            daily = eng.daily(want=(), single_pass=True)
+            vp, sw = eng.daily_for_disagg()
+            util.assert_close(vp.cpu().numpy(), want["vp_daily"], "vp_daily", context=ctx + " single")
+            util.assert_close(sw.cpu().numpy(), want["sw_daily"], "sw_daily", context=ctx + " single")
+            util.assert_close(daily["tskc"].cpu().numpy(), want["tskc_daily"], "tskc_daily", context=ctx)
+        else:
+            daily = eng.daily(want=DAILY_VARS)
+            for oname, ename in util.DAILY.items():
+                if oname in want:
+                    util.assert_close(daily[ename].cpu().numpy(), want[oname], oname, context=ctx + " two-pass")
+        np.testing.assert_array_equal(daily["n_iter"].cpu().numpy(), want["n_iter"],
+                                      err_msg=f"{ctx} {form}: tdew evaluations")
+        for d0, d1 in day_ranges:
+            got = eng.disaggregate(sub_vars, d0, d1, out_dtype or torch.float64)
+            eng.check()
+            torch.cuda.synchronize()
+            for v in sub_vars:
+                e = util.assert_close(got[v].cpu().numpy(), want[v][d0 * tpd:d1 * tpd], v,
+                                      context=f"{ctx} {form} days [{d0},{d1})")
+                worst[v] = max(worst.get(v, 0.0), e)
+            del got
+    return worst
+
+
+@pytest.mark.parametrize("name,cells,days,over,tuning", [
+    ("conus_16th_hourly", 384, 365, {}, BENCH_GEOMETRY),                 # the headline configuration
+    ("global_half_deg", 320, 365, {}, BENCH_GEOMETRY),                   # n* from 3 to 7: the replay list
+    ("conus_16th_hourly", 200, 100, {"tdew_tol": 1e-3}, BENCH_GEOMETRY), # every cell below the candidate window
+    ("conus_16th_hourly", 200, 100, {"tdew_tol": 1e-10}, BENCH_GEOMETRY),  # every cell needs a second round
+    ("conus_16th_hourly", 160, 80, {}, dict(BENCH_GEOMETRY, disagg_path="event")),
+], ids=["conus-year", "global-year", "tol1e-3", "tol1e-10", "event-path"])
+def test_benchmarked_launch_geometry_against_oracle(name, cells, days, over, tuning):
+    """VERDICT r1 'weak' #1: the oracle-compared tests ran tile = 2 and chunks <= 15 days while
+    bench.py runs tile = 16 and 73-day chunks.  Here the benchmarked geometry itself is held to the
+    1e-9 / n_iter-equality bar, whole 365-day records, all ten variables, both daily forms."""
+    from metsim_b200 import synth
+    from metsim_b200._lib import SUB_VARS
+    from oracle import oracle_lib
+    f, params = synth.make_config(name, max_cells=cells, n_days=days)
+    params.update(over)
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    hist = np.bincount(want["n_iter"])
+    worst = run_both_daily_forms(f, params, tuning, want, f"{name} {over} {tuning}", SUB_VARS)
+    print("n_iter histogram", hist.tolist(), "worst", {k: f"{e:.1e}" for k, e in worst.items()})
+
+
+@pytest.mark.parametrize("name,cells,days,chunk,ranges", [
+    # BASELINE configs[3]: 10 years -> 3-hourly, mix; bench.py chunks the daily pass by 731 days
+    ("conus_16th_10yr_3h_mix", 96, 3652, 731, None),
+    # BASELINE configs[4]: 30 years -> 15-minute; 645-day chunks on an 8-way shard.  The whole record
+    # goes through the daily pass (the stop rule is an RMS over all 10,957 days, mtclim.py:63); a few
+    # day ranges -- the record's ends, year boundaries, a leap day -- are disaggregated and compared
+    ("global_8th_30yr_15min", 48, 10957, 645, [(0, 40), (3630, 3700), (7295, 7330), (10900, 10957)]),
+], ids=["C4-3652d", "C5-10957d"])
+def test_long_records_against_oracle(name, cells, days, chunk, ranges):
+    """VERDICT r1 'missing' #3: records longer than 400 days were never oracle-checked."""
+    from metsim_b200 import synth
+    from oracle import oracle_lib
+    f, params = synth.make_config(name, max_cells=cells, n_days=days)
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    assert want["n_iter"].min() >= 1
+    tuning = dict(knot_tile=16, day_tile=16, daily_chunk_len=chunk)
+    worst = run_both_daily_forms(f, params, tuning, want, f"{name} {days} d", util.SUB, day_ranges=ranges)
+    print("n_iter histogram", np.bincount(want["n_iter"]).tolist(), "worst", {k: f"{e:.1e}" for k, e in worst.items()})
+
+
+def test_two_host_contexts_run_concurrently_and_agree():
+    """no global mutable state.  Two Python threads, a context each, on one GPU, run
+    different requests at the same time (ctypes releases the GIL around the C call); each result is
+    bit-equal to the same request run alone, and a context can be reused and destroyed freely."""
+    import threading
+    from metsim_b200 import synth
+    from metsim_b200.engine import HostContext, run_host
+    fa, pa = synth.make_config("conus_16th_hourly", max_cells=900, n_days=50)
+    fb, pb = synth.make_config("global_half_deg", max_cells=700, n_days=35)
+    pb = dict(pb, time_step=30, prec_type="mix")
+    kwa = {k: fa.get(k) for k in util.INPUT_KEYS}
+    kwb = {k: fb.get(k) for k in util.INPUT_KEYS}
+    alone_a = run_host(pa, out_vars=EXAMPLE_VARS, **kwa)
+    alone_b = run_host(pb, out_vars=EXAMPLE_VARS, tile_days=3, **kwb)
+    res, errs = {}, []
+
+    def work(tag, params, kw, tile, reps):
+        try:
+            with HostContext(0) as ctx:
+                for _ in range(reps):
+                    res[tag] = run_host(params, out_vars=EXAMPLE_VARS, tile_days=tile, ctx=ctx, **kw)
+                assert ctx.device_bytes > 0
+        except BaseException as exc:       # surfaced below
+            errs.append(exc)
+    ta = threading.Thread(target=work, args=("a", pa, kwa, 0, 4))
+    tb = threading.Thread(target=work, args=("b", pb, kwb, 3, 4))
+    ta.start(); tb.start(); ta.join(); tb.join()
+    assert not errs, errs
+    for v in EXAMPLE_VARS:
+        np.testing.assert_array_equal(res["a"][v], alone_a[v], err_msg=v)
+        np.testing.assert_array_equal(res["b"][v], alone_b[v], err_msg=v)
+    np.testing.assert_array_equal(res["a"]["daily"]["n_iter"], alone_a["daily"]["n_iter"])
 
 
 @pytest.mark.parametrize("subset", [
@@ -376,8 +502,10 @@ def test_streaming_writer_through_on_tile_hook(tmp_path):
     np.testing.assert_array_equal(again["temp"], ref["temp"])
 
 
-def test_seeded_fuzz_small_records_against_oracle(disagg_path):
-    """Forty seeded random small shards: record lengths 2..13 days (so that the interior range is
+@pytest.mark.parametrize("geometry", ["auto", "bench"])
+def test_seeded_fuzz_small_records_against_oracle(disagg_path, geometry):
+    """(geometry "bench": the per-thread work of the benchmarked configuration pinned through
+    msb_tuning -- one thread then covers the whole short record.)  Forty seeded random small shards: record lengths 2..13 days (so that the interior range is
     empty, one day, or a few days, and every call boundary falls somewhere else), random time step,
     precipitation type, utc offset, start date, call length, latitudes from pole to pole and
     longitudes from -360 to 540.  All ten variables, float64, against the oracle at 1e-9; the
@@ -399,7 +527,7 @@ def test_seeded_fuzz_small_records_against_oracle(disagg_path):
         params = dict(time_step=ts, prec_type=str(rng.choice(["uniform", "triangle", "mix"])),
                       utc_offset=bool(rng.integers(0, 2)))
         want = oracle_lib.run(params, **util.oracle_kwargs(f))
-        eng = Engine(params)
+        eng = Engine(params, tuning=BENCH_GEOMETRY if geometry == "bench" else None)
         eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
         eng.build_solar()
         daily = eng.daily(want=DAILY_VARS)

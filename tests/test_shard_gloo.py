@@ -29,6 +29,28 @@ def test_cell_range_partitions_exactly():
         shard.cell_range(10, 2, 2)
 
 
+def test_shard_inputs_slices_passthrough_columns_and_rejects_unknown_wide_arrays():
+    """The 'passthrough' forcing columns are [D][N] like every other daily input: a rank must get its
+    own cells, never the domain-wide array (silent wrong row stride through run_host)."""
+    n, d = 200, 5
+    rng = np.random.default_rng(0)
+    inputs = dict(lat=np.arange(n, dtype=float), lon=np.zeros(n), elev=np.zeros(n),
+                  doy=np.arange(1, d + 1), month=np.ones(d, int),
+                  t_min=rng.random((d, n)), t_max=rng.random((d, n)) + 2, prec=rng.random((d, n)),
+                  wind=None, state_t_min=rng.random((90, n)), state_t_max=rng.random((90, n)),
+                  state_prec=rng.random((90, n)), t_pk12=rng.random((12, n)), dur12=rng.random((12, n)),
+                  t_end=rng.random((2, n)))
+    for k in ("given_shortwave", "given_vapor_pressure", "given_tskc", "given_longwave"):
+        inputs[k] = rng.random((d, n))
+    parts = [shard.shard_inputs(inputs, r, 3) for r in range(3)]
+    for k, v in inputs.items():
+        if v is None or k in ("doy", "month"):
+            continue
+        np.testing.assert_array_equal(np.concatenate([p[k] for p in parts], axis=-1), v, err_msg=k)
+    with pytest.raises(KeyError):
+        shard.shard_inputs(dict(inputs, some_new_column=rng.random((d, n))), 0, 2)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
