@@ -279,12 +279,15 @@ def verify_against_oracle(eng, f, params, step_tiles, ring, n_days, tpd, sample=
     got = {v: [] for v in OUT_VARS}
     eng.build_solar()
     daily = eng.daily(want=())
-    for k, (d0, d1) in enumerate(step_tiles):
-        res = eng.disaggregate(OUT_VARS, d0, d1, torch.float32, out=ring[k & 1])
-        for v in OUT_VARS:
-            got[v].append(res[v][:(d1 - d0) * tpd].index_select(1, idx_t).cpu())
-    eng.check()
-    n_iter = daily["n_iter"].index_select(0, idx_t).cpu().numpy()
+    with torch.cuda.stream(eng.stream):      # the gathers are ordered after the kernels on the engine's stream
+        for k, (d0, d1) in enumerate(step_tiles):
+            res = eng.disaggregate(OUT_VARS, d0, d1, torch.float32, out=ring[k & 1])
+            for v in OUT_VARS:
+                got[v].append(res[v][:(d1 - d0) * tpd].index_select(1, idx_t))
+        n_iter = daily["n_iter"].index_select(0, idx_t)
+    eng.check()                              # synchronises the stream
+    got = {v: [t.cpu() for t in parts] for v, parts in got.items()}
+    n_iter = n_iter.cpu().numpy()
     cpu = lambda t: t.index_select(-1, idx_t).cpu().numpy() if t.dim() else t.cpu().numpy()
     kw = {k: cpu(f[k]) for k in ("lat", "lon", "elev", "t_min", "t_max", "prec", "wind", "state_t_min",
                                  "state_t_max", "state_prec", "t_pk12", "dur12")}
@@ -416,7 +419,7 @@ class DevicePass:
         self.torch.cuda.empty_cache()
 
 
-def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, consume=True):
+def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, consume=True, world=1):
     """The same step through msb_run_host_ctx (C ABI) with pinned HOST buffers: H2D of the inputs and
     D2H of every output tile inside the timed region, every tile handed to a consumer (the native
     thread pool of csrc/sink.cu: reads every row, scatters / byte-swaps it into its staging --
@@ -433,7 +436,7 @@ def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, co
               month=host["month"], t_min=host["t_min"], t_max=host["t_max"], prec=host["prec"],
               wind=host["wind"], state_t_min=host["state_t_min"], state_t_max=host["state_t_max"],
               state_prec=host["state_prec"], t_pk12=host["t_pk12"], dur12=host["dur12"])
-    n_thr = max(2, min(16, (len(os.sched_getaffinity(0)) or 2) // 2))
+    n_thr = max(2, min(32, (os.cpu_count() or 2) // world - 1))   # the host's cores shared by the ranks
     sink = NativeSink(n_cells=n, elem_bytes=4, byteswap=True, n_threads=n_thr, fd=-1) if consume else None
     consumed = [0]
 
@@ -453,6 +456,13 @@ def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, co
         call()
     barrier()
     dt = reduce_max((time.perf_counter() - t0) / steps)
+    # one step without the consumer beside it: what the copies alone take (tiles overwritten unread)
+    copy_only = None
+    if consume:
+        t0 = time.perf_counter()
+        run_host(params, out_vars=OUT_VARS, tile_days=tile_e2e, out=hring, ring=True, ctx=ctx, **kw)
+        barrier()
+        copy_only = reduce_max(time.perf_counter() - t0)
     ctx.close()
     if sink is not None:
         sink.close()
@@ -460,7 +470,7 @@ def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, co
                                         "wind", "state_t_min", "state_t_max", "state_prec",
                                         "t_pk12", "dur12")) + n * 4
     d2h = len(OUT_VARS) * n_days * tpd * n * 4
-    return dt, int(h2d), int(d2h), int(consumed[0] // max(1, steps)), n_thr, tile_e2e
+    return dt, int(h2d), int(d2h), int(consumed[0] // max(1, steps)), n_thr, tile_e2e, copy_only
 
 
 def main():
@@ -601,11 +611,13 @@ def main():
         torch.cuda.empty_cache()
         ceiling = d2h_ceiling(dev, world)
         e_steps = args.e2e_steps or max(1, min(args.steps, 3))
-        dt, h2d, d2h, consumed, n_thr, tile_e2e = e2e_pass(f_keep, params_keep, n, n_days, tpd, local, e_steps,
-                                                           barrier, reduce_max, consume=not args.no_consumer)
+        dt, h2d, d2h, consumed, n_thr, tile_e2e, copy_only = e2e_pass(
+            f_keep, params_keep, n, n_days, tpd, local, e_steps, barrier, reduce_max,
+            consume=not args.no_consumer, world=world)
         e2e = {"value": total_cell_ts / dt, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": e_steps,
+               "ms_per_step_copies_only": copy_only * 1e3 if copy_only else None,
                "d2h_gbs_all_ranks": world * d2h / dt / 1e9,
                "d2h_ceiling_gbs_all_ranks": ceiling,
                "fraction_of_d2h_ceiling": (world * d2h / dt / 1e9) / ceiling if ceiling else None,
@@ -639,11 +651,12 @@ def main():
             f_keep, params_keep = sp.f, sp.params
             sp.ring = None
             torch.cuda.empty_cache()
-            dt, h2d, d2h, consumed, n_thr, tile_e2e = e2e_pass(f_keep, params_keep, sp.n, n_days, tpd, local,
-                                                               e_steps, barrier, reduce_max,
-                                                               consume=not args.no_consumer)
+            dt, h2d, d2h, consumed, n_thr, tile_e2e, copy_only = e2e_pass(
+                f_keep, params_keep, sp.n, n_days, tpd, local, e_steps, barrier, reduce_max,
+                consume=not args.no_consumer, world=world)
             d2h_all = sum(gather(d2h))
             strong["e2e"] = {"value": dom_cts / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+                             "ms_per_step_copies_only": copy_only * 1e3 if copy_only else None,
                              "d2h_gbs_all_ranks": d2h_all / dt / 1e9,
                              "fraction_of_d2h_ceiling": (d2h_all / dt / 1e9) / ceiling if ceiling else None,
                              "efficiency_vs_n1": (e2e["ms_per_step"] / (dt * 1e3)) / world if e2e else None}

@@ -47,6 +47,28 @@ namespace {
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 inline uint64_t bswap64(uint64_t v) { return __builtin_bswap64(v); }
 
+// The dense rows (no mask: CONUS, or any shard whose cells are the whole grid in order) are plain
+// streaming loops; the AVX2 clone turns the byte swap into one shuffle per 8 values, which is what
+// lets a few threads per GPU keep up with the PCIe stream.  The dispatch is the loader's (ifunc).
+#if defined(__x86_64__) && defined(__GNUC__)
+#define MSB_SIMD_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define MSB_SIMD_CLONES
+#endif
+
+MSB_SIMD_CLONES uint64_t dense_row32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n, bool swap) {
+  uint64_t sum = 0;
+  if (swap) for (int64_t c = 0; c < n; ++c) { const uint32_t v = in[c]; sum += v; out[c] = bswap32(v); }
+  else for (int64_t c = 0; c < n; ++c) { const uint32_t v = in[c]; sum += v; out[c] = v; }
+  return sum;
+}
+MSB_SIMD_CLONES uint64_t dense_row64(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int64_t n, bool swap) {
+  uint64_t sum = 0;
+  if (swap) for (int64_t c = 0; c < n; ++c) { const uint64_t v = in[c]; sum += v; out[c] = bswap64(v); }
+  else for (int64_t c = 0; c < n; ++c) { const uint64_t v = in[c]; sum += v; out[c] = v; }
+  return sum;
+}
+
 template <typename U>
 uint64_t scatter_rows(const msb_sink &s, const U *src, U *dst, int64_t steps) {
   const int64_t n = s.d.n_cells, g = s.d.n_grid;
@@ -62,12 +84,10 @@ uint64_t scatter_rows(const msb_sink &s, const U *src, U *dst, int64_t steps) {
         sum += v;
         out[idx[c]] = swap ? (sizeof(U) == 4 ? (U)bswap32((uint32_t)v) : (U)bswap64((uint64_t)v)) : v;
       }
+    } else if (sizeof(U) == 4) {
+      sum += dense_row32(reinterpret_cast<const uint32_t *>(in), reinterpret_cast<uint32_t *>(out), n, swap);
     } else {
-      for (int64_t c = 0; c < n; ++c) {
-        const U v = in[c];
-        sum += v;
-        out[c] = swap ? (sizeof(U) == 4 ? (U)bswap32((uint32_t)v) : (U)bswap64((uint64_t)v)) : v;
-      }
+      sum += dense_row64(reinterpret_cast<const uint64_t *>(in), reinterpret_cast<uint64_t *>(out), n, swap);
     }
   }
   return sum;

@@ -2,11 +2,14 @@
 fixtures (no h5py / netCDF4 in this image).
 
 Scope: exactly what the bundled files under metsim/data use -- version-2 object headers ("OHDR",
-with "OCHK" continuation chunks), compact link messages in the root group, simple dataspaces,
-fixed-point / IEEE floating-point datatypes, CONTIGUOUS uncompressed layout.  Anything else raises
+with "OCHK" continuation chunks), root-group links stored compactly (link messages) or DENSELY
+(link info message -> fractal heap + version-2 B-tree name index, what netCDF-4 writes once a group
+has more than 8 links: state_vic.nc, passthrough.nc), simple dataspaces, fixed-point / IEEE
+floating-point datatypes, CONTIGUOUS uncompressed layout.  Anything else raises
 ``NotImplementedError`` rather than guessing.  Layout follows the HDF5 File Format Specification 3.0
-(sections III.A "Disk Format: Level 1 - Superblock", IV.A.1.b "Version 2 Data Object Header Prefix",
-IV.A.2 message types 0x01 dataspace, 0x03 datatype, 0x06 link, 0x08 data layout, 0x10 continuation).
+(sections III.A "Disk Format: Level 1 - Superblock", III.A.2 "Version 2 B-trees", III.G "Fractal
+Heap", IV.A.1.b "Version 2 Data Object Header Prefix", IV.A.2 message types 0x01 dataspace, 0x02 link
+info, 0x03 datatype, 0x06 link, 0x08 data layout, 0x10 continuation).
 
     from oracle.mini_hdf5 import read_hdf5
     arrays = read_hdf5("/root/reference/metsim/data/state_nc.nc")   # {name: numpy array}
@@ -52,10 +55,122 @@ def _messages(b: bytes, off: int):
     return out
 
 
-def _links(msgs):
-    """name -> object header address from compact link messages (type 0x06)."""
+def _link_message(body: bytes):
+    """(name, object header address) of one link message body, or None for soft / external links."""
+    flags = body[1]
+    q = 2
+    if flags & 0x08:
+        if body[q] != 0:
+            return None
+        q += 1
+    if flags & 0x04:
+        q += 8                                       # creation order
+    if flags & 0x10:
+        q += 1                                       # charset
+    n = 1 << (flags & 3)
+    ln = int.from_bytes(body[q:q + n], "little")
+    q += n
+    name = body[q:q + ln].decode("utf-8")
+    q += ln
+    return name, struct.unpack("<Q", body[q:q + 8])[0]
+
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+def _dense_links(b: bytes, heap_addr: int, btree_addr: int):
+    """Links of a group with dense storage: the version-2 B-tree (type 5, link names) lists the
+    fractal-heap IDs of the link messages; the IDs are resolved through the heap's block tree."""
+    # ---- fractal heap header (spec III.G) ----
+    if b[heap_addr:heap_addr + 4] != b"FRHP" or b[heap_addr + 4] != 0:
+        raise NotImplementedError("fractal heap header")
+    q = heap_addr + 5
+    id_len, filt_len = struct.unpack("<HH", b[q:q + 4]); q += 4
+    q += 1                                           # flags
+    max_managed = struct.unpack("<I", b[q:q + 4])[0]; q += 4
+    q += 8 * 12                                      # huge-object / free-space / statistics fields
+    width = struct.unpack("<H", b[q:q + 2])[0]; q += 2
+    start_size, max_direct = struct.unpack("<QQ", b[q:q + 16]); q += 16
+    heap_bits = struct.unpack("<H", b[q:q + 2])[0]; q += 2
+    q += 2                                           # starting rows of the root indirect block
+    root_addr = struct.unpack("<Q", b[q:q + 8])[0]; q += 8
+    root_rows = struct.unpack("<H", b[q:q + 2])[0]
+    if filt_len:
+        raise NotImplementedError("filtered fractal heap")
+    off_bytes = (heap_bits + 7) // 8
+    len_bytes = (min(max_direct, max_managed).bit_length() + 7) // 8
+    # ---- direct blocks: (offset in heap space, size, file address) ----
+    blocks = []
+
+    def row_size(r):
+        return start_size if r < 2 else start_size << (r - 1)
+
+    def walk_indirect(addr, rows):
+        if b[addr:addr + 4] != b"FHIB":
+            raise NotImplementedError("fractal heap indirect block")
+        p = addr + 5 + 8
+        block_off = int.from_bytes(b[p:p + off_bytes], "little"); p += off_bytes
+        max_direct_rows = (max_direct.bit_length() - 1) - (start_size.bit_length() - 1) + 2
+        cur = block_off
+        for r in range(rows):
+            for _ in range(width):
+                child = struct.unpack("<Q", b[p:p + 8])[0]; p += 8
+                if r >= max_direct_rows:
+                    raise NotImplementedError("nested indirect blocks")
+                if child != UNDEF:
+                    blocks.append((cur, row_size(r), child))
+                cur += row_size(r)
+
+    if root_addr == UNDEF:
+        return {}
+    if root_rows == 0:
+        blocks.append((0, start_size, root_addr))
+    else:
+        walk_indirect(root_addr, root_rows)
+    for _, _, addr in blocks:
+        if b[addr:addr + 4] != b"FHDB":
+            raise NotImplementedError("fractal heap direct block")
+
+    def heap_object(hid: bytes) -> bytes:
+        if hid[0] & 0xF0:
+            raise NotImplementedError("huge / tiny fractal heap objects")
+        off = int.from_bytes(hid[1:1 + off_bytes], "little")
+        ln = int.from_bytes(hid[1 + off_bytes:1 + off_bytes + len_bytes], "little")
+        for block_off, size, addr in blocks:         # offsets count from the block's own header
+            if block_off <= off < block_off + size:
+                return b[addr + (off - block_off):addr + (off - block_off) + ln]
+        raise NotImplementedError("heap ID outside the allocated blocks")
+
+    # ---- version-2 B-tree, type 5 (link name index): records = hash (4) + heap ID (id_len) ----
+    if b[btree_addr:btree_addr + 4] != b"BTHD" or b[btree_addr + 5] != 5:
+        raise NotImplementedError("link-name B-tree header")
+    rec_size, depth = struct.unpack("<HH", b[btree_addr + 10:btree_addr + 14])
+    root_node = struct.unpack("<Q", b[btree_addr + 16:btree_addr + 24])[0]
+    n_root = struct.unpack("<H", b[btree_addr + 24:btree_addr + 26])[0]
+    if depth != 0:
+        raise NotImplementedError("B-tree deeper than one leaf")
+    if rec_size != 4 + id_len or b[root_node:root_node + 4] != b"BTLF":
+        raise NotImplementedError("link-name B-tree leaf")
+    links = {}
+    for k in range(n_root):
+        rec = b[root_node + 6 + k * rec_size:root_node + 6 + (k + 1) * rec_size]
+        got = _link_message(heap_object(rec[4:4 + id_len]))
+        if got is not None:
+            links[got[0]] = got[1]
+    return links
+
+
+def _links(msgs, b: bytes = b""):
+    """name -> object header address: compact link messages (type 0x06) and, when the group's link
+    info message (0x02) points at a fractal heap, the densely stored ones."""
     links = {}
     for mtype, body in msgs:
+        if mtype == 0x02:
+            q = 2 + (8 if body[1] & 1 else 0)
+            heap_addr, name_btree = struct.unpack("<QQ", body[q:q + 16])
+            if heap_addr != UNDEF:
+                links.update(_dense_links(b, heap_addr, name_btree))
+            continue
         if mtype != 0x06:
             continue
         flags = body[1]
@@ -124,7 +239,7 @@ def read_hdf5(path: str) -> dict:
     else:
         raise NotImplementedError("superblock version %d" % ver)
     out = {}
-    for name, addr in _links(_messages(b, root)).items():
+    for name, addr in _links(_messages(b, root), b).items():
         try:
             out[name] = _dataset(b, addr)
         except NotImplementedError:

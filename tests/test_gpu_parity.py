@@ -292,11 +292,13 @@ def run_both_daily_forms(f, params, tuning, want, ctx, sub_vars, day_ranges=None
         if form == "single":
             daily = eng.daily(want=(), single_pass=True)
             vp, sw = eng.daily_for_disagg()
+            eng.check()                      # synchronises the engine's stream before the host reads
             util.assert_close(vp.cpu().numpy(), want["vp_daily"], "vp_daily", context=ctx + " single")
             util.assert_close(sw.cpu().numpy(), want["sw_daily"], "sw_daily", context=ctx + " single")
             util.assert_close(daily["tskc"].cpu().numpy(), want["tskc_daily"], "tskc_daily", context=ctx)
         else:
             daily = eng.daily(want=DAILY_VARS)
+            eng.check()
             for oname, ename in util.DAILY.items():
                 if oname in want:
                     util.assert_close(daily[ename].cpu().numpy(), want[oname], oname, context=ctx + " two-pass")
