@@ -27,6 +27,7 @@ namespace msb {
 struct PreludeView {
   double *cosegeom, *sinegeom, *hss, *cza0;  // [n_lat][365]
   int32_t *nstep;                            // [n_lat][365]
+  double *beam;                              // [365] dir_beam_topa of the day (latitude-independent) + [2] cos, sin of dh
 };
 
 static PreludeView prelude_view(void *base, int n_lat) {
@@ -38,6 +39,7 @@ static PreludeView prelude_view(void *base, int n_lat) {
   v.hss = d + 2 * n;
   v.cza0 = d + 3 * n;
   v.nstep = reinterpret_cast<int32_t *>(d + 4 * n);
+  v.beam = d + 4 * n + (n + 1) / 2;          // after the int32 block, 8-byte aligned
   return v;
 }
 
@@ -127,9 +129,9 @@ __global__ void __launch_bounds__(kK1Threads)
 solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
                   const double *__restrict__ g_sinegeom, const double *__restrict__ g_hss,
                   const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
-                  msb_solar_tables tb) {
-  __shared__ double row[kTiny];
-  __shared__ double qs[kQLd];
+                  const double *__restrict__ g_beam, msb_solar_tables tb) {
+  __shared__ __align__(16) double row[kTiny];
+  __shared__ __align__(16) double qs[kQLd];
   __shared__ double part[kWarps];
   __shared__ double warp_tot[kWarps];
   __shared__ int s_rise, s_set;
@@ -143,12 +145,11 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const int n = g_nstep[o];
   const double dh = kSwRadDt / kSecPerRad;
 
-  for (int j = tid; j < kTiny; j += kK1Threads) row[j] = 0.0;
+  for (int j = tid; j < kTiny / 2; j += kK1Threads) reinterpret_cast<double2 *>(row)[j] = make_double2(0.0, 0.0);
   if (tid == 0) { s_rise = -1; s_set = -1; }
   __syncthreads();
 
-  // physics.py:238-239
-  const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
+  const double beam = g_beam[i];               // physics.py:238-239 (host prelude)
   const double start = -hss;
 
   double tot_loc = 0.0;    // sum of dir_flat_topa over this thread's steps
@@ -159,7 +160,7 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   const int per = (n + kK1Threads - 1) / kK1Threads;
   const int k_lo = min(tid * per, n), k_hi = min(k_lo + per, n);
   if (k_lo < k_hi) {
-    const double cd = cos(dh), sd = sin(dh);
+    const double cd = g_beam[365], sd = g_beam[366];
     double ch, sh;
     sincos(__dadd_rn(start, __dmul_rn((double)k_lo, dh)), &sh, &ch);
     int ts = tiny_index(__dadd_rn(start, __dmul_rn((double)k_lo, dh)));
@@ -191,11 +192,8 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
 
   const double daylength = fmin(2.0 * hss * kSecPerRad, kSecPerDay);  // physics.py:236
   const bool has_day = daylength != 0.0;
-  if (has_day && total > 0.0)
-    for (int j = tid; j < kTiny; j += kK1Threads) row[j] = row[j] / total;  // :270-271
-  __syncthreads();
-
   // sunrise / sunset: last j with row[j] <= 0 < row[j+1] / row[j] > 0 >= row[j+1]
+  // (disaggregate.py:163-176; signs only, so this runs on the unscaled row)
   int rise = -1, set = -1;
   for (int j = tid; j < kTiny - 1; j += kK1Threads) {
     int a = row[j] > 0.0, b = row[j + 1] > 0.0;
@@ -204,6 +202,14 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   }
   if (rise >= 0) atomicMax(&s_rise, rise);
   if (set >= 0) atomicMax(&s_set, set);
+  __syncthreads();
+  // tiny_rad_fract[i] /= sum_flat_potrad (:270-271) as a multiplication by the reciprocal: the
+  // entries only enter window sums held to 1e-9, and an IEEE divide per entry was a third of this kernel
+  if (has_day && total > 0.0) {
+    const double inv_total = div_nr(1.0, total);
+    for (int j = tid; j < kTiny; j += kK1Threads) row[j] *= inv_total;
+  }
+  __syncthreads();
 
   // signed prefix table: q[j] = sum_{i<j} row[i] for j <= 1440, -sum_{i>=j} row[i] for j > 1440.
   // Threads 0..127 scan the morning half forwards, threads 128..255 the afternoon half backwards,
@@ -257,8 +263,9 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
     for (int e = kTiny + 2; e < kQLd; ++e) qs[e] = 0.0;
   }
   __syncthreads();
-  double *q = tb.q + ((size_t)r * 365 + i) * kQLd;
-  for (int j = tid; j < kQLd; j += kK1Threads) q[j] = qs[j];
+  // rows are kQLd = 2888 doubles = 23,104 bytes apart: every row starts on a 16-byte boundary
+  double2 *q = reinterpret_cast<double2 *>(tb.q + ((size_t)r * 365 + i) * kQLd);
+  for (int j = tid; j < kQLd / 2; j += kK1Threads) q[j] = reinterpret_cast<const double2 *>(qs)[j];
 
   if (tid == 0) {
     const double step_min = kSwRadDt / 60.0;
@@ -290,7 +297,8 @@ __global__ void __launch_bounds__(kMomWarps * 32)
 solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
                      const double *__restrict__ g_sinegeom, const double *__restrict__ g_hss,
                      const double *__restrict__ g_cza0, const int32_t *__restrict__ g_nstep,
-                     msb_solar_tables tb, const __grid_constant__ OptamThr thr) {
+                     const double *__restrict__ g_beam, msb_solar_tables tb,
+                     const __grid_constant__ OptamThr thr) {
   __shared__ double etab[kExpTab];
   __shared__ double s_thr[32];
   __shared__ double s_optam[21];
@@ -307,9 +315,9 @@ solar_moments_kernel(int n_rows, const double *__restrict__ g_cosegeom,
   const int n = g_nstep[w];
   const double dh = kSwRadDt / kSecPerRad;
   const double kLnTBase = -0.13926206733350766;  // ln(0.87)
-  const double beam = (1368.0 + 45.5 * sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
+  const double beam = g_beam[i];
   const double start = -hss;
-  const double cd = cos(dh), sd = sin(dh);
+  const double cd = g_beam[365], sd = g_beam[366];
 
   double m_loc[kTT + 1];   // Taylor moments of trans**am, [kTT] = sum of dir_flat_topa
 #pragma unroll
@@ -387,7 +395,7 @@ using namespace msb;
 
 extern "C" size_t msb_solar_prelude_bytes(int n_lat) {
   size_t n = (size_t)(n_lat > 0 ? n_lat : 0) * 365;
-  return n * (4 * sizeof(double) + sizeof(int32_t)) + 64;
+  return (4 * n + (n + 1) / 2 + 365 + 2) * sizeof(double) + 64;
 }
 
 extern "C" int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_elems,
@@ -426,16 +434,22 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
     }
     for (auto &th : pool) th.join();
   }
+  // latitude-independent scalars of the hour-angle loop, with this host's libm like the rest of K0:
+  // the beam of every day (physics.py:238-239) and the rotation by one 30 s step
+  for (int i = 0; i < 365; ++i)
+    hv.beam[i] = (1368.0 + 45.5 * std::sin((2.0 * M_PI * i / kDaysPerYear) + 1.7)) * kSwRadDt;
+  hv.beam[365] = std::cos(kSwRadDt / kSecPerRad);
+  hv.beam[366] = std::sin(kSwRadDt / kSecPerRad);
   size_t bytes = msb_solar_prelude_bytes(n_lat) - 64;
   MSB_CUDA(cudaMemcpyAsync(dev_ws, host_ws, bytes, cudaMemcpyHostToDevice, st));
   PreludeView dv = prelude_view(dev_ws, n_lat);
   unsigned grid = 365u * (unsigned)n_lat;
   solar_rows_kernel<<<grid, kK1Threads, 0, st>>>(n_lat, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0,
-                                                 dv.nstep, *tb);
+                                                 dv.nstep, dv.beam, *tb);
   OptamThr thr;
   optam_thresholds(thr.c);
   solar_moments_kernel<<<(grid + kMomWarps - 1) / kMomWarps, kMomWarps * 32, 0, st>>>(
-      (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, *tb, thr);
+      (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, dv.beam, *tb, thr);
   MSB_CUDA(cudaGetLastError());
   MSB_CUDA(cudaMemsetAsync(tb->q + (size_t)n_lat * 365 * kQLd, 0, MSB_Q_PAD * sizeof(double), st));
   return MSB_OK;

@@ -14,14 +14,26 @@ Two levels are offered:
   full-day shortwave averaging on the literal name ``'passthrough'``, so with the unmodified
   driver ``passthrough_b200`` behaves like ``sw_averaging = daylight`` there -- the batched
   engine implements both modes).
-* :func:`batched_metsim_class` returns a ``MetSim`` subclass whose ``run_slice`` hands the whole
-  chunk to the batched engine (solar tables, daily pass and disaggregation all on the GPU).  It
-  needs the reference's xarray stack, which is not part of this repo's requirements.
+* :func:`run_slice_batched` is the body of ``MetSim.run_slice`` (metsim/metsim.py:456-493) with the
+  cell loop replaced by ONE call of the batched engine (solar tables, daily pass and
+  disaggregation all on the GPU).  It only touches the attributes ``run_slice`` itself touches
+  (``params``, ``domain``, ``met_data``, ``state``, ``output``) through the small part of the
+  xarray interface it needs (``.values``, ``.dims``), so it runs -- and is tested -- against
+  stand-ins where the xarray stack is absent.  :func:`batched_metsim_class` wraps it into a
+  ``MetSim`` subclass for installations that have the reference importable.
 """
 from __future__ import annotations
 
+import numpy as np
+
 METHOD_NAME = "mtclim_b200"
 PASSTHROUGH_NAME = "passthrough_b200"
+
+# metsim/metsim.py:660-666
+DAILY_OUT_VARS = ("t_min", "t_max", "t_day", "prec", "vapor_pressure", "shortwave", "tskc", "pet",
+                  "wind", "daylength")
+SUBDAILY_OUT_VARS = ("temp", "prec", "shortwave", "vapor_pressure", "air_pressure", "rel_humid",
+                     "spec_humid", "longwave", "tskc", "wind")
 
 
 def register(methods: dict | None = None) -> dict:
@@ -40,57 +52,151 @@ def register(methods: dict | None = None) -> dict:
     return methods
 
 
-def batched_metsim_class():
-    """``MetSim`` subclass running whole chunks through :class:`metsim_b200.engine.Engine`."""
-    import numpy as np
-    import metsim.constants as cnst
-    from metsim.metsim import MetSim
-    from metsim.units import converters  # noqa: F401  (units are applied on the device)
+def _cells(da, lead: str, mask_dims: tuple, sel: tuple) -> np.ndarray:
+    """``[lead][active cells]`` float64 view of a DataArray-like whose dimensions are ``lead`` plus
+    the mask's dimensions in ANY order (the reference selects by name, ``isel(**locs)``)."""
+    vals = np.asarray(da.values, dtype=np.float64)
+    dims = tuple(da.dims)
+    want = (lead,) + tuple(mask_dims)
+    if sorted(dims) != sorted(want):
+        raise ValueError(f"expected dimensions {want}, got {dims}")
+    vals = np.transpose(vals, [dims.index(d) for d in want])
+    return np.ascontiguousarray(vals[(slice(None),) + sel])
 
-    from .engine import Engine
+
+def _per_cell(ds, name: str, mask_dims: tuple, mask_shape: tuple, sel: tuple) -> np.ndarray:
+    """lat / lon / elev of the active cells: 1-D coordinate or an array over the mask's dimensions."""
+    da = ds[name]
+    vals = np.asarray(da.values, dtype=np.float64)
+    dims = tuple(da.dims)
+    if vals.ndim == 1:
+        axis = mask_dims.index(dims[0])
+        shape = [1] * len(mask_dims)
+        shape[axis] = -1
+        return np.broadcast_to(vals.reshape(shape), mask_shape)[sel].copy()
+    vals = np.transpose(vals, [dims.index(d) for d in mask_dims])
+    return vals[sel].copy()
+
+
+def _calendar(time_values):
+    """1-based day of year and month of a standard-calendar time axis (numpy datetime64 or anything
+    ``np.asarray`` turns into it)."""
+    t = np.asarray(time_values)
+    if not np.issubdtype(t.dtype, np.datetime64):
+        raise NotImplementedError("the batched path handles standard (datetime64) calendars only; "
+                                  f"got a time axis of dtype {t.dtype}")
+    days = t.astype("datetime64[D]")
+    if days.size > 1 and not (np.diff(days).astype(np.int64) == 1).all():
+        raise ValueError("the forcing time axis must be daily and contiguous")
+    years = days.astype("datetime64[Y]")
+    doy = (days - years.astype("datetime64[D]")).astype(np.int64) + 1
+    month = days.astype("datetime64[M]").astype(np.int64) % 12 + 1
+    return doy.astype(np.int32), month.astype(np.int32)
+
+
+def run_slice_batched(ms, device="cuda:0") -> None:
+    """Body of ``MetSim.run_slice`` (metsim/metsim.py:456-493) for the whole chunk at once.
+
+    ``ms`` needs ``params`` (the MetSim parameter dict), ``domain`` (``mask``, ``lat``, ``lon``,
+    ``elev`` and, for triangle / mix precipitation, ``t_pk`` / ``dur`` over ``month``), ``met_data``
+    (``time`` plus the daily forcings over ``time``), ``state`` (``t_min``, ``t_max``, ``prec`` over
+    the 90 state days) and ``output`` (one ``(time, *mask.dims)`` array per ``out_vars`` entry,
+    NaN-initialised by ``setup_output``); ``_validate_setup`` / ``setup_output`` are called when
+    present.  Mirrors the reference: masked cells are skipped and stay NaN (:477-481), units are
+    converted per ``out_vars[v]['units']`` (:489-492), ``time_step = 1440`` writes the daily columns
+    with shortwave as the daily mean flux (:779-792).  The values do not depend on the output-time
+    bookkeeping of wrap_run_cell (:764-795): it relabels / keeps every step of the record."""
+    from .engine import Engine, unit_scale_offset
+    params = ms.params
+    if hasattr(ms, "_validate_setup"):
+        ms._validate_setup()
+    ts = int(params["time_step"])
+    daily_mode = ts >= 1440
+    if hasattr(ms, "setup_output"):
+        ms.disagg = not daily_mode
+        ms.setup_output()
+    out_vars = list(params["out_vars"])
+    allowed = DAILY_OUT_VARS if daily_mode else SUBDAILY_OUT_VARS
+    for v in out_vars:
+        if v not in allowed:
+            raise ValueError(f"Cannot output variable {v} at timestep {ts}")      # metsim.py:667-670
+    dom, md, st = ms.domain, ms.met_data, ms.state
+    mask_da = dom["mask"]
+    mask = np.asarray(mask_da.values)
+    mdims = tuple(mask_da.dims)
+    active = np.argwhere(mask > 0)            # row-major, like np.ndenumerate (:477)
+    if active.size == 0:
+        return
+    sel = tuple(active[:, i] for i in range(active.shape[1]))
+    doy, month = _calendar(md["time"].values)
+    method = str(params.get("method", "mtclim")).lower()
+    has = lambda ds, k: k in ds
+    kw = {}
+    if str(params.get("prec_type", "uniform")).upper() in ("TRIANGLE", "MIX"):
+        kw["t_pk12"] = _cells(dom["t_pk"], "month", mdims, sel)
+        kw["dur12"] = _cells(dom["dur"], "month", mdims, sel)
+    if "passthrough" in method:
+        for k in ("shortwave", "vapor_pressure", "tskc", "longwave"):
+            if has(md, k):
+                kw["given_" + k] = _cells(md[k], "time", mdims, sel)
+    wind = _cells(md["wind"], "time", mdims, sel) if has(md, "wind") else None
+    if "wind" in out_vars and wind is None:
+        raise KeyError("wind")                # df['wind'] in the reference (:492)
+    forc = {k: _cells(md[k], "time", mdims, sel) for k in ("t_min", "t_max", "prec")}
+    eng = Engine(params, device)
+    eng.load(lat=_per_cell(dom, "lat", mdims, mask.shape, sel),
+             lon=_per_cell(dom, "lon", mdims, mask.shape, sel),
+             elev=_per_cell(dom, "elev", mdims, mask.shape, sel),
+             doy=doy, month=month, wind=wind, **forc,
+             state_t_min=_cells(st["t_min"], "time", mdims, sel),
+             state_t_max=_cells(st["t_max"], "time", mdims, sel),
+             state_prec=_cells(st["prec"], "time", mdims, sel), **kw)
+    units = {v: (params["out_vars"][v] or {}).get("units") for v in out_vars}
+
+    def put(v, block):
+        """rows [time][active cells] -> ms.output[v], whose dimensions are (time, *mask.dims)"""
+        target = ms.output[v]
+        tdims = tuple(target.dims)
+        if tdims[0] != "time" or sorted(tdims[1:]) != sorted(mdims):
+            raise ValueError(f"output[{v!r}] has dimensions {tdims}, expected ('time', *{mdims})")
+        order = [mdims.index(d) for d in tdims[1:]]
+        vals = target.values
+        if block.shape[0] != vals.shape[0]:
+            raise ValueError(f"output[{v!r}] holds {vals.shape[0]} time steps, the run produced {block.shape[0]}")
+        vals[(slice(None),) + tuple(sel[i] for i in order)] = block
+
+    if daily_mode:
+        res = eng.run(daily_vars=("t_day", "vapor_pressure", "tskc", "pet", "daylength"))
+        daily = res["daily"]
+        for v in out_vars:
+            if v in forc:
+                block = forc[v]
+            elif v == "wind":
+                block = wind
+            elif v == "shortwave":
+                block = res["shortwave"].cpu().numpy()       # daily mean flux (:779-781)
+            else:
+                block = daily[v].cpu().numpy()
+            sc, of = unit_scale_offset(v, units[v], ts)
+            put(v, block * sc + of if (sc, of) != (1.0, 0.0) else block)
+        return
+    import torch
+    prec = str(params.get("out_precision", "f4"))
+    res = eng.run(out_vars=out_vars, units=units,
+                  out_dtype=torch.float64 if prec == "f8" else torch.float32)
+    for v in out_vars:
+        put(v, res[v].cpu().numpy())
+
+
+def batched_metsim_class():
+    """``MetSim`` subclass whose ``run_slice`` is :func:`run_slice_batched` (needs the reference's
+    xarray stack to be importable)."""
+    from metsim.metsim import MetSim
 
     register(MetSim.methods)
 
     class MetSimB200(MetSim):
         def run_slice(self):  # replaces metsim/metsim.py:456-493
-            self._validate_setup()
-            self.disagg = int(self.params["time_step"]) < cnst.MIN_PER_DAY
-            self.setup_output()
-            mask = np.asarray(self.domain["mask"].values)
-            active = np.argwhere(mask > 0)
-            if active.size == 0:
-                return
-            dims = self.domain["mask"].dims
-            sel = tuple(active[:, i] for i in range(active.shape[1]))
-            grab = lambda da: np.asarray(da.values, dtype=np.float64)[(slice(None),) + sel]
-            md, st, dom = self.met_data, self.state, self.domain
-            lat = np.broadcast_to(dom["lat"].values.reshape(
-                [-1 if d == "lat" else 1 for d in dims]) if dom["lat"].ndim == 1 else dom["lat"].values,
-                mask.shape)[sel]
-            lon = np.broadcast_to(dom["lon"].values.reshape(
-                [-1 if d == "lon" else 1 for d in dims]) if dom["lon"].ndim == 1 else dom["lon"].values,
-                mask.shape)[sel]
-            times = md["time"].to_index()
-            eng = Engine(self.params)
-            kw = {}
-            if self.params["prec_type"].upper() in ("TRIANGLE", "MIX"):
-                kw = dict(t_pk12=np.asarray(dom["t_pk"].values, float)[(slice(None),) + sel],
-                          dur12=np.asarray(dom["dur"].values, float)[(slice(None),) + sel])
-            eng.load(lat=lat, lon=lon, elev=np.asarray(dom["elev"].values, float)[sel],
-                     doy=times.dayofyear.values, month=times.month.values,
-                     t_min=grab(md["t_min"]), t_max=grab(md["t_max"]), prec=grab(md["prec"]),
-                     wind=grab(md["wind"]) if "wind" in md else None,
-                     **{"given_" + k: grab(md[k]) for k in
-                        ("shortwave", "vapor_pressure", "tskc", "longwave")
-                        if "passthrough" in str(self.params["method"]) and k in md},
-                     state_t_min=grab(st["t_min"]), state_t_max=grab(st["t_max"]),
-                     state_prec=grab(st["prec"]), **kw)
-            out_vars = list(self.params["out_vars"])
-            units = {v: self.params["out_vars"][v]["units"] for v in out_vars}
-            res = eng.run(out_vars=out_vars, units=units)
-            for v in out_vars:
-                block = res[v].cpu().numpy()
-                target = self.output[v].values
-                target[(slice(None),) + sel] = block
+            run_slice_batched(self)
 
     return MetSimB200

@@ -11,9 +11,9 @@ not.  Fixture families:
 * ``stehekin_*``   the reference's only known-answer test (metsim/tests/test_metsim.py:397-464):
                    VIC binary forcings of cell 48.3125/-120.5625 for 1949, domain stehekin.nc,
                    plus the reference repo's own golden tables (validated_48.3125_-120.5625 and
-                   three_hourly_48.3125_-120.5625, stored as float32).  state_vic.nc is HDF5 and
-                   not readable in this image, so the 90-day state is DECLARED SYNTHETIC: the last
-                   90 days of the 1949 record.
+                   three_hourly_48.3125_-120.5625, stored as float32) and the 90-day state of
+                   state_vic.nc, exactly as that test configures it (NetCDF-4 / HDF5 with densely
+                   stored links and chunked datasets: read by oracle/mini_hdf5.py).
 * ``testdomain``   BASELINE config #1 as literally configured by examples/example_nc.conf:
                    metsim/data/test.nc + domain.nc + the 90-day state of state_nc.nc (81 cells, 31
                    days, 30 min, triangle, utc_offset), float32 inputs upcast exactly to float64.
@@ -88,8 +88,13 @@ def stehekin(root):
     elev = float(dom.variables["elev"].data[la, lo])
     assert abs(lat - 48.3125) < 1e-9 and abs(lon + 120.5625) < 1e-9
     prec, tmax, tmin, wind = read_vic_binary(os.path.join(data, "binary", "data_48.3125_-120.5625"), 365)
+    state = read_hdf5(os.path.join(data, "state_vic.nc"))      # test_metsim.py:408 'state'
+    assert abs(state["lat"][la] - lat) < 1e-9 and abs(state["lon"][lo] - lon) < 1e-9
+    assert state["t_min"].shape == (90, 4, 5) and (np.diff(state["time"]) == 1).all()
+    st = {k: state[k][:, la, lo].astype(np.float64) for k in ("t_min", "t_max", "prec")}
+    assert all(np.isfinite(v).all() and np.abs(v).max() < 1e3 for v in st.values())   # no fill values here
     cell = dict(lat=lat, lon=lon, elev=elev, start="1949-01-01", t_min=tmin, t_max=tmax, prec=prec,
-                wind=wind, state_t_min=tmin[-90:], state_t_max=tmax[-90:], state_prec=prec[-90:],
+                wind=wind, state_t_min=st["t_min"], state_t_max=st["t_max"], state_prec=st["prec"],
                 t_pk12=dom.variables["t_pk"].data[:, la, lo].astype(np.float64),
                 dur12=dom.variables["dur"].data[:, la, lo].astype(np.float64))
     for ts, fname, tag in ((60, "validated_48.3125_-120.5625", "hourly"),

@@ -5,7 +5,8 @@ Scope: exactly what the bundled files under metsim/data use -- version-2 object 
 with "OCHK" continuation chunks), root-group links stored compactly (link messages) or DENSELY
 (link info message -> fractal heap + version-2 B-tree name index, what netCDF-4 writes once a group
 has more than 8 links: state_vic.nc, passthrough.nc), simple dataspaces, fixed-point / IEEE
-floating-point datatypes, CONTIGUOUS uncompressed layout.  Anything else raises
+floating-point datatypes, CONTIGUOUS layout or CHUNKED layout without filters (version-1 B-tree
+of raw data chunks -- every variable with the unlimited time dimension).  Anything else raises
 ``NotImplementedError`` rather than guessing.  Layout follows the HDF5 File Format Specification 3.0
 (sections III.A "Disk Format: Level 1 - Superblock", III.A.2 "Version 2 B-trees", III.G "Fractal
 Heap", IV.A.1.b "Version 2 Data Object Header Prefix", IV.A.2 message types 0x01 dataspace, 0x02 link
@@ -192,8 +193,32 @@ def _links(msgs, b: bytes = b""):
     return links
 
 
+def _chunks(b: bytes, addr: int, rank1: int):
+    """(offsets, size, address) of every raw data chunk under the version-1 B-tree node at ``addr``
+    (spec III.A.1, node type 1)."""
+    if b[addr:addr + 4] != b"TREE" or b[addr + 4] != 1:
+        raise NotImplementedError("chunk B-tree node")
+    level = b[addr + 5]
+    used = struct.unpack("<H", b[addr + 6:addr + 8])[0]
+    q = addr + 8 + 16                                # past the sibling pointers
+    key = 8 + 8 * rank1
+    out = []
+    for _ in range(used):
+        size, mask = struct.unpack("<II", b[q:q + 8])
+        offs = struct.unpack("<%dQ" % rank1, b[q + 8:q + key])
+        child = struct.unpack("<Q", b[q + key:q + key + 8])[0]
+        q += key + 8
+        if level > 0:
+            out += _chunks(b, child, rank1)
+        else:
+            if mask:
+                raise NotImplementedError("filtered chunk")
+            out.append((offs[:-1], size, child))
+    return out
+
+
 def _dataset(b: bytes, off: int):
-    dims = dtype = layout = None
+    dims = dtype = layout = chunked = None
     for mtype, body in _messages(b, off):
         if mtype == 0x01:                            # dataspace
             ver, rank = body[0], body[1]
@@ -211,11 +236,31 @@ def _dataset(b: bytes, off: int):
             else:
                 raise NotImplementedError("datatype class %d" % cls)
         elif mtype == 0x08:                          # data layout
-            if body[0] != 3 or body[1] != 1:
-                raise NotImplementedError("only contiguous layout (version 3, class 1) is supported")
-            layout = struct.unpack("<QQ", body[2:18])
+            if body[0] == 3 and body[1] == 1:
+                layout = struct.unpack("<QQ", body[2:18])
+            elif body[0] == 3 and body[1] == 2:      # chunked: dimensionality, B-tree address, chunk dims
+                rank1 = body[2]
+                tree = struct.unpack("<Q", body[3:11])[0]
+                cdims = struct.unpack("<%dI" % rank1, body[11:11 + 4 * rank1])
+                chunked = (rank1, tree, cdims)
+            else:
+                raise NotImplementedError("only contiguous / chunked layouts (version 3) are supported")
         elif mtype == 0x0B:
             raise NotImplementedError("filtered (compressed) dataset")
+    if dims is not None and dtype is not None and chunked is not None:
+        rank1, tree, cdims = chunked
+        if rank1 != len(dims) + 1 or cdims[-1] != dtype.itemsize:
+            raise NotImplementedError("chunk shape does not match the dataspace")
+        out = np.zeros(dims, dtype=dtype)
+        if tree != UNDEF:
+            for offs, size, addr in _chunks(b, tree, rank1):
+                cshape = cdims[:-1]
+                if size != int(np.prod(cshape)) * dtype.itemsize:
+                    raise NotImplementedError("chunk size does not match its shape (filtered?)")
+                block = np.frombuffer(b, dtype=dtype, count=int(np.prod(cshape)), offset=addr).reshape(cshape)
+                sl = tuple(slice(o, min(o + c, d)) for o, c, d in zip(offs, cshape, dims))
+                out[sl] = block[tuple(slice(0, s_.stop - s_.start) for s_ in sl)]
+        return out
     if dims is None or dtype is None or layout is None:
         raise NotImplementedError("not a simple dataset")
     addr, size = layout

@@ -1,7 +1,10 @@
 import csv, sys, collections
+"""per-source-line executed instructions / stall samples of one kernel of an ncu report:
+python ncu_lines.py rep.ncu-rep [warp-steps to normalise by] [lines to print] [kernel-name regex]"""
 rep, steps = sys.argv[1], float(sys.argv[2]) if len(sys.argv) > 2 else 8*24*482560/32
 import subprocess
-out = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'],capture_output=True,text=True).stdout
+kern = ['-k', 'regex:' + sys.argv[4]] if len(sys.argv) > 4 else []
+out = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'] + kern,capture_output=True,text=True).stdout
 rows=list(csv.reader(out.splitlines()))
 hi=[i for i,r in enumerate(rows) if r and r[0]=='Line No'][0]
 hdr=rows[hi]

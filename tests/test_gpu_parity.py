@@ -945,3 +945,134 @@ def test_daily_output_mode():
     util.assert_close(res["shortwave"].cpu().numpy(), want, "sw_daily", context="daily mode")
     for oname, ename in util.DAILY.items():
         util.assert_close(res["daily"][ename].cpu().numpy(), ref_daily[ename], oname, context="daily mode")
+
+
+# ---- the MetSim-object drop-in (Level 2 of the boundary): run_slice for a whole chunk -------------
+class _DA:
+    """Stand-in for the part of xarray.DataArray that MetSim.run_slice touches: values + dims."""
+    def __init__(self, values, dims):
+        self.values = np.asarray(values)
+        self.dims = tuple(dims)
+        assert self.values.ndim == len(self.dims)
+
+    @property
+    def ndim(self):
+        return self.values.ndim
+
+
+class _MS:
+    """Stand-in for a MetSim object after load_inputs(): params, domain, met_data, state, output."""
+    def __init__(self, params, domain, met_data, state, n_steps, mask_dims, mask_shape, out_dims=None):
+        self.params, self.domain, self.met_data, self.state = params, domain, met_data, state
+        self._n_steps, self._mdims, self._mshape, self._odims = n_steps, mask_dims, mask_shape, out_dims
+        self.validated = False
+
+    def _validate_setup(self):
+        self.validated = True
+
+    def setup_output(self):               # metsim/metsim.py:560-587: NaN-filled (time, *mask.dims)
+        dims = self._odims or ("time",) + tuple(self._mdims)
+        shape = (self._n_steps,) + tuple(self._mshape[self._mdims.index(d)] for d in dims[1:])
+        prec = {"f4": np.float32, "f8": np.float64}[self.params.get("out_precision", "f4")]
+        self.output = {v: _DA(np.full(shape, np.nan, dtype=prec), dims) for v in self.params["out_vars"]}
+
+
+def test_metsim_run_slice_drop_in_on_the_bundled_test_domain():
+    """examples/example_nc.conf's settings through run_slice_batched -- the body of the MetSim
+    subclass of registry.batched_metsim_class -- on the bundled 9x9 test domain (test.nc +
+    domain.nc + state_nc.nc, as stored in tests/golden/testdomain.npz), against what the unmodified
+    reference produced for nine of its cells.  The stand-in hands over xarray-like arrays in a
+    scrambled dimension order, a mask with holes (masked cells must stay NaN, :477-481 / :584) and
+    unit conversions (:489-492)."""
+    from metsim_b200.registry import run_slice_batched
+    inputs, params, _, ref_sub, extra = util.load_golden(os.path.join(util.GOLDEN, "testdomain.npz"))
+    cells = extra["ref_cells"]
+    ny = nx = 9
+    lat1, lon1 = np.unique(inputs["lat"]), np.unique(inputs["lon"])
+    assert lat1.size == ny and lon1.size == nx
+    grid = lambda a: a.reshape(a.shape[0], ny, nx)             # cells are latitude-row-major
+    mask = np.ones((ny, nx), dtype=np.int32)
+    holes = [c for c in (3, 17, 40, 41, 80) if c not in set(cells.tolist())]
+    mask.ravel()[holes] = 0
+    days, tpd = inputs["t_min"].shape[0], 1440 // int(params["time_step"])
+    time = np.datetime64("1950-01-01") + np.arange(days)
+    assert (inputs["doy"] == np.arange(1, days + 1)).all()
+    domain = {"mask": _DA(mask, ("lat", "lon")), "lat": _DA(lat1, ("lat",)), "lon": _DA(lon1, ("lon",)),
+              "elev": _DA(inputs["elev"].reshape(ny, nx).T, ("lon", "lat")),            # transposed on purpose
+              "t_pk": _DA(grid(inputs["t_pk12"]), ("month", "lat", "lon")),
+              "dur": _DA(np.moveaxis(grid(inputs["dur12"]), 0, 2), ("lat", "lon", "month"))}
+    met = {"time": _DA(time, ("time",)),
+           "t_min": _DA(grid(inputs["t_min"]), ("time", "lat", "lon")),
+           "t_max": _DA(np.moveaxis(grid(inputs["t_max"]), 0, 1), ("lat", "time", "lon")),
+           "prec": _DA(grid(inputs["prec"]), ("time", "lat", "lon")),
+           "wind": _DA(np.transpose(grid(inputs["wind"]), (2, 1, 0)), ("lon", "lat", "time"))}
+    state = {k: _DA(grid(inputs["state_" + k]), ("time", "lat", "lon")) for k in ("t_min", "t_max", "prec")}
+    out_units = {"temp": "K", "prec": "mm s-1", "shortwave": "W m-2", "longwave": "W m-2",
+                 "vapor_pressure": "hPa", "rel_humid": "fraction", "air_pressure": "Pa", "wind": "m s-1"}
+    p = dict(params, method="mtclim_b200", out_precision="f8",
+             out_vars={v: {"out_name": v, "units": u} for v, u in out_units.items()})
+    ms = _MS(p, domain, met, state, days * tpd, ("lat", "lon"), (ny, nx), out_dims=("time", "lat", "lon"))
+    run_slice_batched(ms)
+    assert ms.validated
+    conv = {"temp": (1.0, 273.15), "prec": (1.0 / (30 * 60.0), 0.0), "vapor_pressure": (0.01, 0.0),
+            "rel_humid": (0.01, 0.0), "air_pressure": (1000.0, 0.0)}
+    for v in out_units:
+        got = ms.output[v].values.reshape(days * tpd, ny * nx)
+        sc, of = conv.get(v, (1.0, 0.0))
+        e = util.relerr(got[:, cells], ref_sub[v] * sc + of, util.FLOORS[v] * sc)
+        assert e <= 2e-9, (v, e)
+        assert np.isnan(got[:, holes]).all() and not np.isnan(np.delete(got, holes, axis=1)).any(), v
+    # default out_precision (f4), default units, output dimensions in another order
+    p4 = dict(params, method="mtclim_b200", out_vars={v: {"out_name": v} for v in ("temp", "shortwave")})
+    ms4 = _MS(p4, domain, met, state, days * tpd, ("lat", "lon"), (ny, nx), out_dims=("time", "lon", "lat"))
+    run_slice_batched(ms4)
+    got = np.transpose(ms4.output["temp"].values, (0, 2, 1)).reshape(days * tpd, ny * nx)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got[:, cells], ref_sub["temp"], rtol=0, atol=2e-6 * 40)
+    # an output the time step does not offer, and wind without a wind forcing (KeyError in the reference)
+    with pytest.raises(ValueError):
+        run_slice_batched(_MS(dict(p4, out_vars={"pet": {}}), domain, met, state, days * tpd, ("lat", "lon"), (ny, nx)))
+    met_nowind = {k: v for k, v in met.items() if k != "wind"}
+    with pytest.raises(KeyError):
+        run_slice_batched(_MS(dict(p4, out_vars={"wind": {}}), domain, met_nowind, state, days * tpd, ("lat", "lon"), (ny, nx)))
+
+
+def test_metsim_run_slice_drop_in_daily_mode():
+    """time_step = 1440 through the drop-in: the daily out_vars of metsim/metsim.py:660-666 come from
+    the forcings and the daily pass, shortwave as the daily mean flux (:779-781) -- the round-1 code
+    raised KeyError for every one of them but shortwave.  2-D lat / lon arrays (curvilinear-style
+    domain) on a 2 x 5 grid."""
+    from metsim_b200.registry import run_slice_batched
+    inputs, params, ref_daily, _, _ = util.load_golden(os.path.join(util.GOLDEN, "synth_daily.npz"))
+    days, n = inputs["t_min"].shape
+    ny, nx = 2, n // 2
+    g2 = lambda a: a.reshape(ny, nx)
+    g3 = lambda a: a.reshape(a.shape[0], ny, nx)
+    start = np.datetime64("2001-01-01")
+    doy0 = int(inputs["doy"][0])
+    time = start + (doy0 - 1) + np.arange(days)
+    from metsim_b200.engine import calendar_vectors
+    d_chk, m_chk = calendar_vectors(str(time[0]), days)
+    if not ((d_chk == inputs["doy"]).all() and (m_chk == inputs["month"]).all()):
+        pytest.skip("fixture calendar is not a 2001 record")
+    domain = {"mask": _DA(np.ones((ny, nx)), ("y", "x")), "lat": _DA(g2(inputs["lat"]), ("y", "x")),
+              "lon": _DA(g2(inputs["lon"]), ("y", "x")), "elev": _DA(g2(inputs["elev"]), ("y", "x"))}
+    met = {"time": _DA(time, ("time",))}
+    for k in ("t_min", "t_max", "prec", "wind"):
+        met[k] = _DA(g3(inputs[k]), ("time", "y", "x"))
+    state = {k: _DA(g3(inputs["state_" + k]), ("time", "y", "x")) for k in ("t_min", "t_max", "prec")}
+    out_vars = {v: {} for v in ("t_min", "t_max", "t_day", "prec", "vapor_pressure", "shortwave", "tskc",
+                                "pet", "wind", "daylength")}
+    out_vars["t_max"] = {"units": "K"}
+    p = dict(params, out_precision="f8", out_vars=out_vars)
+    ms = _MS(p, domain, met, state, days, ("y", "x"), (ny, nx))
+    run_slice_batched(ms)
+    flat = lambda v: ms.output[v].values.reshape(days, n)
+    np.testing.assert_array_equal(flat("t_min"), inputs["t_min"])
+    np.testing.assert_array_equal(flat("prec"), inputs["prec"])
+    np.testing.assert_array_equal(flat("wind"), inputs["wind"])
+    np.testing.assert_allclose(flat("t_max"), inputs["t_max"] + 273.15, rtol=1e-15)
+    util.assert_close(flat("shortwave"), ref_daily["shortwave"] * ref_daily["daylength"] / 86400.0, "sw_daily")
+    for v, o in (("t_day", "t_day"), ("vapor_pressure", "vp_daily"), ("tskc", "tskc_daily"), ("pet", "pet"),
+                 ("daylength", "daylength")):
+        util.assert_close(flat(v), ref_daily[v], o, context="drop-in daily mode")
