@@ -90,7 +90,8 @@ typedef struct msb_tuning {
                                1 = event-driven kernel for every day */
   int32_t day_prefetch;     /* L1 prefetch distance of the table stream in steps (0 = default 4, -1 = off) */
   int32_t prep_days;        /* padded days per thread of the day-record kernel */
-  int32_t reserved;
+  int32_t streams_path;     /* 0 = one kernel per stream variable (sw_day_kernel, prec_day_kernel),
+                               1 = the fused event-driven stream kernel of round 1 (A/B measurements) */
 } msb_tuning;
 
 /* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ("api.cu", "solar.cu", "daily.cu", "disagg.cu", "disagg_event.cu", "disagg_interior.cu",
-           "sink.cu")
+           "disagg_streams.cu", "sink.cu")
 HEADERS = ("msb_common.cuh", "disagg_common.cuh")
 OUT = os.path.join(CSRC, "libmetsim_b200.so")
 

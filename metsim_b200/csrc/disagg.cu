@@ -132,7 +132,9 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     MSB_TRY(launch_edge(out->day0, a0));
     MSB_TRY(launch_edge(b0, out->day1));
     if (a.var_mask & knot_bits) MSB_TRY(launch_interior_thermo(a, a0, b0, cell_blocks, st));
-    if (a.var_mask & day_bits) MSB_TRY(launch_interior_streams(a, a0, b0, cell_blocks, st));
+    if (a.var_mask & day_bits)
+      MSB_TRY(out->tune.streams_path == 1 ? launch_interior_streams_fused(a, a0, b0, cell_blocks, st)
+                                          : launch_interior_streams(a, a0, b0, cell_blocks, st));
   } else {
     MSB_TRY(launch_day_records(a, a.e0, e1, e1, cell_blocks, st));
     if (full) {            // too short for interior days: the thermodynamic half and the stream half

@@ -420,6 +420,8 @@ int launch_lw_rescale(const DisaggArgs &a, int cell_blocks, cudaStream_t st);
 int exp_tables_ready(cudaStream_t st);
 // interior days [a0, b0) of the default variable set: thermo_knot_kernel / streams_day_kernel
 int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
+int launch_interior_streams_fused(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
+// disagg_streams.cu: sw_day_kernel + prec_day_kernel over the interior days [a0, b0)
 int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
 
 }  // namespace msb

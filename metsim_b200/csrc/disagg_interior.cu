@@ -656,7 +656,9 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   return MSB_OK;
 }
 
-int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
+// round-1 form of the stream half (precipitation + shortwave in one event-driven kernel), kept
+// behind msb_tuning.streams_path = 1 for A/B measurements against disagg_streams.cu
+int launch_interior_streams_fused(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
   a.k.i_lo = a.k.i_hi = 0;
   a.k.e0 = a0; a.k.e1 = b0;            // output days, day_tile per thread
   a.k.tile = kDayTile;
