@@ -131,28 +131,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     };
     MSB_TRY(launch_edge(out->day0, a0));
     MSB_TRY(launch_edge(b0, out->day1));
-    if (a.var_mask & knot_bits) {
-      // thermo_knot_kernel indexes a call's outputs with 32 bits: day ranges of more than 2^31
-      // elements per variable go out as several launches with shifted output pointers
-      const long per_day = (long)a.tpd * (long)out->ld;
-      const int max_days = (int)((1L << 31) / per_day);
-      if (max_days < 1) {
-        set_error("msb_disaggregate: one day of output (%d steps x ld %lld) exceeds the 32-bit store index",
-                  a.tpd, (long long)out->ld);
-        return MSB_E_ARG;
-      }
-      for (int s0 = a0; s0 < b0; s0 += max_days) {
-        const int s1 = s0 + max_days < b0 ? s0 + max_days : b0;
-        DisaggArgs b = a;
-        b.out.day0 = s0; b.out.day1 = s1;
-        for (int v = 0; v < MSB_N_SUBVARS; ++v)
-          if (b.out.var[v])
-            b.out.var[v] = reinterpret_cast<char *>(b.out.var[v]) +
-                           (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld * (size_t)out->dtype;
-        if (b.lw_raw) b.lw_raw += (size_t)(s0 - out->day0) * a.tpd * (size_t)out->ld;
-        MSB_TRY(launch_interior_thermo(b, s0, s1, cell_blocks, st));
-      }
-    }
+    if (a.var_mask & knot_bits) MSB_TRY(launch_interior_thermo(a, a0, b0, cell_blocks, st));
     if (a.var_mask & day_bits)
       MSB_TRY(out->tune.streams_path == 1 ? launch_interior_streams_fused(a, a0, b0, cell_blocks, st)
                                           : launch_interior_streams(a, a0, b0, cell_blocks, st));

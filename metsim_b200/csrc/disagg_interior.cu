@@ -69,24 +69,6 @@ __device__ __forceinline__ double sqrt_2(double x) {
   const double e = fma(-xy, y, 1.0);
   return fma(xy, 0.5 * e, xy);
 }
-// entry j of the table at 32-bit shared-memory address tab_s: an explicit ld.shared keeps the
-// generic-to-shared window arithmetic (S2UR SR_CgaCtaId + ULEA + UMOV per use) out of the step loop
-__device__ __forceinline__ double lds_f64(unsigned tab_s, int j) {
-  double s;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(s) : "r"(tab_s + ((unsigned)j << 3)));
-  return s;
-}
-__device__ __forceinline__ double exp_big_s(double x, unsigned tab_s, const KnotK &K) {
-  const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
-  double kd = fma(x, __hiloint2double(0x40971547, 0), kMagic);
-  const int k = __double2loint(kd);
-  kd -= kMagic;
-  const double r = fma(-kd, K.l, x);
-  const double q = fma(r * 0.5, r, r);            // exp(r) - 1 = r + r^2/2 (+ r^3/6 < 7e-12)
-  double s = lds_f64(tab_s, k & (kExpBig - 1));
-  s = __hiloint2double(__double2hiint(s) + (k << kExpBigShift), __double2loint(s));
-  return fma(q, s, s);
-}
 __device__ __forceinline__ double exp_big(double x, const double *tab, const KnotK &K) {
   const double kMagic = 6755399441055744.0;       // 1.5 * 2^52
   // 1024/ln2 truncated to its high word (an instruction immediate): k may differ by one from
@@ -124,8 +106,6 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   for (int j = threadIdx.x; j < kExpBig; j += blockDim.x) etab[j] = g_exp2_big[j];
   for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = a.f.doy[win0 + j];
   __syncthreads();
-  unsigned etab_s = (unsigned)__cvta_generic_to_shared(etab);
-  asm volatile("mov.u32 %0, %0;" : "+r"(etab_s));   // opaque: computed once, not re-derived per step
   const int tid = threadIdx.x;
   const int cell = blockIdx.x * blockDim.x + tid;
   if (cell >= a.f.n_cells || e_lo >= e_hi) return;
@@ -166,20 +146,16 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
              w_lw = (vm >> MSB_V_LONGWAVE) & 1u, w_wd = (vm >> MSB_V_WIND) & 1u,
              w_sh = (vm >> MSB_V_SPEC_HUMID) & 1u, w_tk = (vm >> MSB_V_TSKC) & 1u;   // MASKED only
 
-  // Store addressing: one 32-bit element index per thread, [step - first step of the call][cell],
-  // against the six base pointers as they sit in the kernel's parameter bank -- one IMAD.WIDE.U32
-  // per store instead of a 64-bit offset add per pointer (the launcher keeps a call below 2^31
-  // output elements per variable, splitting longer day ranges).
-  const unsigned ostride = (unsigned)a.out.ld;
+  const size_t ostride = (size_t)a.out.ld;
   const long i_base = (long)a.out.day0 * a.tpd;
-  OutT *const o_temp = reinterpret_cast<OutT *>(a.out.var[MSB_V_TEMP]);
-  OutT *const o_lw = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]);
-  OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]);
-  OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]);
-  OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]);
-  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]);
-  OutT *const o_sh = reinterpret_cast<OutT *>(a.out.var[MSB_V_SPEC_HUMID]);
-  OutT *const o_tk = reinterpret_cast<OutT *>(a.out.var[MSB_V_TSKC]);
+  OutT *const o_temp = reinterpret_cast<OutT *>(a.out.var[MSB_V_TEMP]) + cell;
+  OutT *const o_lw = reinterpret_cast<OutT *>(a.out.var[MSB_V_LONGWAVE]) + cell;
+  OutT *const o_vp = reinterpret_cast<OutT *>(a.out.var[MSB_V_VAPOR_PRESSURE]) + cell;
+  OutT *const o_rh = reinterpret_cast<OutT *>(a.out.var[MSB_V_REL_HUMID]) + cell;
+  OutT *const o_ap = reinterpret_cast<OutT *>(a.out.var[MSB_V_AIR_PRESSURE]) + cell;
+  OutT *const o_wd = reinterpret_cast<OutT *>(a.out.var[MSB_V_WIND]) + cell;
+  OutT *const o_sh = reinterpret_cast<OutT *>(a.out.var[MSB_V_SPEC_HUMID]) + cell;
+  OutT *const o_tk = reinterpret_cast<OutT *>(a.out.var[MSB_V_TSKC]) + cell;
 
   // tskc and wind: repeated per minute, rolled by off_min, block mean over ts minutes
   // (:593-615, :355-380); wind rides along here because it shares this stream's roll exactly
@@ -262,7 +238,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     const int lo_w = __reduce_min_sync(lanes, any ? ja : kNever);
     const int hi_w = __reduce_max_sync(lanes, any ? jb : -kNever);
     double x = (double)ts * (double)lo_w;
-    unsigned ooff = (unsigned)((long)lo_w - i_base) * ostride + (unsigned)cell;
+    size_t ooff = (size_t)((long)lo_w - i_base) * ostride;
 #pragma unroll 1
     for (int i = lo_w; i < hi_w; ++i, x += dx, ooff += ostride) {
       if (i < ja || i >= jb) continue;
@@ -306,7 +282,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       }
       // -- temperature (PCHIP), saturation vapour pressure in kPa (physics.py:124-152) --
       const double temp = cubic_eval(cub, x);
-      const double es0 = exp_big_s(fma(K.ka, rcp_2(K.k237 + temp), K.kb), etab_s, K);
+      const double es0 = exp_big(fma(K.ka, rcp_2(K.k237 + temp), K.kb), etab, K);
       const double corr = fma(fma(K.kc2, temp, K.kc1), temp, 1.0);
       const double es = es0 * (temp < 0.0 ? corr : 1.0);
       // -- vapour pressure (linear, clamped to saturation) :480-487 --
@@ -315,11 +291,11 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       // -- relative humidity :444-446, air pressure :401-403 --
       const double rh_raw = 100.0 * (vp * rcp_2(es));
       const double rh = rh_raw > 100.0 ? 100.0 : rh_raw;      // np.minimum; vp, es are finite here
-      const double ap = exp_big_s(fma(pr_num, rcp_2(pr_corr + temp), K.ln_p), etab_s, K);
+      const double ap = exp_big(fma(pr_num, rcp_2(pr_corr + temp), K.ln_p), etab, K);
       // -- longwave :491-590 (PRATA + CLOUD_DEARDORFF; tk_a / tk_b carry STEFAN_B) --
       const double at = temp + K.kelvin;
       const double xx = (465.0 * vp) * rcp_2(at);              // 46.5 * (10 vp) / T
-      const double ee = exp_big_s(-sqrt_2(fma(3., xx, K.k12)), etab_s, K);
+      const double ee = exp_big(-sqrt_2(fma(3., xx, K.k12)), etab, K);
       const double e1 = fma(-(1.0 + xx), ee, 1.0);
       const double t2 = at * at;
       double lw = fma(tk_b, e1, tk_a) * (t2 * t2);
@@ -329,7 +305,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
       if (w_rh) __stcs(o_rh + ooff, conv(MSB_V_REL_HUMID, rh));
       if (w_ap) __stcs(o_ap + ooff, conv(MSB_V_AIR_PRESSURE, ap));
       if (w_lw) {
-        if (MASKED && a.lw_raw) a.lw_raw[ooff] = lw;           // passthrough: rescaled by lw_rescale_kernel
+        if (MASKED && a.lw_raw) a.lw_raw[ooff + cell] = lw;    // passthrough: rescaled by lw_rescale_kernel
         else __stcs(o_lw + ooff, conv(MSB_V_LONGWAVE, lw));
       }
       if (w_wd) __stcs(o_wd + ooff, wd_o);
