@@ -275,7 +275,8 @@ def verify_against_oracle(eng, f, params, step_tiles, ring, n_days, tpd, sample=
     n = eng.n_cells
     rng = np.random.default_rng(seed)
     idx = np.sort(rng.choice(n, size=min(sample, n), replace=False))
-    idx_t = torch.as_tensor(idx, device=eng.device)
+    idx_t = torch.as_tensor(idx, device=eng.device)            # columns of the engine's outputs
+    idx_in = idx_t if eng.order is None else eng.order.index_select(0, idx_t)   # the same cells in f
     got = {v: [] for v in OUT_VARS}
     eng.build_solar()
     daily = eng.daily(want=())
@@ -288,7 +289,7 @@ def verify_against_oracle(eng, f, params, step_tiles, ring, n_days, tpd, sample=
     eng.check()                              # synchronises the stream
     got = {v: [t.cpu() for t in parts] for v, parts in got.items()}
     n_iter = n_iter.cpu().numpy()
-    cpu = lambda t: t.index_select(-1, idx_t).cpu().numpy() if t.dim() else t.cpu().numpy()
+    cpu = lambda t: t.index_select(-1, idx_in).cpu().numpy() if t.dim() else t.cpu().numpy()
     kw = {k: cpu(f[k]) for k in ("lat", "lon", "elev", "t_min", "t_max", "prec", "wind", "state_t_min",
                                  "state_t_max", "state_prec", "t_pk12", "dur12")}
     kw["doy"], kw["month"] = f["doy"].cpu().numpy(), f["month"].cpu().numpy()
@@ -341,7 +342,7 @@ def d2h_ceiling(dev, world, nbytes=2 << 30, reps=3):
 class DevicePass:
     """One shard on this rank's GPU: inputs resident in HBM, the timed step, its launch count."""
 
-    def __init__(self, args, dev, lat, lon, n_days, start, ts, prec_type, seed, tile_days=None):
+    def __init__(self, args, dev, lat, lon, n_days, start, ts, prec_type, seed, tile_days=None, patch_rows=0):
         import torch
         from metsim_b200 import synth
         from metsim_b200.engine import Engine
@@ -351,7 +352,11 @@ class DevicePass:
         self.f = synth.make_forcing_torch(lat, lon, n_days, start, dev, seed=seed)
         torch.cuda.empty_cache()
         self.eng = Engine(self.params, dev)
-        self.eng.load(**self.f)
+        order = None
+        if patch_rows and patch_rows > 1:     # masked grids: engine-defined cell order (shard.patch_order)
+            from metsim_b200.shard import patch_order
+            order = patch_order(lat, lon, patch_rows)
+        self.eng.load(order=order, **self.f)
         n, tpd = self.n, self.tpd
         if tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
             tile_days = max(1, int(24.0e9 // (len(OUT_VARS) * tpd * n * 4)))
@@ -499,6 +504,9 @@ def main():
     ap.add_argument("--no-consumer", action="store_true", help="e2e without the native tile consumer")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--verify-cells", type=int, default=512)
+    ap.add_argument("--patch-rows", type=int, default=None,
+                    help="masked grids: latitude rows per patch of the engine-defined cell order "
+                         "(metsim_b200.shard.patch_order; default 4 on the masked global grids, 1 = caller's order)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -561,7 +569,10 @@ def main():
         lat, lon = lat_all, lon_all
 
     # ---- headline pass: every rank owns a shard (different seed = different part of a larger domain)
-    dp = DevicePass(args, dev, lat, lon, n_days, start, ts, prec_type, synth.SEED + rank, args.tile_days)
+    if args.patch_rows is None:
+        args.patch_rows = 4 if grid.startswith("global") else 1
+    dp = DevicePass(args, dev, lat, lon, n_days, start, ts, prec_type, synth.SEED + rank, args.tile_days,
+                    patch_rows=args.patch_rows)
     n, tile = dp.n, dp.tile
     sampler = ClockSampler(local) if rank == 0 else None
     my_ms, br = dp.timed(args.steps, args.warmup, barrier, sampler)
@@ -635,7 +646,7 @@ def main():
     if world > 1 and not headline_strong and not args.no_strong:
         lo, hi = cell_range(n_domain, rank, world)
         sp = DevicePass(args, dev, lat_all[lo:hi], lon_all[lo:hi], n_days, start, ts, prec_type,
-                        synth.SEED + 100 + rank, None)
+                        synth.SEED + 100 + rank, None, patch_rows=args.patch_rows)
         s_ms, s_br = sp.timed(args.steps, args.warmup, barrier)
         s_rank = gather(s_ms)
         s_max = max(s_rank)
@@ -686,6 +697,8 @@ def main():
                        "cells_per_gpu": int(n), "n_days": int(n_days), "time_step_min": ts,
                        "prec_type": prec_type, "utc_offset": True, "out_vars": list(OUT_VARS),
                        "out_precision": "f4", "tile_days": tile,
+                       "cell_order": ("caller's (latitude-row-major)" if args.patch_rows <= 1 else
+                                      f"engine-defined patches of {args.patch_rows} latitude rows (shard.patch_order)"),
                        "launch_geometry": "library defaults: 16 knot-days / 16 output days per thread, daily chunks of "
                                           "ceil(n_days / (2^21 / cells + 1)) days, single-pass daily form",
                        "sharding": (f"one domain of {n_domain} cells cut into {world} contiguous cell ranges, no collective"

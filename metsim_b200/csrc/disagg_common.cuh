@@ -282,8 +282,10 @@ __device__ __forceinline__ double prec_cum(const PrecDay &pd, int m) {
 }
 
 // m = calendar month of day d (1..12)
+// (total: optionally, the unscaled sum of the day's shape = prec_cum(pd, 1440))
 __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_forcing &f,
-                                               int cell, int d, int m, PrecDay &pd) {
+                                               int cell, int d, int m, PrecDay &pd,
+                                               double *total = nullptr) {
   const size_t o = (size_t)d * f.ld + cell;
   const double P = f.prec[o];
   const bool uniform = p.prec_type == MSB_PREC_UNIFORM ||
@@ -292,6 +294,7 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
     pd.p0 = 0; pd.nps = 0; pd.pth = kNever; pd.q0 = 0; pd.nqs = kMinPerDay;
     pd.hsp = 0.0; pd.hsq = 0.0;
     pd.f = P * (1.0 / (double)kMinPerDay);
+    if (total) *total = (double)kMinPerDay;
     return;
   }
   // metsim.py:278-284: month m (1..12) takes domain entry m (0..11); December keeps prec
@@ -318,6 +321,7 @@ __device__ __forceinline__ void prec_day_setup(const msb_params &p, const msb_fo
   pd.hsq = 0.5 * stepq;
   const double S = prec_cum(pd, kMinPerDay);               // np.sum(prec_day), :327
   pd.f = (S > 0.0 && P == P) ? div_nr(P, S) : nan("");     // 0/0 or x/0 * 0 -> NaN day (:327)
+  if (total) *total = S;
 }
 
 // value of output step i for the rolled per-minute record (disaggregate.py:347-351); NaN when the

@@ -22,7 +22,36 @@
 
 namespace msb {
 
-constexpr int kSwBatch = 8;   // table entries in flight per thread
+// One segment of a day's windows: all of them inside one table row, so the entries are an arithmetic
+// progression of addresses and a window is rd * (next entry - this entry).  The loop is unrolled by
+// four with the loads first: four independent 8-byte loads in flight per thread.
+template <typename OutT, bool UNITS>
+__device__ __forceinline__ void sw_segment(const double *__restrict__ ptr, int stride, int n, double rd,
+                                           double &v0, OutT *&o_sw, size_t ostride, double sc, double of) {
+  int t = 0;
+  for (; t + 4 <= n; t += 4) {
+    const double a0 = __ldg(ptr), a1 = __ldg(ptr + stride), a2 = __ldg(ptr + 2 * stride),
+                 a3 = __ldg(ptr + 3 * stride);
+    ptr += 4 * stride;
+    double s0 = rd * (a0 - v0), s1 = rd * (a1 - a0), s2 = rd * (a2 - a1), s3 = rd * (a3 - a2);
+    if (UNITS) { s0 = fma(s0, sc, of); s1 = fma(s1, sc, of); s2 = fma(s2, sc, of); s3 = fma(s3, sc, of); }
+    __stcs(o_sw, (OutT)s0);
+    __stcs(o_sw + ostride, (OutT)s1);
+    __stcs(o_sw + 2 * ostride, (OutT)s2);
+    __stcs(o_sw + 3 * ostride, (OutT)s3);
+    o_sw += 4 * ostride;
+    v0 = a3;
+  }
+  for (; t < n; ++t) {
+    const double a0 = __ldg(ptr);
+    ptr += stride;
+    double s0 = rd * (a0 - v0);
+    if (UNITS) s0 = fma(s0, sc, of);
+    __stcs(o_sw, (OutT)s0);
+    o_sw += ostride;
+    v0 = a0;
+  }
+}
 
 template <typename OutT, bool UNITS>
 __global__ void __launch_bounds__(kDisaggThreads)
@@ -44,13 +73,14 @@ sw_day_kernel(const __grid_constant__ DisaggArgs a) {
   const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;   // :655
   // The day's windows start at tiny step c0 of table row / radiation day A = (.) + q and cross
   // into B = A + 1 at window t_b (the first one that starts at or beyond the end of row A);
-  // window t_x = t_b - 1 straddles the two when the crossing is not clean.
+  // window t_a = t_b - 1 straddles the two when the crossing is not clean.
   const int q = off_tiny < 0 ? -1 : 0;
   const int c0 = off_tiny - q * kTiny;                       // [0, 2880)
   const int t_b = (kTiny - c0 + C - 1) / C;
-  const int t_x = (kTiny - c0) % C ? t_b - 1 : -1;
-  // the window that contains tiny step 1440 of its row: the signed prefix table changes sign there
-  // and the row total goes on once (solar.cu)
+  const bool straddle = (kTiny - c0) % C != 0;
+  const int t_a = straddle ? t_b - 1 : t_b;                  // windows [0, t_a) lie inside row A
+  // The window that contains tiny step 1440 of its row: the signed prefix table changes sign there
+  // and the row total goes on once (solar.cu).  It splits its row's segment in two.
   const bool noon_in_a = c0 <= kNoon;
   const int t_n = ((noon_in_a ? kNoon : kNoon + kTiny) - c0) / C;
   const int row0 = f.lat_row[cell];
@@ -76,37 +106,41 @@ sw_day_kernel(const __grid_constant__ DisaggArgs a) {
   double rd_a = rad_of(d_lo + q);
   for (int d = d_lo; d < d_hi; ++d) {
     const int y = s_doy[d - win0] - 1;
-    const int ra = row_of(y + q), rb = row_of(y + q + 1);
-    // element offsets from qrow such that entry t of the day is at (t < t_b ? e_a : e_b) + t C
-    const int e_a = ra * kQLd + c0, e_b = rb * kQLd + c0 - kTiny;
+    const double *const qa = qrow + row_of(y + q) * kQLd + c0;                    // entry t of row A at qa[t C]
+    const double *const qb = qrow + row_of(y + q + 1) * kQLd + (c0 - kTiny);      // entry t of row B at qb[t C]
     const double rd_b = rad_of(d + q + 1);
-    const double rowtot = qrow[(noon_in_a ? ra : rb) * kQLd + kTiny + 1];
-    double v0 = qrow[(0 < t_b ? e_a : e_b)];
-    for (int t0 = 0; t0 < tpd; t0 += kSwBatch) {
-      double v[kSwBatch];
-#pragma unroll
-      for (int j = 0; j < kSwBatch; ++j) {
-        const int t = t0 + j + 1;
+    const double rowtot = (noon_in_a ? qa : qb)[kTiny + 1 - (noon_in_a ? c0 : c0 - kTiny)];
 #ifdef MSB_BOUNDS
-        if (t <= tpd && (unsigned)((t < t_b ? e_a : e_b) + t * C) >= 365u * kQLd) asm volatile("trap;");
+    if (qa + (long)t_a * C >= qrow + (size_t)365 * kQLd || qb + (long)tpd * C >= qrow + (size_t)365 * kQLd ||
+        qb + (long)t_b * C < qrow) asm volatile("trap;");
 #endif
-        v[j] = t <= tpd ? __ldg(qrow + ((t < t_b ? e_a : e_b) + t * C)) : 0.0;
-      }
-#pragma unroll
-      for (int j = 0; j < kSwBatch; ++j) {
-        const int t = t0 + j;
-        if (t < tpd) {
-          const double v1 = v[j];
-          const double lo = t == t_n ? v0 - rowtot : v0;
-          double sw = (t < t_b ? rd_a : rd_b) * (v1 - lo);
-          // straddling window: [.., 2880) of row A (q_A[2880] = 0) + [0, ..) of row B (q_B[0] = 0)
-          if (t == t_x) sw = fma(rd_b, v1, -(rd_a * lo));
-          if (UNITS) sw = fma(sw, sc, of);
-          __stcs(o_sw, (OutT)sw);
-          o_sw += ostride;
-          v0 = v1;
-        }
-      }
+    double v0 = __ldg(qa);
+    // ---- windows inside row A: [0, t_a), the noon window (if it is here) splitting them ----
+    if (noon_in_a) {
+      sw_segment<OutT, UNITS>(qa + C, C, t_n, rd_a, v0, o_sw, ostride, sc, of);
+      v0 -= rowtot;
+      sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * C, C, t_a - t_n, rd_a, v0, o_sw, ostride, sc, of);
+    } else {
+      sw_segment<OutT, UNITS>(qa + C, C, t_a, rd_a, v0, o_sw, ostride, sc, of);
+    }
+    // ---- the straddling window: [.., 2880) of row A (q_A[2880] = 0) + [0, ..) of row B (q_B[0] = 0) ----
+    if (straddle) {
+      const double v1 = __ldg(qb + (long)t_b * C);
+      double sw = fma(rd_b, v1, -(rd_a * v0));
+      if (UNITS) sw = fma(sw, sc, of);
+      __stcs(o_sw, (OutT)sw);
+      o_sw += ostride;
+      v0 = v1;
+    } else {
+      v0 = 0.0;                    // clean crossing: row B starts at its entry 0 (an empty prefix)
+    }
+    // ---- windows inside row B: [t_b, tpd) ----
+    if (noon_in_a) {
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, tpd - t_b, rd_b, v0, o_sw, ostride, sc, of);
+    } else {
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, t_n - t_b, rd_b, v0, o_sw, ostride, sc, of);
+      v0 -= rowtot;
+      sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * C, C, tpd - t_n, rd_b, v0, o_sw, ostride, sc, of);
     }
     rd_a = rd_b;
   }
@@ -166,11 +200,11 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
   const int t_b = (kMinPerDay - r0 + ts - 1) / ts;
   const int n1 = (kMinPerDay - r0) % ts;
   const int t_a = n1 ? t_b - 1 : t_b;                        // windows [0, t_a) lie inside day A
-  auto setup = [&](int d, PrecDay &pd) {
+  auto setup = [&](int d, PrecDay &pd, double &tot) {
 #ifdef MSB_BOUNDS
     if ((unsigned)(d - win0) >= (unsigned)nwin || (unsigned)d >= (unsigned)D) asm volatile("trap;");
 #endif
-    prec_day_setup(p, f, cell, d, s_month[d - win0], pd);
+    prec_day_setup(p, f, cell, d, s_month[d - win0], pd, &tot);
   };
   const double sc = UNITS ? a.out.scale[MSB_V_PREC] : 1.0, of = UNITS ? a.out.offset[MSB_V_PREC] : 0.0;
   const size_t ostride = (size_t)a.out.ld;
@@ -185,7 +219,8 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
   };
 
   PrecDay pa, pb;
-  setup(d_lo + q, pa);
+  double tot_a, tot_b;           // unscaled totals of the two days' shapes, S(1440)
+  setup(d_lo + q, pa, tot_a);
   // What pandas' ffill repeats into a NaN step is the last valid value before it: inside the chunk
   // that is simply the value of the previous step (`last`); a chunk that OPENS with a NaN step
   // looks back once (cold), and if nothing valid precedes it the run is back-filled afterwards.
@@ -198,10 +233,13 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
       have_last = true;
     }
   };
+  // cumulative shape of day A at the day's first window start; from the second day on it is where
+  // the previous day's windows inside (then) day B ended
+  double s_a = (pa.f == pa.f) ? prec_cum(pa, r0) : 0.0;
   for (int d = d_lo; d < d_hi; ++d) {
-    setup(d + q + 1, pb);
+    setup(d + q + 1, pb, tot_b);
     const bool nan_a = !(pa.f == pa.f), nan_b = !(pb.f == pb.f);
-    double s_prev = nan_a ? 0.0 : prec_cum(pa, r0);
+    double s_prev = s_a;
     // windows inside source day A
     if (t_a > 0) {
       if (nan_a) {
@@ -221,20 +259,22 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
       }
     }
     // the straddling window: n1 minutes of day A, ts - n1 of day B; a NaN part makes it NaN
+    double s_b = 0.0;              // cumulative shape of day B where its first full window starts
     if (n1) {
+      if (!nan_b) s_b = prec_cum(pb, ts - n1);
       if (nan_a || nan_b) need_last();
-      else last = fma(pb.f, prec_cum(pb, ts - n1), pa.f * (prec_cum(pa, kMinPerDay) - s_prev));
+      else last = fma(pb.f, s_b, pa.f * (tot_a - s_prev));
       put(last);
       have_last = true;
     }
     // windows inside source day B
+    s_prev = s_b;
     if (t_b < tpd) {
       if (nan_b) {
         need_last();
         for (int t = t_b; t < tpd; ++t) put(last);
       } else {
         int m = t_b * ts + r0 - kMinPerDay;                  // minute of day B at which window t_b starts
-        s_prev = prec_cum(pb, m);
 #pragma unroll 2
         for (int t = t_b; t < tpd; ++t) {
           m += ts;
@@ -247,6 +287,8 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
       }
     }
     pa = pb;
+    tot_a = tot_b;
+    s_a = s_prev;                  // = S_B(r0): day B is tomorrow's day A
   }
 
   // a NaN run that reaches back to the start of the record: bfill (disaggregate.py:130)

@@ -87,6 +87,7 @@ class Engine:
         self._solar_bufs = None
         self._solar_done = None
         self.n_cells = self.n_days = 0
+        self.order = None
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, a, dtype, shape=None):
@@ -114,10 +115,32 @@ class Engine:
     def load(self, *, lat, lon, elev, doy, month, t_min, t_max, prec, wind=None,
              state_t_min, state_t_max, state_prec, t_pk12=None, dur12=None, t_end=None,
              given_shortwave=None, given_vapor_pressure=None, given_tskc=None,
-             given_longwave=None):
+             given_longwave=None, order=None):
         """``given_*`` are the forcing columns of the 'passthrough' method
-        (metsim/methods/passthrough.py:28-46), daily ``[D][N]``; shortwave is required there."""
+        (metsim/methods/passthrough.py:28-46), daily ``[D][N]``; shortwave is required there.
+
+        ``order``: optional engine cell order (a permutation, engine position -> caller position,
+        e.g. :func:`metsim_b200.shard.patch_order` for masked grids).  Every per-cell input is
+        gathered into that order once, on the device; :meth:`disaggregate` / :meth:`daily` then work
+        and return in ENGINE order (``self.order`` maps back), :meth:`run` returns the caller's
+        order unless asked otherwise."""
         f64, i32 = torch.float64, torch.int32
+        self.order = None
+        if order is not None:
+            o = np.asarray(order, dtype=np.int64)
+            if o.ndim != 1 or not np.array_equal(np.sort(o), np.arange(o.size)):
+                raise ValueError("order must be a permutation of the cells")
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                self.order = torch.as_tensor(o, device=self.device)
+            pick = lambda a: None if a is None else (
+                a.to(self.device).index_select(a.dim() - 1, self.order) if isinstance(a, torch.Tensor)
+                else np.ascontiguousarray(np.asarray(a)[..., o]))
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                (lat, lon, elev, t_min, t_max, prec, wind, state_t_min, state_t_max, state_prec, t_pk12, dur12,
+                 t_end, given_shortwave, given_vapor_pressure, given_tskc, given_longwave) = (
+                    pick(a) for a in (lat, lon, elev, t_min, t_max, prec, wind, state_t_min, state_t_max,
+                                      state_prec, t_pk12, dur12, t_end, given_shortwave,
+                                      given_vapor_pressure, given_tskc, given_longwave))
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             t = self._t
             t["t_min"] = self._dev(t_min, f64)
@@ -327,8 +350,20 @@ class Engine:
                                                  C.byref(sd), C.c_void_p(self.stream.cuda_stream)))
         return res
 
-    def run(self, out_vars=DEFAULT_OUT_VARS, out_dtype=torch.float32, units=None, daily_vars=()):
-        """solar tables -> daily -> disaggregate for the whole record; returns tensors.
+    def _user_order(self, t):
+        """[rows][cells in engine order] -> the caller's cell order (an extra pass; a streaming
+        consumer takes ``self.order`` into its ``cell_index`` instead)."""
+        if self.order is None or t is None or t.dim() == 0:
+            return t
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            out = torch.empty_like(t)
+            out.index_copy_(t.dim() - 1, self.order, t)
+        return out
+
+    def run(self, out_vars=DEFAULT_OUT_VARS, out_dtype=torch.float32, units=None, daily_vars=(),
+            engine_order: bool = False):
+        """solar tables -> daily -> disaggregate for the whole record; returns tensors (in the caller's
+        cell order unless ``engine_order``).
 
         ``time_step=1440`` is the reference's daily-output mode (metsim/metsim.py:779-792): no
         disaggregation, and ``res['shortwave']`` is the daily average flux
@@ -342,6 +377,9 @@ class Engine:
             res["shortwave"] = daily["shortwave_daily"]
         else:
             res = self.disaggregate(out_vars, 0, self.n_days, out_dtype, units)
+        if self.order is not None and not engine_order:
+            res = {k: self._user_order(v) for k, v in res.items()}
+            daily = {k: self._user_order(v) for k, v in daily.items()}
         self.check()
         self.stream.synchronize()
         res["daily"] = daily

@@ -37,6 +37,32 @@ def cell_range(n_cells: int, rank: int, world: int, align: int = 32) -> tuple[in
     return edge(rank), edge(rank + 1)
 
 
+def patch_order(lat, lon, rows: int = 4) -> np.ndarray:
+    """Engine cell order for MASKED grids: a permutation ``order`` (engine position -> position in
+    the caller's latitude-row-major enumeration) that makes every run of 32 consecutive cells -- one
+    warp -- compact in longitude.
+
+    The kernels put consecutive cells on the lanes of a warp.  On a dense grid a warp then holds 32
+    neighbouring longitudes of one latitude row (2 degrees at 1/16 degree) and the lanes share their
+    daily schedule: sunrise / sunset knots, the step at which the longitude roll falls, the table
+    rows they read.  With a one-in-three land mask on a 0.5 degree grid the same 32 cells span ~48
+    degrees = 3.2 hours of local time, so per-lane state updates run 4-5 times per warp and the
+    lanes' step ranges no longer coincide (profiles/README.md).  Taking the cells of ``rows``
+    neighbouring latitude rows together, ordered by longitude, divides that span by ``rows`` at the
+    price of ``rows`` latitudes (table rows) per warp.  ``rows = 1`` is the identity for
+    row-major input.  Results come out in engine order; ``order`` maps them back
+    (``out_user[..., order] = out_engine``) or goes into the writer's ``cell_index``."""
+    lat = np.asarray(lat, dtype=np.float64)
+    lon = np.asarray(lon, dtype=np.float64)
+    if lat.shape != lon.shape or lat.ndim != 1:
+        raise ValueError("lat and lon must be 1-D arrays of the same length")
+    rows = max(1, int(rows))
+    ulat, row = np.unique(lat, return_inverse=True)
+    band = row // rows
+    # bands in latitude order; inside a band by longitude, then latitude (stable: ties keep input order)
+    return np.lexsort((row, lon, band)).astype(np.int64)
+
+
 def shard_inputs(inputs: dict, rank: int, world: int, align: int = 32) -> dict:
     """Slice an engine input dict (numpy arrays or torch tensors) to this rank's cells."""
     n = len(inputs["lat"])

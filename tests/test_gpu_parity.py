@@ -1076,3 +1076,28 @@ def test_metsim_run_slice_drop_in_daily_mode():
     for v, o in (("t_day", "t_day"), ("vapor_pressure", "vp_daily"), ("tskc", "tskc_daily"), ("pet", "pet"),
                  ("daylength", "daylength")):
         util.assert_close(flat(v), ref_daily[v], o, context="drop-in daily mode")
+
+
+@pytest.mark.parametrize("rows", [2, 4, 8])
+def test_patch_cell_order_for_masked_grids_changes_nothing_but_the_order(rows):
+    """The engine-defined cell order for masked grids (shard.patch_order): inputs are gathered into
+    patch order on the device, the kernels run on it, results equal the oracle's in the caller's order
+    (Engine.run) and, in engine order, are the same numbers permuted (what a writer's cell_index absorbs)."""
+    import torch
+    from metsim_b200 import shard, synth
+    from metsim_b200._lib import SUB_VARS
+    from metsim_b200.engine import Engine
+    from oracle import oracle_lib
+    f, params = synth.make_config("global_half_deg", max_cells=1500, n_days=40)
+    want = oracle_lib.run(params, **util.oracle_kwargs(f))
+    order = shard.patch_order(f["lat"], f["lon"], rows)
+    assert not np.array_equal(order, np.arange(order.size))
+    eng = Engine(params)
+    eng.load(order=order, **{k: f.get(k) for k in util.INPUT_KEYS})
+    res = eng.run(out_vars=SUB_VARS, out_dtype=torch.float64)
+    for v in util.SUB:
+        util.assert_close(res[v].cpu().numpy(), want[v], v, context=f"patch order rows={rows}")
+    np.testing.assert_array_equal(res["daily"]["n_iter"].cpu().numpy(), want["n_iter"])
+    raw = eng.run(out_vars=("temp", "prec"), out_dtype=torch.float64, engine_order=True)
+    for v in ("temp", "prec"):
+        np.testing.assert_array_equal(raw[v].cpu().numpy(), res[v].cpu().numpy()[:, order])

@@ -97,3 +97,25 @@ def test_two_rank_gloo_sharded_run_matches_unsharded():
     status, shapes = q.get(timeout=10)
     assert status == "ok"
     assert shapes["temp"] == (12 * 24, 150)
+
+
+def test_patch_order_is_a_permutation_that_makes_warps_compact():
+    """Masked 0.5 degree grid, one cell in three: 32 consecutive cells of the row-major order span
+    ~48 degrees of longitude; in patch order (4 latitude rows together) a quarter of that."""
+    from metsim_b200 import synth
+    lat, lon = synth.grid_cells("global0.5", np.random.default_rng(synth.SEED))
+    for rows in (1, 2, 4, 8):
+        order = shard.patch_order(lat, lon, rows)
+        assert np.array_equal(np.sort(order), np.arange(lat.size))
+        la, lo = lat[order], lon[order]
+        n_warps = lat.size // 32
+        span = np.ptp(lo[:n_warps * 32].reshape(n_warps, 32), axis=1)
+        lats = np.array([np.unique(w).size for w in la[:n_warps * 32].reshape(n_warps, 32)])
+        if rows == 1:
+            assert np.array_equal(order, np.arange(lat.size))          # row-major input stays as it is
+            base = np.median(span)
+            assert base > 40.0
+        else:
+            assert np.median(span) < 1.3 * base / rows and np.median(lats) <= rows and lats.max() <= 2 * rows
+    with pytest.raises(ValueError):
+        shard.patch_order(np.zeros(3), np.zeros(4))
