@@ -54,7 +54,7 @@ __device__ __forceinline__ void sw_segment(const double *__restrict__ ptr, int s
 }
 
 template <typename OutT, bool UNITS>
-__global__ void __launch_bounds__(kDisaggThreads)
+__global__ void __launch_bounds__(kDisaggThreads, 8)
 sw_day_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ int s_doy[kDayWin];
   const msb_params &p = a.p;
@@ -114,6 +114,16 @@ sw_day_kernel(const __grid_constant__ DisaggArgs a) {
     if (qa + (long)t_a * C >= qrow + (size_t)365 * kQLd || qb + (long)tpd * C >= qrow + (size_t)365 * kQLd ||
         qb + (long)t_b * C < qrow) asm volatile("trap;");
 #endif
+    // Tomorrow's entries into L1 while today computes: the segments below are short loops of dependent
+    // batches (a batch of four loads, then its four windows), so what hides the table latency is
+    // that the loads hit L1.  One prefetch per entry; neighbouring lanes share the lines.
+    if (a.k.pf && d + 1 < d_hi) {
+      const int y1 = s_doy[d + 1 - win0] - 1;
+      const double *pa = qrow + row_of(y1 + q) * kQLd + c0;
+      const double *pb = qrow + row_of(y1 + q + 1) * kQLd + (c0 - kTiny) + (long)t_b * C;
+      for (int t = 0; t <= t_a; ++t, pa += C) prefetch_l1(pa);
+      for (int t = t_b; t <= tpd; ++t, pb += C) prefetch_l1(pb);
+    }
     double v0 = __ldg(qa);
     // ---- windows inside row A: [0, t_a), the noon window (if it is here) splitting them ----
     if (noon_in_a) {
@@ -312,7 +322,7 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
   while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 8 * 6)
     a.k.tile >>= 1;
   if (a.out.tune.day_tile > 0) a.k.tile = a.out.tune.day_tile < kDayWin - 8 ? a.out.tune.day_tile : kDayWin - 8;
-  a.k.pf = 0;
+  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : 1;      // sw_day_kernel: L1 prefetch of the next day's table entries
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
   const bool f4 = a.out.dtype == 4;
   if (a.var_mask & (1u << MSB_V_SHORTWAVE)) {
