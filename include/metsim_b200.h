@@ -85,13 +85,12 @@ typedef struct msb_tuning {
   int32_t daily_chunk_len;  /* days per thread of the daily pass */
   int32_t daily_two_pass;   /* != 0: two-pass daily form even when candidate planes are supplied */
   int32_t knot_tile;        /* knot-days per thread of the interior thermodynamic kernel, used as given */
-  int32_t day_tile;         /* output days per thread of the interior stream kernel, used as given */
+  int32_t day_tile;         /* output days per thread of the interior shortwave / precipitation kernels, used as given */
   int32_t disagg_path;      /* 0 = specialised interior-day kernels + event kernel on the edge days,
                                1 = event-driven kernel for every day */
-  int32_t day_prefetch;     /* L1 prefetch distance of the table stream in steps (0 = default 4, -1 = off) */
+  int32_t day_prefetch;     /* -1 = no L1 prefetch of the next day's table entries in the shortwave kernel */
   int32_t prep_days;        /* padded days per thread of the day-record kernel */
-  int32_t streams_path;     /* 0 = one kernel per stream variable (sw_day_kernel, prec_day_kernel),
-                               1 = the fused event-driven stream kernel of round 1 (A/B measurements) */
+  int32_t reserved;
 } msb_tuning;
 
 /* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of

@@ -102,7 +102,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
   const bool f4 = out->dtype == 4;
   const bool full = example && a.var_mask == kExampleMask && f4 && !units && fast_lw && !a.lw_raw;
   const unsigned knot_bits = kThermoBits | (1u << MSB_V_WIND) | (1u << MSB_V_TSKC);   // thermo_knot_kernel's outputs
-  const unsigned day_bits = (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE);  // streams_day_kernel's
+  const unsigned day_bits = (1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE);  // sw_day_kernel, prec_day_kernel
   a.inv_sw_den = 1.0 / (3600.0 * ((double)ts / 60.0));
   const int D = f->n_days;
   // interior days [a0, b0) of this call: every knot exists, no NaN ends, no wrapped stream
@@ -111,7 +111,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
 #define MSB_TRY(expr) do { rc = (expr); if (rc != MSB_OK) return rc; } while (0)
   if (example && a0 < b0) {
     // the record's first / last two days: day records + disagg_kernel on that sub-range (output
-    // pointers shifted); everything else: thermo_knot_kernel + streams_day_kernel, no records
+    // pointers shifted); everything else: thermo_knot_kernel + sw_day_kernel + prec_day_kernel, no records
     // (all records first: with the utc roll the first day of a record reads the last one's)
     if (out->day0 < a0) MSB_TRY(launch_day_records(a, out->day0 - MSB_REC_MARGIN, a0 + MSB_REC_MARGIN, e1, cell_blocks, st));
     if (b0 < out->day1) MSB_TRY(launch_day_records(a, b0 - MSB_REC_MARGIN, out->day1 + MSB_REC_MARGIN, e1, cell_blocks, st));
@@ -132,9 +132,7 @@ extern "C" int msb_disaggregate(const msb_params *p, const msb_forcing *f,
     MSB_TRY(launch_edge(out->day0, a0));
     MSB_TRY(launch_edge(b0, out->day1));
     if (a.var_mask & knot_bits) MSB_TRY(launch_interior_thermo(a, a0, b0, cell_blocks, st));
-    if (a.var_mask & day_bits)
-      MSB_TRY(out->tune.streams_path == 1 ? launch_interior_streams_fused(a, a0, b0, cell_blocks, st)
-                                          : launch_interior_streams(a, a0, b0, cell_blocks, st));
+    if (a.var_mask & day_bits) MSB_TRY(launch_interior_streams(a, a0, b0, cell_blocks, st));
   } else {
     MSB_TRY(launch_day_records(a, a.e0, e1, e1, cell_blocks, st));
     if (full) {            // too short for interior days: the thermodynamic half and the stream half

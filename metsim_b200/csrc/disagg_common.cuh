@@ -54,7 +54,7 @@ struct DisaggArgs {
   int fill[4];           // padded days whose records are valid: [fill[0], fill[1]) and [fill[2], fill[3])
                          // (the specialised path only builds the records around the edge days)
   bool sw_full_day;    // passthrough without sw_averaging='daylight': daylength := 86400 (disaggregate.py:78-80)
-  // work range of the interior-day kernels (thermo_knot_kernel, streams_day_kernel)
+  // work range of the interior-day kernels (thermo_knot_kernel, sw_day_kernel, prec_day_kernel)
   struct { int e0, e1, tile, i_lo, i_hi, pf; } k;   // pf: L1 prefetch distance of the table stream (steps)
   int e0, n_rec;       // e runs over [-1, D]: -1 / D are the padded PCHIP ends
 };
@@ -422,9 +422,8 @@ int launch_lw_rescale(const DisaggArgs &a, int cell_blocks, cudaStream_t st);
 
 // disagg_interior.cu
 int exp_tables_ready(cudaStream_t st);
-// interior days [a0, b0) of the default variable set: thermo_knot_kernel / streams_day_kernel
+// interior days [a0, b0): thermo_knot_kernel
 int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
-int launch_interior_streams_fused(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
 // disagg_streams.cu: sw_day_kernel + prec_day_kernel over the interior days [a0, b0)
 int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st);
 

@@ -1,7 +1,7 @@
-// The two specialised kernels of the interior days [2, D-2) of a record, default variable set
-// (examples/example_nc.conf: temp, prec, shortwave, longwave, vapor_pressure, rel_humid,
-// air_pressure, wind; no unit conversion), float32 or float64 outputs -- and the accuracy probe
-// of every hand-written fp64 sequence (msb_selftest_math).
+// The thermodynamic kernel of the interior days [2, D-2) of a record (temp, vapor_pressure,
+// rel_humid, air_pressure, longwave, wind -- and spec_humid / tskc in the masked instantiation),
+// float32 or float64 outputs -- and the accuracy probe of every hand-written fp64 sequence
+// (msb_selftest_math).  Shortwave and precipitation of the same days: disagg_streams.cu.
 #include <mutex>
 
 #include "disagg_common.cuh"
@@ -320,270 +320,6 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   }
 }
 
-// ---- interior days of the fast path: source-stream kernel with a fixed daily schedule -------------
-// Precipitation (minute stream) and shortwave (30 s stream) of the interior days [2, D-2) -- wind
-// is written by thermo_knot_kernel, which already follows the minute stream's roll for tskc --
-// where neither rolled stream wraps around the record.  Same closed forms as disagg_kernel, but the
-// daily schedule is made explicit: for a given cell the roll of the minute stream, the roll of the
-// 30 s stream and the noon crossing happen at the SAME step of every output day (they depend on
-// the longitude offsets only), so they are four per-cell constants instead of a searched event
-// queue, and what a roll needs about the next source day is fetched at the start of the output
-// day into per-thread shared-memory slots.  The handlers are short, load-free state updates.
-enum { kY_PPACK = 0, kY_HSP, kY_HSQ, kY_PF, kY_RAD, kY_QB0, kY_QBK, kY_QAEND, kY_ROWTOT,
-       kY_ROWTOT_CUR, kY_COUNT };
-
-template <typename OutT, int MINB, bool MASKED>
-__global__ void __launch_bounds__(kDisaggThreads, MINB)
-streams_day_kernel(const __grid_constant__ DisaggArgs a) {
-  __shared__ double slot[kY_COUNT][kDisaggThreads];
-  __shared__ int s_doy[kDayWin], s_month[kDayWin];
-  const msb_params &p = a.p;
-  const msb_forcing &f = a.f;
-  const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
-  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
-  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
-  const int win0 = max(d_lo - 4, 0), nwin = min(min(d_hi + 4, D) - win0, kDayWin);
-  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
-    s_doy[j] = f.doy[win0 + j];
-    s_month[j] = f.month[win0 + j];
-  }
-  __syncthreads();
-  const int tid = threadIdx.x;
-  const int cell = blockIdx.x * blockDim.x + tid;
-  if (cell >= f.n_cells || d_lo >= d_hi) return;
-  const long ld = f.ld;
-  const int C = 2 * ts;                                     // tiny steps per output step (:660)
-  const bool w_prec = !MASKED || ((a.var_mask >> MSB_V_PREC) & 1u);
-  const bool w_sw = !MASKED || ((a.var_mask >> MSB_V_SHORTWAVE) & 1u);
-  const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
-  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349,:376
-  const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;      // :655
-  const double *const qrow = a.t.q + (size_t)f.lat_row[cell] * 365 * kQLd;
-  auto q_of = [&](int y) {     // table row y rolled over the table's own 366 rows (:656)
-    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
-    return qrow + (size_t)min(y, 364) * kQLd;               // row 365 is a copy of row 364
-  };
-#ifdef MSB_BOUNDS   // debug build (python -m metsim_b200.build --bounds): window / table accesses checked
-#define MSB_CHECK_WIN(d) do { if ((unsigned)((d) - win0) >= (unsigned)nwin) asm volatile("trap;"); } while (0)
-#define MSB_CHECK_Q(ptr) do { if ((ptr) < qrow || (ptr) >= qrow + (size_t)365 * kQLd + MSB_Q_PAD / 2) asm volatile("trap;"); } while (0)
-#else
-#define MSB_CHECK_WIN(d) do { } while (0)
-#define MSB_CHECK_Q(ptr) do { } while (0)
-#endif
-  // what disagg_prepare_kernel would put into the record of source day d: done here, once per
-  // (cell, day) with the warp converged, so the interior days need no record traffic at all
-  const double *const dayl = a.t.daylength + (size_t)f.lat_row[cell] * kRows;
-  const double *const sw_d = daily_plane(a, a.sw_d, cell);
-  auto rad_of = [&](int d) {   // tmp_rad of day d, disaggregate.py:645
-    MSB_CHECK_WIN(d);
-    const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
-    return (sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
-  };
-  auto lookback = [&](int i, bool &none) {   // what pandas ffill repeats at step i (cold)
-    Cell c;
-    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
-    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
-    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
-    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
-    c.t_end = f.t_end;
-    const double v = prec_lookback(p, f, c, i);
-    if (!(v == v)) none = true;
-    return v;
-  };
-
-  // ---- the cell's daily schedule (steps of the output day at which something happens) ----------
-  // minute stream: output day d reads source day d + mq - 1 up to the roll at step t_s, then
-  // source day d + mq; n2m minutes of the straddling window belong to the new day (0 = clean)
-  const int qm = off_min < 0 ? -1 : 0;
-  const int r0 = off_min - qm * kMinPerDay;                 // [0, 1440)
-  const int mq = r0 == 0 ? qm : qm + 1;
-  const int t_s = r0 == 0 ? 0 : (kMinPerDay - r0) / ts;
-  const int n1m = r0 == 0 ? 0 : kMinPerDay - r0 - t_s * ts;
-  const int n2m = n1m > 0 ? ts - n1m : 0;
-  // 30 s stream: same for the table row / radiation day
-  const int qs = off_tiny < 0 ? -1 : 0;
-  const int c0 = off_tiny - qs * kTiny;                     // [0, 2880)
-  const int tq = c0 == 0 ? qs : qs + 1;
-  const int t_r = c0 == 0 ? 0 : (kTiny - c0) / C;
-  const int k2 = c0 == 0 ? 0 : (c0 + (t_r + 1) * C - kTiny) % C;        // 0 = clean switch
-  const int t_n = ((c0 <= kNoon ? kNoon : kNoon + kTiny) - c0) / C;     // window that contains noon
-  const unsigned ev = (unsigned)t_s | ((unsigned)t_r << 8) | ((unsigned)t_n << 16);
-  auto next_event = [ev](int t) {      // first scheduled step after t (255 = none left today)
-    unsigned best = 255u;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const unsigned b = (ev >> (8 * k)) & 255u;
-      if ((int)b > t && b < best) best = b;
-    }
-    return (int)best;
-  };
-
-  // ---- state at the first step of the chunk -----------------------------------------------------
-  const int i_lo = d_lo * tpd;
-  int sm = r0 == 0 ? kMinPerDay : r0;                       // start of the next window in its source day
-  PrecDay pd;
-  {
-    const int md0 = d_lo + mq - 1;
-    MSB_CHECK_WIN(md0);
-    pd.p0 = pd.nps = pd.q0 = pd.nqs = 0; pd.pth = kNever; pd.hsp = pd.hsq = pd.f = 0.0;
-    if (w_prec) prec_day_setup(p, f, cell, md0, s_month[md0 - win0], pd);
-  }
-  bool nan_cur = !(pd.f == pd.f), need_fixup = false;
-  double p_base = 0.0, pr = 0.0;
-  if (nan_cur && r0 != 0) {            // the chunk opens inside a NaN day
-    p_base = lookback(i_lo, need_fixup);
-    pd.f = 0.0;
-  }
-  if (r0 == 0) nan_cur = false;        // the roll at the first step decides (and looks back itself)
-  double p_carry = p_base;
-  double s_prev = prec_cum(pd, sm);
-  double rd_cur = rad_of(d_lo + tq - 1);
-  double q_prev, q_pref, sw_carry = 0.0;
-  const double *q_ptr;                 // table entry the step after next will need
-  {
-    const double *q0 = q_of(s_doy[d_lo - win0] - 1 + tq - 1);
-    const int ss = c0 == 0 ? kTiny : c0;
-    q_prev = q0[ss];
-    q_pref = q0[ss + C];
-    q_ptr = q0 + ss + 2 * C;
-    slot[kY_ROWTOT_CUR][tid] = q0[kTiny + 1];
-  }
-
-  const size_t ostride = (size_t)a.out.ld;
-  size_t ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
-  OutT *const o_prec = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + cell;
-  OutT *const o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell;
-  const unsigned lanes = __activemask();
-  const int pf_off = a.k.pf * C;
-  auto conv = [&](int v, double val) {     // unit conversion, MASKED instantiation only
-    if (MASKED) val = fma(val, a.out.scale[v], a.out.offset[v]);
-    return (OutT)val;
-  };
-
-  for (int d = d_lo; d < d_hi; ++d) {
-    // ---- output day d starts (warp converged): fetch what today's rolls need --------------------
-    {
-      const int y = s_doy[d - win0] - 1;
-      const double *qa = q_of(y + tq - 1);
-      if (d > d_lo && c0 != 0 && s_doy[d - win0] != s_doy[d - 1 - win0] + 1) {
-        // the day of year jumped (year boundary): row of the "lo" part of today's windows (:656)
-        q_prev = qa[c0];
-        q_pref = qa[c0 + C];
-        q_ptr = qa + c0 + 2 * C;
-        slot[kY_ROWTOT_CUR][tid] = qa[kTiny + 1];
-      }
-      const double *qb = q_of(y + tq);
-      const int mdn = d + mq, sdn = d + tq;
-      const double w5 = rad_of(sdn), w6 = qb[0], w7 = qb[k2], w8 = qa[kTiny], w9 = qb[kTiny + 1];
-      PrecDay pn;
-      MSB_CHECK_WIN(mdn); MSB_CHECK_WIN(d); MSB_CHECK_WIN(d - 1 + (d == d_lo));
-      pn.p0 = pn.nps = pn.q0 = pn.nqs = 0; pn.pth = kNever; pn.hsp = pn.hsq = pn.f = 0.0;
-      if (w_prec) prec_day_setup(p, f, cell, mdn, s_month[mdn - win0], pn);
-      const double w0 = pack_prec(pn), w1 = pn.hsp, w2 = pn.hsq, w3 = pn.f;
-      prefetch_l2(q_of(y + tq + 1) + (c0 & ~15));   // tomorrow's row, where this cell starts
-      slot[kY_PPACK][tid] = w0; slot[kY_HSP][tid] = w1; slot[kY_HSQ][tid] = w2;
-      slot[kY_PF][tid] = w3; slot[kY_RAD][tid] = w5;
-      slot[kY_QB0][tid] = w6; slot[kY_QBK][tid] = w7; slot[kY_QAEND][tid] = w8;
-      slot[kY_ROWTOT][tid] = w9;
-    }
-    int t_next = next_event(-1);
-    int t = 0;
-    while (t < tpd) {
-      if (t == t_next) {   // ---- scheduled state updates (cold, lanes with an event at this step) ----
-        if (t == t_s) {      // minute stream reaches the end of its source day (:347-351, :376)
-          PrecDay pn;
-          unpack_prec(slot[kY_PPACK][tid], pn);
-          pn.hsp = slot[kY_HSP][tid]; pn.hsq = slot[kY_HSQ][tid]; pn.f = slot[kY_PF][tid];
-          const bool nan_new = !(pn.f == pn.f);
-          double fill = 0.0;               // pandas ffill: a NaN step repeats the last valid value
-          if (nan_cur) fill = p_base;      // already inside a NaN run
-          else if (nan_new) {
-            if (d > d_lo || t > 0) fill = pr;      // the previous step of this chunk
-            else fill = lookback(i_lo, need_fixup); // the chunk starts at a NaN day
-          }
-          int pos;
-          if (n1m == 0) {                  // clean switch
-            pos = 0;
-            sm = 0;
-            p_carry = nan_new ? fill : 0.0;
-          } else {                         // straddle: n1m minutes of the old day, n2m of the new one
-            p_carry = (nan_cur || nan_new)
-                          ? fill
-                          : pd.f * (prec_cum(pd, kMinPerDay) - s_prev) + pn.f * prec_cum(pn, n2m);
-            pos = n2m;
-            sm = n2m - ts;                 // the step advances it to n2m
-          }
-          pd = pn;
-          if (nan_new) pd.f = 0.0;         // every step of a NaN day is p_base = the fill value
-          p_base = nan_new ? fill : 0.0;
-          nan_cur = nan_new;
-          s_prev = prec_cum(pd, pos);
-        }
-        if (t == t_r) {      // 30 s stream reaches the end of its table row / radiation day (:656-678)
-          const double rd_n = slot[kY_RAD][tid];
-          const double *qb = q_of(s_doy[d - win0] - 1 + tq);
-          int ss;
-          if (k2 > 0) {                    // straddle: [ss, 2880) of the old row + [0, k2) of the new
-            const double qk = slot[kY_QBK][tid];
-            sw_carry = fma(rd_n, qk - slot[kY_QB0][tid], rd_cur * (slot[kY_QAEND][tid] - q_prev));
-            q_prev = qk;
-            ss = k2 - C;                   // the step advances it to k2
-          } else {
-            q_prev = slot[kY_QB0][tid];
-            ss = 0;
-          }
-          rd_cur = rd_n;
-          q_pref = qb[ss + C];
-          q_ptr = qb + ss + 2 * C;
-          slot[kY_ROWTOT_CUR][tid] = slot[kY_ROWTOT][tid];
-        }
-        if (t == t_n) q_prev -= slot[kY_ROWTOT_CUR][tid];   // window contains tiny step 1440: + row total
-        t_next = next_event(t);
-      }
-      // ---- event-free run up to the earliest event of any lane of the warp ---------------------
-      const int t_stop = min(__reduce_min_sync(lanes, t_next), tpd);
-#pragma unroll 2
-      for (; t < t_stop; ++t, ooff += ostride) {
-        // step: precipitation :265-352, shortwave :618-680, wind :355-380
-        const double qn = q_pref;
-        MSB_CHECK_Q(q_ptr);
-        q_pref = load_early(q_ptr);
-        prefetch_l1(q_ptr + pf_off);
-        q_ptr += C;
-        sm += ts;
-        const double s1 = prec_cum(pd, sm);
-        pr = fma(pd.f, s1 - s_prev, p_carry);
-        s_prev = s1;
-        p_carry = p_base;
-        const double sw = fma(rd_cur, qn - q_prev, sw_carry);
-        q_prev = qn;
-        sw_carry = 0.0;
-        if (w_prec) __stcs(o_prec + ooff, conv(MSB_V_PREC, pr));
-        if (w_sw) __stcs(o_sw + ooff, conv(MSB_V_SHORTWAVE, sw));
-      }
-    }
-  }
-
-  // a NaN run that reaches back to the start of the record: bfill (disaggregate.py:130)
-  if (need_fixup) {
-    Cell c;
-    c.cell = cell; c.D = D; c.ts = ts; c.tpd = tpd; c.nk = 2 * D + 4; c.ld = ld;
-    c.off_min = off_min; c.utc_min = 0.0; c.frac = 0.0; c.rise = c.set = nullptr;
-    c.doy = f.doy; c.sdoy = nullptr; c.win0 = 0; c.nwin = 0;
-    c.t_min = f.t_min; c.t_max = f.t_max; c.st_t_min = f.st_t_min; c.st_t_max = f.st_t_max;
-    c.t_end = f.t_end;
-    const int T = D * tpd, i_hi = d_hi * tpd;
-    double fillv = nan("");
-    int j = i_lo;
-    for (; j < T; ++j) {
-      fillv = prec_step_generic(p, f, c, j);
-      if (fillv == fillv) break;
-    }
-    ooff = (size_t)((long)i_lo - (long)a.out.day0 * tpd) * ostride;
-    for (int jj = i_lo; jj < min(j, i_hi); ++jj, ooff += ostride) __stcs(o_prec + ooff, conv(MSB_V_PREC, fillv));
-  }
-}
-
 // accuracy probe of the hand-written fp64 sequences (tests only touch it through the C ABI)
 __global__ void math_selftest_kernel(int n, const double *__restrict__ x, double *__restrict__ out) {
   __shared__ double etab[kExpTab];
@@ -651,31 +387,6 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   } else {
     if (masked) thermo_knot_kernel<double, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
     else thermo_knot_kernel<double, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
-  }
-  MSB_CUDA(cudaGetLastError());
-  return MSB_OK;
-}
-
-// round-1 form of the stream half (precipitation + shortwave in one event-driven kernel), kept
-// behind msb_tuning.streams_path = 1 for A/B measurements against disagg_streams.cu
-int launch_interior_streams_fused(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
-  a.k.i_lo = a.k.i_hi = 0;
-  a.k.e0 = a0; a.k.e1 = b0;            // output days, day_tile per thread
-  a.k.tile = kDayTile;
-  while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 6 * 6)
-    a.k.tile >>= 1;
-  if (a.out.tune.day_tile > 0) a.k.tile = a.out.tune.day_tile < kDayWin - 8 ? a.out.tune.day_tile : kDayWin - 8;
-  a.k.pf = a.out.tune.day_prefetch > 0 ? (a.out.tune.day_prefetch < 16 ? a.out.tune.day_prefetch : 16)
-                                       : (a.out.tune.day_prefetch < 0 ? 0 : 4);
-  const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
-  const bool masked = a.units || (a.var_mask & ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE))) !=
-                                     ((1u << MSB_V_PREC) | (1u << MSB_V_SHORTWAVE));
-  if (a.out.dtype == 4) {
-    if (masked) streams_day_kernel<float, 6, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else streams_day_kernel<float, 6, false><<<grid, kDisaggThreads, 0, st>>>(a);
-  } else {
-    if (masked) streams_day_kernel<double, 6, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else streams_day_kernel<double, 6, false><<<grid, kDisaggThreads, 0, st>>>(a);
   }
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
