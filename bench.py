@@ -441,7 +441,8 @@ def e2e_pass(dp_f, params, n, n_days, tpd, local, steps, barrier, reduce_max, co
               month=host["month"], t_min=host["t_min"], t_max=host["t_max"], prec=host["prec"],
               wind=host["wind"], state_t_min=host["state_t_min"], state_t_max=host["state_t_max"],
               state_prec=host["state_prec"], t_pk12=host["t_pk12"], dur12=host["dur12"])
-    n_thr = max(2, min(32, (os.cpu_count() or 2) // world - 1))   # the host's cores shared by the ranks
+    # the host's cores shared by the ranks (the calling thread sleeps in a blocking event wait between tiles)
+    n_thr = max(2, min(32, (os.cpu_count() or 2) // world - (1 if world == 1 else 0)))
     sink = NativeSink(n_cells=n, elem_bytes=4, byteswap=True, n_threads=n_thr, fd=-1) if consume else None
     consumed = [0]
 

@@ -127,7 +127,10 @@ extern "C" int msb_host_ctx_create(int device, msb_host_ctx **out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking);
   for (auto &x : c->ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
   for (auto &x : c->ev_k) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
-  for (auto &x : c->ev_c) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+  // "tile copied": the calling thread WAITS on these between tiles; a blocking wait leaves its core to
+  // the consumer's worker threads instead of spinning on it
+  for (auto &x : c->ev_c)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming | cudaEventBlockingSync);
   if (e != cudaSuccess) {
     int rc = cuda_fail(e, "msb_host_ctx_create");
     msb_host_ctx_destroy(c);

@@ -188,6 +188,11 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     // knots at t_Tmin / t_Tmax of day e and t_Tmin of day e+1 (disaggregate.py:198-200) with
     // scipy's derivatives, and the daily vapour pressure in kPa at the two t_Tmin knots (:480)
     const size_t o0 = (size_t)e * ld + cell, o1 = o0 + ld;
+    if (a.k.pf && e + 2 < f.n_days) {     // the next knot-day's input rows on their way to L2 while this one computes
+      prefetch_l2(f.t_min + o1 + ld);
+      prefetch_l2(f.t_max + o1 + ld);
+      prefetch_l2(vp_d + o1 + ld);
+    }
     const int j2 = 2 * (e + 2);
     const double x2 = knot_x(c, j2), x3 = knot_x(c, j2 + 1);
     const double y2 = knot_y(c, j2), y3 = knot_y(c, j2 + 1);
@@ -379,6 +384,7 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   while (a.k.tile > 2 && (long)cell_blocks * ((a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile) < 148L * 7 * 6)
     a.k.tile >>= 1;
   if (a.out.tune.knot_tile > 0) a.k.tile = a.out.tune.knot_tile < kDayWin - 8 ? a.out.tune.knot_tile : kDayWin - 8;
+  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : 1;
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
   const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw || a.lw_raw;
   if (a.out.dtype == 4) {

@@ -188,7 +188,7 @@ __device__ __noinline__ double prec_fill_after(const msb_params &p, const msb_fo
 }
 
 template <typename OutT, bool UNITS>
-__global__ void __launch_bounds__(kDisaggThreads)
+__global__ void __launch_bounds__(kDisaggThreads, 6)
 prec_day_kernel(const __grid_constant__ DisaggArgs a) {
   __shared__ int s_month[kDayWin];
   const msb_params &p = a.p;
