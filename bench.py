@@ -358,8 +358,9 @@ class DevicePass:
             order = patch_order(lat, lon, patch_rows)
         self.eng.load(order=order, **self.f)
         n, tpd = self.n, self.tpd
-        if tile_days is None:    # one ring slot of the 8 float32 outputs within ~24 GB
-            tile_days = max(1, int(24.0e9 // (len(OUT_VARS) * tpd * n * 4)))
+        if tile_days is None:    # one ring slot of the 8 float32 outputs within ~36 GB (two slots + inputs,
+            # candidate planes and the 4.4 GB table stay below half of the 180 GB of HBM)
+            tile_days = max(1, int(36.0e9 // (len(OUT_VARS) * tpd * n * 4)))
             if 7 * n_days * n * 8 > 60e9:       # multi-year records: inputs + daily arrays already fill HBM
                 tile_days = min(tile_days, 64)
                 self.eng.single_pass_budget = 0  # ... and leave no room for candidate planes
@@ -489,7 +490,7 @@ def main():
     ap.add_argument("--cells", type=int, default=None, help="truncate the grid (debugging only)")
     ap.add_argument("--days", type=int, default=None, help="truncate the record (debugging only)")
     ap.add_argument("--tile-days", type=int, default=None,
-                    help="days per msb_disaggregate call (default: as many as keep one ring slot <= 24 GB, at most 64 "
+                    help="days per msb_disaggregate call (default: as many as keep one ring slot <= 36 GB, at most 64 "
                          "for the headline grid)")
     ap.add_argument("--sample-cells", type=int, default=None)
     ap.add_argument("--shard", action="store_true",
