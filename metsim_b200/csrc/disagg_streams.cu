@@ -8,13 +8,14 @@
 // and the step at which the roll falls is the same on every day of a cell.  That makes a
 // (cell, day) self-contained: no event queue, no state carried from step to step.
 //
-//   sw_day_kernel    the day's tpd + 1 entries of the signed prefix table q (solar.cu) are fetched
-//                    in batches of eight INDEPENDENT loads (the round-1 kernel issued one dependent
-//                    8-byte load per step and stalled 3.6 warps per issue on it), a window is one
-//                    subtraction of neighbouring entries, times the radiation of its source day.
-//   prec_day_kernel  pure arithmetic: the cumulative closed form of the day's per-minute shape
-//                    (prec_cum, disagg_common.cuh) differenced at the window ends; NaN days
-//                    (0/0, :327) are forward-filled in-stream like pandas does (:130).
+//   SwCell    a day is at most five segments of windows inside ONE row of the signed prefix table q
+//             (solar.cu); a segment is a loop of four INDEPENDENT 8-byte table loads followed by
+//             their four windows (the round-1 kernel issued one dependent load per step and stalled
+//             3.6 warps per issue on it); tomorrow's entries are prefetched into L1.
+//   PrecCell  pure arithmetic: the cumulative closed form of the day's per-minute shape
+//             (prec_cum, disagg_common.cuh) differenced at the window ends; NaN days
+//             (0/0, :327) are forward-filled in-stream like pandas does (:130).
+//   streams_kernel<.., WHAT>  runs either of them, or both for the same cell day after day.
 //
 // Each thread walks one cell through a chunk of days; lanes are consecutive cells, so every store
 // is a full 128-byte row.  wind is written by thermo_knot_kernel (it shares tskc's minute roll).
@@ -53,58 +54,55 @@ __device__ __forceinline__ void sw_segment(const double *__restrict__ ptr, int s
   }
 }
 
+// ---- shortwave of one cell: per-cell constants, then one call per output day --------------------
 template <typename OutT, bool UNITS>
-__global__ void __launch_bounds__(kDisaggThreads, 8)
-sw_day_kernel(const __grid_constant__ DisaggArgs a) {
-  __shared__ int s_doy[kDayWin];
-  const msb_params &p = a.p;
-  const msb_forcing &f = a.f;
-  const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
-  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
-  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
-  const int win0 = max(d_lo - 2, 0), nwin = min(min(d_hi + 2, D) - win0, kDayWin);
-  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_doy[j] = f.doy[win0 + j];
-  __syncthreads();
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= f.n_cells || d_lo >= d_hi) return;
-  const long ld = f.ld;
-  const int C = 2 * ts;                                      // tiny steps per output step (:660)
-  const double lon = wrap_lon(f.lon[cell]);                  // disaggregate.py:67
-  const int off_tiny = p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;   // :655
-  // The day's windows start at tiny step c0 of table row / radiation day A = (.) + q and cross
-  // into B = A + 1 at window t_b (the first one that starts at or beyond the end of row A);
-  // window t_a = t_b - 1 straddles the two when the crossing is not clean.
-  const int q = off_tiny < 0 ? -1 : 0;
-  const int c0 = off_tiny - q * kTiny;                       // [0, 2880)
-  const int t_b = (kTiny - c0 + C - 1) / C;
-  const bool straddle = (kTiny - c0) % C != 0;
-  const int t_a = straddle ? t_b - 1 : t_b;                  // windows [0, t_a) lie inside row A
-  // The window that contains tiny step 1440 of its row: the signed prefix table changes sign there
-  // and the row total goes on once (solar.cu).  It splits its row's segment in two.
-  const bool noon_in_a = c0 <= kNoon;
-  const int t_n = ((noon_in_a ? kNoon : kNoon + kTiny) - c0) / C;
-  const int row0 = f.lat_row[cell];
-  const double *const qrow = a.t.q + (size_t)row0 * 365 * kQLd;
-  const double *const dayl = a.t.daylength + (size_t)row0 * kRows;
-  const double *const sw_d = daily_plane(a, a.sw_d, cell);
-  auto row_of = [](int y) {      // table row y rolled over the table's own 366 rows (:656)
-    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
-    return min(y, 364);          // row 365 is a copy of row 364 (physics.py:281-284)
-  };
-  auto rad_of = [&](int d) {     // tmp_rad of source day d, disaggregate.py:645
-#ifdef MSB_BOUNDS
-    if ((unsigned)(d - win0) >= (unsigned)nwin || (unsigned)d >= (unsigned)D) asm volatile("trap;");
-#endif
-    const double dl = a.sw_full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
-    return (sw_d[(size_t)d * ld + cell] * dl) * a.inv_sw_den;
-  };
-  const double sc = UNITS ? a.out.scale[MSB_V_SHORTWAVE] : 1.0, of = UNITS ? a.out.offset[MSB_V_SHORTWAVE] : 0.0;
-  const size_t ostride = (size_t)a.out.ld;
-  OutT *o_sw = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell +
-               (size_t)((long)d_lo - (long)a.out.day0) * tpd * ostride;
+struct SwCell {
+  const double *qrow, *dayl, *sw_col;   // latitude row of the table / daylength, the cell's daily shortwave column
+  const int *s_doy;
+  OutT *o;
+  size_t ostride, ld;
+  double rd_a, inv_den, sc, of;
+  int C, c0, q, t_a, t_b, t_n, tpd, win0;
+  bool straddle, noon_in_a, full_day, pf;
 
-  double rd_a = rad_of(d_lo + q);
-  for (int d = d_lo; d < d_hi; ++d) {
+  static __device__ __forceinline__ int row_of(int y) {   // table row y rolled over the table's own 366 rows (:656)
+    y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
+    return min(y, 364);                                   // row 365 is a copy of row 364 (physics.py:281-284)
+  }
+  __device__ __forceinline__ double rad_of(int d) const {  // tmp_rad of source day d, disaggregate.py:645
+    const double dl = full_day ? kSecPerDay : dayl[s_doy[d - win0] - 1];
+    return (sw_col[(size_t)d * ld] * dl) * inv_den;
+  }
+  __device__ __forceinline__ void init(const DisaggArgs &a, int cell, int d_lo, int win0_, const int *s_doy_) {
+    const msb_forcing &f = a.f;
+    s_doy = s_doy_; win0 = win0_; tpd = a.tpd; ld = (size_t)f.ld;
+    C = 2 * a.p.time_step;                                     // tiny steps per output step (:660)
+    const double lon = wrap_lon(f.lon[cell]);                  // disaggregate.py:67
+    const int off_tiny = a.p.utc_offset ? (int)((lon / kDegPerRev) * kTiny) : 0;   // :655
+    // The day's windows start at tiny step c0 of table row / radiation day A = (.) + q and cross
+    // into B = A + 1 at window t_b (the first one that starts at or beyond the end of row A);
+    // window t_a = t_b - 1 straddles the two when the crossing is not clean.
+    q = off_tiny < 0 ? -1 : 0;
+    c0 = off_tiny - q * kTiny;                                 // [0, 2880)
+    t_b = (kTiny - c0 + C - 1) / C;
+    straddle = (kTiny - c0) % C != 0;
+    t_a = straddle ? t_b - 1 : t_b;                            // windows [0, t_a) lie inside row A
+    // The window that contains tiny step 1440 of its row: the signed prefix table changes sign
+    // there and the row total goes on once (solar.cu).  It splits its row's segment in two.
+    noon_in_a = c0 <= kNoon;
+    t_n = ((noon_in_a ? kNoon : kNoon + kTiny) - c0) / C;
+    const int row0 = f.lat_row[cell];
+    qrow = a.t.q + (size_t)row0 * 365 * kQLd;
+    dayl = a.t.daylength + (size_t)row0 * kRows;
+    sw_col = daily_plane(a, a.sw_d, cell) + cell;
+    full_day = a.sw_full_day; inv_den = a.inv_sw_den; pf = a.k.pf != 0;
+    sc = UNITS ? a.out.scale[MSB_V_SHORTWAVE] : 1.0; of = UNITS ? a.out.offset[MSB_V_SHORTWAVE] : 0.0;
+    ostride = (size_t)a.out.ld;
+    o = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell +
+        (size_t)((long)d_lo - (long)a.out.day0) * tpd * ostride;
+    rd_a = rad_of(d_lo + q);
+  }
+  __device__ __forceinline__ void day(int d, bool more) {
     const int y = s_doy[d - win0] - 1;
     const double *const qa = qrow + row_of(y + q) * kQLd + c0;                    // entry t of row A at qa[t C]
     const double *const qb = qrow + row_of(y + q + 1) * kQLd + (c0 - kTiny);      // entry t of row B at qb[t C]
@@ -117,7 +115,7 @@ sw_day_kernel(const __grid_constant__ DisaggArgs a) {
     // Tomorrow's entries into L1 while today computes: the segments below are short loops of dependent
     // batches (a batch of four loads, then its four windows), so what hides the table latency is
     // that the loads hit L1.  One prefetch per entry; neighbouring lanes share the lines.
-    if (a.k.pf && d + 1 < d_hi) {
+    if (pf && more) {
       const int y1 = s_doy[d + 1 - win0] - 1;
       const double *pa = qrow + row_of(y1 + q) * kQLd + c0;
       const double *pb = qrow + row_of(y1 + q + 1) * kQLd + (c0 - kTiny) + (long)t_b * C;
@@ -127,34 +125,34 @@ sw_day_kernel(const __grid_constant__ DisaggArgs a) {
     double v0 = __ldg(qa);
     // ---- windows inside row A: [0, t_a), the noon window (if it is here) splitting them ----
     if (noon_in_a) {
-      sw_segment<OutT, UNITS>(qa + C, C, t_n, rd_a, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qa + C, C, t_n, rd_a, v0, o, ostride, sc, of);
       v0 -= rowtot;
-      sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * C, C, t_a - t_n, rd_a, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * C, C, t_a - t_n, rd_a, v0, o, ostride, sc, of);
     } else {
-      sw_segment<OutT, UNITS>(qa + C, C, t_a, rd_a, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qa + C, C, t_a, rd_a, v0, o, ostride, sc, of);
     }
     // ---- the straddling window: [.., 2880) of row A (q_A[2880] = 0) + [0, ..) of row B (q_B[0] = 0) ----
     if (straddle) {
       const double v1 = __ldg(qb + (long)t_b * C);
       double sw = fma(rd_b, v1, -(rd_a * v0));
       if (UNITS) sw = fma(sw, sc, of);
-      __stcs(o_sw, (OutT)sw);
-      o_sw += ostride;
+      __stcs(o, (OutT)sw);
+      o += ostride;
       v0 = v1;
     } else {
       v0 = 0.0;                    // clean crossing: row B starts at its entry 0 (an empty prefix)
     }
     // ---- windows inside row B: [t_b, tpd) ----
     if (noon_in_a) {
-      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, tpd - t_b, rd_b, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, tpd - t_b, rd_b, v0, o, ostride, sc, of);
     } else {
-      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, t_n - t_b, rd_b, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, t_n - t_b, rd_b, v0, o, ostride, sc, of);
       v0 -= rowtot;
-      sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * C, C, tpd - t_n, rd_b, v0, o_sw, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * C, C, tpd - t_n, rd_b, v0, o, ostride, sc, of);
     }
     rd_a = rd_b;
   }
-}
+};
 
 // value of the last valid step before step i / first valid step at or after it: the cold paths of
 // pandas' ffill / bfill (disaggregate.py:130) around NaN days
@@ -187,66 +185,64 @@ __device__ __noinline__ double prec_fill_after(const msb_params &p, const msb_fo
   return v;
 }
 
+// ---- precipitation of one cell: per-cell constants and carried state, one call per output day ---
 template <typename OutT, bool UNITS>
-__global__ void __launch_bounds__(kDisaggThreads, 6)
-prec_day_kernel(const __grid_constant__ DisaggArgs a) {
-  __shared__ int s_month[kDayWin];
-  const msb_params &p = a.p;
-  const msb_forcing &f = a.f;
-  const int D = f.n_days, ts = p.time_step, tpd = a.tpd;
-  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
-  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
-  const int win0 = max(d_lo - 2, 0), nwin = min(min(d_hi + 2, D) - win0, kDayWin);
-  for (int j = threadIdx.x; j < nwin; j += blockDim.x) s_month[j] = f.month[win0 + j];
-  __syncthreads();
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= f.n_cells || d_lo >= d_hi) return;
-  const double lon = wrap_lon(f.lon[cell]);                                      // disaggregate.py:67
-  const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :349
-  // the day's windows start at minute r0 of source day A = d + q and cross into B = A + 1 at
-  // window t_b; n1 minutes of the straddling window t_x = t_b - 1 belong to day A (0 = clean)
-  const int q = off_min < 0 ? -1 : 0;
-  const int r0 = off_min - q * kMinPerDay;                   // [0, 1440)
-  const int t_b = (kMinPerDay - r0 + ts - 1) / ts;
-  const int n1 = (kMinPerDay - r0) % ts;
-  const int t_a = n1 ? t_b - 1 : t_b;                        // windows [0, t_a) lie inside day A
-  auto setup = [&](int d, PrecDay &pd, double &tot) {
-#ifdef MSB_BOUNDS
-    if ((unsigned)(d - win0) >= (unsigned)nwin || (unsigned)d >= (unsigned)D) asm volatile("trap;");
-#endif
-    prec_day_setup(p, f, cell, d, s_month[d - win0], pd, &tot);
-  };
-  const double sc = UNITS ? a.out.scale[MSB_V_PREC] : 1.0, of = UNITS ? a.out.offset[MSB_V_PREC] : 0.0;
-  const size_t ostride = (size_t)a.out.ld;
-  const long i_lo = (long)d_lo * tpd;
-  OutT *const o_base = reinterpret_cast<OutT *>(a.out.var[MSB_V_PREC]) + cell +
-                       (size_t)(i_lo - (long)a.out.day0 * tpd) * ostride;
-  OutT *o_pr = o_base;
-  auto put = [&](double v) {
-    if (UNITS) v = fma(v, sc, of);
-    __stcs(o_pr, (OutT)v);
-    o_pr += ostride;
-  };
+struct PrecCell {
+  const DisaggArgs *a;
+  const int *s_month;
+  OutT *o, *o_base;
+  size_t ostride;
+  PrecDay pa;
+  double tot_a, s_a, last, sc, of;
+  long i_lo;
+  int cell, off_min, q, r0, t_a, t_b, n1, ts, tpd, win0;
+  bool have_last, need_fixup;
 
-  PrecDay pa, pb;
-  double tot_a, tot_b;           // unscaled totals of the two days' shapes, S(1440)
-  setup(d_lo + q, pa, tot_a);
+  __device__ __forceinline__ void put(double v) {
+    if (UNITS) v = fma(v, sc, of);
+    __stcs(o, (OutT)v);
+    o += ostride;
+  }
   // What pandas' ffill repeats into a NaN step is the last valid value before it: inside the chunk
   // that is simply the value of the previous step (`last`); a chunk that OPENS with a NaN step
   // looks back once (cold), and if nothing valid precedes it the run is back-filled afterwards.
-  double last = 0.0;
-  bool have_last = false, need_fixup = false;
-  auto need_last = [&]() {
+  __device__ __forceinline__ void need_last() {
     if (!have_last) {      // nothing emitted yet: the NaN step is the chunk's first, i_lo
-      last = prec_fill_before(p, f, cell, tpd, off_min, i_lo);
+      last = prec_fill_before(a->p, a->f, cell, tpd, off_min, i_lo);
       need_fixup = !(last == last);
       have_last = true;
     }
-  };
-  // cumulative shape of day A at the day's first window start; from the second day on it is where
-  // the previous day's windows inside (then) day B ended
-  double s_a = (pa.f == pa.f) ? prec_cum(pa, r0) : 0.0;
-  for (int d = d_lo; d < d_hi; ++d) {
+  }
+  __device__ __forceinline__ void setup(int d, PrecDay &pd, double &tot) const {
+    prec_day_setup(a->p, a->f, cell, d, s_month[d - win0], pd, &tot);
+  }
+  __device__ __forceinline__ void init(const DisaggArgs &args, int cell_, int d_lo, int win0_, const int *s_month_) {
+    a = &args; cell = cell_; win0 = win0_; s_month = s_month_;
+    ts = args.p.time_step; tpd = args.tpd;
+    const double lon = wrap_lon(args.f.lon[cell]);                                      // disaggregate.py:67
+    off_min = args.p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;          // :349
+    // the day's windows start at minute r0 of source day A = d + q and cross into B = A + 1 at
+    // window t_b; n1 minutes of the straddling window t_b - 1 belong to day A (0 = clean)
+    q = off_min < 0 ? -1 : 0;
+    r0 = off_min - q * kMinPerDay;                   // [0, 1440)
+    t_b = (kMinPerDay - r0 + ts - 1) / ts;
+    n1 = (kMinPerDay - r0) % ts;
+    t_a = n1 ? t_b - 1 : t_b;                        // windows [0, t_a) lie inside day A
+    sc = UNITS ? args.out.scale[MSB_V_PREC] : 1.0; of = UNITS ? args.out.offset[MSB_V_PREC] : 0.0;
+    ostride = (size_t)args.out.ld;
+    i_lo = (long)d_lo * tpd;
+    o_base = reinterpret_cast<OutT *>(args.out.var[MSB_V_PREC]) + cell +
+             (size_t)(i_lo - (long)args.out.day0 * tpd) * ostride;
+    o = o_base;
+    setup(d_lo + q, pa, tot_a);
+    last = 0.0; have_last = false; need_fixup = false;
+    // cumulative shape of day A at the day's first window start; from the second day on it is where
+    // the previous day's windows inside (then) day B ended
+    s_a = (pa.f == pa.f) ? prec_cum(pa, r0) : 0.0;
+  }
+  __device__ __forceinline__ void day(int d) {
+    PrecDay pb;
+    double tot_b;
     setup(d + q + 1, pb, tot_b);
     const bool nan_a = !(pa.f == pa.f), nan_b = !(pb.f == pb.f);
     double s_prev = s_a;
@@ -300,15 +296,51 @@ prec_day_kernel(const __grid_constant__ DisaggArgs a) {
     tot_a = tot_b;
     s_a = s_prev;                  // = S_B(r0): day B is tomorrow's day A
   }
-
   // a NaN run that reaches back to the start of the record: bfill (disaggregate.py:130)
-  if (need_fixup) {
+  __device__ __forceinline__ void finish(int d_hi) {
+    if (!need_fixup) return;
     long first_valid;
-    const double fillv = prec_fill_after(p, f, cell, tpd, off_min, i_lo, &first_valid);
+    const double fillv = prec_fill_after(a->p, a->f, cell, tpd, off_min, i_lo, &first_valid);
     const long i_hi = (long)d_hi * tpd;
-    o_pr = o_base;
+    o = o_base;
     for (long j = i_lo; j < (first_valid < i_hi ? first_valid : i_hi); ++j) put(fillv);
   }
+};
+
+// which of the two variables a launch produces
+enum { kStreamSw = 1, kStreamPrec = 2, kStreamBoth = 3 };
+
+// WHAT = kStreamBoth: a thread walks its cell's days doing the shortwave segments (table-load latency)
+// and then the precipitation loops (pure arithmetic) of each day; warps drift apart, so one warp's
+// table loads are covered by another's arithmetic -- what two back-to-back kernels cannot do.
+template <typename OutT, bool UNITS, int WHAT, int MINB>
+__global__ void __launch_bounds__(kDisaggThreads, MINB)
+streams_kernel(const __grid_constant__ DisaggArgs a) {
+  __shared__ int s_doy[kDayWin], s_month[kDayWin];
+  const msb_forcing &f = a.f;
+  const int D = f.n_days;
+  const int d_lo = a.k.e0 + blockIdx.y * a.k.tile;
+  const int d_hi = min(a.k.e1, d_lo + a.k.tile);
+  const int win0 = max(d_lo - 2, 0), nwin = min(min(d_hi + 2, D) - win0, kDayWin);
+  for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+    s_doy[j] = f.doy[win0 + j];
+    s_month[j] = f.month[win0 + j];
+  }
+  __syncthreads();
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= f.n_cells || d_lo >= d_hi) return;
+#ifdef MSB_BOUNDS   // every day the two cells touch: d_lo - 1 .. d_hi of the staged calendar window
+  if (d_lo - 1 < win0 || d_hi >= win0 + nwin || d_hi >= D) asm volatile("trap;");
+#endif
+  SwCell<OutT, UNITS> sw;
+  PrecCell<OutT, UNITS> pr;
+  if (WHAT & kStreamSw) sw.init(a, cell, d_lo, win0, s_doy);
+  if (WHAT & kStreamPrec) pr.init(a, cell, d_lo, win0, s_month);
+  for (int d = d_lo; d < d_hi; ++d) {
+    if (WHAT & kStreamSw) sw.day(d, d + 1 < d_hi);
+    if (WHAT & kStreamPrec) pr.day(d);
+  }
+  if (WHAT & kStreamPrec) pr.finish(d_hi);
 }
 
 constexpr int kStreamTile = 16;   // output days per thread on full-size grids
@@ -325,26 +357,27 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
   a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : 1;      // sw_day_kernel: L1 prefetch of the next day's table entries
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
   const bool f4 = a.out.dtype == 4;
-  if (a.var_mask & (1u << MSB_V_SHORTWAVE)) {
-    const bool units = a.out.scale[MSB_V_SHORTWAVE] != 1.0 || a.out.offset[MSB_V_SHORTWAVE] != 0.0;
-    if (f4) {
-      if (units) sw_day_kernel<float, true><<<grid, kDisaggThreads, 0, st>>>(a);
-      else sw_day_kernel<float, false><<<grid, kDisaggThreads, 0, st>>>(a);
-    } else {
-      if (units) sw_day_kernel<double, true><<<grid, kDisaggThreads, 0, st>>>(a);
-      else sw_day_kernel<double, false><<<grid, kDisaggThreads, 0, st>>>(a);
-    }
+  const bool want_sw = a.var_mask & (1u << MSB_V_SHORTWAVE), want_pr = a.var_mask & (1u << MSB_V_PREC);
+  const bool units = (want_sw && (a.out.scale[MSB_V_SHORTWAVE] != 1.0 || a.out.offset[MSB_V_SHORTWAVE] != 0.0)) ||
+                     (want_pr && (a.out.scale[MSB_V_PREC] != 1.0 || a.out.offset[MSB_V_PREC] != 0.0));
+#define MSB_STREAMS(WHAT, MINB)                                                              \
+  do {                                                                                      \
+    if (f4) {                                                                               \
+      if (units) streams_kernel<float, true, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);   \
+      else streams_kernel<float, false, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);        \
+    } else {                                                                                \
+      if (units) streams_kernel<double, true, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);  \
+      else streams_kernel<double, false, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);       \
+    }                                                                                       \
+  } while (0)
+  // msb_tuning.streams_split = 1: one launch per variable (A/B against the paired kernel)
+  if (want_sw && want_pr && a.out.tune.streams_split != 1) {
+    MSB_STREAMS(kStreamBoth, 5);
+  } else {
+    if (want_sw) MSB_STREAMS(kStreamSw, 8);
+    if (want_pr) MSB_STREAMS(kStreamPrec, 6);
   }
-  if (a.var_mask & (1u << MSB_V_PREC)) {
-    const bool units = a.out.scale[MSB_V_PREC] != 1.0 || a.out.offset[MSB_V_PREC] != 0.0;
-    if (f4) {
-      if (units) prec_day_kernel<float, true><<<grid, kDisaggThreads, 0, st>>>(a);
-      else prec_day_kernel<float, false><<<grid, kDisaggThreads, 0, st>>>(a);
-    } else {
-      if (units) prec_day_kernel<double, true><<<grid, kDisaggThreads, 0, st>>>(a);
-      else prec_day_kernel<double, false><<<grid, kDisaggThreads, 0, st>>>(a);
-    }
-  }
+#undef MSB_STREAMS
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
 }

@@ -47,14 +47,19 @@ static PreludeView prelude_view(void *base, int n_lat) {
 // compiler with -ffp-contract=off: numba/LLVM does not fuse multiply-add.
 static void prelude_rows(const double *lat_deg, int r0, int r1, PreludeView v) {
   const double dh = kSwRadDt / kSecPerRad;
+  // the declination terms depend on the day alone: once per call, not once per latitude
+  double cosdecl[365], sindecl[365];
+  for (int i = 0; i < 365; ++i) {
+    const double decl = kMinDecl * std::cos((i + kDaysOff) * kRadPerDay);
+    cosdecl[i] = std::cos(decl);
+    sindecl[i] = std::sin(decl);
+  }
   for (int r = r0; r < r1; ++r) {
     double lat = std::fmin(std::fmax(lat_deg[r] * kRadPerDeg, -M_PI / 2.), M_PI / 2.0);
     double coslat = std::cos(lat), sinlat = std::sin(lat);
     for (int i = 0; i < 365; ++i) {
-      double decl = kMinDecl * std::cos((i + kDaysOff) * kRadPerDay);
-      double cosdecl = std::cos(decl), sindecl = std::sin(decl);
-      double cosegeom = coslat * cosdecl;
-      double sinegeom = sinlat * sindecl;
+      double cosegeom = coslat * cosdecl[i];
+      double sinegeom = sinlat * sindecl[i];
       double coshss = std::fmin(std::fmax(-sinegeom / cosegeom, -1.0), 1.0);
       double hss = std::acos(coshss);
       double start = -hss;

@@ -8,5 +8,5 @@ timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2> gpur
 timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_reference.log 2> gpurun_out/bench_reference.err
 K='regex:solar|daily|thermo|sw_day|prec_day|disagg|lw_rescale'
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-verify > gpurun_out/ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:solar_rows|solar_moments|daily_fused_kernel|thermo_knot|sw_day|prec_day' -s 6 -c 6 -o gpurun_out/r02_step_kernels python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --no-verify > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:solar_rows|solar_moments|daily_fused_kernel|thermo_knot|sw_day|prec_day' -c 6 -o gpurun_out/r02_step_kernels python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --no-verify > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/pytest.log; cat gpurun_out/probe_solar.log; tail -2 gpurun_out/bench.err; cat gpurun_out/bench.log | cut -c1-300
