@@ -90,8 +90,7 @@ typedef struct msb_tuning {
                                1 = event-driven kernel for every day */
   int32_t day_prefetch;     /* -1 = no L1 prefetch of the next day's table entries in the shortwave kernel */
   int32_t prep_days;        /* padded days per thread of the day-record kernel */
-  int32_t streams_split;    /* 1 = shortwave and precipitation of the interior days as two launches
-                               instead of the paired kernel (A/B measurements) */
+  int32_t reserved;
 } msb_tuning;
 
 /* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of

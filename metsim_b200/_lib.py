@@ -61,15 +61,15 @@ class Tuning(C.Structure):
     """msb_tuning: launch-geometry / path overrides, 0 = the library's choice."""
     _fields_ = [("daily_chunk_len", C.c_int32), ("daily_two_pass", C.c_int32),
                 ("knot_tile", C.c_int32), ("day_tile", C.c_int32), ("disagg_path", C.c_int32),
-                ("day_prefetch", C.c_int32), ("prep_days", C.c_int32), ("streams_split", C.c_int32)]
+                ("day_prefetch", C.c_int32), ("prep_days", C.c_int32), ("reserved", C.c_int32)]
 
 
-TUNING_KEYS = tuple(n for n, _ in Tuning._fields_)
+TUNING_KEYS = tuple(n for n, _ in Tuning._fields_ if n != "reserved")
 # environment spellings of the same knobs (read here, in Python, once per Engine / run_host call --
 # the C library itself never looks at the environment)
 _TUNING_ENV = {"MSB_DAILY_CHUNK": "daily_chunk_len", "MSB_DAILY_TWO_PASS": "daily_two_pass",
                "MSB_KNOT_TILE": "knot_tile", "MSB_DAY_TILE": "day_tile", "MSB_DAY_PF": "day_prefetch",
-               "MSB_PREP_DAYS": "prep_days", "MSB_STREAMS_SPLIT": "streams_split"}
+               "MSB_PREP_DAYS": "prep_days"}
 
 
 def make_tuning(user: dict | None = None) -> Tuning:

@@ -15,7 +15,7 @@
 //   PrecCell  pure arithmetic: the cumulative closed form of the day's per-minute shape
 //             (prec_cum, disagg_common.cuh) differenced at the window ends; NaN days
 //             (0/0, :327) are forward-filled in-stream like pandas does (:130).
-//   streams_kernel<.., WHAT>  runs either of them, or both for the same cell day after day.
+//   sw_day_kernel / prec_day_kernel run one of them for a (cell, chunk of days) per thread.
 //
 // Each thread walks one cell through a chunk of days; lanes are consecutive cells, so every store
 // is a full 128-byte row.  wind is written by thermo_knot_kernel (it shares tskc's minute roll).
@@ -307,15 +307,14 @@ struct PrecCell {
   }
 };
 
-// which of the two variables a launch produces
-enum { kStreamSw = 1, kStreamPrec = 2, kStreamBoth = 3 };
+// which of the two variables a launch produces.  (Both in one kernel -- a thread doing the shortwave
+// segments and then the precipitation loops of each day, so that one warp's table loads would be
+// covered by another's arithmetic -- was measured and dropped: 96 registers, 20 warps per SM and a
+// shared L1 cost more than the overlap gives, 4.42 ms against 1.72 + 1.66 ms per 97-day call.)
+enum { kStreamSw = 1, kStreamPrec = 2 };
 
-// WHAT = kStreamBoth: a thread walks its cell's days doing the shortwave segments (table-load latency)
-// and then the precipitation loops (pure arithmetic) of each day; warps drift apart, so one warp's
-// table loads are covered by another's arithmetic -- what two back-to-back kernels cannot do.
-template <typename OutT, bool UNITS, int WHAT, int MINB>
-__global__ void __launch_bounds__(kDisaggThreads, MINB)
-streams_kernel(const __grid_constant__ DisaggArgs a) {
+template <typename OutT, bool UNITS, int WHAT>
+__device__ __forceinline__ void streams_body(const DisaggArgs &a) {
   __shared__ int s_doy[kDayWin], s_month[kDayWin];
   const msb_forcing &f = a.f;
   const int D = f.n_days;
@@ -343,6 +342,16 @@ streams_kernel(const __grid_constant__ DisaggArgs a) {
   if (WHAT & kStreamPrec) pr.finish(d_hi);
 }
 
+// latency-bound: 64 registers, 32 warps per SM
+template <typename OutT, bool UNITS>
+__global__ void __launch_bounds__(kDisaggThreads, 8)
+sw_day_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamSw>(a); }
+
+// arithmetic: 80 registers, 24 warps per SM
+template <typename OutT, bool UNITS>
+__global__ void __launch_bounds__(kDisaggThreads, 6)
+prec_day_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamPrec>(a); }
+
 constexpr int kStreamTile = 16;   // output days per thread on full-size grids
 
 int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
@@ -360,23 +369,19 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
   const bool want_sw = a.var_mask & (1u << MSB_V_SHORTWAVE), want_pr = a.var_mask & (1u << MSB_V_PREC);
   const bool units = (want_sw && (a.out.scale[MSB_V_SHORTWAVE] != 1.0 || a.out.offset[MSB_V_SHORTWAVE] != 0.0)) ||
                      (want_pr && (a.out.scale[MSB_V_PREC] != 1.0 || a.out.offset[MSB_V_PREC] != 0.0));
-#define MSB_STREAMS(WHAT, MINB)                                                              \
-  do {                                                                                      \
-    if (f4) {                                                                               \
-      if (units) streams_kernel<float, true, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);   \
-      else streams_kernel<float, false, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);        \
-    } else {                                                                                \
-      if (units) streams_kernel<double, true, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);  \
-      else streams_kernel<double, false, WHAT, MINB><<<grid, kDisaggThreads, 0, st>>>(a);       \
-    }                                                                                       \
+  // (one flag for both launches: a variable without a conversion multiplies by 1 and adds 0)
+#define MSB_STREAMS(KERNEL)                                                    \
+  do {                                                                        \
+    if (f4) {                                                                 \
+      if (units) KERNEL<float, true><<<grid, kDisaggThreads, 0, st>>>(a);     \
+      else KERNEL<float, false><<<grid, kDisaggThreads, 0, st>>>(a);          \
+    } else {                                                                  \
+      if (units) KERNEL<double, true><<<grid, kDisaggThreads, 0, st>>>(a);    \
+      else KERNEL<double, false><<<grid, kDisaggThreads, 0, st>>>(a);         \
+    }                                                                         \
   } while (0)
-  // msb_tuning.streams_split = 1: one launch per variable (A/B against the paired kernel)
-  if (want_sw && want_pr && a.out.tune.streams_split != 1) {
-    MSB_STREAMS(kStreamBoth, 5);
-  } else {
-    if (want_sw) MSB_STREAMS(kStreamSw, 8);
-    if (want_pr) MSB_STREAMS(kStreamPrec, 6);
-  }
+  if (want_sw) MSB_STREAMS(sw_day_kernel);
+  if (want_pr) MSB_STREAMS(prec_day_kernel);
 #undef MSB_STREAMS
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;
