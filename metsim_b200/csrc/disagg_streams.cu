@@ -63,7 +63,8 @@ struct SwCell {
   size_t ostride, ld;
   double rd_a, inv_den, sc, of;
   int C, c0, q, t_a, t_b, t_n, tpd, win0;
-  bool straddle, noon_in_a, full_day, pf;
+  bool straddle, noon_in_a, full_day;
+  int pf;
 
   static __device__ __forceinline__ int row_of(int y) {   // table row y rolled over the table's own 366 rows (:656)
     y = y < 0 ? y + kRows : (y >= kRows ? y - kRows : y);
@@ -95,7 +96,7 @@ struct SwCell {
     qrow = a.t.q + (size_t)row0 * 365 * kQLd;
     dayl = a.t.daylength + (size_t)row0 * kRows;
     sw_col = daily_plane(a, a.sw_d, cell) + cell;
-    full_day = a.sw_full_day; inv_den = a.inv_sw_den; pf = a.k.pf != 0;
+    full_day = a.sw_full_day; inv_den = a.inv_sw_den; pf = a.k.pf;
     sc = UNITS ? a.out.scale[MSB_V_SHORTWAVE] : 1.0; of = UNITS ? a.out.offset[MSB_V_SHORTWAVE] : 0.0;
     ostride = (size_t)a.out.ld;
     o = reinterpret_cast<OutT *>(a.out.var[MSB_V_SHORTWAVE]) + cell +
@@ -112,23 +113,35 @@ struct SwCell {
     if (qa + (long)t_a * C >= qrow + (size_t)365 * kQLd || qb + (long)tpd * C >= qrow + (size_t)365 * kQLd ||
         qb + (long)t_b * C < qrow) asm volatile("trap;");
 #endif
-    // Tomorrow's entries into L1 while today computes: the segments below are short loops of dependent
-    // batches (a batch of four loads, then its four windows), so what hides the table latency is
-    // that the loads hit L1.  One prefetch per entry; neighbouring lanes share the lines.
+    // The segments below are short loops of dependent batches (four loads, then their four windows),
+    // so what hides the table latency is that the loads hit L1: pf = 1 prefetches tomorrow's entries
+    // while today computes, pf = 2 the NEXT SEGMENT's entries while this one computes (a third of
+    // the L1 footprint, a lead of a few thousand cycles).  One prefetch per entry; neighbouring
+    // lanes share the lines.
+    auto fetch = [&](const double *ptr, int n) {
+      for (int t = 0; t < n; ++t, ptr += C) prefetch_l1(ptr);
+    };
+    const double *na = qa, *nb = qb;      // tomorrow's rows (pf = 2: its first segment goes out last)
     if (pf && more) {
       const int y1 = s_doy[d + 1 - win0] - 1;
-      const double *pa = qrow + row_of(y1 + q) * kQLd + c0;
-      const double *pb = qrow + row_of(y1 + q + 1) * kQLd + (c0 - kTiny) + (long)t_b * C;
-      for (int t = 0; t <= t_a; ++t, pa += C) prefetch_l1(pa);
-      for (int t = t_b; t <= tpd; ++t, pb += C) prefetch_l1(pb);
+      na = qrow + row_of(y1 + q) * kQLd + c0;
+      nb = qrow + row_of(y1 + q + 1) * kQLd + (c0 - kTiny);
+      if (pf == 1) {
+        fetch(na, t_a + 1);
+        fetch(nb + (long)t_b * C, tpd - t_b + 1);
+      }
     }
+    const bool seg = pf == 2;
     double v0 = __ldg(qa);
     // ---- windows inside row A: [0, t_a), the noon window (if it is here) splitting them ----
     if (noon_in_a) {
+      if (seg) fetch(qa + (long)(t_n + 1) * C, t_a - t_n);
       sw_segment<OutT, UNITS>(qa + C, C, t_n, rd_a, v0, o, ostride, sc, of);
       v0 -= rowtot;
+      if (seg) fetch(qb + (long)t_b * C, tpd - t_b + 1);
       sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * C, C, t_a - t_n, rd_a, v0, o, ostride, sc, of);
     } else {
+      if (seg) fetch(qb + (long)t_b * C, t_n - t_b + 1);
       sw_segment<OutT, UNITS>(qa + C, C, t_a, rd_a, v0, o, ostride, sc, of);
     }
     // ---- the straddling window: [.., 2880) of row A (q_A[2880] = 0) + [0, ..) of row B (q_B[0] = 0) ----
@@ -144,10 +157,13 @@ struct SwCell {
     }
     // ---- windows inside row B: [t_b, tpd) ----
     if (noon_in_a) {
+      if (seg && more) fetch(na, t_n + 1);
       sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, tpd - t_b, rd_b, v0, o, ostride, sc, of);
     } else {
+      if (seg) fetch(qb + (long)(t_n + 1) * C, tpd - t_n);
       sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, t_n - t_b, rd_b, v0, o, ostride, sc, of);
       v0 -= rowtot;
+      if (seg && more) fetch(na, t_a + 1);
       sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * C, C, tpd - t_n, rd_b, v0, o, ostride, sc, of);
     }
     rd_a = rd_b;
@@ -363,7 +379,8 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
   while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 8 * 6)
     a.k.tile >>= 1;
   if (a.out.tune.day_tile > 0) a.k.tile = a.out.tune.day_tile < kDayWin - 8 ? a.out.tune.day_tile : kDayWin - 8;
-  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : 1;      // sw_day_kernel: L1 prefetch of the next day's table entries
+  // sw_day_kernel: L1 prefetch of the next day's (1, default) or the next segment's (2) table entries, -1 = none
+  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : (a.out.tune.day_prefetch == 2 ? 2 : 1);
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
   const bool f4 = a.out.dtype == 4;
   const bool want_sw = a.var_mask & (1u << MSB_V_SHORTWAVE), want_pr = a.var_mask & (1u << MSB_V_PREC);

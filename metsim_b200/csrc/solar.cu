@@ -100,8 +100,11 @@ static void optam_thresholds(double *c32) {
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int kK1Threads = 256;
-constexpr int kChunk = 12;                       // 240 active scan threads x 12 = 2880
+// 320 threads, each scanning a contiguous chunk of 9 row entries: 320 x 9 = 2880, and an ODD stride in
+// 8-byte words keeps the 16 lanes of a half-warp on 16 different shared-memory banks (the earlier
+// 256 x 12 layout put them on 4: short-scoreboard stalls of 7 warps per issue in the scan passes)
+constexpr int kK1Threads = 320;
+constexpr int kChunk = 9;
 
 __constant__ double c_optam[21] = {2.90, 3.05, 3.21, 3.39, 3.69, 3.82, 4.07, 4.37, 4.72, 5.12, 5.60,
                                    6.18, 6.88, 7.77, 8.90, 10.39, 12.44, 15.36, 19.79, 26.96, 30.00};
@@ -126,9 +129,11 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-constexpr int kWarps = kK1Threads / 32;          // 8
-constexpr int kHalfSlots = kK1Threads / 2;       // 128 scan slots per half, 120 of them used
-constexpr int kHalfChunks = kTiny / 2 / kChunk;  // 120
+constexpr int kWarps = kK1Threads / 32;          // 10
+constexpr int kHalfSlots = kK1Threads / 2;       // 160 scan slots per half (five warps), all used
+constexpr int kHalfChunks = kTiny / 2 / kChunk;  // 160
+static_assert(kHalfChunks * kChunk * 2 == kTiny && kHalfChunks <= kHalfSlots && kHalfSlots % 32 == 0,
+              "the two half-row scans must tile the row with whole warps");
 
 __global__ void __launch_bounds__(kK1Threads)
 solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
