@@ -88,7 +88,8 @@ typedef struct msb_tuning {
   int32_t day_tile;         /* output days per thread of the interior shortwave / precipitation kernels, used as given */
   int32_t disagg_path;      /* 0 = specialised interior-day kernels + event kernel on the edge days,
                                1 = event-driven kernel for every day */
-  int32_t day_prefetch;     /* -1 = no L1 prefetch of the next day's table entries in the shortwave kernel */
+  int32_t day_prefetch;     /* shortwave kernel, L1 prefetch of table entries: 0 = the next segment's (default),
+                               1 = the next day's, -1 = none */
   int32_t prep_days;        /* padded days per thread of the day-record kernel */
   int32_t reserved;
 } msb_tuning;

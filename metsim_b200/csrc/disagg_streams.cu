@@ -24,34 +24,35 @@
 namespace msb {
 
 // One segment of a day's windows: all of them inside one table row, so the entries are an arithmetic
-// progression of addresses and a window is rd * (next entry - this entry).  The loop is unrolled by
-// four with the loads first: four independent 8-byte loads in flight per thread.
+// progression of addresses and a window is rd * (next entry - this entry).  A segment of n windows
+// goes out as batches of 8, 4, 2, 1 with the loads of a batch issued together.
+// B windows at once: B independent 8-byte table loads in flight, then their B windows
+template <typename OutT, bool UNITS, int B>
+__device__ __forceinline__ void sw_batch(const double *__restrict__ &ptr, int stride, double rd, double &v0,
+                                         OutT *&o_sw, size_t ostride, double sc, double of) {
+  double e[B];
+#pragma unroll
+  for (int k = 0; k < B; ++k) e[k] = __ldg(ptr + (long)k * stride);
+  ptr += (long)B * stride;
+#pragma unroll
+  for (int k = 0; k < B; ++k) {
+    double s = rd * (e[k] - (k ? e[k - 1] : v0));
+    if (UNITS) s = fma(s, sc, of);
+    __stcs(o_sw + (size_t)k * ostride, (OutT)s);
+  }
+  o_sw += (size_t)B * ostride;
+  v0 = e[B - 1];
+}
+
 template <typename OutT, bool UNITS>
 __device__ __forceinline__ void sw_segment(const double *__restrict__ ptr, int stride, int n, double rd,
                                            double &v0, OutT *&o_sw, size_t ostride, double sc, double of) {
   int t = 0;
-  for (; t + 4 <= n; t += 4) {
-    const double a0 = __ldg(ptr), a1 = __ldg(ptr + stride), a2 = __ldg(ptr + 2 * stride),
-                 a3 = __ldg(ptr + 3 * stride);
-    ptr += 4 * stride;
-    double s0 = rd * (a0 - v0), s1 = rd * (a1 - a0), s2 = rd * (a2 - a1), s3 = rd * (a3 - a2);
-    if (UNITS) { s0 = fma(s0, sc, of); s1 = fma(s1, sc, of); s2 = fma(s2, sc, of); s3 = fma(s3, sc, of); }
-    __stcs(o_sw, (OutT)s0);
-    __stcs(o_sw + ostride, (OutT)s1);
-    __stcs(o_sw + 2 * ostride, (OutT)s2);
-    __stcs(o_sw + 3 * ostride, (OutT)s3);
-    o_sw += 4 * ostride;
-    v0 = a3;
-  }
-  for (; t < n; ++t) {
-    const double a0 = __ldg(ptr);
-    ptr += stride;
-    double s0 = rd * (a0 - v0);
-    if (UNITS) s0 = fma(s0, sc, of);
-    __stcs(o_sw, (OutT)s0);
-    o_sw += ostride;
-    v0 = a0;
-  }
+#pragma unroll 1
+  for (; t + 8 <= n; t += 8) sw_batch<OutT, UNITS, 8>(ptr, stride, rd, v0, o_sw, ostride, sc, of);
+  if (t + 4 <= n) { sw_batch<OutT, UNITS, 4>(ptr, stride, rd, v0, o_sw, ostride, sc, of); t += 4; }
+  if (t + 2 <= n) { sw_batch<OutT, UNITS, 2>(ptr, stride, rd, v0, o_sw, ostride, sc, of); t += 2; }
+  if (t < n) sw_batch<OutT, UNITS, 1>(ptr, stride, rd, v0, o_sw, ostride, sc, of);
 }
 
 // ---- shortwave of one cell: per-cell constants, then one call per output day --------------------
@@ -379,8 +380,8 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
   while (a.k.tile > 2 && (long)cell_blocks * ((b0 - a0 + a.k.tile - 1) / a.k.tile) < 148L * 8 * 6)
     a.k.tile >>= 1;
   if (a.out.tune.day_tile > 0) a.k.tile = a.out.tune.day_tile < kDayWin - 8 ? a.out.tune.day_tile : kDayWin - 8;
-  // sw_day_kernel: L1 prefetch of the next day's (1, default) or the next segment's (2) table entries, -1 = none
-  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : (a.out.tune.day_prefetch == 2 ? 2 : 1);
+  // sw_day_kernel: L1 prefetch of the next segment's (default) or the next day's (1) table entries, -1 = none
+  a.k.pf = a.out.tune.day_prefetch < 0 ? 0 : (a.out.tune.day_prefetch == 1 ? 1 : 2);
   const dim3 grid(cell_blocks, (b0 - a0 + a.k.tile - 1) / a.k.tile);
   const bool f4 = a.out.dtype == 4;
   const bool want_sw = a.var_mask & (1u << MSB_V_SHORTWAVE), want_pr = a.var_mask & (1u << MSB_V_PREC);
