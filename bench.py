@@ -503,6 +503,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--other-configs", default="auto", choices=("auto", "on", "off"),
+                    help="after the headline, also time BASELINE configs[3] (CONUS 10 years -> 3-hourly, mix) and "
+                         "configs[4] (global 1/8 deg, 30 years -> 15-minute) cut into cell ranges over the ranks; "
+                         "auto = on 8 GPUs (what BASELINE.json quotes them on)")
     ap.add_argument("--no-consumer", action="store_true", help="e2e without the native tile consumer")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--verify-cells", type=int, default=512)
@@ -675,6 +679,47 @@ def main():
                              "efficiency_vs_n1": (e2e["ms_per_step"] / (dt * 1e3)) / world if e2e else None}
         sp.release()
 
+    # ---- BASELINE configs[3] and configs[4]: quoted on 8 B200, cell-chunk sharded ----
+    others = None
+    if (args.other_configs == "on" or (args.other_configs == "auto" and world == 8)) \
+            and args.workload == "conus_16th_hourly" and not args.cells and not args.days:
+        others = {}
+        for name in ("conus_16th_10yr_3h_mix", "global_8th_30yr_15min"):
+            g2, d2, start2, ts2, pt2 = synth.CONFIGS[name]
+            la2, lo2 = synth.grid_cells(g2, np.random.default_rng(synth.SEED))
+            lo_c, hi_c = cell_range(la2.size, rank, world)
+            op, err = None, None
+            try:                                 # allocation is the part that can fail (memory): every rank
+                op = DevicePass(args, dev, la2[lo_c:hi_c], lo2[lo_c:hi_c], d2, start2, ts2, pt2,   # learns of it
+                                synth.SEED + 200 + rank, None, patch_rows=4 if g2.startswith("global") else 1)
+            except Exception as exc:             # before anyone enters a collective
+                err = repr(exc)
+                torch.cuda.empty_cache()
+            if reduce_max(1.0 if err else 0.0) > 0:
+                others[name] = {"error": err or "another rank could not set the shard up"}
+                if op is not None:
+                    op.release()
+                continue
+            o_ms, o_br = op.timed(3, 3, barrier)
+            o_rank = gather(o_ms)
+            tpd2 = 1440 // ts2
+            cts = la2.size * d2 * tpd2
+            b2 = algorithmic_bytes_per_cell_ts(tpd2, len(OUT_VARS))
+            others[name] = {"value": cts / (max(o_rank) * 1e-3), "unit": UNIT, "ms_per_step": max(o_rank),
+                            "rank_ms_per_step": o_rank, "cells": int(la2.size), "cells_per_gpu": int(hi_c - lo_c),
+                            "n_days": d2, "time_step_min": ts2, "prec_type": pt2, "tile_days": op.tile,
+                            "daily_form": ("single pass" if op.eng.single_pass_budget
+                                           else "two pass (the candidate planes do not fit beside the record)"),
+                            "disaggregate_frac_of_hbm_rank0":
+                                b2 * (hi_c - lo_c) * d2 * tpd2 / (float(o_br[2]) * 1e-3) / 1e9 / peak,
+                            "breakdown_ms_rank0": {"solar_tables": float(o_br[0]), "daily_mtclim": float(o_br[1]),
+                                                   "disaggregate": float(o_br[2])},
+                            "sharding": f"one domain of {la2.size} cells cut into {world} contiguous cell ranges, "
+                                        "no collective"}
+            op.release()
+            del op
+            barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:      # reported baseline: rank 0 at N = 1 only
         cores = os.cpu_count() or 1
@@ -721,7 +766,7 @@ def main():
                          "algorithmic_bytes_per_cell_timestep": bytes_per_cts,
                          "bytes_per_launch": bytes_per_launch, "ms_per_launch": float(disagg_ms_per_launch),
                          "whole_step_frac": bytes_per_cts * cell_ts_rank / (ms_per_step * 1e-3) / 1e9 / peak},
-            "verify": verify, "strong": strong,
+            "verify": verify, "strong": strong, "other_configs": others,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "build": {"library": "metsim_b200/csrc/libmetsim_b200.so", "source_hash": src_hash,
