@@ -708,8 +708,8 @@ def main():
             others[name] = {"value": cts / (max(o_rank) * 1e-3), "unit": UNIT, "ms_per_step": max(o_rank),
                             "rank_ms_per_step": o_rank, "cells": int(la2.size), "cells_per_gpu": int(hi_c - lo_c),
                             "n_days": d2, "time_step_min": ts2, "prec_type": pt2, "tile_days": op.tile,
-                            "daily_form": ("single pass" if op.eng.single_pass_budget
-                                           else "two pass (the candidate planes do not fit beside the record)"),
+                            "daily_form": ("single pass" if op.eng._daily and op.eng._daily[5][0] is not None
+                                           else "two pass (the candidate planes do not fit the budget beside the record)"),
                             "disaggregate_frac_of_hbm_rank0":
                                 b2 * (hi_c - lo_c) * d2 * tpd2 / (float(o_br[2]) * 1e-3) / 1e9 / peak,
                             "breakdown_ms_rank0": {"solar_tables": float(o_br[0]), "daily_mtclim": float(o_br[1]),
