@@ -22,8 +22,10 @@ fall-back when the reference install is absent.
 Beyond the contract keys the line carries: ``verify`` (a sample of cells of one extra full pass, same
 launch geometry as the timed ones, checked against the oracle after the timed region), ``strong``
 (N > 1: ONE domain cut into contiguous cell ranges, the north_star's partition, run after the weak
-pass in the same process), ``d2h_ceiling`` (bare pinned device-to-host copies on all ranks at once:
-what the box can deliver to host memory, the yardstick of ``e2e``).
+pass in the same process), ``e2e.d2h_ceiling_gbs_all_ranks`` (bare pinned device-to-host copies on all
+ranks at once: what the box can deliver to host memory, the yardstick of ``e2e``) and, on 8 GPUs,
+``other_configs`` (BASELINE configs[3] and configs[4] -- the 10-year 3-hourly and the 30-year 15-minute
+domains -- cut into cell ranges over the ranks, device-timed like the headline).
 """
 from __future__ import annotations
 
@@ -638,6 +640,8 @@ def main():
                "d2h_gbs_all_ranks": world * d2h / dt / 1e9,
                "d2h_ceiling_gbs_all_ranks": ceiling,
                "fraction_of_d2h_ceiling": (world * d2h / dt / 1e9) / ceiling if ceiling else None,
+               "fraction_of_d2h_ceiling_copies_only": ((world * d2h / copy_only / 1e9) / ceiling
+                                                       if ceiling and copy_only else None),
                "consumer": (f"native sink (csrc/sink.cu), {n_thr} threads per rank: every tile read, byte-swapped "
                             f"and scattered into staging while the next tile computes; {consumed} bytes per step"
                             if not args.no_consumer else "none"),
