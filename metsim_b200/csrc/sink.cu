@@ -28,6 +28,7 @@ struct msb_sink {
   std::vector<std::vector<char>> stage;   // per thread: chunk_steps rows of the grid, NaN-prefilled
   int64_t chunk_steps = 1;
   // one job at a time: rows [0, n_steps) of src to file_offset
+  std::mutex call_mu;                // serialises msb_sink_write() callers (mu is released while waiting)
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   const char *src = nullptr;
@@ -210,6 +211,7 @@ extern "C" int msb_sink_create(const msb_sink_desc *d, msb_sink **out) {
 extern "C" int msb_sink_write(msb_sink *s, const void *src, int64_t n_steps, int64_t file_offset) {
   if (!s || !src || n_steps < 0 || file_offset < 0) { set_error("msb_sink_write: bad argument"); return MSB_E_ARG; }
   if (n_steps == 0) return MSB_OK;
+  std::lock_guard<std::mutex> one_caller(s->call_mu);
   std::unique_lock<std::mutex> lk(s->mu);
   s->src = reinterpret_cast<const char *>(src);
   s->n_steps = n_steps;
