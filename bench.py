@@ -374,13 +374,13 @@ class DevicePass:
         # kernels of mine per step: 2 solar kernels; daily single pass = fused + reduce, then for the
         # replay list 3 x (pass 1 + reduce) + pass 2 (they exit at once when the list is empty) -- the
         # two-pass form is 4 x (pass 1 + reduce) + pass 2, the same count; per msb_disaggregate call
-        # thermo_knot_kernel + streams_day_kernel over the interior days [2, D-2), plus day records +
-        # disagg_kernel<thermo> / <streams> over the first / last two days of the record
+        # thermo_knot_kernel + sw_day_kernel + prec_day_kernel over the interior days [2, D-2), plus day
+        # records + disagg_kernel<thermo> / <streams> over the first / last two days of the record
         def disagg_launches(d0, d1):
             a0, b0 = max(d0, 2), min(d1, n_days - 2)
             if a0 >= b0:
                 return 3
-            return 2 + (3 if d0 < a0 else 0) + (3 if b0 < d1 else 0)
+            return 3 + (3 if d0 < a0 else 0) + (3 if b0 < d1 else 0)
         self.launches_per_step = 2 + 9 + sum(disagg_launches(*t) for t in self.tiles)
 
     def step(self, marks=None):
@@ -761,7 +761,7 @@ def main():
             # the metric with and without the (time-independent) solar-geometry set-up
             "rank_ms_per_step": rank_ms,      # device time of every rank (value uses the maximum)
             "value_excl_solar_tables": total_cell_ts / max(1e-9, (ms_per_step - float(br[0])) * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = thermo_knot_kernel + streams_day_kernel (+ "
+            "roofline": {"bound": "hbm", "kernel": "msb_disaggregate = thermo_knot_kernel + sw_day_kernel + prec_day_kernel (+ "
                                                    "disagg_prepare_kernel and disagg_kernel on the record's first / last "
                                                    "two days), timed together per call (--tile-days days)",
                          "achieved": achieved,
