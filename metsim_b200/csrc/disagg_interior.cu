@@ -114,7 +114,6 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
   const int ts = p.time_step;
   const long ld = f.ld;
   const double inv_ts = 1.0 / (double)ts;
-  const float inv_ts_f = 1.0f / (float)ts;
   const double lon = wrap_lon(f.lon[cell]);                            // disaggregate.py:67
   const int off_min = p.utc_offset ? (int)((lon / kDegPerRev) * kMinPerDay) : 0;  // :611
   const double elev = f.elev[cell];
@@ -205,13 +204,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     const double d1 = pchip_mid(h01, h12, m01, m12), d2 = pchip_mid(h12, h23, m12, m23);
     slot[kT_KX0][tid] = x2; slot[kT_KY0][tid] = y2; slot[kT_KD0][tid] = d2;
     slot[kT_KX1][tid] = x3; slot[kT_KY1][tid] = y3; slot[kT_KM01][tid] = m23;
-    // daily vapour pressure in kPa (:480): x / 1000 as a product with one residual step (within an ulp
-    // of the IEEE quotient; two 40-instruction divides per knot-day otherwise)
-    auto kpa = [](double pa) {
-      const double q = pa * 1e-3;
-      return fma(fma(-1000.0, q, pa), 1e-3, q);
-    };
-    const double v0 = kpa(vp_d[o0]), v1 = kpa(vp_d[o1]);
+    const double v0 = vp_d[o0] / 1000.0, v1 = vp_d[o1] / 1000.0;
     const int ia = first_step_ge_fast(x0, ts, inv_ts), ib = first_step_ge_fast(x2, ts, inv_ts);
     int isw = first_step_ge_fast(x1, ts, inv_ts);
     // Hermite -> scipy power basis (CubicHermiteSpline, _cubic.py:158-165), both intervals
@@ -283,12 +276,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
             wd = (w1 * wd + w2 * slot[kT_WDB][tid]) * inv_ts;
             i_tk = i + 1;
           } else {
-            // steps until the window reaches the end of its source day: floor((1440 - r) / ts) from a
-            // float reciprocal (the operands are integers below 2^11, exact in float) + one fix-up
-            const int left = kMinPerDay - r;
-            int g = (int)((float)left * inv_ts_f);
-            g += ((g + 1) * ts <= left) - (g * ts > left);
-            i_tk = i + g;
+            i_tk = i + (kMinPerDay - r) / ts;
           }
           tk_a = kStefanB * tk; tk_b = kStefanB * (1.0 - tk);
           if (MASKED) tk_cur = tk;
