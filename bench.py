@@ -359,6 +359,8 @@ class DevicePass:
             from metsim_b200.shard import patch_order
             order = patch_order(lat, lon, patch_rows)
         self.eng.load(order=order, **self.f)
+        self.sw_table = ("window-major copy" if self.eng.use_window_major() else "plain") + \
+            " (a warp's cells touch %.1f sectors of the plain table per load)" % self.eng.sw_sectors_per_load
         n, tpd = self.n, self.tpd
         if tile_days is None:    # one ring slot of the 8 float32 outputs within ~36 GB (two slots + inputs,
             # candidate planes and the 4.4 GB table stay below half of the 180 GB of HBM)
@@ -712,6 +714,7 @@ def main():
             others[name] = {"value": cts / (max(o_rank) * 1e-3), "unit": UNIT, "ms_per_step": max(o_rank),
                             "rank_ms_per_step": o_rank, "cells": int(la2.size), "cells_per_gpu": int(hi_c - lo_c),
                             "n_days": d2, "time_step_min": ts2, "prec_type": pt2, "tile_days": op.tile,
+                            "shortwave_table": op.sw_table,
                             "daily_form": ("single pass" if op.eng._daily and op.eng._daily[5][0] is not None
                                            else "two pass (the candidate planes do not fit the budget beside the record)"),
                             "disaggregate_frac_of_hbm_rank0":
@@ -747,7 +750,7 @@ def main():
             "config": {"workload": args.workload, "description": WORKLOADS[args.workload],
                        "cells_per_gpu": int(n), "n_days": int(n_days), "time_step_min": ts,
                        "prec_type": prec_type, "utc_offset": True, "out_vars": list(OUT_VARS),
-                       "out_precision": "f4", "tile_days": tile,
+                       "out_precision": "f4", "tile_days": tile, "shortwave_table": dp.sw_table,
                        "cell_order": ("caller's (latitude-row-major)" if args.patch_rows <= 1 else
                                       f"engine-defined patches of {args.patch_rows} latitude rows (shard.patch_order)"),
                        "launch_geometry": "library defaults: 16 knot-days / 16 output days per thread, daily chunks of "

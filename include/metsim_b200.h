@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MSB_VERSION 200
+#define MSB_VERSION 201
 
 enum {
   MSB_OK = 0,
@@ -91,7 +91,9 @@ typedef struct msb_tuning {
   int32_t day_prefetch;     /* shortwave kernel, L1 prefetch of table entries: 0 = the next segment's (default),
                                1 = the next day's, -1 = none */
   int32_t prep_days;        /* padded days per thread of the day-record kernel */
-  int32_t reserved;
+  int32_t sw_table;         /* msb_run_host only (elsewhere the caller decides by what it puts into
+                               msb_solar_tables.q_win): 0 = window-major copy of the table when
+                               neighbouring cells are far apart in longitude, 1 = never, 2 = always */
 } msb_tuning;
 
 /* Geometry of the per-latitude solar tables (replaces the per-cell 366x2880 tiny_rad_fract of
@@ -111,6 +113,17 @@ typedef struct msb_solar_tables {
   double *set_min;      /* [n_lat][366]  minutes, 960 default applied */
   double *q;            /* [n_lat][365][MSB_Q_LD] (+ MSB_Q_PAD) signed prefix sums of the normalised row */
   double *tt_coef;      /* [n_lat][365][MSB_TT_TERMS] Taylor coefficients of tt_max0(p) */
+  /* Optional second copy of q for ONE time step (NULL = none), [n_lat][365][msb_solar_q_win_ld(step)]
+   * (+ MSB_Q_PAD): the entries regrouped by their phase inside an output window of C = 2*step
+   * tiny steps -- tiny step s sits at [(s % C) * W + s / C], the row total at [C * W], with
+   * W = 1440/step + 1 rounded up to a multiple of 4 (whole 32-byte sectors per phase).  The windows of an output day read every C-th entry of a row
+   * (disaggregate.py:660-667): here those are CONSECUTIVE, so a cell's day touches ~7 sectors
+   * instead of 25.  It pays where neighbouring cells do not share table entries anyway (coarse or
+   * sparsely masked grids: global 0.5 deg, masked 1/8 deg); on dense fine grids (CONUS 1/16 deg:
+   * 16 consecutive entries per warp load) the plain table coalesces better and q_win stays NULL. */
+  double *q_win;
+  int32_t q_win_step;   /* minutes; the shortwave kernel uses q_win only when it equals params.time_step */
+  int32_t reserved_;
 } msb_solar_tables;
 
 /* inputs of one shard (contiguous chunk of active cells), all device pointers */
@@ -186,6 +199,10 @@ void msb_default_params(msb_params *p);                          /* metsim.py:14
  * memory makes the upload asynchronous), dev_ws the same number of bytes on the device. */
 size_t msb_solar_prelude_bytes(int n_lat);
 int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_elems, size_t *tt_elems);
+/* row pitch / element count (pad included) of msb_solar_tables.q_win for a time step that divides
+ * 1440 and is below it; 0 otherwise */
+size_t msb_solar_q_win_ld(int time_step);
+size_t msb_solar_q_win_elems(int n_lat, int time_step);
 int msb_solar_tables_build(int n_lat, const double *lat_deg_host, void *host_ws, void *dev_ws,
                            const msb_solar_tables *tables, int n_host_threads, void *stream);
 

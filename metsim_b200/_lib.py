@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmetsim_b200.so")
+# MSB_LIBRARY: a differently-compiled build of the same sources (profiles/tools/build_variants.py);
+# still the CUDA library, never a fallback
+LIB_PATH = os.environ.get("MSB_LIBRARY") or os.path.join(_HERE, "csrc", "libmetsim_b200.so")
 
 N_SUBVARS = 10
 N_DAILYVARS = 13
@@ -34,7 +36,8 @@ DAILY_CAND = 3          # MSB_DAILY_CAND: candidate planes of the single-pass da
 DAILY_CAND_K0 = 4       # MSB_DAILY_CAND_K0
 
 EXPORTS = ("msb_version", "msb_last_error", "msb_default_params", "msb_solar_prelude_bytes",
-           "msb_solar_table_sizes", "msb_solar_tables_build", "msb_daily_scratch_bytes",
+           "msb_solar_table_sizes", "msb_solar_q_win_ld", "msb_solar_q_win_elems",
+           "msb_solar_tables_build", "msb_daily_scratch_bytes",
            "msb_daily_scratch_bytes_chunk", "msb_daily_single_pass",
            "msb_mtclim_daily", "msb_daily_check", "msb_disagg_workspace_bytes",
            "msb_disagg_workspace_bytes_lw", "msb_disaggregate",
@@ -61,15 +64,15 @@ class Tuning(C.Structure):
     """msb_tuning: launch-geometry / path overrides, 0 = the library's choice."""
     _fields_ = [("daily_chunk_len", C.c_int32), ("daily_two_pass", C.c_int32),
                 ("knot_tile", C.c_int32), ("day_tile", C.c_int32), ("disagg_path", C.c_int32),
-                ("day_prefetch", C.c_int32), ("prep_days", C.c_int32), ("reserved", C.c_int32)]
+                ("day_prefetch", C.c_int32), ("prep_days", C.c_int32), ("sw_table", C.c_int32)]
 
 
-TUNING_KEYS = tuple(n for n, _ in Tuning._fields_ if n != "reserved")
+TUNING_KEYS = tuple(n for n, _ in Tuning._fields_)
 # environment spellings of the same knobs (read here, in Python, once per Engine / run_host call --
 # the C library itself never looks at the environment)
 _TUNING_ENV = {"MSB_DAILY_CHUNK": "daily_chunk_len", "MSB_DAILY_TWO_PASS": "daily_two_pass",
                "MSB_KNOT_TILE": "knot_tile", "MSB_DAY_TILE": "day_tile", "MSB_DAY_PF": "day_prefetch",
-               "MSB_PREP_DAYS": "prep_days"}
+               "MSB_PREP_DAYS": "prep_days", "MSB_SW_TABLE": "sw_table"}
 
 
 def make_tuning(user: dict | None = None) -> Tuning:
@@ -94,7 +97,8 @@ def make_tuning(user: dict | None = None) -> Tuning:
 class SolarTables(C.Structure):
     _fields_ = [("n_lat", C.c_int32), ("daylength", C.c_void_p), ("potrad", C.c_void_p),
                 ("rise_min", C.c_void_p), ("set_min", C.c_void_p), ("q", C.c_void_p),
-                ("tt_coef", C.c_void_p)]
+                ("tt_coef", C.c_void_p), ("q_win", C.c_void_p), ("q_win_step", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 class Forcing(C.Structure):
@@ -185,6 +189,10 @@ def lib():
     l.msb_solar_table_sizes.restype = C.c_int
     l.msb_solar_table_sizes.argtypes = [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
                                         C.POINTER(C.c_size_t)]
+    l.msb_solar_q_win_ld.restype = C.c_size_t
+    l.msb_solar_q_win_ld.argtypes = [C.c_int]
+    l.msb_solar_q_win_elems.restype = C.c_size_t
+    l.msb_solar_q_win_elems.argtypes = [C.c_int, C.c_int]
     l.msb_solar_tables_build.restype = C.c_int
     l.msb_solar_tables_build.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(SolarTables), C.c_int, C.c_void_p]

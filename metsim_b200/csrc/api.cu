@@ -11,6 +11,8 @@
 // pinned staging, the two streams, events) belongs to a caller-owned msb_host_ctx.  The reference
 // calls its per-cell path from concurrent threads (scheduler='threading', metsim/metsim.py:63,
 // :195): give each thread its own context and the runs overlap, on one device or on several.
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -168,7 +170,7 @@ namespace {
 struct Plan {
   int N, D, ts, tpd, osz, n_lat, n_out, tile_days;
   bool sub, single_pass, lw_rescale;
-  size_t dn, sn, small_e, q_e, tt_e, prelude, ld_out, tile_elems, ws_bytes, scratch_bytes, need;
+  size_t dn, sn, small_e, q_e, qw_e, tt_e, prelude, ld_out, tile_elems, ws_bytes, scratch_bytes, need;
 };
 
 int check_run(const msb_params *p, const msb_host_run *run) {
@@ -199,7 +201,28 @@ int check_run(const msb_params *p, const msb_host_run *run) {
   return MSB_OK;
 }
 
-void make_plan(const msb_params *p, const msb_host_run *run, int n_lat, Plan &pl) {
+// Window-major copy of the shortwave table (msb_solar_tables.q_win)?  tune.sw_table 0: when the 32
+// consecutive cells of a warp touch more than 8 sectors of the plain table per load on average
+// (distinct (latitude row, tiny offset / 4) among them) -- coarse or sparsely masked grids.
+bool want_window_major(const msb_params *p, const msb_host_run *run, const std::vector<int32_t> &lat_row) {
+  if (p->time_step >= kMinPerDay || run->tune.sw_table == 1) return false;
+  if (run->tune.sw_table == 2) return true;
+  const int N = run->n_cells;
+  if (N < 64) return false;
+  long sectors = 0, warps = 0;
+  int64_t key[32];
+  for (int w0 = 0; w0 + 32 <= N; w0 += 32, ++warps) {
+    for (int l = 0; l < 32; ++l) {
+      const double lon = std::remainder(run->lon[w0 + l], 360.0);
+      key[l] = ((int64_t)lat_row[w0 + l] << 12) + (((int)(lon / 360.0 * kTiny) + kTiny / 2) >> 2);
+    }
+    std::sort(key, key + 32);
+    sectors += std::unique(key, key + 32) - key;
+  }
+  return sectors > 8 * warps;
+}
+
+void make_plan(const msb_params *p, const msb_host_run *run, int n_lat, bool win, Plan &pl) {
   pl.N = run->n_cells; pl.D = run->n_days; pl.ts = p->time_step;
   pl.sub = pl.ts < kMinPerDay;
   pl.tpd = pl.sub ? kMinPerDay / pl.ts : 1;
@@ -219,6 +242,7 @@ void make_plan(const msb_params *p, const msb_host_run *run, int n_lat, Plan &pl
   pl.tile_days = tile_days;
   pl.dn = D * N; pl.sn = (size_t)kState * N;
   msb_solar_table_sizes(n_lat, &pl.small_e, &pl.q_e, &pl.tt_e);
+  pl.qw_e = win ? msb_solar_q_win_elems(n_lat, pl.ts) : 0;
   pl.prelude = msb_solar_prelude_bytes(n_lat);
   // single-pass daily form (daily.cu): no daily column is wanted on the host, the method is mtclim
   // and the six candidate planes are affordable beside the inputs
@@ -245,7 +269,7 @@ void make_plan(const msb_params *p, const msb_host_run *run, int n_lat, Plan &pl
   for (int k = 0; k < 3; ++k) add(pl.sn * 8);
   add(12 * N * 8); add(12 * N * 8); add(2 * N * 8);
   for (int k = 0; k < 4; ++k) add(pl.small_e * 8);
-  add(pl.q_e * 8); add(pl.tt_e * 8); add(pl.prelude);
+  add(pl.q_e * 8); add(pl.qw_e * 8); add(pl.tt_e * 8); add(pl.prelude);
   if (pl.single_pass) {
     add(pl.dn * 8);                                              // tskc
     add(2 * MSB_DAILY_CAND * pl.dn * 8); add(N * 4); add((N + 1) * 4);
@@ -290,7 +314,7 @@ extern "C" int msb_run_host_bytes(const msb_params *p, const msb_host_run *run, 
   std::vector<double> ulat;
   unique_lats(run->lat, run->n_cells, lat_row, ulat);
   Plan pl;
-  make_plan(p, run, (int)ulat.size(), pl);
+  make_plan(p, run, (int)ulat.size(), want_window_major(p, run, lat_row), pl);
   if (device_bytes) *device_bytes = pl.need;
   if (pinned_bytes) *pinned_bytes = pl.prelude + 4096;
   return MSB_OK;
@@ -303,7 +327,7 @@ static int run_locked(msb_host_ctx *ctx, const msb_params *p, msb_host_run *run)
   unique_lats(run->lat, N, lat_row, ulat);
   const int n_lat = (int)ulat.size();
   Plan pl;
-  make_plan(p, run, n_lat, pl);
+  make_plan(p, run, n_lat, want_window_major(p, run, lat_row), pl);
   const int tpd = pl.tpd, osz = pl.osz, tile_days = pl.tile_days, n_out = pl.n_out;
   const bool sub = pl.sub;
   const size_t dn = pl.dn, sn = pl.sn, ld_out = pl.ld_out, tile_elems = pl.tile_elems, ws_bytes = pl.ws_bytes;
@@ -324,10 +348,13 @@ static int run_locked(msb_host_ctx *ctx, const msb_params *p, msb_host_run *run)
   double *d_dur = run->dur12 ? cv.take<double>(12 * (size_t)N) : nullptr;
   double *d_tend = run->t_end ? cv.take<double>(2 * (size_t)N) : nullptr;
   msb_solar_tables tb;
+  std::memset(&tb, 0, sizeof(tb));
   tb.n_lat = n_lat;
   tb.daylength = cv.take<double>(pl.small_e); tb.potrad = cv.take<double>(pl.small_e);
   tb.rise_min = cv.take<double>(pl.small_e); tb.set_min = cv.take<double>(pl.small_e);
-  tb.q = cv.take<double>(pl.q_e); tb.tt_coef = cv.take<double>(pl.tt_e);
+  tb.q = cv.take<double>(pl.q_e);
+  if (pl.qw_e) { tb.q_win = cv.take<double>(pl.qw_e); tb.q_win_step = pl.ts; }
+  tb.tt_coef = cv.take<double>(pl.tt_e);
   void *d_prelude = cv.take<char>(pl.prelude);
   msb_daily dl;
   std::memset(&dl, 0, sizeof(dl));

@@ -92,6 +92,15 @@ __device__ __forceinline__ int first_step_ge_fast(double xk, int ts, double inv_
   return i;
 }
 
+// compile-time experiment knobs (profiles/tools/build_variants.py); the defaults are the product
+#ifndef MSB_THERMO_MINB
+#define MSB_THERMO_MINB 7
+#endif
+#ifndef MSB_THERMO_UNROLL
+#define MSB_THERMO_UNROLL 1
+#endif
+constexpr int kThermoUnroll = MSB_THERMO_UNROLL;
+
 // MASKED = false: the whole default variable set, every store unconditional (the benchmarked
 // instantiation); true: any subset of it, stores under the request mask.
 template <typename OutT, int MINB, bool MASKED>
@@ -244,7 +253,7 @@ thermo_knot_kernel(const __grid_constant__ DisaggArgs a) {
     const int hi_w = __reduce_max_sync(lanes, any ? jb : -kNever);
     double x = (double)ts * (double)lo_w;
     size_t ooff = (size_t)((long)lo_w - i_base) * ostride;
-#pragma unroll 1
+#pragma unroll(kThermoUnroll)
     for (int i = lo_w; i < hi_w; ++i, x += dx, ooff += ostride) {
       if (i < ja || i >= jb) continue;
       if (i == i_next) {
@@ -367,7 +376,7 @@ int exp_tables_ready(cudaStream_t st) {
   return MSB_OK;
 }
 
-constexpr int kKnotTile = 16, kDayTile = 16;   // knot-days / output days per thread on full-size grids
+constexpr int kKnotTile = 16;   // knot-days per thread on full-size grids
 
 int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaStream_t st) {
   const int D = a.f.n_days;
@@ -388,11 +397,11 @@ int launch_interior_thermo(DisaggArgs &a, int a0, int b0, int cell_blocks, cudaS
   const dim3 grid(cell_blocks, (a.k.e1 - a.k.e0 + a.k.tile - 1) / a.k.tile);
   const bool masked = a.var_mask != kExampleMask || a.units || !a.fast_lw || a.lw_raw;
   if (a.out.dtype == 4) {
-    if (masked) thermo_knot_kernel<float, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else thermo_knot_kernel<float, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
+    if (masked) thermo_knot_kernel<float, MSB_THERMO_MINB, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else thermo_knot_kernel<float, MSB_THERMO_MINB, false><<<grid, kDisaggThreads, 0, st>>>(a);
   } else {
-    if (masked) thermo_knot_kernel<double, 7, true><<<grid, kDisaggThreads, 0, st>>>(a);
-    else thermo_knot_kernel<double, 7, false><<<grid, kDisaggThreads, 0, st>>>(a);
+    if (masked) thermo_knot_kernel<double, MSB_THERMO_MINB, true><<<grid, kDisaggThreads, 0, st>>>(a);
+    else thermo_knot_kernel<double, MSB_THERMO_MINB, false><<<grid, kDisaggThreads, 0, st>>>(a);
   }
   MSB_CUDA(cudaGetLastError());
   return MSB_OK;

@@ -56,7 +56,10 @@ __device__ __forceinline__ void sw_segment(const double *__restrict__ ptr, int s
 }
 
 // ---- shortwave of one cell: per-cell constants, then one call per output day --------------------
-template <typename OutT, bool UNITS>
+// WIN: the window-major copy of the table (msb_solar_tables.q_win) instead of the plain one -- a
+// compile-time choice, so that the plain path keeps its constant row pitch and the window-major
+// one its unit stride.
+template <typename OutT, bool UNITS, bool WIN>
 struct SwCell {
   const double *qrow, *dayl, *sw_col;   // latitude row of the table / daylength, the cell's daily shortwave column
   const int *s_doy;
@@ -64,7 +67,17 @@ struct SwCell {
   size_t ostride, ld;
   double rd_a, inv_den, sc, of;
   int C, c0, q, t_a, t_b, t_n, tpd, win0;
+  // where the windows' entries sit in a table row: entry t of row A at row + qa_off + t*S, of row B at
+  // row + qb_off + t*S, the row total at row + tot_off.  Plain table: S = C; window-major copy
+  // (coarse / masked grids): S = 1 -- a day's entries are consecutive.
+  size_t pitch_w;
+  int qa_w, qb_w, tot_w;
   bool straddle, noon_in_a, full_day;
+  __device__ __forceinline__ size_t pitch() const { return WIN ? pitch_w : (size_t)kQLd; }
+  __device__ __forceinline__ int stride() const { return WIN ? 1 : C; }
+  __device__ __forceinline__ int qa_off() const { return WIN ? qa_w : c0; }
+  __device__ __forceinline__ int qb_off() const { return WIN ? qb_w : c0 - kTiny; }
+  __device__ __forceinline__ int tot_off() const { return WIN ? tot_w : kTiny + 1; }
   int pf;
 
   static __device__ __forceinline__ int row_of(int y) {   // table row y rolled over the table's own 366 rows (:656)
@@ -94,7 +107,14 @@ struct SwCell {
     noon_in_a = c0 <= kNoon;
     t_n = ((noon_in_a ? kNoon : kNoon + kTiny) - c0) / C;
     const int row0 = f.lat_row[cell];
-    qrow = a.t.q + (size_t)row0 * 365 * kQLd;
+    if (WIN) {
+      const int W = q_win_w(a.p.time_step), ph = c0 % C, j0 = c0 / C;   // c0 = ph + C j0; row B: c0 - 2880 = ph + C (j0 - tpd)
+      pitch_w = (size_t)q_win_ld(a.p.time_step);
+      qa_w = ph * W + j0; qb_w = ph * W + j0 - tpd; tot_w = C * W;
+      qrow = a.t.q_win + (size_t)row0 * 365 * pitch_w;
+    } else {
+      qrow = a.t.q + (size_t)row0 * 365 * kQLd;
+    }
     dayl = a.t.daylength + (size_t)row0 * kRows;
     sw_col = daily_plane(a, a.sw_d, cell) + cell;
     full_day = a.sw_full_day; inv_den = a.inv_sw_den; pf = a.k.pf;
@@ -106,13 +126,15 @@ struct SwCell {
   }
   __device__ __forceinline__ void day(int d, bool more) {
     const int y = s_doy[d - win0] - 1;
-    const double *const qa = qrow + row_of(y + q) * kQLd + c0;                    // entry t of row A at qa[t C]
-    const double *const qb = qrow + row_of(y + q + 1) * kQLd + (c0 - kTiny);      // entry t of row B at qb[t C]
+    const int S = stride();
+    const double *const ra = qrow + row_of(y + q) * pitch(), *const rb = qrow + row_of(y + q + 1) * pitch();
+    const double *const qa = ra + qa_off();                // entry t of row A at qa[t S]
+    const double *const qb = rb + qb_off();                // entry t of row B at qb[t S]
     const double rd_b = rad_of(d + q + 1);
-    const double rowtot = (noon_in_a ? qa : qb)[kTiny + 1 - (noon_in_a ? c0 : c0 - kTiny)];
+    const double rowtot = (noon_in_a ? ra : rb)[tot_off()];
 #ifdef MSB_BOUNDS
-    if (qa + (long)t_a * C >= qrow + (size_t)365 * kQLd || qb + (long)tpd * C >= qrow + (size_t)365 * kQLd ||
-        qb + (long)t_b * C < qrow) asm volatile("trap;");
+    if (qa + (long)t_a * S >= qrow + (size_t)365 * pitch() || qb + (long)tpd * S >= qrow + (size_t)365 * pitch() ||
+        qb + (long)t_b * S < qrow) asm volatile("trap;");
 #endif
     // The segments below are short loops of dependent batches (four loads, then their four windows),
     // so what hides the table latency is that the loads hit L1: pf = 1 prefetches tomorrow's entries
@@ -120,34 +142,39 @@ struct SwCell {
     // the L1 footprint, a lead of a few thousand cycles).  One prefetch per entry; neighbouring
     // lanes share the lines.
     auto fetch = [&](const double *ptr, int n) {
-      for (int t = 0; t < n; ++t, ptr += C) prefetch_l1(ptr);
+      if (WIN) {                          // consecutive entries: one prefetch per 128-byte line
+        for (int t = 0; t < n; t += 16) prefetch_l1(ptr + t);
+        prefetch_l1(ptr + n - 1);
+      } else {
+        for (int t = 0; t < n; ++t, ptr += S) prefetch_l1(ptr);
+      }
     };
     const double *na = qa, *nb = qb;      // tomorrow's rows (pf = 2: its first segment goes out last)
     if (pf && more) {
       const int y1 = s_doy[d + 1 - win0] - 1;
-      na = qrow + row_of(y1 + q) * kQLd + c0;
-      nb = qrow + row_of(y1 + q + 1) * kQLd + (c0 - kTiny);
+      na = qrow + row_of(y1 + q) * pitch() + qa_off();
+      nb = qrow + row_of(y1 + q + 1) * pitch() + qb_off();
       if (pf == 1) {
         fetch(na, t_a + 1);
-        fetch(nb + (long)t_b * C, tpd - t_b + 1);
+        fetch(nb + (long)t_b * S, tpd - t_b + 1);
       }
     }
     const bool seg = pf == 2;
     double v0 = __ldg(qa);
     // ---- windows inside row A: [0, t_a), the noon window (if it is here) splitting them ----
     if (noon_in_a) {
-      if (seg) fetch(qa + (long)(t_n + 1) * C, t_a - t_n);
-      sw_segment<OutT, UNITS>(qa + C, C, t_n, rd_a, v0, o, ostride, sc, of);
+      if (seg) fetch(qa + (long)(t_n + 1) * S, t_a - t_n);
+      sw_segment<OutT, UNITS>(qa + S, S, t_n, rd_a, v0, o, ostride, sc, of);
       v0 -= rowtot;
-      if (seg) fetch(qb + (long)t_b * C, tpd - t_b + 1);
-      sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * C, C, t_a - t_n, rd_a, v0, o, ostride, sc, of);
+      if (seg) fetch(qb + (long)t_b * S, tpd - t_b + 1);
+      sw_segment<OutT, UNITS>(qa + (long)(t_n + 1) * S, S, t_a - t_n, rd_a, v0, o, ostride, sc, of);
     } else {
-      if (seg) fetch(qb + (long)t_b * C, t_n - t_b + 1);
-      sw_segment<OutT, UNITS>(qa + C, C, t_a, rd_a, v0, o, ostride, sc, of);
+      if (seg) fetch(qb + (long)t_b * S, t_n - t_b + 1);
+      sw_segment<OutT, UNITS>(qa + S, S, t_a, rd_a, v0, o, ostride, sc, of);
     }
     // ---- the straddling window: [.., 2880) of row A (q_A[2880] = 0) + [0, ..) of row B (q_B[0] = 0) ----
     if (straddle) {
-      const double v1 = __ldg(qb + (long)t_b * C);
+      const double v1 = __ldg(qb + (long)t_b * S);
       double sw = fma(rd_b, v1, -(rd_a * v0));
       if (UNITS) sw = fma(sw, sc, of);
       __stcs(o, (OutT)sw);
@@ -159,13 +186,13 @@ struct SwCell {
     // ---- windows inside row B: [t_b, tpd) ----
     if (noon_in_a) {
       if (seg && more) fetch(na, t_n + 1);
-      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, tpd - t_b, rd_b, v0, o, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * S, S, tpd - t_b, rd_b, v0, o, ostride, sc, of);
     } else {
-      if (seg) fetch(qb + (long)(t_n + 1) * C, tpd - t_n);
-      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * C, C, t_n - t_b, rd_b, v0, o, ostride, sc, of);
+      if (seg) fetch(qb + (long)(t_n + 1) * S, tpd - t_n);
+      sw_segment<OutT, UNITS>(qb + (long)(t_b + 1) * S, S, t_n - t_b, rd_b, v0, o, ostride, sc, of);
       v0 -= rowtot;
       if (seg && more) fetch(na, t_a + 1);
-      sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * C, C, tpd - t_n, rd_b, v0, o, ostride, sc, of);
+      sw_segment<OutT, UNITS>(qb + (long)(t_n + 1) * S, S, tpd - t_n, rd_b, v0, o, ostride, sc, of);
     }
     rd_a = rd_b;
   }
@@ -330,7 +357,7 @@ struct PrecCell {
 // shared L1 cost more than the overlap gives, 4.42 ms against 1.72 + 1.66 ms per 97-day call.)
 enum { kStreamSw = 1, kStreamPrec = 2 };
 
-template <typename OutT, bool UNITS, int WHAT>
+template <typename OutT, bool UNITS, int WHAT, bool WIN = false>
 __device__ __forceinline__ void streams_body(const DisaggArgs &a) {
   __shared__ int s_doy[kDayWin], s_month[kDayWin];
   const msb_forcing &f = a.f;
@@ -348,7 +375,7 @@ __device__ __forceinline__ void streams_body(const DisaggArgs &a) {
 #ifdef MSB_BOUNDS   // every day the two cells touch: d_lo - 1 .. d_hi of the staged calendar window
   if (d_lo - 1 < win0 || d_hi >= win0 + nwin || d_hi >= D) asm volatile("trap;");
 #endif
-  SwCell<OutT, UNITS> sw;
+  SwCell<OutT, UNITS, WIN> sw;
   PrecCell<OutT, UNITS> pr;
   if (WHAT & kStreamSw) sw.init(a, cell, d_lo, win0, s_doy);
   if (WHAT & kStreamPrec) pr.init(a, cell, d_lo, win0, s_month);
@@ -363,6 +390,9 @@ __device__ __forceinline__ void streams_body(const DisaggArgs &a) {
 template <typename OutT, bool UNITS>
 __global__ void __launch_bounds__(kDisaggThreads, 8)
 sw_day_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamSw>(a); }
+template <typename OutT, bool UNITS>
+__global__ void __launch_bounds__(kDisaggThreads, 8)
+sw_day_win_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamSw, true>(a); }
 
 // arithmetic: 80 registers, 24 warps per SM
 template <typename OutT, bool UNITS>
@@ -398,7 +428,9 @@ int launch_interior_streams(DisaggArgs &a, int a0, int b0, int cell_blocks, cuda
       else KERNEL<double, false><<<grid, kDisaggThreads, 0, st>>>(a);         \
     }                                                                         \
   } while (0)
-  if (want_sw) MSB_STREAMS(sw_day_kernel);
+  const bool win = a.t.q_win && a.t.q_win_step == a.p.time_step;   // the table copy laid out for this time step
+  if (want_sw && win) MSB_STREAMS(sw_day_win_kernel);
+  if (want_sw && !win) MSB_STREAMS(sw_day_kernel);
   if (want_pr) MSB_STREAMS(prec_day_kernel);
 #undef MSB_STREAMS
   MSB_CUDA(cudaGetLastError());

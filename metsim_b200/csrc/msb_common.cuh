@@ -35,6 +35,10 @@ constexpr double kTBase = 0.870;
 constexpr double kABase = -6.1e-5;
 constexpr int kRows = 366;           // ceil(DAYS_PER_YEAR)
 constexpr int kTiny = MSB_TINY_PER_DAY;
+// window-major table (metsim_b200.h, msb_solar_tables.q_win): C = 2 ts phases x q_win_w(ts) window
+// slots (tpd + 1 entries, padded to a multiple of 4 = whole 32-byte sectors), then the row total
+__host__ __device__ inline int q_win_w(int ts) { return (1440 / ts + 1 + 3) & ~3; }
+__host__ __device__ inline int q_win_ld(int ts) { return 2 * ts * q_win_w(ts) + 4; }   // pitch: whole sectors too
 constexpr int kNoon = 1440;          // tiny step of hour angle 0: (12*3600 + 0)/30
 constexpr int kQLd = MSB_Q_LD;
 constexpr int kTT = MSB_TT_TERMS;

@@ -19,6 +19,9 @@
 #include <cstring>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "msb_common.cuh"
 
@@ -41,6 +44,33 @@ static PreludeView prelude_view(void *base, int n_lat) {
   v.nstep = reinterpret_cast<int32_t *>(d + 4 * n);
   v.beam = d + 4 * n + (n + 1) / 2;          // after the int32 block, 8-byte aligned
   return v;
+}
+
+// The prelude workspace is written by a pool of host threads and then read ONCE by the copy engine.
+// Plain stores leave its lines dirty in the caches of cores that go idle right after; the DMA read
+// then has to pull every line out of a sleeping core (measured on the 32-vCPU B200 host: 6.8 MB at
+// 6.7 GB/s, 1.0 ms of a 5.3 ms table build, against 0.2 ms when one awake thread had written it).
+// Streaming stores put the values in memory, where the copy engine reads them at PCIe rate.
+static inline void store_stream(double *p, double v) {
+#if defined(__x86_64__)
+  long long b;
+  std::memcpy(&b, &v, 8);
+  _mm_stream_si64(reinterpret_cast<long long *>(p), b);
+#else
+  *p = v;
+#endif
+}
+static inline void store_stream(int32_t *p, int32_t v) {
+#if defined(__x86_64__)
+  _mm_stream_si32(reinterpret_cast<int *>(p), v);
+#else
+  *p = v;
+#endif
+}
+static inline void store_fence() {
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
 }
 
 // K0 -- physics.py:212-236, :243 (first iteration of the hour-angle loop).  Compiled by the host
@@ -69,13 +99,14 @@ static void prelude_rows(const double *lat_deg, int r0, int r1, PreludeView v) {
       volatile double prod = cosegeom * cosh0;        // keep the product rounded on its own
       double cza0 = prod + sinegeom;
       size_t o = (size_t)r * 365 + i;
-      v.cosegeom[o] = cosegeom;
-      v.sinegeom[o] = sinegeom;
-      v.hss[o] = hss;
-      v.cza0[o] = cza0;
-      v.nstep[o] = (int32_t)n;
+      store_stream(v.cosegeom + o, cosegeom);
+      store_stream(v.sinegeom + o, sinegeom);
+      store_stream(v.hss + o, hss);
+      store_stream(v.cza0 + o, cza0);
+      store_stream(v.nstep + o, (int32_t)n);
     }
   }
+  store_fence();
 }
 
 // Class boundaries of the OPTAM lookup for solar_moments_kernel: for j < 20 the largest double c
@@ -276,6 +307,24 @@ solar_rows_kernel(int n_lat, const double *__restrict__ g_cosegeom,
   // rows are kQLd = 2888 doubles = 23,104 bytes apart: every row starts on a 16-byte boundary
   double2 *q = reinterpret_cast<double2 *>(tb.q + ((size_t)r * 365 + i) * kQLd);
   for (int j = tid; j < kQLd / 2; j += kK1Threads) q[j] = reinterpret_cast<const double2 *>(qs)[j];
+  if (tb.q_win) {
+    // window-major copy (metsim_b200.h): entry s at [(s % C) * W + s / C].  A warp moves a tile of
+    // 8 phases x 4 windows: the 16 lanes of a half-warp read 8 consecutive entries at two multiples
+    // of C (for the usual steps C = 8 mod 16 doubles: 16 different bank pairs), and the 4 windows
+    // of a phase fill one aligned 32-byte sector of the row (W is a multiple of 4).
+    const int ts = tb.q_win_step, C = 2 * ts, W = q_win_w(ts);
+    double *qw = tb.q_win + ((size_t)r * 365 + i) * q_win_ld(ts);
+    const int n_rt = (C + 7) / 8, n_jt = (W + 3) / 4;
+    for (int w = warp; w < n_rt * n_jt; w += kWarps) {
+      const int rt = w % n_rt, jt = w / n_rt;
+      const int ph = rt * 8 + (lane & 7), j = jt * 4 + (lane >> 3);
+      if (ph < C && j < W) {
+        const int pos = ph + C * j;
+        qw[ph * W + j] = pos <= kTiny ? qs[pos] : 0.0;     // beyond 2880: never read (padding, phase > 0 of the last window)
+      }
+    }
+    if (tid < 4) qw[C * W + tid] = tid == 0 ? qs[kTiny + 1] : 0.0;
+  }
 
   if (tid == 0) {
     const double step_min = kSwRadDt / 60.0;
@@ -417,6 +466,16 @@ extern "C" int msb_solar_table_sizes(int n_lat, size_t *small_elems, size_t *q_e
   return MSB_OK;
 }
 
+extern "C" size_t msb_solar_q_win_ld(int time_step) {
+  if (time_step <= 0 || time_step >= 1440 || 1440 % time_step) return 0;
+  return (size_t)q_win_ld(time_step);
+}
+
+extern "C" size_t msb_solar_q_win_elems(int n_lat, int time_step) {
+  const size_t ld = msb_solar_q_win_ld(time_step);
+  return ld && n_lat > 0 ? (size_t)n_lat * 365 * ld + MSB_Q_PAD : 0;
+}
+
 extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, void *host_ws,
                                       void *dev_ws, const msb_solar_tables *tb,
                                       int n_host_threads, void *stream) {
@@ -427,6 +486,10 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
   if (!tb->daylength || !tb->potrad || !tb->rise_min || !tb->set_min || !tb->q || !tb->tt_coef ||
       tb->n_lat != n_lat) {
     set_error("msb_solar_tables_build: table buffers missing or n_lat mismatch");
+    return MSB_E_ARG;
+  }
+  if (tb->q_win && msb_solar_q_win_ld(tb->q_win_step) == 0) {
+    set_error("msb_solar_tables_build: q_win_step %d must divide 1440 and be below it", tb->q_win_step);
     return MSB_E_ARG;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -462,5 +525,8 @@ extern "C" int msb_solar_tables_build(int n_lat, const double *lat_deg_host, voi
       (int)grid, dv.cosegeom, dv.sinegeom, dv.hss, dv.cza0, dv.nstep, dv.beam, *tb, thr);
   MSB_CUDA(cudaGetLastError());
   MSB_CUDA(cudaMemsetAsync(tb->q + (size_t)n_lat * 365 * kQLd, 0, MSB_Q_PAD * sizeof(double), st));
+  if (tb->q_win)
+    MSB_CUDA(cudaMemsetAsync(tb->q_win + (size_t)n_lat * 365 * q_win_ld(tb->q_win_step), 0,
+                             MSB_Q_PAD * sizeof(double), st));
   return MSB_OK;
 }

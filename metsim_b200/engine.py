@@ -170,6 +170,7 @@ class Engine:
                 u, inv = np.unique(np.asarray(lat, dtype=np.float64), return_inverse=True)
                 self._ulat = np.ascontiguousarray(u)
                 t["lat_row"] = self._dev(inv.astype(np.int32), i32, (n,))
+            self.sw_sectors_per_load = self._sw_sectors(t["lon"], t["lat_row"])
         self._tables = None
         self._daily = None
         return self
@@ -183,10 +184,33 @@ class Engine:
             setattr(f, name, self._ptr(t.get(name)))
         return f
 
+    @staticmethod
+    def _sw_sectors(lon, lat_row) -> float:
+        """Mean number of 32-byte sectors of the plain table q that one warp (32 consecutive cells)
+        touches per load of the shortwave kernel: the distinct (latitude row, tiny offset // 4) among
+        its lanes.  CONUS 1/16 deg: ~4.5 (neighbours share entries); global 0.5 deg land: ~30."""
+        n = lon.numel()
+        if n < 64:
+            return 0.0
+        w = torch.remainder(lon + 180.0, 360.0) - 180.0
+        key = (lat_row.to(torch.int64) << 12) + (torch.trunc(w / 360.0 * 2880.0).to(torch.int64) + 1440 >> 2)
+        key = key[: n // 32 * 32].view(-1, 32).sort(dim=1).values
+        return float(((key[:, 1:] != key[:, :-1]).sum(dim=1) + 1).double().mean().item())
+
+    def use_window_major(self) -> bool:
+        """Build / use the window-major copy of the table (msb_solar_tables.q_win)?  tuning.sw_table:
+        0 = when a warp's cells touch more than 8 sectors of the plain table per load, 1 = never,
+        2 = always (sub-daily time steps only)."""
+        if self.params.time_step >= 1440:
+            return False
+        mode = self.tuning.sw_table
+        return mode == 2 or (mode == 0 and self.sw_sectors_per_load > 8.0)
+
     # ------------------------------------------------------------------ solar tables
     def build_solar(self, n_host_threads: int | None = None):
         n_lat = len(self._ulat)
-        if self._solar_bufs is None or self._solar_bufs[0] != n_lat:
+        win_step = self.params.time_step if self.use_window_major() else 0
+        if self._solar_bufs is None or self._solar_bufs[0] != (n_lat, win_step):
             # device tables + pinned / device prelude workspaces, allocated once per latitude count
             small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
             _lib.check(self.lib.msb_solar_table_sizes(n_lat, C.byref(small), C.byref(q), C.byref(tt)))
@@ -196,14 +220,17 @@ class Engine:
                       for k in ("daylength", "potrad", "rise_min", "set_min")}
                 tb["q"] = torch.empty(q.value, **opts)
                 tb["tt_coef"] = torch.empty(tt.value, **opts)
+                if win_step:
+                    tb["q_win"] = torch.empty(self.lib.msb_solar_q_win_elems(n_lat, win_step), **opts)
                 nbytes = self.lib.msb_solar_prelude_bytes(n_lat)
                 host_ws = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
                 dev_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             st = _lib.SolarTables()
             st.n_lat = n_lat
+            st.q_win_step = win_step
             for k, v in tb.items():
                 setattr(st, k, self._ptr(v))
-            self._solar_bufs = (n_lat, st, tb, host_ws, dev_ws)
+            self._solar_bufs = ((n_lat, win_step), st, tb, host_ws, dev_ws)
         _, st, tb, host_ws, dev_ws = self._solar_bufs
         nthr = n_host_threads or min(os.cpu_count() or 1, 32)
         if self._solar_done is not None:
@@ -269,7 +296,16 @@ class Engine:
                                                  C.byref(dl), C.c_void_p(self.stream.cuda_stream)))
         out["n_iter"] = n_iter
         self._daily = (dl, out, scratch, status, (d, n), (cand, sel, lst))
+        self._publish()
         return out
+
+    def _publish(self):
+        """The kernels run on the engine's own stream; torch code that follows on the caller's current
+        stream (``.cpu()``, arithmetic on the returned tensors) is ordered after them here -- a
+        stream-side wait, the host does not block."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur != self.stream:
+            cur.wait_stream(self.stream)
 
     def daily_for_disagg(self):
         """The daily vapour pressure and shortwave the disaggregation reads, as ``[D][N]`` tensors
@@ -348,6 +384,7 @@ class Engine:
             _lib.check(self.lib.msb_disaggregate(C.byref(self.params), C.byref(f),
                                                  C.byref(self._tables[0]), C.byref(self._daily[0]),
                                                  C.byref(sd), C.c_void_p(self.stream.cuda_stream)))
+        self._publish()
         return res
 
     def _user_order(self, t):

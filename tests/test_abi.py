@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_defaults_and_error_text():
     lib = _lib.lib()
-    assert lib.msb_version() == 200
+    assert lib.msb_version() == 201
     p = _lib.make_params({})
     # metsim/metsim.py:140-171
     assert (p.time_step, p.prec_type, p.utc_offset) == (60, 0, 0)
@@ -39,6 +39,10 @@ def test_version_defaults_and_error_text():
     small, q, tt = C.c_size_t(), C.c_size_t(), C.c_size_t()
     assert lib.msb_solar_table_sizes(3, C.byref(small), C.byref(q), C.byref(tt)) == 0
     assert (small.value, q.value, tt.value) == (3 * 366, 3 * 365 * _lib.Q_LD + _lib.Q_PAD, 3 * 365 * _lib.TT_TERMS)
+    # window-major copy of the shortwave table: C phases x (tpd + 1 windows padded to a multiple of 4) + the row total
+    assert lib.msb_solar_q_win_ld(60) == 120 * 28 + 4 and lib.msb_solar_q_win_ld(15) == 30 * 100 + 4
+    assert lib.msb_solar_q_win_ld(1440) == 0 and lib.msb_solar_q_win_ld(7) == 0 and lib.msb_solar_q_win_ld(0) == 0
+    assert lib.msb_solar_q_win_elems(3, 180) == 3 * 365 * (360 * 12 + 4) + _lib.Q_PAD
     assert lib.msb_daily_scratch_bytes(1000, 365) % 8 == 0 and lib.msb_daily_scratch_bytes(1000, 365) > 0
     assert lib.msb_mtclim_daily(None, None, None, None, None) == _lib.E_ARG
     assert lib.msb_disaggregate(None, None, None, None, None, None) == _lib.E_ARG
@@ -47,7 +51,7 @@ def test_version_defaults_and_error_text():
 def test_struct_layouts_match_header():
     # sizes implied by the header on LP64 (natural alignment)
     assert C.sizeof(_lib.Params) == 8 * 4 + 6 * 8
-    assert C.sizeof(_lib.SolarTables) == 8 + 6 * 8
+    assert C.sizeof(_lib.SolarTables) == 8 + 7 * 8 + 8
     assert C.sizeof(_lib.Forcing) == 16 + 24 * 8
     assert C.sizeof(_lib.Tuning) == 8 * 4
     assert C.sizeof(_lib.Daily) == (13 + 3 + 3) * 8 + 32

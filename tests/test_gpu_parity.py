@@ -271,7 +271,10 @@ def test_fast_path_example_vars_f4_against_oracle(name, cells, days, over):
 # 16 output days per thread in the interior kernels and day chunks of 73 (CONUS year), 731 (CONUS
 # decade) and 645 days (30-year global shard) in the daily pass.  Small shards would shorten all of
 # these; msb_tuning pins them, so the oracle comparisons below run what the benchmark runs.
-BENCH_GEOMETRY = dict(knot_tile=16, day_tile=16, daily_chunk_len=73)
+# sw_table=1: the plain shortwave table, what the library picks for the dense CONUS grid (a sample
+# of a few hundred cells of it is sparse, and would get the window-major copy on its own)
+BENCH_GEOMETRY = dict(knot_tile=16, day_tile=16, daily_chunk_len=73, sw_table=1)
+WINDOW_MAJOR = dict(BENCH_GEOMETRY, sw_table=2)      # ... and what it picks for the masked global grids
 
 
 def run_both_daily_forms(f, params, tuning, want, ctx, sub_vars, day_ranges=None, out_dtype=None):
@@ -318,7 +321,7 @@ def run_both_daily_forms(f, params, tuning, want, ctx, sub_vars, day_ranges=None
 
 @pytest.mark.parametrize("name,cells,days,over,tuning", [
     ("conus_16th_hourly", 384, 365, {}, BENCH_GEOMETRY),                 # the headline configuration
-    ("global_half_deg", 320, 365, {}, BENCH_GEOMETRY),                   # n* from 3 to 7: the replay list
+    ("global_half_deg", 320, 365, {}, WINDOW_MAJOR),                     # n* from 3 to 7: the replay list
     ("conus_16th_hourly", 200, 100, {"tdew_tol": 1e-3}, BENCH_GEOMETRY), # every cell below the candidate window
     ("conus_16th_hourly", 200, 100, {"tdew_tol": 1e-10}, BENCH_GEOMETRY),  # every cell needs a second round
     ("conus_16th_hourly", 160, 80, {}, dict(BENCH_GEOMETRY, disagg_path="event")),
@@ -504,10 +507,11 @@ def test_streaming_writer_through_on_tile_hook(tmp_path):
     np.testing.assert_array_equal(again["temp"], ref["temp"])
 
 
-@pytest.mark.parametrize("geometry", ["auto", "bench"])
+@pytest.mark.parametrize("geometry", ["auto", "bench", "window"])
 def test_seeded_fuzz_small_records_against_oracle(disagg_path, geometry):
     """(geometry "bench": the per-thread work of the benchmarked configuration pinned through
-    msb_tuning -- one thread then covers the whole short record.)  Forty seeded random small shards: record lengths 2..13 days (so that the interior range is
+    msb_tuning -- one thread then covers the whole short record; "window": the same with the
+    window-major copy of the shortwave table, which only the interior-day kernel reads.)  Forty seeded random small shards: record lengths 2..13 days (so that the interior range is
     empty, one day, or a few days, and every call boundary falls somewhere else), random time step,
     precipitation type, utc offset, start date, call length, latitudes from pole to pole and
     longitudes from -360 to 540.  All ten variables, float64, against the oracle at 1e-9; the
@@ -517,6 +521,9 @@ def test_seeded_fuzz_small_records_against_oracle(disagg_path, geometry):
     from metsim_b200._lib import DAILY_VARS, SUB_VARS
     from metsim_b200.engine import Engine
     from oracle import oracle_lib
+    if geometry == "window" and disagg_path == "event":
+        pytest.skip("the event-driven kernel reads the plain table only")
+    tuning = {"auto": None, "bench": BENCH_GEOMETRY, "window": WINDOW_MAJOR}[geometry]
     rng = np.random.default_rng(20261020)
     for case in range(int(os.environ.get("MSB_FUZZ_CASES", "40"))):   # more cases: a longer one-off hunt
         n = int(rng.integers(33, 97))
@@ -529,7 +536,7 @@ def test_seeded_fuzz_small_records_against_oracle(disagg_path, geometry):
         params = dict(time_step=ts, prec_type=str(rng.choice(["uniform", "triangle", "mix"])),
                       utc_offset=bool(rng.integers(0, 2)))
         want = oracle_lib.run(params, **util.oracle_kwargs(f))
-        eng = Engine(params, tuning=BENCH_GEOMETRY if geometry == "bench" else None)
+        eng = Engine(params, tuning=tuning)
         eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
         eng.build_solar()
         daily = eng.daily(want=DAILY_VARS)
@@ -640,6 +647,50 @@ def test_precipitation_nan_days_and_fill(disagg_path):
         compare_to_oracle(got, want, f"nan-days ts={ts}")
         # placement is integer work: zero / non-zero pattern must be identical
         np.testing.assert_array_equal(got["prec"] == 0, want["prec"] == 0)
+
+
+@pytest.mark.parametrize("ts,prec_type", [(60, "triangle"), (15, "triangle"), (180, "mix"), (360, "uniform"), (20, "uniform")])
+def test_window_major_shortwave_table_is_bit_identical(ts, prec_type):
+    """msb_solar_tables.q_win holds the SAME entries as q in another order, and the shortwave
+    kernel does the same arithmetic on them: float64 outputs must agree bit for bit, on the device
+    path (forced through msb_tuning.sw_table) and through msb_run_host, where the library decides
+    by the longitude spacing of the cells (scattered cells -> window-major, a dense row -> plain)."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200._lib import SUB_VARS
+    from metsim_b200.engine import Engine, run_host
+    rng = np.random.default_rng(77 + ts)
+    n, days = 700, 23
+    lat = np.sort(rng.choice(np.linspace(-80.0, 84.0, 41), n))     # 41 table rows (both copies stay small)
+    lon = rng.uniform(-200.0, 400.0, n)
+    f = synth.make_forcing(lat, lon, days, "2003-11-20", rng)
+    params = dict(time_step=ts, prec_type=prec_type, utc_offset=True)
+    res = {}
+    for mode in (1, 2):
+        eng = Engine(params, tuning=dict(sw_table=mode))
+        eng.load(**{k: f.get(k) for k in util.INPUT_KEYS})
+        assert eng.sw_sectors_per_load > 8.0 and eng.use_window_major() == (mode == 2)
+        tb = eng.build_solar()
+        assert ("q_win" in tb) == (mode == 2)
+        eng.daily(want=())
+        got = eng.disaggregate(SUB_VARS, 0, days, torch.float64)
+        eng.check()                          # synchronises the engine's stream before the host reads
+        res[mode] = {v: t.cpu().numpy() for v, t in got.items()}
+    for v in SUB_VARS:
+        np.testing.assert_array_equal(res[1][v].view(np.uint64), res[2][v].view(np.uint64), err_msg=v)
+    assert np.isfinite(res[2]["shortwave"]).all() and res[2]["shortwave"].max() > 100.0
+    # host path: the auto rule picks the window-major copy for these scattered cells, the plain table when told to
+    kw = {k: f.get(k) for k in util.INPUT_KEYS}
+    host = {mode: run_host(params, out_vars=("shortwave", "temp"), out_dtype=np.float64, tile_days=7,
+                           tuning=dict(sw_table=mode), **kw) for mode in (0, 1)}
+    for mode in (0, 1):
+        np.testing.assert_array_equal(host[mode]["shortwave"].view(np.uint64), res[1]["shortwave"].view(np.uint64))
+    # a dense CONUS row keeps the plain table under the auto rule
+    la, lo = synth.grid_cells("conus1/16", np.random.default_rng(synth.SEED))
+    eng = Engine(params)
+    fd = synth.make_forcing(la[:928], lo[:928], 3, "2001-01-01", rng)
+    eng.load(**{k: fd.get(k) for k in util.INPUT_KEYS})
+    assert eng.sw_sectors_per_load < 8.0 and not eng.use_window_major()
 
 
 def test_run_host_equals_device_path_and_tiling():
