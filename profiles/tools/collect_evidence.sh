@@ -9,6 +9,8 @@ cp gpurun_out/bench_reference.log profiles/r02/bench_reference.json
 cp gpurun_out/launches.csv profiles/r02/launch_list_bench.csv
 python profiles/tools/launch_sum.py gpurun_out/launches.csv > profiles/r02_launch_list_summary.txt
 python profiles/tools/ncu_summary.py gpurun_out/r02_step_kernels.ncu-rep > profiles/r02_step_kernels_ncu_full.txt 2>&1
-# the first captured call covers the interior days 2..96 of a 97-day tile: 95 days x 24 steps
-python profiles/tools/make_traffic.py gpurun_out/r02_step_kernels.ncu-rep 482560 $((95*24)) "$H" r02_step_kernels > /dev/null
+grep -q "$H" gpurun_out/disagg_traffic.json && cp gpurun_out/disagg_traffic.json profiles/disagg_traffic.json
+cp gpurun_out/bench_c2.log profiles/r02/bench_c2_global_half_deg.json
+grep -v "Warn\|_warn_once" gpurun_out/timeline_c3.log > profiles/r02_timeline_conus.txt
+grep -v "Warn\|_warn_once" gpurun_out/timeline_c2.log > profiles/r02_timeline_global_half_deg.txt
 echo "evidence collected for sources $H"
