@@ -27,6 +27,11 @@
 
 #include "msb_common.cuh"
 
+// compile-time experiment knob (profiles/tools/build_variants.py): 0 = no software prefetch in the fused daily kernel
+#ifndef MSB_DAILY_PF
+#define MSB_DAILY_PF 0
+#endif
+
 namespace msb {
 
 constexpr int kEvalsPerRound = 6;   // the fixed point needs 4-6 evaluations on realistic forcings
@@ -345,6 +350,17 @@ daily_fused_kernel(msb_params p, msb_forcing f, msb_solar_tables t, msb_daily ou
   for (int d = d_lo; d < d_hi; ++d) {
     const size_t o = (size_t)d * ld + cell;
     DayInv v;
+#if MSB_DAILY_PF == 1     // the input rows of the next day into L1 while this one computes
+    if (d + 1 < d_hi) {
+      prefetch_l1(f.t_min + o + ld); prefetch_l1(f.t_max + o + ld); prefetch_l1(f.prec + o + ld);
+      if (d + 1 >= 89) prefetch_l1(f.prec + o + ld - (size_t)89 * ld);
+    }
+#elif MSB_DAILY_PF == 2   // ... of the day after next into L2
+    if (d + 2 < d_hi) {
+      prefetch_l2(f.t_min + o + 2 * ld); prefetch_l2(f.t_max + o + 2 * ld); prefetch_l2(f.prec + o + 2 * ld);
+      if (d + 2 >= 89) prefetch_l2(f.prec + o + 2 * ld - (size_t)89 * ld);
+    }
+#endif
     const double t_min = f.t_min[o], t_max = f.t_max[o], prec = f.prec[o];
     // the value leaving the 90-day window (d is uniform across the block: no divergence)
     const double prec_out = d >= 89 ? f.prec[o - (size_t)89 * ld]

@@ -223,13 +223,6 @@ __device__ __forceinline__ int first_step_gt(double xk, int ts, double inv_ts) {
   return i;
 }
 
-// L2 prefetch of data a later event / step will load (the streaming stores keep evicting it)
-__device__ __forceinline__ void prefetch_l2(const void *ptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
-__device__ __forceinline__ void prefetch_l1(const void *ptr) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-}
 // a load the scheduler must not sink towards its use (issued where it is written)
 __device__ __forceinline__ double load_early(const double *ptr) {
   double v;

@@ -394,9 +394,12 @@ template <typename OutT, bool UNITS>
 __global__ void __launch_bounds__(kDisaggThreads, 8)
 sw_day_win_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamSw, true>(a); }
 
-// arithmetic: 80 registers, 24 warps per SM
+// arithmetic: 80 registers, 24 warps per SM (MSB_PREC_MINB: compile-time experiment knob)
+#ifndef MSB_PREC_MINB
+#define MSB_PREC_MINB 6
+#endif
 template <typename OutT, bool UNITS>
-__global__ void __launch_bounds__(kDisaggThreads, 6)
+__global__ void __launch_bounds__(kDisaggThreads, MSB_PREC_MINB)
 prec_day_kernel(const __grid_constant__ DisaggArgs a) { streams_body<OutT, UNITS, kStreamPrec>(a); }
 
 constexpr int kStreamTile = 16;   // output days per thread on full-size grids

@@ -39,6 +39,13 @@ constexpr int kTiny = MSB_TINY_PER_DAY;
 // slots (tpd + 1 entries, padded to a multiple of 4 = whole 32-byte sectors), then the row total
 __host__ __device__ inline int q_win_w(int ts) { return (1440 / ts + 1 + 3) & ~3; }
 __host__ __device__ inline int q_win_ld(int ts) { return 2 * ts * q_win_w(ts) + 4; }   // pitch: whole sectors too
+// prefetch of data a later day / event / step will load (the streaming stores keep evicting it)
+__device__ __forceinline__ void prefetch_l2(const void *ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+__device__ __forceinline__ void prefetch_l1(const void *ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+}
 constexpr int kNoon = 1440;          // tiny step of hour angle 0: (12*3600 + 0)/30
 constexpr int kQLd = MSB_Q_LD;
 constexpr int kTT = MSB_TT_TERMS;
