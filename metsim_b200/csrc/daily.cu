@@ -27,9 +27,11 @@
 
 #include "msb_common.cuh"
 
-// compile-time experiment knob (profiles/tools/build_variants.py): 0 = no software prefetch in the fused daily kernel
+// software prefetch of the fused daily kernel's input rows: 0 = none, 1 = the next day's into L1,
+// 2 = the day after next's into L2 (measured per launch on CONUS: 6.12 / 6.10 / 5.91 ms; L1 is nearly
+// all shared memory here -- six CTAs of 34 KB -- so only the L2 variant pays)
 #ifndef MSB_DAILY_PF
-#define MSB_DAILY_PF 0
+#define MSB_DAILY_PF 2
 #endif
 
 namespace msb {
