@@ -25,7 +25,7 @@ struct msb_sink {
   msb_sink_desc d;
   std::vector<int64_t> index;        // private copy of cell_index (empty = identity)
   std::vector<std::thread> pool;
-  std::vector<std::vector<char>> stage;   // per thread: chunk_steps rows of the grid, NaN-prefilled
+  std::vector<std::vector<char>> stage;   // per thread: one dense piece, or chunk_steps rows of the grid, NaN-prefilled
   int64_t chunk_steps = 1;           // masked grids: whole rows per chunk (the scatter needs the NaN background)
   int64_t piece_elems = 0;           // dense grids (> 0): chunks are flat runs of this many values
   int64_t n_total = 0;               // dense: values of the current job
@@ -190,15 +190,12 @@ extern "C" int msb_sink_create(const msb_sink_desc *d, msb_sink **out) {
   // staging per thread: a dense grid is cut into flat pieces; a masked one needs whole grid rows
   // (as few as fit the same budget, at least one)
   const int64_t row_out = d->n_grid * d->elem_bytes;
-  if (s->index.empty()) {
-    s->piece_elems = kPieceBytes / d->elem_bytes;
-    s->chunk_steps = (s->piece_elems + d->n_grid - 1) / d->n_grid;   // rows that hold one piece (sizes the staging)
-  } else {
-    s->chunk_steps = std::max<int64_t>(1, (2 * kPieceBytes) / std::max<int64_t>(1, row_out));
-  }
+  if (s->index.empty()) s->piece_elems = kPieceBytes / d->elem_bytes;
+  else s->chunk_steps = std::max<int64_t>(1, (2 * kPieceBytes) / std::max<int64_t>(1, row_out));
   try {
     s->stage.resize(nt);
     for (auto &b : s->stage) {
+      if (s->piece_elems > 0) { b.resize((size_t)kPieceBytes); continue; }   // every byte is overwritten per piece
       b.resize((size_t)(s->chunk_steps * row_out));
       // cells outside the mask hold NaN (metsim.py:584); written once, the scatter never touches them
       if (d->elem_bytes == 4) {
