@@ -69,3 +69,31 @@ def test_register_adds_both_method_modules():
     out = registry.register(methods)
     assert out is methods and set(methods) == {"mtclim", "mtclim_b200", "passthrough_b200"}
     assert callable(methods["mtclim_b200"].run) and callable(methods["passthrough_b200"].run)
+
+
+def test_shortwave_table_layout_rule_on_the_benchmark_grids():
+    """Engine._sw_sectors: how many 32-byte sectors of the plain shortwave table the 32 cells of a
+    warp touch per load decides between the plain table and its window-major copy (above 8).  Pure
+    index arithmetic on (lon, lat_row): the dense CONUS grid stays plain, the masked global grids
+    and any scattered cell set get the copy, with and without the patch cell order."""
+    import torch
+    from metsim_b200 import synth
+    from metsim_b200.engine import Engine
+    from metsim_b200.shard import patch_order
+
+    def sectors(lat, lon, order=None):
+        if order is not None:
+            lat, lon = lat[order], lon[order]
+        _, inv = np.unique(lat, return_inverse=True)
+        return Engine._sw_sectors(torch.as_tensor(lon), torch.as_tensor(inv.astype(np.int32)))
+
+    la, lo = synth.grid_cells("conus1/16", np.random.default_rng(synth.SEED))
+    dense = sectors(la[:928 * 40], lo[:928 * 40])
+    assert 4.0 < dense < 6.0                       # 16 consecutive tiny offsets = 128 bytes per warp load
+    la, lo = synth.grid_cells("global0.5", np.random.default_rng(synth.SEED))
+    assert sectors(la, lo) > 24.0 and sectors(la, lo, patch_order(la, lo, 4)) > 24.0
+    la, lo = synth.grid_cells("global1/8", np.random.default_rng(synth.SEED))
+    keep = slice(0, 200000)
+    assert sectors(la[keep], lo[keep]) > 8.0
+    assert sectors(la[keep], lo[keep], patch_order(la[keep], lo[keep], 4)) > 8.0
+    assert sectors(la[:40], lo[:40]) == 0.0        # too few cells to matter
