@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from metsim_b200 import build as B  # noqa: E402
 
 OUTDIR = os.path.join(ROOT, "profiles", "variants")
-KNOB_SOURCES = ("disagg_interior.cu", "disagg_streams.cu", "daily.cu", "solar.cu")
+KNOB_SOURCES = ("disagg.cu", "disagg_interior.cu", "disagg_streams.cu", "daily.cu", "solar.cu")
 WATCH = ("thermo_knot_kernelIfLi", "sw_day_kernelIfLb0", "prec_day_kernelIfLb0", "daily_fused_kernel",
          "solar_rows_kernel", "solar_moments_kernel")
 
