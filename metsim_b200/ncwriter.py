@@ -61,40 +61,54 @@ def _att_list(atts: dict) -> bytes:
 
 
 class NC3Writer:
-    """``(time, lat, lon)`` NetCDF-3 (64-bit offset) file written in time tiles.
+    """``(time, lat, lon)`` -- or ``(time, *grid_dims)`` -- NetCDF-3 (64-bit offset) file written in
+    time tiles.
 
-    ``cell_index`` maps the engine's cell order to flat ``lat * n_lon + lon`` positions of the
-    domain grid (``np.flatnonzero(mask > 0)`` for a latitude-row-major shard)."""
+    ``cell_index`` maps the engine's cell order to flat row-major positions of the domain grid
+    (``lat * n_lon + lon``; ``np.flatnonzero(mask > 0)`` for a latitude-row-major shard)."""
 
-    def __init__(self, path: str, *, n_steps: int, lat, lon, cell_index, variables: dict,
+    def __init__(self, path: str, *, n_steps: int, lat=None, lon=None, cell_index, variables: dict,
                  time_values=None, time_units: str = "minutes since start",
                  global_attrs: dict | None = None, native: bool = True, n_threads: int = 0,
-                 version: int | None = None):
-        self.lat = np.asarray(lat, dtype=np.float64)
-        self.lon = np.asarray(lon, dtype=np.float64)
+                 version: int | None = None, grid_dims=None, time_attrs: dict | None = None):
+        """``grid_dims``: ``[(name, coordinate values), ...]`` for a domain whose mask is not over
+        ``(lat, lon)`` (the reference writes ``('time',) + mask.dims``, metsim/metsim.py:367-368 --
+        e.g. ``('time', 'hru')`` for dim_test.nc); ``lat`` / ``lon`` are then ignored.  An integer
+        ``time_values`` array is written as NC_INT (the reference's ``i4`` time variable, :384);
+        ``time_attrs`` adds to the time variable's attributes (calendar, long_name ...)."""
+        if grid_dims is None:
+            grid_dims = [("lat", np.asarray(lat, dtype=np.float64)), ("lon", np.asarray(lon, dtype=np.float64))]
+            coord_atts = {"lat": {"units": "degrees_north"}, "lon": {"units": "degrees_east"}}
+        else:
+            grid_dims = [(str(k), np.asarray(v)) for k, v in grid_dims]
+            coord_atts = {}
+        self.grid_dims = grid_dims
         self.n_steps = int(n_steps)
-        self.n_grid = self.lat.size * self.lon.size
+        self.n_grid = int(np.prod([v.size for _, v in grid_dims]))
         self.cell_index = np.asarray(cell_index, dtype=np.int64)
         if self.cell_index.size and (self.cell_index.min() < 0 or self.cell_index.max() >= self.n_grid):
-            raise ValueError("cell_index outside the (lat, lon) grid")
+            raise ValueError("cell_index outside the domain grid")
         self.vars = {}
-        dims = (("time", self.n_steps), ("lat", self.lat.size), ("lon", self.lon.size))
-        coord = {"time": (np.arange(self.n_steps, dtype=np.float64) if time_values is None
-                          else np.asarray(time_values, dtype=np.float64)),
-                 "lat": self.lat, "lon": self.lon}
-        coord_atts = {"time": {"units": time_units}, "lat": {"units": "degrees_north"},
-                      "lon": {"units": "degrees_east"}}
+        dims = (("time", self.n_steps),) + tuple((k, v.size) for k, v in grid_dims)
+        tvals = np.arange(self.n_steps, dtype=np.float64) if time_values is None else np.asarray(time_values)
+        coord = {"time": tvals, **dict(grid_dims)}
+        coord_atts["time"] = dict({"units": time_units}, **(time_attrs or {}))
         if coord["time"].size != self.n_steps:
             raise ValueError("time_values must have n_steps entries")
         # ---- header (classic format spec: magic, numrecs, dim_list, gatt_list, var_list) ----
         entries = []   # (name, dimids, atts, nc_type, be_dtype, n_elems)
         for i, (dname, _) in enumerate(dims):
-            entries.append((dname, (i,), coord_atts[dname], NC_DOUBLE, ">f8", coord[dname].size))
+            if coord[dname].dtype.kind in "iu":       # classic NetCDF has no 64-bit integers
+                if coord[dname].size and np.abs(coord[dname]).max() > 0x7FFFFFFF:
+                    raise ValueError(f"integer coordinate {dname!r} does not fit NC_INT")
+                entries.append((dname, (i,), coord_atts.get(dname, {}), NC_INT, ">i4", coord[dname].size))
+            else:
+                entries.append((dname, (i,), coord_atts.get(dname, {}), NC_DOUBLE, ">f8", coord[dname].size))
         for vname, spec in variables.items():
             dt = np.dtype(spec.get("dtype", "float32"))
             nct, be = _TYPES[dt]
             atts = {k: v for k, v in spec.items() if k != "dtype"}   # units, long_name, ...
-            entries.append((vname, (0, 1, 2), atts, nct, be, self.n_steps * self.n_grid))
+            entries.append((vname, tuple(range(len(dims))), atts, nct, be, self.n_steps * self.n_grid))
 
         # CDF-2 (64-bit offsets) holds fixed-size variables of up to 2**32 - 4 bytes (only the last one
         # may be larger); beyond that the file is CDF-5: 64-bit counts, dimension lengths and vsize
