@@ -317,7 +317,7 @@ def _pinned(shape, dtype) -> np.ndarray:
         import torch
         if torch.cuda.is_available():
             tdt = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}[np.dtype(dtype)]
-            return torch.empty(shape, dtype=tdt).pin_memory().numpy()
+            return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
     except (ImportError, RuntimeError):
         pass
     return np.empty(shape, dtype=dtype)
@@ -333,6 +333,7 @@ class MetSimB200:
         self.params.update(params)
         self.device = int(device)
         self._domain = self._met_data = self._state = None
+        self._ring = None
         self.logger = logging.getLogger("metsim_b200")
         self.logger.setLevel(self.params["verbose"] or logging.INFO)
         self.var_attrs = {k: {"units": a[0], "long_name": a[1], "standard_name": a[2]}
@@ -563,7 +564,7 @@ class MetSimB200:
         return out
 
     # -------------------------------------------------------------- run
-    def run(self, host_budget_bytes: int = 4 << 30) -> list:
+    def run(self, host_budget_bytes: int = 1 << 30) -> list:
         """``MetSim.run`` (metsim.py:330-352): validate, create the output files, compute, write.
         The whole domain is one ``msb_run_host`` call; its time tiles stream into the files through
         the ``on_tile`` hook while the next tile computes.  Returns the output file names."""
@@ -572,12 +573,15 @@ class MetSimB200:
         p = self.params
         ts = int(p["time_step"])
         out_vars = p["out_vars"]
+        t0 = _time.perf_counter()
         g = self.gather()
         cell_index = g.pop("cell_index")
         n, d = cell_index.size, g["t_min"].shape[0]
         if "wind" in out_vars and g["wind"] is None:
             raise KeyError("wind")                                # df['wind'] in the reference (:492)
+        t1 = _time.perf_counter()
         writers = self._writers()
+        t2 = _time.perf_counter()
         names = [w.path for w in writers]
         bounds = np.cumsum([0] + [w.n_steps for w in writers])   # global step range of each file
 
@@ -615,7 +619,11 @@ class MetSimB200:
                     for v in out_vars:
                         write(v, 0, res[v])
                 else:
-                    ring = {v: _pinned((2 * tile_days * tpd, n), odt) for v in out_vars}
+                    key = (tuple(out_vars), 2 * tile_days * tpd, n, odt)
+                    if self._ring is None or self._ring[0] != key:     # page-locking a ring costs ~0.3 s per GB: keep it
+                        self._ring = None
+                        self._ring = (key, {v: _pinned((2 * tile_days * tpd, n), odt) for v in out_vars})
+                    ring = self._ring[1]
 
                     def on_tile(tile, day0, day1, slot):
                         rows = slice(slot * tile_days * tpd, slot * tile_days * tpd + (day1 - day0) * tpd)
@@ -628,6 +636,7 @@ class MetSimB200:
         finally:
             for w in writers:
                 w.close()
+        self.timings.update(s_gather=t1 - t0, s_create_files=t2 - t1, s_compute_and_write=_time.perf_counter() - t2)
         return names
 
     def open_output(self) -> list:
