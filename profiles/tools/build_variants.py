@@ -2,7 +2,8 @@
 
     python profiles/tools/build_variants.py name=-DMSB_THERMO_MINB=6 other="-DMSB_THERMO_MINB=8 -DX=1" ...
 
-Writes profiles/variants/lib_<name>.so (git-ignored like every .so; it travels with gpurun) plus
+A token ``SRC:disagg_interior.cu=profiles/tools/experiments/x.cu`` among a variant's flags compiles that
+file in place of the product source.  Writes profiles/variants/lib_<name>.so (git-ignored like every .so; it travels with gpurun) plus
 lib_base.so (no extra flags).  Only the sources that honour a knob are recompiled per variant; the
 others are compiled once to objects.  Select one at run time with MSB_LIBRARY=<path>
 (metsim_b200/_lib.py).  Prints registers / spills of the kernels the knobs touch.
@@ -41,9 +42,15 @@ def main():
     variants = [("base", "")] + [a.split("=", 1) for a in sys.argv[1:]]
     for name, flags in variants:
         vobjs = []
+        # a token SRC:<file.cu>=<path> compiles <path> in place of csrc/<file.cu> (experimental kernels
+        # kept under profiles/tools/experiments/, outside the product sources and their hash)
+        toks = shlex.split(flags)
+        override = dict(t[4:].split("=", 1) for t in toks if t.startswith("SRC:"))
+        toks = [t for t in toks if not t.startswith("SRC:")]
         for s in KNOB_SOURCES:
             o = os.path.join(OUTDIR, f"{name}_{s.replace('.cu', '.o')}")
-            run([nvcc, *cflags, *shlex.split(flags), "-I", B.INCLUDE, "-c", os.path.join(B.CSRC, s), "-o", o])
+            src = os.path.join(ROOT, override[s]) if s in override else os.path.join(B.CSRC, s)
+            run([nvcc, *cflags, *toks, "-I", B.INCLUDE, "-I", B.CSRC, "-c", src, "-o", o])
             vobjs.append(o)
         out = os.path.join(OUTDIR, f"lib_{name}.so")
         run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs.values(), *vobjs])
