@@ -25,8 +25,9 @@ and follows the reference for everything a user can observe:
   the variable / global attributes of ``setup_netcdf_output`` (:363-436) -- as NetCDF classic
   (CDF-2 / CDF-5, ``ncwriter.py``) because no NetCDF-4 library exists in this image.
 
-What it does NOT do: dask scheduling (``scheduler`` / ``num_workers`` / ``chunks`` are accepted and
-recorded, the whole domain is one batched call on one GPU), non-standard calendars (the reference
+What it does NOT do: dask scheduling (``scheduler`` and ``[chunks]`` are accepted and recorded;
+``-n N`` spreads the active cells over N GPUs as contiguous ranges, one batched call each, see
+:meth:`MetSimB200.run`), non-standard calendars (the reference
 needs cftime for them) and in-memory ``forcing_fmt = data``.  No arithmetic of the path happens
 here: every number written comes from ``msb_run_host`` (CUDA); without a GPU :meth:`MetSimB200.run`
 raises.
@@ -564,10 +565,17 @@ class MetSimB200:
         return out
 
     # -------------------------------------------------------------- run
-    def run(self, host_budget_bytes: int = 1 << 30) -> list:
+    def run(self, host_budget_bytes: int = 1 << 30, devices=None) -> list:
         """``MetSim.run`` (metsim.py:330-352): validate, create the output files, compute, write.
         The whole domain is one ``msb_run_host`` call; its time tiles stream into the files through
-        the ``on_tile`` hook while the next tile computes.  Returns the output file names."""
+        the ``on_tile`` hook while the next tile computes.  Returns the output file names.
+
+        ``devices``: CUDA device indices to spread the active cells over (default: this object's
+        one device).  The cells are cut into contiguous ranges (``shard.cell_range``), one host
+        thread + ``msb_host_ctx`` per range, no exchange between them; their tiles are gathered on
+        the host into full rows before they go to the file (the north_star's "optional host gather
+        of outputs").  The reference's counterpart is one dask task per ``[chunks]`` slice
+        (metsim.py:339-343)."""
         from .engine import run_host, unit_scale_offset
         self._validate_setup()
         p = self.params
@@ -594,13 +602,18 @@ class MetSimB200:
                 if s0 < s1:
                     w.write_steps(oname, int(s0 - a), block[s0 - lo:s1 - lo])
 
+        devices = [int(x) for x in devices] if devices else [self.device]
+        n_shards = max(1, min(len(devices), n // 32))             # at least a warp of cells per range
+        daily_cols = ("t_day", "vapor_pressure", "tskc", "pet", "daylength", "shortwave_daily")
         try:
             if n == 0:
                 pass
             elif not self.disagg:                                 # daily outputs, metsim.py:779-792
-                res = run_host(p, **g, device=self.device, timings=self.timings,
-                               daily_vars=("t_day", "vapor_pressure", "tskc", "pet", "daylength",
-                                           "shortwave_daily"))
+                if n_shards > 1:
+                    parts = self._run_shards(g, devices[:n_shards], dict(daily_vars=daily_cols))
+                    res = {"daily": {c: np.concatenate([r["daily"][c] for r in parts], axis=1) for c in daily_cols}}
+                else:
+                    res = run_host(p, **g, device=self.device, timings=self.timings, daily_vars=daily_cols)
                 odt = np.dtype({"f4": "float32", "f8": "float64"}[p["out_precision"]])
                 for v in out_vars:
                     src = (g[v] if v in ("t_min", "t_max", "prec", "wind")
@@ -613,7 +626,16 @@ class MetSimB200:
                 row_bytes = n * odt.itemsize * len(out_vars)
                 tile_days = int(max(1, min(d, host_budget_bytes // max(1, 2 * tpd * row_bytes))))
                 units = {v: out_vars[v]["units"] for v in out_vars}
-                if tile_days >= d:                                # the record fits: one piece, no ring
+                if n_shards > 1:
+                    kw = dict(out_vars=tuple(out_vars), out_dtype=odt, units=units)
+                    if tile_days >= d:                            # the record fits: whole columns per range
+                        parts = self._run_shards(g, devices[:n_shards], kw)
+                        for v in out_vars:
+                            write(v, 0, np.concatenate([r[v] for r in parts], axis=1))
+                    else:
+                        self._run_shards(g, devices[:n_shards], kw, tile_days=tile_days, tpd=tpd,
+                                         consume=lambda v, step0, block: write(v, step0, block))
+                elif tile_days >= d:                              # the record fits: one piece, no ring
                     res = run_host(p, **g, out_vars=tuple(out_vars), out_dtype=odt, units=units,
                                    device=self.device, timings=self.timings)
                     for v in out_vars:
@@ -639,6 +661,69 @@ class MetSimB200:
         self.timings.update(s_gather=t1 - t0, s_create_files=t2 - t1, s_compute_and_write=_time.perf_counter() - t2)
         return names
 
+    def _run_shards(self, g: dict, devices: list, kw: dict, tile_days: int = 0, tpd: int = 0, consume=None) -> list:
+        """One host thread and one ``msb_host_ctx`` per contiguous cell range (``shard.cell_range``;
+        the devices may repeat).  Without ``consume``: returns the ranges' ``run_host`` results in
+        cell order.  With it (streaming): every range runs a 2-slot ring of ``tile_days``; a tile's
+        rows are gathered into one of two full-width host buffers, and when all ranges have
+        delivered tile *t* the first thread hands the full rows to ``consume(var, step0, block)``
+        while the others already compute tile *t + 1*."""
+        import threading
+        from . import engine
+        from .shard import cell_range, shard_inputs
+        p, K = self.params, len(devices)
+        n = g["t_min"].shape[1]
+        ranges = [cell_range(n, k, K) for k in range(K)]
+        results, errors, timings = [None] * K, [], [dict() for _ in range(K)]
+        barrier = threading.Barrier(K)
+        full = rings = None
+        if consume is not None:
+            odt = np.dtype(kw["out_dtype"])
+            key = ("ranges", tuple(kw["out_vars"]), tile_days * tpd, tuple(ranges), odt)
+            if self._ring is None or self._ring[0] != key:        # page-locked rings + gather buffers: kept between runs
+                self._ring = None
+                self._ring = (key, ([{v: np.empty((tile_days * tpd, n), dtype=odt) for v in kw["out_vars"]} for _ in range(2)],
+                                    [{v: _pinned((2 * tile_days * tpd, hi - lo), odt) for v in kw["out_vars"]}
+                                     for lo, hi in ranges]))
+            full, rings = self._ring[1]
+
+        def work(k):
+            lo, hi = ranges[k]
+            try:
+                gk = shard_inputs(g, k, K)
+                with engine.HostContext(devices[k]) as ctx:
+                    if consume is None:
+                        results[k] = engine.run_host(p, **gk, **kw, ctx=ctx, timings=timings[k])
+                        return
+                    ring = rings[k]
+
+                    def on_tile(tile, day0, day1, slot):
+                        rows, src0 = (day1 - day0) * tpd, slot * tile_days * tpd
+                        dst = full[tile % 2]
+                        for v in kw["out_vars"]:
+                            dst[v][:rows, lo:hi] = ring[v][src0:src0 + rows]
+                        barrier.wait()                  # every range has delivered this tile
+                        if k == 0:                      # ... and the others are on their way to the next one
+                            for v in kw["out_vars"]:
+                                consume(v, day0 * tpd, dst[v][:rows])
+
+                    engine.run_host(p, **gk, **kw, out=ring, ring=True, tile_days=tile_days, on_tile=on_tile,
+                                    ctx=ctx, timings=timings[k])
+            except BaseException as exc:                # noqa: BLE001 -- re-raised by the caller's thread
+                errors.append(exc)
+                barrier.abort()
+
+        threads = [threading.Thread(target=work, args=(k,), name=f"msb-range-{k}") for k in range(K)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+        if errors:
+            raise (real or errors)[0]
+        self.timings["ranges"] = [dict(cells=hi - lo, device=dev, **tm) for (lo, hi), dev, tm in zip(ranges, devices, timings)]
+        return results
+
     def open_output(self) -> list:
         """The output files read back (``MetSim.open_output``, metsim.py:326-328), one
         :class:`metsim_b200.ncio.Dataset` per file."""
@@ -651,11 +736,14 @@ def parse(args):
     parser = argparse.ArgumentParser(prog="python -m metsim_b200.driver")
     parser.add_argument("config", help="Input configuration file")
     parser.add_argument("-n", "--num_workers", default=1, type=int,
-                        help="accepted for compatibility: the domain is one batched GPU call")
+                        help="number of GPUs to spread the domain over (contiguous cell ranges); the "
+                             "reference's number of worker processes")
     parser.add_argument("-s", "--scheduler", default="distributed", type=str,
                         help="accepted for compatibility (no dask here)")
     parser.add_argument("-v", "--verbose", action="store_true", help="Increase the verbosity")
-    parser.add_argument("-d", "--device", default=0, type=int, help="CUDA device index")
+    parser.add_argument("-d", "--device", default=0, type=int, help="CUDA device index (single-GPU run)")
+    parser.add_argument("--devices", default=None, type=str,
+                        help="comma-separated CUDA device indices, one cell range each (overrides -n / -d)")
     opts = parser.parse_args(args)
     if not os.path.isfile(opts.config):
         parser.print_help()
@@ -668,7 +756,13 @@ def main(argv=None) -> list:
     setup = read_config(opts.config, scheduler=opts.scheduler, num_workers=opts.num_workers,
                         verbose=opts.verbose)
     ms = MetSimB200(setup, device=opts.device)
-    files = ms.run()
+    devices = None
+    if opts.devices:
+        devices = [int(x) for x in opts.devices.split(",")]
+    elif opts.num_workers > 1:
+        import torch
+        devices = list(range(min(opts.num_workers, max(1, torch.cuda.device_count()))))
+    files = ms.run(devices=devices)
     for f in files:
         print(f)
     return files

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--days", type=int, default=90)
     ap.add_argument("--dir", default="/tmp/msb_driver")
     ap.add_argument("--budget-gb", type=float, default=1.0, help="host ring budget (forces tiling)")
+    ap.add_argument("--devices", default=None, help="comma-separated device indices, one cell range each")
     a = ap.parse_args()
     from scipy.io import netcdf_file
     from metsim_b200 import driver, synth
@@ -113,9 +114,10 @@ dur = dur
     ms = driver.MetSimB200(driver.read_config(conf))
     ms.state
     t1 = time.perf_counter()
-    ms.run(host_budget_bytes=int(a.budget_gb * (1 << 30)))     # first run: arena, pinned ring, page cache
+    devs = [int(x) for x in a.devices.split(",")] if a.devices else None
+    ms.run(host_budget_bytes=int(a.budget_gb * (1 << 30)), devices=devs)     # first run: arena, pinned ring, page cache
     t2 = time.perf_counter()
-    files = ms.run(host_budget_bytes=int(a.budget_gb * (1 << 30)))
+    files = ms.run(host_budget_bytes=int(a.budget_gb * (1 << 30)), devices=devs)
     t3 = time.perf_counter()
     out_bytes = sum(os.path.getsize(p) for p in files)
     cts = ny * nx * d * 24
@@ -130,11 +132,14 @@ dur = dur
     pick = np.linspace(0, ny * nx - 1, 64).astype(int)
     same = all(np.array_equal(ds[v].values.reshape(d * 24, -1)[:, pick], ref[v].cpu().numpy()[:, pick])
                for v in ("temp", "prec", "longwave"))
-    print(json.dumps({"cells": ny * nx, "days": d, "cell_timesteps": cts, "read_inputs_s": round(t1 - t0, 3),
+    tm = {k: (round(v, 3) if not isinstance(v, list) else [{kk: (round(vv, 2) if isinstance(vv, float) else vv)
+                                                                for kk, vv in r.items()} for r in v])
+          for k, v in ms.timings.items()}
+    print(json.dumps({"devices": devs, "cells": ny * nx, "days": d, "cell_timesteps": cts, "read_inputs_s": round(t1 - t0, 3),
                       "first_run_s": round(t2 - t1, 3), "run_s": round(t3 - t2, 3),
                       "cell_timesteps_per_s_files_to_files": cts / (t3 - t2),
                       "output_gb": round(out_bytes / 1e9, 3), "output_gb_per_s": round(out_bytes / 1e9 / (t3 - t2), 2),
-                      "timings": {k: round(v, 3) for k, v in ms.timings.items()},
+                      "timings": tm,
                       "file_equals_direct_engine_run_on_64_cells": bool(same)}))
 
 

@@ -362,6 +362,114 @@ def test_run_writes_reference_shaped_files(tmp_path, monkeypatch, budget):
         step0 += nsteps
 
 
+class _NoCtx:
+    """Stands in for engine.HostContext where there is no CUDA device."""
+    def __init__(self, device=0):
+        self.device = device
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _fake_run_host_tagged(calls, fail_on=None):
+    """Like _fake_run_host, but a value carries its cell's elevation (unique per cell) instead of its
+    position in the call, so that ranges of cells computed by separate calls can be told apart:
+    value = 1000 * variable index + step + elev / 1e4."""
+    import threading
+    from metsim_b200._lib import SUB_VARS
+    lock = threading.Lock()
+
+    def fake(params, *, out_vars=(), out_dtype=np.float64, units=None, daily_vars=(), out=None, ring=False,
+             tile_days=0, on_tile=None, timings=None, device=0, ctx=None, **arrays):
+        ts = int(params["time_step"])
+        d, n = arrays["t_min"].shape
+        with lock:
+            calls.append(dict(n=n, device=getattr(ctx, "device", device), ring=ring, tile_days=tile_days,
+                              thread=threading.current_thread().name))
+        tag = np.asarray(arrays["elev"])[None, :] / 1e4
+        if ts >= 1440:
+            return {"daily": {v: 10.0 * (1 + i) + np.arange(d)[:, None] + tag for i, v in enumerate(daily_vars)}}
+        tpd = 1440 // ts
+        pat = lambda v, s0, s1: (1000.0 * SUB_VARS.index(v) + np.arange(s0, s1)[:, None] + tag).astype(out_dtype)
+        if not ring:
+            return {v: pat(v, 0, d * tpd) for v in out_vars}
+        for tile, day0 in enumerate(range(0, d, tile_days)):
+            if fail_on is not None and tile == 1 and n == fail_on:
+                raise RuntimeError("range failed")
+            day1, slot = min(day0 + tile_days, d), tile % 2
+            for v in out_vars:
+                out[v][slot * tile_days * tpd:slot * tile_days * tpd + (day1 - day0) * tpd] = pat(v, day0 * tpd, day1 * tpd)
+            on_tile(tile, day0, day1, slot)
+        return {}
+    return fake
+
+
+@pytest.mark.parametrize("budget", [4 << 30, 40000])
+def test_run_over_several_devices_gathers_cell_ranges(tmp_path, monkeypatch, budget):
+    """``run(devices=[...])``: contiguous cell ranges on their own threads / contexts, gathered on the host
+    into full rows -- whole columns when the record fits the budget, tile by tile through the barrier
+    otherwise; the files equal what one range would have written."""
+    from metsim_b200 import engine
+    from metsim_b200._lib import SUB_VARS
+    rng = np.random.default_rng(5)
+    mask = (rng.random((10, 13)) < 0.9).astype("i4")
+    conf, case = small_case(str(tmp_path), ny=10, nx=13, mask=mask, out_freq="1M", extra="out_precision = f8")
+    calls = []
+    monkeypatch.setattr(engine, "run_host", _fake_run_host_tagged(calls))
+    monkeypatch.setattr(engine, "HostContext", _NoCtx)
+    ms = driver.MetSimB200(driver.read_config(conf))
+    files = ms.run(host_budget_bytes=budget, devices=[0, 1, 1])
+    n = int(mask.sum())
+    from metsim_b200.shard import cell_range
+    widths = [hi - lo for lo, hi in (cell_range(n, k, 3) for k in range(3))]
+    assert sorted(c["n"] for c in calls) == sorted(widths) and sum(widths) == n and widths[0] % 32 == 0
+    assert sorted(c["device"] for c in calls) == [0, 1, 1] and len({c["thread"] for c in calls}) == 3
+    assert all(c["ring"] == (budget < 1 << 20) for c in calls)
+    assert [r["cells"] for r in ms.timings["ranges"]] == widths and [r["device"] for r in ms.timings["ranges"]] == [0, 1, 1]
+    elev = ms.gather()["elev"]
+    sel = np.flatnonzero(mask.ravel())
+    step0 = 0
+    for ds, nsteps in zip(ms.open_output(), (28, 12)):
+        for v in ("temp", "prec", "shortwave", "wind"):
+            flat = ds[v].values.reshape(nsteps, -1)
+            want = 1000.0 * SUB_VARS.index(v) + np.arange(step0, step0 + nsteps)[:, None] + elev[None, :] / 1e4
+            np.testing.assert_array_equal(flat[:, sel], want)
+            assert np.isnan(np.delete(flat, sel, axis=1)).all()
+        step0 += nsteps
+    # too few cells for the devices offered: fewer ranges, same files
+    calls.clear()
+    conf2, _ = small_case(str(tmp_path), ny=5, nx=8)
+    driver.MetSimB200(driver.read_config(conf2)).run(devices=[0, 1, 2, 3])
+    assert len(calls) == 1 and calls[0]["n"] == 40
+
+
+def test_run_over_several_devices_daily_mode_and_a_failing_range(tmp_path, monkeypatch):
+    from metsim_b200 import engine
+    conf, _ = small_case(str(tmp_path), ny=10, nx=13, ts=1440)
+    calls = []
+    monkeypatch.setattr(engine, "run_host", _fake_run_host_tagged(calls))
+    monkeypatch.setattr(engine, "HostContext", _NoCtx)
+    p = driver.read_config(conf)
+    av = driver.available_outputs()
+    p["out_vars"] = {"prec": dict(av["prec"]), "pet": dict(av["pet"])}
+    ms = driver.MetSimB200(dict(p, out_precision="f8"))
+    ms.run(devices=[0, 1])
+    (ds,) = ms.open_output()
+    g = ms.gather()
+    np.testing.assert_array_equal(ds["prec"].values.reshape(10, -1), g["prec"])
+    np.testing.assert_array_equal(ds["pet"].values.reshape(10, -1), 40.0 + np.arange(10)[:, None] + g["elev"][None, :] / 1e4)
+    assert len(calls) == 2
+    # a range that fails mid-run: the others are released from the barrier and the first real error is raised
+    conf, _ = small_case(str(tmp_path), ny=10, nx=13, ts=360)
+    monkeypatch.setattr(engine, "run_host", _fake_run_host_tagged([], fail_on=64))
+    ms = driver.MetSimB200(dict(driver.read_config(conf), out_precision="f8"))
+    with pytest.raises(RuntimeError, match="range failed"):
+        ms.run(host_budget_bytes=40000, devices=[0, 1])
+
+
 def test_run_daily_mode_writes_forcings_and_daily_columns(tmp_path, monkeypatch):
     """time_step = 1440 (metsim/metsim.py:779-792): t_min / prec come from the forcings, shortwave is the
     daily mean flux column, the rest the daily MTCLIM columns; units converted on the host."""

@@ -239,3 +239,36 @@ def test_driver_daily_mode(tmp_path):
     for v, o in (("vapor_pressure", "vp_daily"), ("tskc", "tskc_daily"), ("pet", "pet"), ("daylength", "daylength")):
         util.assert_close(flat(v), ref_daily[v], o, context="driver daily mode")
     assert ds["time"].values.size == days and ds["pet"].attrs["units"] == "mm timestep-1"
+
+
+@pytest.mark.parametrize("budget", [1 << 30, 60000])
+def test_driver_cell_ranges_on_several_contexts_equal_the_single_call(tmp_path, budget):
+    """``run(devices=[0, 0])``: two contiguous cell ranges, each on its own host thread and
+    msb_host_ctx (here both on device 0 -- contexts are independent, tests/test_gpu_parity.py), gathered
+    on the host.  Whole columns when the record fits the budget, the tile barrier otherwise.  The files
+    must equal the single-call run bit for bit, and the reference within float32 rounding."""
+    from metsim_b200 import driver, ncio
+    tmp = str(tmp_path)
+    inputs, params, _, ref_sub, extra = util.load_golden(os.path.join(util.GOLDEN, "testdomain.npz"))
+    cells = extra["ref_cells"]
+    holes = [c for c in (3, 17, 40, 41, 80) if c not in set(cells.tolist())]
+    mask = np.ones(81, "i4")
+    mask[holes] = 0
+    _files_from_fixture(tmp, inputs, 9, 9, "1950-01-01", mask=mask.reshape(9, 9))
+    out_vars = "['temp', 'prec', 'shortwave', 'longwave', 'vapor_pressure', 'rel_humid', 'air_pressure', 'wind']"
+    conf = _conf(tmp, ts=30, start="1950/1/1", stop="1950/1/31", out_vars=out_vars,
+                 body="prec_type = triangle\nutc_offset = True")
+    ms = driver.MetSimB200(driver.read_config(conf))
+    (path,) = ms.run()
+    one = {v: ncio.open_dataset(path)[v].values.copy() for v in ("temp", "prec", "shortwave", "longwave",
+                                                                 "vapor_pressure", "rel_humid", "air_pressure", "wind")}
+    os.remove(path)
+    (path,) = ms.run(host_budget_bytes=budget, devices=[0, 0])
+    from metsim_b200.shard import cell_range
+    n_act = int(mask.sum())
+    assert [r["cells"] for r in ms.timings["ranges"]] == [hi - lo for lo, hi in (cell_range(n_act, k, 2) for k in range(2))]
+    two = ncio.open_dataset(path)
+    for v, a in one.items():
+        np.testing.assert_array_equal(two[v].values, a, err_msg=v)
+        e = util.relerr(a.reshape(1488, 81)[:, cells], ref_sub[v], util.FLOORS[v])
+        assert e <= 2e-7, (v, e)
