@@ -14,6 +14,8 @@ not.  Fixture families:
                    three_hourly_48.3125_-120.5625, stored as float32) and the 90-day state of
                    state_vic.nc, exactly as that test configures it (NetCDF-4 / HDF5 with densely
                    stored links and chunked datasets: read by oracle/mini_hdf5.py).
+* ``stehekin_domain`` inputs of the whole 4 x 5 Stehekin domain (16 cells, 1949) for the driver tests that
+                   mirror the reference's own (variable rename, unit conversion, passthrough, examples).
 * ``testdomain``   BASELINE config #1 as literally configured by examples/example_nc.conf:
                    metsim/data/test.nc + domain.nc + the 90-day state of state_nc.nc (81 cells, 31
                    days, 30 min, triangle, utc_offset), float32 inputs upcast exactly to float64.
@@ -110,6 +112,35 @@ def stehekin(root):
         print("stehekin", tag, good.shape)
 
 
+def stehekin_domain(root):
+    """The whole Stehekin domain of the reference's driver-level tests (metsim/tests/test_metsim.py:212-395:
+    time offset, variable rename, passthrough, unit conversion; examples/example_bin.conf): stehekin.nc
+    (4 x 5, 16 active cells), the 16 VIC-4 binary forcing files cut to 1949, the 90-day state of
+    state_vic.nc -- inputs only, as arrays; tests/test_gpu_driver.py rebuilds the files from them."""
+    data = os.path.join(root, "metsim", "data")
+    dom = netcdf_file(os.path.join(data, "stehekin.nc"), "r", mmap=False)
+    lat, lon = dom.variables["lat"].data.astype(float), dom.variables["lon"].data.astype(float)
+    mask = np.nan_to_num(dom.variables["mask"].data.astype(float), nan=0.0)
+    state = read_hdf5(os.path.join(data, "state_vic.nc"))
+    assert np.allclose(state["lat"], lat) and np.allclose(state["lon"], lon) and (np.diff(state["time"]) == 1).all()
+    z = dict(lat=lat, lon=lon, mask=mask.astype(np.int32), elev=dom.variables["elev"].data.astype(float),
+             t_pk=dom.variables["t_pk"].data.astype(np.float32), dur=dom.variables["dur"].data.astype(np.float32),
+             start=np.array("1949-01-01"),
+             state_t_min=state["t_min"], state_t_max=state["t_max"], state_prec=state["prec"])
+    for k in ("prec", "t_max", "t_min", "wind"):
+        z[k] = np.full((365, lat.size, lon.size), np.nan)
+    n = 0
+    for i, la in enumerate(lat):
+        for j, lo in enumerate(lon):
+            path = os.path.join(data, "binary", f"data_{la}_{lo}")
+            if mask[i, j] > 0 and os.path.exists(path):
+                z["prec"][:, i, j], z["t_max"][:, i, j], z["t_min"][:, i, j], z["wind"][:, i, j] = read_vic_binary(path, 365)
+                n += 1
+    assert n == int((mask > 0).sum()) == 16
+    np.savez_compressed(os.path.join(GOLDEN, "stehekin_domain.npz"), **z)
+    print("stehekin_domain", n, "cells")
+
+
 def testdomain(root):
     data = os.path.join(root, "metsim", "data")
     frc = netcdf_file(os.path.join(data, "test.nc"), "r", mmap=False)
@@ -201,8 +232,8 @@ def main():
     import warnings
     warnings.filterwarnings("ignore")
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
-    steps = dict(stehekin=lambda: stehekin(root), testdomain=lambda: testdomain(root), synth=synth,
-                 passthrough=passthrough)
+    steps = dict(stehekin=lambda: stehekin(root), stehekin_domain=lambda: stehekin_domain(root),
+                 testdomain=lambda: testdomain(root), synth=synth, passthrough=passthrough)
     for name, fn in steps.items():
         if not only or name in only:
             fn()

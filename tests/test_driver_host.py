@@ -550,6 +550,9 @@ def test_every_example_configuration_loads(monkeypatch, conf, cells, days, nfile
         assert (g["wind"] == 2.0).all()
     if conf == "example_dimtest.conf":                       # a 1-D ('hru',) domain, NetCDF-4 with big-endian scales
         assert ms.domain["mask"].dims == ("hru",) and g["cell_index"].tolist() == list(range(9))
+        # test_metsim.py:467-483 (test_coordinate_dimension_matchup): the file has no `hru` coordinate variable,
+        # the run gets a sequential one
+        assert "hru" not in ms.domain and driver._coordinate(ms.domain, "hru").tolist() == list(range(9))
 
 
 @needs_reference
