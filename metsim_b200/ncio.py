@@ -3,7 +3,9 @@
 The reference opens its domain / state / forcing files with ``xr.open_dataset`` (metsim/io.py:264-303).
 xarray and netCDF4 are absent from this image, so :func:`open_dataset` reads
 
-* NetCDF classic / 64-bit offset (``CDF\\x01``, ``CDF\\x02``) through ``scipy.io.netcdf_file``;
+* NetCDF classic / 64-bit offset / 64-bit data (``CDF\\x01``, ``CDF\\x02``, ``CDF\\x05``) with its own
+  parser of the classic format (scipy reads the first two only; ``ncwriter.py`` writes the third for
+  variables beyond 4 GiB);
 * NetCDF-4 (HDF5) through :mod:`metsim_b200.hdf5_min`;
 
 and hands back what the driver needs of an ``xarray.Dataset``: per variable ``values`` / ``dims`` /
@@ -109,19 +111,124 @@ def _finish(ds: Dataset) -> Dataset:
     return ds
 
 
+_NC_TYPES = {1: ">i1", 2: "S1", 3: ">i2", 4: ">i4", 5: ">f4", 6: ">f8",
+             7: ">u1", 8: ">u2", 9: ">u4", 10: ">i8", 11: ">u8"}        # 7..11: CDF-5 only
+_NC_DIMENSION, _NC_VARIABLE, _NC_ATTRIBUTE = 10, 11, 12
+
+
 def _open_classic(path: str) -> Dataset:
-    from scipy.io import netcdf_file
-    txt = lambda a: a.decode("utf-8", "replace") if isinstance(a, bytes) else a
-    with netcdf_file(path, "r", mmap=False, maskandscale=False) as f:
-        ds = Dataset(dims={k: (0 if n is None else int(n)) for k, n in f.dimensions.items()},
-                     attrs={k: txt(v) for k, v in f._attributes.items()})
-        for name, var in f.variables.items():
-            vals = np.array(var.data)
-            if vals.dtype.byteorder == ">" or (vals.dtype.byteorder == "=" and not np.little_endian):
-                vals = vals.astype(vals.dtype.newbyteorder("="))
-            ds[name] = Var(vals, var.dimensions, {k: txt(v) for k, v in var._attributes.items()})
-            for d, n in zip(var.dimensions, vals.shape):
-                ds.dims[d] = int(n)                  # the record dimension reads as None above
+    """NetCDF classic (``CDF\\x01``), 64-bit offset (``\\x02``) and 64-bit data (``\\x05``) files, parsed
+    here from the format specification (header = magic numrecs dim_list gatt_list var_list; fixed-size
+    variables contiguous at ``begin``, record variables interleaved record by record) -- scipy reads
+    the first two only, and the writer of this package (ncwriter.py) emits CDF-5 once a variable
+    exceeds 4 GiB, so the driver reads what it writes at any size."""
+    import struct
+    buf = np.memmap(path, dtype=np.uint8, mode="r")
+    version = int(buf[3])
+    wide = version == 5
+    pos = 4
+
+    def u32():
+        nonlocal pos
+        v = struct.unpack(">I", buf[pos:pos + 4].tobytes())[0]
+        pos += 4
+        return v
+
+    def cnt():                                   # NON_NEG: 32-bit, 64-bit in CDF-5
+        nonlocal pos
+        if not wide:
+            return u32()
+        v = struct.unpack(">Q", buf[pos:pos + 8].tobytes())[0]
+        pos += 8
+        return v
+
+    def name():
+        nonlocal pos
+        n = cnt()
+        s = buf[pos:pos + n].tobytes().decode("utf-8", "replace")
+        pos += n + (-n % 4)
+        return s
+
+    def att_list():
+        nonlocal pos
+        tag, n = u32(), cnt()
+        if tag == 0 and n == 0:
+            return {}
+        if tag != _NC_ATTRIBUTE:
+            raise ValueError(f"{path}: malformed attribute list")
+        out = {}
+        for _ in range(n):
+            k = name()
+            t, m = u32(), cnt()
+            dt = np.dtype(_NC_TYPES[t])
+            nbytes = m * dt.itemsize
+            raw = buf[pos:pos + nbytes].tobytes()
+            pos += nbytes + (-nbytes % 4)
+            if t == 2:
+                out[k] = raw.decode("utf-8", "replace").rstrip("\x00")
+            else:
+                v = np.frombuffer(raw, dtype=dt).astype(dt.newbyteorder("="))
+                out[k] = v[0] if m == 1 else v
+        return out
+
+    numrecs = cnt()
+    streaming = numrecs == (0xFFFFFFFFFFFFFFFF if wide else 0xFFFFFFFF)
+    tag, n = u32(), cnt()
+    dims = []
+    if not (tag == 0 and n == 0):
+        if tag != _NC_DIMENSION:
+            raise ValueError(f"{path}: malformed dimension list")
+        for _ in range(n):
+            dims.append((name(), cnt()))
+    gatts = att_list()
+    tag, n = u32(), cnt()
+    variables = []
+    if not (tag == 0 and n == 0):
+        if tag != _NC_VARIABLE:
+            raise ValueError(f"{path}: malformed variable list")
+        for _ in range(n):
+            vname = name()
+            dimids = [cnt() for _ in range(cnt())]
+            atts = att_list()
+            t = u32()
+            vsize = cnt()
+            if version == 1:
+                begin = u32()
+            else:
+                begin = struct.unpack(">Q", buf[pos:pos + 8].tobytes())[0]
+                pos += 8
+            variables.append((vname, dimids, atts, np.dtype(_NC_TYPES[t]), vsize, begin))
+    is_rec = lambda dimids: bool(dimids) and dims[dimids[0]][1] == 0
+    rec_vars = [v for v in variables if is_rec(v[1])]
+    # record size: the sum of the record variables' vsize -- except that a single record variable is
+    # not padded to 4 bytes (classic format specification, "Note on padding")
+    if len(rec_vars) == 1:
+        v = rec_vars[0]
+        recsize = int(np.prod([dims[d][1] for d in v[1][1:]], dtype=np.int64)) * v[3].itemsize
+    else:
+        recsize = sum(v[4] for v in rec_vars)
+    if streaming:
+        if not rec_vars or recsize == 0:
+            numrecs = 0
+        else:
+            numrecs = (buf.size - min(v[5] for v in rec_vars)) // recsize
+    ds = Dataset(dims={k: (numrecs if ln == 0 else int(ln)) for k, ln in dims}, attrs=gatts)
+    for vname, dimids, atts, dt, vsize, begin in variables:
+        shape = tuple(ds.dims[dims[d][0]] for d in dimids)
+        if is_rec(dimids):
+            inner = shape[1:]
+            if numrecs == 0:
+                vals = np.empty(shape, dtype=dt.newbyteorder("="))
+            else:
+                strides = (recsize,) + tuple(int(np.prod(inner[i + 1:], dtype=np.int64)) * dt.itemsize
+                                             for i in range(len(inner)))
+                view = np.ndarray(shape=(numrecs,) + inner, dtype=dt, buffer=buf, offset=begin, strides=strides)
+                vals = view.astype(dt.newbyteorder("=") if dt.kind != "S" else dt)
+        else:
+            view = np.ndarray(shape=shape, dtype=dt, buffer=buf, offset=begin)
+            vals = view.astype(dt.newbyteorder("=") if dt.kind != "S" else dt)
+        ds[vname] = Var(vals, tuple(dims[d][0] for d in dimids), atts)
+    del buf
     return _finish(ds)
 
 
@@ -138,10 +245,8 @@ def open_dataset(path: str) -> Dataset:
     """Read a whole NetCDF file (classic, 64-bit offset or NetCDF-4) into memory, CF-decoded."""
     with open(path, "rb") as f:
         magic = f.read(8)
-    if magic[:3] == b"CDF" and magic[3] in (1, 2):
+    if magic[:3] == b"CDF" and magic[3] in (1, 2, 5):
         return _open_classic(path)
     if magic == b"\x89HDF\r\n\x1a\n":
         return _open_hdf5(path)
-    if magic[:3] == b"CDF" and magic[3] == 5:
-        raise NotImplementedError(f"{path}: CDF-5 input files are not read by the minimal driver")
     raise ValueError(f"{path}: not a NetCDF file")

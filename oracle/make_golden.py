@@ -137,7 +137,7 @@ def stehekin_domain(root):
                 z["prec"][:, i, j], z["t_max"][:, i, j], z["t_min"][:, i, j], z["wind"][:, i, j] = read_vic_binary(path, 365)
                 n += 1
     assert n == int((mask > 0).sum()) == 16
-    np.savez_compressed(os.path.join(GOLDEN, "stehekin_domain.npz"), **z)
+    np.savez_compressed(os.path.join(GOLDEN, "inputs_stehekin_domain.npz"), **z)
     print("stehekin_domain", n, "cells")
 
 

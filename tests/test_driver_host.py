@@ -565,3 +565,80 @@ def test_hdf5_reader_recovers_dimensions_and_attributes():
     assert dims == {"time": 180, "hru": 9} and "hru" not in v and v["pptrate"].dims == ("time", "hru")
     v, _, _ = read_hdf5_vars(os.path.join(REF, "metsim", "data", "tiny_domain.nc"))
     assert v["t_pk"].dims == ("month", "lat", "lon") and v["t_pk"].values.dtype == np.float32
+
+
+def _same_as_scipy(path):
+    """ncio's own parser of the classic format against scipy's, variable by variable."""
+    ds = ncio.open_dataset(path)
+    with netcdf_file(path, "r", mmap=False, maskandscale=False) as f:
+        assert set(f.variables) == set(ds)
+        for k, v in f.variables.items():
+            a, b = np.array(v.data), ds[k].values
+            assert tuple(v.dimensions) == ds[k].dims
+            for kk, vv in v._attributes.items():
+                w = ds[k].attrs[kk]
+                if isinstance(vv, bytes):
+                    assert vv.decode() == w
+                else:
+                    assert np.array_equal(np.atleast_1d(vv), np.atleast_1d(w), equal_nan=True)
+            if b.dtype.kind == "M":
+                continue
+            if a.dtype.kind == "S":
+                assert a.tobytes() == b.tobytes()
+                continue
+            keep = ~np.isnan(b) if b.dtype.kind == "f" else np.ones(b.shape, bool)     # decoded fill values
+            assert np.array_equal(a.astype(a.dtype.newbyteorder("="))[keep], b[keep]), k
+    return ds
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_classic_reader_record_variables_against_scipy(tmp_path, version):
+    """Fixed-size and record variables (interleaved record by record; a lone 2-byte record variable is
+    not padded), text, attributes, classic and 64-bit offset."""
+    rng = np.random.default_rng(1)
+    p = os.path.join(str(tmp_path), "rec.nc")
+    with netcdf_file(p, "w", version=version) as f:
+        f.createDimension("time", None), f.createDimension("x", 3), f.createDimension("s", 5)
+        t = f.createVariable("time", "i4", ("time",))
+        a = f.createVariable("a", "f8", ("time", "x"))
+        b = f.createVariable("b", "i2", ("time", "x"))
+        c = f.createVariable("c", "f4", ("x",))
+        s = f.createVariable("name", "c", ("s",))
+        t[:], a[:], b[:], c[:] = np.arange(7), rng.random((7, 3)), np.arange(21).reshape(7, 3), [1.5, 2.5, 3.5]
+        s[:] = np.array(list("hello"), "S1")
+        t.units, f.title, a.gain = "days since 2000-01-01", "record test", np.float32(2.0)
+    ds = _same_as_scipy(p)
+    assert ds.dims == {"time": 7, "x": 3, "s": 5} and ds.attrs["title"] == "record test"
+    assert ds["time"].values[6] == np.datetime64("2000-01-07")
+    p = os.path.join(str(tmp_path), "single.nc")
+    with netcdf_file(p, "w", version=version) as f:
+        f.createDimension("time", None), f.createDimension("x", 3)
+        f.createVariable("b", "i2", ("time", "x"))[:] = np.arange(15).reshape(5, 3)
+    assert _same_as_scipy(p)["b"].values.tolist() == np.arange(15).reshape(5, 3).tolist()
+
+
+def test_classic_reader_reads_what_the_writer_writes_including_cdf5(tmp_path):
+    """The driver must be able to read its own outputs back (open_output, the passthrough workflow) at
+    any size: ncwriter switches to CDF-5 beyond 4 GiB per variable, which scipy cannot read."""
+    from metsim_b200.ncwriter import NC3Writer
+    rng = np.random.default_rng(2)
+    for version in (2, 5):
+        p = os.path.join(str(tmp_path), f"w{version}.nc")
+        blk = rng.random((6, 5)).astype("f4")
+        with NC3Writer(p, n_steps=6, lat=[1.0, 2.0], lon=[3.0, 4.0, 5.0], cell_index=[0, 1, 2, 4, 5],
+                       variables={"temp": {"units": "C", "dtype": "float32"}}, time_values=np.arange(6, dtype=np.int32) * 30,
+                       time_units=driver.DEFAULT_TIME_UNITS, version=version, native=False) as w:
+            w.write_steps("temp", 0, blk)
+        assert open(p, "rb").read(4) == b"CDF" + bytes([version])
+        ds = ncio.open_dataset(p)
+        g = ds["temp"].values.reshape(6, 6)
+        assert np.array_equal(g[:, [0, 1, 2, 4, 5]], blk) and np.isnan(g[:, 3]).all()
+        assert ds["temp"].attrs["units"] == "C" and ds["time"].values[1] == np.datetime64("2000-01-01T00:30")
+        if version == 2:
+            _same_as_scipy(p)
+
+
+@needs_reference
+@pytest.mark.parametrize("name", ["test.nc", "domain.nc", "stehekin.nc"])
+def test_classic_reader_on_the_reference_files(name):
+    _same_as_scipy(os.path.join(REF, "metsim", "data", name))

@@ -10,7 +10,7 @@ binary forcings of the Stehekin domain, ``out_vars`` with ``out_name`` / ``units
   test_disaggregation_values  :397-464    test_disaggregation_values (same NRMSE thresholds, same golden tables)
   test_examples[ascii|bin]    :486-496    test_examples
 
-The Stehekin files are rebuilt from tests/golden/stehekin_domain.npz (the reference checkout does not
+The Stehekin files are rebuilt from tests/golden/inputs_stehekin_domain.npz (the reference checkout does not
 exist on the GPU box); the golden tables are those of tests/golden/stehekin_*.npz."""
 import os
 from collections import OrderedDict
@@ -33,7 +33,7 @@ DOMAIN_SECTION = OrderedDict(lat="lat", lon="lon", mask="mask", elev="elev")
 
 def stehekin_files(tmp: str) -> dict:
     """stehekin.nc, state_vic.nc, binary/ and ascii/ per-cell forcing files, as in metsim/data."""
-    z = np.load(os.path.join(util.GOLDEN, "stehekin_domain.npz"))
+    z = np.load(os.path.join(util.GOLDEN, "inputs_stehekin_domain.npz"))
     lat, lon, mask = z["lat"], z["lon"], z["mask"]
     ny, nx = mask.shape
     write_nc3(os.path.join(tmp, "stehekin.nc"), {"lat": ny, "lon": nx, "month": 12}, {
