@@ -742,6 +742,9 @@ def parse(args):
                         help="accepted for compatibility (no dask here)")
     parser.add_argument("-v", "--verbose", action="store_true", help="Increase the verbosity")
     parser.add_argument("-d", "--device", default=0, type=int, help="CUDA device index (single-GPU run)")
+    from . import __version__
+    parser.add_argument("--version", action="version", version=f"metsim_b200 {__version__}",
+                        help="Name and version number")
     parser.add_argument("--devices", default=None, type=str,
                         help="comma-separated CUDA device indices, one cell range each (overrides -n / -d)")
     opts = parser.parse_args(args)
@@ -763,6 +766,11 @@ def main(argv=None) -> list:
         import torch
         devices = list(range(min(opts.num_workers, max(1, torch.cuda.device_count()))))
     files = ms.run(devices=devices)
+    if opts.verbose:
+        tm = ms.timings
+        ms.logger.info("ran %d cell range(s); gather %.2f s, create files %.2f s, compute + write %.2f s",
+                       len(tm.get("ranges", [0])), tm.get("s_gather", 0.0), tm.get("s_create_files", 0.0),
+                       tm.get("s_compute_and_write", 0.0))
     for f in files:
         print(f)
     return files
