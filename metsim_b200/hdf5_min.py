@@ -8,8 +8,9 @@ Scope: exactly what the bundled files under metsim/data use -- version-2 object 
 with "OCHK" continuation chunks), root-group links stored compactly (link messages) or DENSELY
 (link info message -> fractal heap + version-2 B-tree name index, what netCDF-4 writes once a group
 has more than 8 links: state_vic.nc, passthrough.nc), simple dataspaces, fixed-point / IEEE
-floating-point datatypes, CONTIGUOUS layout or CHUNKED layout without filters (version-1 B-tree
-of raw data chunks -- every variable with the unlimited time dimension), little- or big-endian;
+floating-point datatypes, CONTIGUOUS layout or CHUNKED layout (version-1 B-tree of raw data chunks --
+every variable with the unlimited time dimension), unfiltered or through the deflate / shuffle /
+fletcher32 filters netCDF-4 applies (filter pipeline message, versions 1 and 2), little- or big-endian;
 attributes stored compactly (attribute messages, versions 1-3) or densely (attribute info message ->
 fractal heap + version-2 B-tree), with fixed-length / variable-length strings, numbers and the
 ``DIMENSION_LIST`` object references of netCDF-4 (global heap), from which every variable's
@@ -234,10 +235,57 @@ def _chunks(b: bytes, addr: int, rank1: int):
         if level > 0:
             out += _chunks(b, child, rank1)
         else:
-            if mask:
-                raise NotImplementedError("filtered chunk")
-            out.append((offs[:-1], size, child))
+            out.append((offs[:-1], size, child, mask))
     return out
+
+
+def _filter_pipeline(body: bytes):
+    """[(filter id, client data)] of a filter pipeline message (0x0B; spec IV.A.2.l, versions 1 and 2)."""
+    ver, n = body[0], body[1]
+    if ver == 1:
+        q = 8
+    elif ver == 2:
+        q = 2
+    else:
+        raise NotImplementedError("filter pipeline message version %d" % ver)
+    out = []
+    for _ in range(n):
+        fid = struct.unpack("<H", body[q:q + 2])[0]
+        q += 2
+        nlen = 0
+        if ver == 1 or fid >= 256:
+            nlen = struct.unpack("<H", body[q:q + 2])[0]
+            q += 2
+        _flags, ncd = struct.unpack("<HH", body[q:q + 4])
+        q += 4
+        q += nlen + ((-nlen % 8) if ver == 1 else 0)         # the optional name
+        cd = struct.unpack("<%dI" % ncd, body[q:q + 4 * ncd])
+        q += 4 * ncd + (4 if ver == 1 and ncd % 2 else 0)
+        out.append((fid, cd))
+    return out
+
+
+def _unfilter(raw: bytes, filters, mask: int, itemsize: int) -> bytes:
+    """Undo a chunk's filters, last applied first; bit i of ``mask`` set = filter i was skipped for this
+    chunk.  1 = deflate (zlib), 2 = shuffle (bytes of the elements de-interleaved), 3 = fletcher32
+    (a 4-byte checksum after the data, not verified here)."""
+    import zlib
+    for idx in reversed(range(len(filters))):
+        if (mask >> idx) & 1:
+            continue
+        fid, cd = filters[idx]
+        if fid == 1:
+            raw = zlib.decompress(raw)
+        elif fid == 2:
+            width = cd[0] if cd else itemsize
+            n = len(raw) // width
+            body = np.frombuffer(raw, dtype=np.uint8, count=n * width).reshape(width, n).T
+            raw = body.tobytes() + raw[n * width:]
+        elif fid == 3:
+            raw = raw[:-4]
+        else:
+            raise NotImplementedError("HDF5 filter %d (only deflate, shuffle and fletcher32 are undone here)" % fid)
+    return raw
 
 
 def _datatype(body: bytes):
@@ -362,7 +410,7 @@ def _attributes(b: bytes, msgs) -> dict:
 
 
 def _dataset(b: bytes, off: int, msgs=None):
-    dims = dtype = layout = chunked = None
+    dims = dtype = layout = chunked = filters = None
     for mtype, body in (msgs if msgs is not None else _messages(b, off)):
         if mtype == 0x01:                            # dataspace
             dims = _dataspace(body)
@@ -381,7 +429,7 @@ def _dataset(b: bytes, off: int, msgs=None):
             else:
                 raise NotImplementedError("only contiguous / chunked layouts (version 3) are supported")
         elif mtype == 0x0B:
-            raise NotImplementedError("filtered (compressed) dataset")
+            filters = _filter_pipeline(body)
     native = None if dtype is None else dtype.newbyteorder("=")
     if dims is not None and dtype is not None and chunked is not None:
         rank1, tree, cdims = chunked
@@ -389,11 +437,16 @@ def _dataset(b: bytes, off: int, msgs=None):
             raise NotImplementedError("chunk shape does not match the dataspace")
         out = np.zeros(dims, dtype=native)
         if tree != UNDEF:
-            for offs, size, addr in _chunks(b, tree, rank1):
+            for offs, size, addr, mask in _chunks(b, tree, rank1):
                 cshape = cdims[:-1]
-                if size != int(np.prod(cshape)) * dtype.itemsize:
-                    raise NotImplementedError("chunk size does not match its shape (filtered?)")
-                block = np.frombuffer(b, dtype=dtype, count=int(np.prod(cshape)), offset=addr).reshape(cshape)
+                raw = b[addr:addr + size]
+                if filters:
+                    raw = _unfilter(raw, filters, mask, dtype.itemsize)
+                elif mask:
+                    raise NotImplementedError("chunk with a filter mask in a dataset without filters")
+                if len(raw) != int(np.prod(cshape)) * dtype.itemsize:
+                    raise NotImplementedError("chunk size does not match its shape")
+                block = np.frombuffer(raw, dtype=dtype, count=int(np.prod(cshape))).reshape(cshape)
                 sl = tuple(slice(o, min(o + c, d)) for o, c, d in zip(offs, cshape, dims))
                 out[sl] = block[tuple(slice(0, s_.stop - s_.start) for s_ in sl)]
         return out
