@@ -27,8 +27,8 @@ and follows the reference for everything a user can observe:
 
 What it does NOT do: dask scheduling (``scheduler`` and ``[chunks]`` are accepted and recorded;
 ``-n N`` spreads the active cells over N GPUs as contiguous ranges, one batched call each, see
-:meth:`MetSimB200.run`), non-standard calendars (the reference
-needs cftime for them) and in-memory ``forcing_fmt = data``.  No arithmetic of the path happens
+:meth:`MetSimB200.run`), calendars other than standard / noleap / all_leap / 360_day (the reference
+needs cftime for every non-standard one) and in-memory ``forcing_fmt = data``.  No arithmetic of the path happens
 here: every number written comes from ``msb_run_host`` (CUDA); without a GPU :meth:`MetSimB200.run`
 raises.
 """
@@ -169,6 +169,14 @@ def read_config(config_file: str, scheduler: str = "distributed", num_workers: i
                  "forcing": _forcing_files(conf["forcing"]),
                  "out_dir": os.path.abspath(conf["out_dir"])})
     return {k: v for k, v in conf.items() if v != []}
+
+
+def _date_range(start, stop, calendar: str = "standard") -> np.ndarray:
+    """Daily ``date_range(start, stop, calendar=...)`` (metsim/datetime.py:11-72): every day of the
+    calendar between the two dates, labelled with Gregorian dates."""
+    units = "days since 1900-01-01"
+    a, b = (ncio.encode_time(np.asarray(x, dtype="datetime64[s]"), units, calendar) for x in (start, stop))
+    return ncio.decode_time(np.arange(int(round(float(a))), int(round(float(b))) + 1), units, calendar)
 
 
 def _parse_date(value):
@@ -360,6 +368,7 @@ class MetSimB200:
             if fmt == "netcdf":
                 ds = _read_netcdf(p["forcing"], p.get("forcing_vars"))
                 ds = _select_domain(ds, self.domain)
+                p["calendar"] = ds["time"].attrs.get("calendar", p["calendar"])      # metsim.py:252-254
                 self._validate_force_times(ds["time"].values)
                 ds = _select_time(ds, p["start"], p["stop"])
             elif fmt in ("ascii", "binary"):
@@ -367,8 +376,7 @@ class MetSimB200:
                     if p[key] == "forcing":
                         raise ValueError(f"{fmt} forcings carry no time axis: `{key}` must be a date")
                     p[key] = _parse_date(p[key])
-                times = p["start"] + np.arange(int((p["stop"] - p["start"]) // np.timedelta64(1, "D")) + 1
-                                               ) * np.timedelta64(1, "D")
+                times = _date_range(p["start"], p["stop"], p["calendar"])
                 self._validate_force_times(times)
                 ds = _read_vic(p, self.domain, times.astype("datetime64[s]"))
             else:
@@ -504,7 +512,7 @@ class MetSimB200:
         mdims = mask.dims
         active = np.argwhere(mask.values > 0)                    # row-major, like np.ndenumerate (:477)
         sel = tuple(active[:, i] for i in range(active.shape[1]))
-        doy, month = _calendar(md["time"].values)
+        doy, month = _calendar(md["time"].values, p["calendar"])
         g = dict(lat=_per_cell(dom, "lat", mdims, mask.values.shape, sel),
                  lon=_per_cell(dom, "lon", mdims, mask.values.shape, sel),
                  elev=_per_cell(dom, "elev", mdims, mask.values.shape, sel), doy=doy, month=month)
@@ -556,7 +564,10 @@ class MetSimB200:
         cell_index = np.flatnonzero(mask.values.ravel() > 0)
         out = []
         for times in self._times:
-            minutes = ((times - _EPOCH) // np.timedelta64(60, "s")).astype(np.int64)
+            if str(p["calendar"]).lower() in ncio.STANDARD_CALENDARS:
+                minutes = ((times - _EPOCH) // np.timedelta64(60, "s")).astype(np.int64)
+            else:                                   # date2num in the run's own calendar (metsim.py:385-388)
+                minutes = np.round(ncio.encode_time(times, DEFAULT_TIME_UNITS, p["calendar"])).astype(np.int64)
             out.append(NC3Writer(self._get_output_filename(times), n_steps=times.size, grid_dims=grid,
                                  cell_index=cell_index, variables=variables,
                                  time_values=minutes.astype(np.int32), time_units=DEFAULT_TIME_UNITS,

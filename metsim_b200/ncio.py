@@ -55,23 +55,82 @@ class Dataset(dict):
         return self
 
 
-def decode_time(values, units: str, calendar: str = "standard") -> np.ndarray:
-    """CF time axis -> ``datetime64[s]`` (standard / gregorian / proleptic_gregorian calendars, all
-    treated as numpy's proleptic Gregorian; the record lengths in scope start after 1582)."""
-    cal = (calendar or "standard").lower()
-    if cal not in STANDARD_CALENDARS:
-        raise NotImplementedError(f"calendar {calendar!r}: the minimal driver decodes standard calendars only "
-                                  "(the reference needs cftime for the others)")
+# calendars whose years all have the same length: days per month (CF conventions 4.4.1)
+UNIFORM_CALENDARS = {
+    "noleap": (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31),
+    "365_day": (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31),
+    "all_leap": (31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31),
+    "366_day": (31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31),
+    "360_day": (30,) * 12,
+}
+
+
+def _parse_units(units: str):
     m = re.match(r"\s*(\w+)\s+since\s+(\d{1,4})-(\d{1,2})-(\d{1,2})"
                  r"(?:[ T]+(\d{1,2}):(\d{1,2})(?::(\d{1,2})(?:\.\d*)?)?)?", units or "")
     if not m or m.group(1).lower() not in _UNIT_SECONDS:
         raise ValueError(f"cannot decode time units {units!r}")
     y, mo, d = int(m.group(2)), int(m.group(3)), int(m.group(4))
     hh, mi, ss = (int(g) if g else 0 for g in m.group(5, 6, 7))
-    ref = (np.datetime64(f"{y:04d}-{mo:02d}-{d:02d}", "s")
-           + np.timedelta64(hh * 3600 + mi * 60 + ss, "s"))
-    secs = np.round(np.asarray(values, dtype=np.float64) * _UNIT_SECONDS[m.group(1).lower()])
-    return ref + secs.astype(np.int64).astype("timedelta64[s]")
+    return _UNIT_SECONDS[m.group(1).lower()], (y, mo, d), hh * 3600 + mi * 60 + ss
+
+
+def _check_calendar(calendar: str) -> str:
+    cal = (calendar or "standard").lower()
+    if cal not in STANDARD_CALENDARS and cal not in UNIFORM_CALENDARS:
+        raise NotImplementedError(f"calendar {calendar!r} is not decoded here (standard, gregorian, "
+                                  "proleptic_gregorian, noleap / 365_day, all_leap / 366_day, 360_day are)")
+    return cal
+
+
+def decode_time(values, units: str, calendar: str = "standard") -> np.ndarray:
+    """CF time axis -> ``datetime64[s]``.  Standard / gregorian / proleptic_gregorian are numpy's
+    proleptic Gregorian calendar (the records in scope start after 1582).  For noleap / all_leap /
+    360_day the date is computed in that calendar and then LABELLED as the Gregorian date with the
+    same year, month and day -- what the reference does with ``CFTimeIndex.to_datetimeindex()``
+    (metsim/io.py:281-283); a date that does not exist there (30 February) is an error, as it is for
+    the reference."""
+    cal = _check_calendar(calendar)
+    unit, (y, mo, d), ref_secs = _parse_units(units)
+    secs = np.round(np.asarray(values, dtype=np.float64) * unit).astype(np.int64)
+    if cal in STANDARD_CALENDARS:
+        ref = np.datetime64(f"{y:04d}-{mo:02d}-{d:02d}", "s") + np.timedelta64(ref_secs, "s")
+        return ref + secs.astype("timedelta64[s]")
+    months = np.asarray(UNIFORM_CALENDARS[cal])
+    cum = np.concatenate([[0], np.cumsum(months)])
+    total = (y * int(cum[-1]) + int(cum[mo - 1]) + (d - 1)) * 86400 + ref_secs + secs
+    day, tod = total // 86400, total % 86400
+    year, doy0 = day // int(cum[-1]), day % int(cum[-1])
+    month0 = np.searchsorted(cum, doy0, side="right") - 1
+    dom0 = doy0 - cum[month0]
+    first = (year - 1970).astype("datetime64[Y]").astype("datetime64[M]") + month0.astype("timedelta64[M]")
+    out = first.astype("datetime64[D]") + dom0.astype("timedelta64[D]")
+    if (out.astype("datetime64[M]") != first).any():
+        bad = np.atleast_1d(out)[np.atleast_1d(out.astype("datetime64[M]") != first)][0]
+        raise ValueError(f"a date of the {cal} calendar has no Gregorian label (rolled over to {bad})")
+    return out.astype("datetime64[s]") + tod.astype("timedelta64[s]")
+
+
+def encode_time(times, units: str, calendar: str = "standard") -> np.ndarray:
+    """Inverse of :func:`decode_time` (float64; what ``netCDF4.date2num`` gives the reference's writer,
+    metsim/metsim.py:385-388)."""
+    cal = _check_calendar(calendar)
+    unit, (y, mo, d), ref_secs = _parse_units(units)
+    t = np.asarray(times).astype("datetime64[s]")
+    if cal in STANDARD_CALENDARS:
+        ref = np.datetime64(f"{y:04d}-{mo:02d}-{d:02d}", "s") + np.timedelta64(ref_secs, "s")
+        return (t - ref).astype(np.int64) / unit
+    months = np.asarray(UNIFORM_CALENDARS[cal])
+    cum = np.concatenate([[0], np.cumsum(months)])
+    year = t.astype("datetime64[Y]").astype(np.int64) + 1970
+    month0 = t.astype("datetime64[M]").astype(np.int64) % 12
+    dom0 = (t.astype("datetime64[D]") - t.astype("datetime64[M]").astype("datetime64[D]")).astype(np.int64)
+    if (dom0 >= months[month0]).any():
+        raise ValueError(f"a date does not exist in the {cal} calendar (29 February?)")
+    tod = (t - t.astype("datetime64[D]").astype("datetime64[s]")).astype(np.int64)
+    total = (year * int(cum[-1]) + cum[month0] + dom0) * 86400 + tod
+    ref_total = (y * int(cum[-1]) + int(cum[mo - 1]) + (d - 1)) * 86400 + ref_secs
+    return (total - ref_total) / unit
 
 
 def _decode(values: np.ndarray, attrs: dict) -> np.ndarray:

@@ -78,15 +78,21 @@ def _per_cell(ds, name: str, mask_dims: tuple, mask_shape: tuple, sel: tuple) ->
     return vals[sel].copy()
 
 
-def _calendar(time_values):
-    """1-based day of year and month of a standard-calendar time axis (numpy datetime64 or anything
-    ``np.asarray`` turns into it)."""
+def _calendar(time_values, calendar: str = "standard"):
+    """1-based day of year and month of a daily time axis (numpy datetime64 or anything ``np.asarray``
+    turns into it).  A noleap / all_leap / 360_day axis arrives labelled with Gregorian dates
+    (``CFTimeIndex.to_datetimeindex()`` in the reference, metsim/io.py:281-283): consecutive records
+    are then up to three calendar days apart (28 February -> 1 March of a leap year) and the day of
+    year is the label's, as ``dates.dayofyear`` is for the reference (io.py:291)."""
     t = np.asarray(time_values)
     if not np.issubdtype(t.dtype, np.datetime64):
-        raise NotImplementedError("the batched path handles standard (datetime64) calendars only; "
+        raise NotImplementedError("the batched path needs a datetime64 time axis; "
                                   f"got a time axis of dtype {t.dtype}")
     days = t.astype("datetime64[D]")
-    if days.size > 1 and not (np.diff(days).astype(np.int64) == 1).all():
+    step = np.diff(days).astype(np.int64)
+    uniform = str(calendar or "standard").lower() in ("noleap", "365_day", "all_leap", "366_day", "360_day")
+    ok = ((step >= 1) & (step <= 3)).all() if uniform else (step == 1).all()
+    if not ok:
         raise ValueError("the forcing time axis must be daily and contiguous")
     years = days.astype("datetime64[Y]")
     doy = (days - years.astype("datetime64[D]")).astype(np.int64) + 1

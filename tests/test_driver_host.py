@@ -240,6 +240,61 @@ def test_checks_raise_what_the_reference_raises(tmp_path):
     assert ms.params["out_vars"]["temp"] == {"units": "C", "out_name": "temp"}
 
 
+def test_noleap_calendar_through_the_driver(tmp_path):
+    """A forcing file on the noleap calendar across February of a leap year: the records are labelled
+    28 February, 1 March (no 29th), the day of year is the label's (59, 61), the state window is the
+    90 records before `start`, and the output time axis is written in the run's own calendar."""
+    tmp = str(tmp_path)
+    conf, case = small_case(tmp, start="2004-02-25", days=10)
+    rng = np.random.default_rng(9)
+    ny, nx = 3, 4
+    coords = {"lat": (("lat",), case["lat"], {}), "lon": (("lon",), case["lon"], {})}
+    # noleap day numbers: 2004-02-25 is day 4 * 365 + 55 since 2000-01-01
+    d0 = 4 * 365 + 55
+    tu = {"units": "days since 2000-01-01 00:00:00", "calendar": "noleap"}
+    tmin = rng.normal(0, 5, (16, ny, nx))
+    write_nc3(os.path.join(tmp, "forcing.nc"), {"time": 16, "lat": ny, "lon": nx}, dict(
+        coords, time=(("time",), (d0 - 3 + np.arange(16)).astype("f8"), tu),
+        Tmin=(("time", "lat", "lon"), tmin, {}), Tmax=(("time", "lat", "lon"), tmin + 5.0, {}),
+        Prec=(("time", "lat", "lon"), rng.gamma(0.8, 6, tmin.shape), {}),
+        wind=(("time", "lat", "lon"), rng.uniform(0.5, 8, tmin.shape), {})))
+    smin = rng.normal(0, 5, (90, ny, nx))
+    write_nc3(os.path.join(tmp, "state.nc"), {"time": 90, "lat": ny, "lon": nx}, dict(
+        coords, time=(("time",), (d0 - 90 + np.arange(90)).astype("f8"), tu),
+        t_min=(("time", "lat", "lon"), smin, {}), t_max=(("time", "lat", "lon"), smin + 8.0, {}),
+        prec=(("time", "lat", "lon"), rng.gamma(0.8, 6, smin.shape), {})))
+    p = driver.read_config(conf)
+    p["stop"] = "2004/3/6"                                   # ten noleap days from 25 February
+    ms = driver.MetSimB200(p)
+    assert ms.params["calendar"] == "noleap"                 # taken from the forcing file (metsim.py:252-254)
+    days = ms.met_data["time"].values.astype("datetime64[D]")
+    assert days.size == 10 and str(days[3]) == "2004-02-28" and str(days[4]) == "2004-03-01"
+    g = ms.gather()
+    assert g["doy"].tolist() == [56, 57, 58, 59, 61, 62, 63, 64, 65, 66] and g["month"].tolist() == [2] * 4 + [3] * 6
+    assert g["state_t_min"].shape == (90, 12)
+    np.testing.assert_array_equal(g["t_min"], tmin[3:13].reshape(10, -1))
+    # the time variable of the output: minutes since 2000-01-01 in the noleap calendar
+    from metsim_b200 import engine
+    import pytest as _pt
+    mp = _pt.MonkeyPatch()
+    mp.setattr(engine, "run_host", _fake_run_host([]))
+    try:
+        (path,) = ms.run()
+    finally:
+        mp.undo()
+    from scipy.io import netcdf_file as _nc
+    with _nc(path, "r", mmap=False) as f:
+        tv = np.array(f.variables["time"].data)
+        assert f.variables["time"].calendar == b"noleap"
+    assert tv[0] == d0 * 1440 and tv[4 * 4] == (d0 + 4) * 1440 and tv[1] - tv[0] == 360
+    (ds,) = ms.open_output()
+    assert ds["time"].values[4 * 4] == np.datetime64("2004-03-01T00:00")
+    # VIC forcings have no time axis of their own: the run's days are the calendar's
+    assert [str(x)[:10] for x in driver._date_range(np.datetime64("2004-02-27"), np.datetime64("2004-03-02"), "noleap")] == \
+        ["2004-02-27", "2004-02-28", "2004-03-01", "2004-03-02"]
+    assert driver._date_range(np.datetime64("2004-02-27"), np.datetime64("2004-03-02"), "standard").size == 5
+
+
 def test_vic_ascii_and_binary_cell_files(tmp_path):
     tmp = str(tmp_path)
     conf, case = small_case(tmp, ny=2, nx=2, mask=[[1, 1], [0, 1]])
@@ -282,8 +337,23 @@ def test_decode_time_and_cf_masking():
     assert t.tolist() == np.array(["1900-01-01T00", "1900-01-02T12", "1901-01-02T00"], "datetime64[s]").tolist()
     assert ncio.decode_time([90], "minutes since 2000-01-01 00:00:00.0")[0] == np.datetime64("2000-01-01T01:30")
     assert ncio.decode_time([2], "hours since 1990-1-1 6:30", "gregorian")[0] == np.datetime64("1990-01-01T08:30")
-    with pytest.raises(NotImplementedError, match="noleap"):
-        ncio.decode_time([0], "days since 2000-01-01", "noleap")
+    with pytest.raises(NotImplementedError, match="julian"):
+        ncio.decode_time([0], "days since 2000-01-01", "julian")
+    # uniform-year calendars: computed in the calendar, labelled with the Gregorian date of the same
+    # year / month / day (CFTimeIndex.to_datetimeindex() in the reference)
+    t = ncio.decode_time([0, 58, 59, 365 + 59], "days since 2000-01-01", "noleap")
+    assert t.tolist() == np.array(["2000-01-01", "2000-02-28", "2000-03-01", "2001-03-01"], "datetime64[s]").tolist()
+    np.testing.assert_array_equal(ncio.encode_time(t, "days since 2000-01-01", "noleap"), [0, 58, 59, 424])
+    assert ncio.encode_time(np.datetime64("2001-03-01"), driver.DEFAULT_TIME_UNITS, "noleap") == (365 + 59) * 1440
+    assert ncio.decode_time([59], "days since 2004-01-01 06:00", "all_leap")[0] == np.datetime64("2004-02-29T06:00")
+    assert ncio.decode_time([30, 360], "days since 2001-01-01", "360_day").tolist() == \
+        np.array(["2001-02-01", "2002-01-01"], "datetime64[s]").tolist()
+    with pytest.raises(ValueError, match="no Gregorian label"):           # 30 February
+        ncio.decode_time([59], "days since 2000-01-01", "360_day")
+    with pytest.raises(ValueError, match="does not exist in the noleap calendar"):
+        ncio.encode_time(np.datetime64("2000-02-29"), "days since 2000-01-01", "noleap")
+    std = ncio.decode_time([1.5], "days since 1900-01-01")
+    assert ncio.encode_time(std, "days since 1900-01-01")[0] == 1.5
     with pytest.raises(ValueError):
         ncio.decode_time([0], "fortnights since 2000-01-01")
     a = ncio._decode(np.array([1.0, 1e20, 3.0], "f4"), {"_FillValue": np.float32(1e20)})
